@@ -1,0 +1,965 @@
+/*
+ * gl_oracle.c -- CPU ORACLE (test infrastructure, NOT product code).  See gl_oracle.h for the
+ * parity status ("pinned" for Poseidon, "parity unpinned" for NTT/LDE/Merkle/FRI layouts).
+ *
+ * Every function states which reference call site reaches it (paths relative to /root/reference)
+ * and which upstream (plonky2 v0.1.4, source absent) routine it restates.  Values handed out are
+ * always canonical (< p).  OpenMP is used only where upstream uses rayon.
+ */
+#include "gl_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define P GLO_P
+#define EPS 0xFFFFFFFFULL /* 2^64 mod p */
+
+/* ------------------------------------------------------------------------------------------------
+ * P0  GoldilocksField (plonky2_field::goldilocks_field; type used at
+ *     src/smt/goldilocks_poseidon/mod.rs:9,179 and src/zkdsa/circuits/mod.rs:81-100)
+ * ---------------------------------------------------------------------------------------------- */
+static inline u64 canon(u64 x) { return x >= P ? x - P : x; }
+
+static inline u64 reduce128(u128 x) {
+    /* 2^64 = 2^32 - 1, 2^96 = -1 (mod p); written without data-dependent branches */
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hi_hi = hi >> 32, hi_lo = hi & EPS;
+    u64 t0 = lo - hi_hi;
+    t0 -= EPS & (0 - (u64)(lo < hi_hi)); /* borrow: -2^64 = -(2^32-1) */
+    u64 t1 = hi_lo * EPS;
+    u64 r = t0 + t1;
+    r += EPS & (0 - (u64)(r < t1)); /* carry: +2^64 = +(2^32-1) */
+    return canon(r);
+}
+
+static inline u64 f_add(u64 a, u64 b) {
+    u128 s = (u128)canon(a) + canon(b);
+    return s >= P ? (u64)(s - P) : (u64)s;
+}
+static inline u64 f_sub(u64 a, u64 b) {
+    a = canon(a); b = canon(b);
+    return a >= b ? a - b : a + (P - b);
+}
+static inline u64 f_mul(u64 a, u64 b) { return reduce128((u128)a * b); }
+u64 glo_add(u64 a, u64 b) { return f_add(a, b); }
+u64 glo_sub(u64 a, u64 b) { return f_sub(a, b); }
+u64 glo_mul(u64 a, u64 b) { return f_mul(a, b); }
+u64 glo_pow(u64 a, u64 e) {
+    u64 r = 1;
+    a = canon(a);
+    while (e) {
+        if (e & 1) r = f_mul(r, a);
+        a = f_mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+u64 glo_inv(u64 a) { return glo_pow(a, P - 2); }
+
+/* Field::primitive_root_of_unity: POWER_OF_TWO_GENERATOR^(2^(32-k)), POWER_OF_TWO_GENERATOR = 7^((p-1)/2^32) */
+u64 glo_primitive_root_of_unity(unsigned lg_n) {
+    u64 g = glo_pow(7, (P - 1) >> 32); /* = 1753635133440165772 */
+    for (unsigned i = lg_n; i < 32; i++) g = f_mul(g, g);
+    return g;
+}
+
+/* QuadraticExtension<GoldilocksField>: F[X]/(X^2 - 7), element [a0, a1] */
+void glo_ext_mul(const u64 a[2], const u64 b[2], u64 out[2]) {
+    u64 c0 = f_add(f_mul(a[0], b[0]), f_mul(7, f_mul(a[1], b[1])));
+    u64 c1 = f_add(f_mul(a[0], b[1]), f_mul(a[1], b[0]));
+    out[0] = c0;
+    out[1] = c1;
+}
+static void ext_add(const u64 a[2], const u64 b[2], u64 out[2]) {
+    out[0] = f_add(a[0], b[0]);
+    out[1] = f_add(a[1], b[1]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P5  Poseidon constants.  plonky2's ALL_ROUND_CONSTANTS table is not on this disk; SURVEY.md 8c:
+ *     it is ChaCha8Rng::seed_from_u64(0) sampled with rand 0.8.5 gen_range(0..p)
+ *     (rand / rand_chacha versions locked at Cargo.lock:1135-1149).  The result is pinned by the
+ *     reference KAT src/zkdsa/circuits/mod.rs:85-105.
+ * ---------------------------------------------------------------------------------------------- */
+static inline u32 rotl32(u32 x, int k) { return (x << k) | (x >> (32 - k)); }
+static inline u32 rotr32(u32 x, unsigned k) { k &= 31; return k ? (x >> k) | (x << (32 - k)) : x; }
+
+static void chacha8_block(const u32 key[8], u64 counter, u32 out[16]) {
+    u32 s[16] = {0x61707865, 0x3320646e, 0x79622d32, 0x6b206574};
+    for (int i = 0; i < 8; i++) s[4 + i] = key[i];
+    s[12] = (u32)counter;
+    s[13] = (u32)(counter >> 32);
+    s[14] = s[15] = 0;
+    u32 x[16];
+    memcpy(x, s, sizeof x);
+#define QR(a, b, c, d)                                                                              \
+    x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);     \
+    x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+    for (int r = 0; r < 4; r++) { /* 8 rounds = 4 double rounds */
+        QR(0, 4, 8, 12) QR(1, 5, 9, 13) QR(2, 6, 10, 14) QR(3, 7, 11, 15)
+        QR(0, 5, 10, 15) QR(1, 6, 11, 12) QR(2, 7, 8, 13) QR(3, 4, 9, 14)
+    }
+#undef QR
+    for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+
+void glo_poseidon_round_constants(u64 out[360]) {
+    /* rand_core::SeedableRng::seed_from_u64(0): PCG32 expands the u64 into the 32-byte key */
+    u32 key[8];
+    u64 st = 0;
+    for (int i = 0; i < 8; i++) {
+        st = st * 6364136223846793005ULL + 11634580027462260723ULL;
+        u32 xs = (u32)(((st >> 18) ^ st) >> 27);
+        key[i] = rotr32(xs, (unsigned)(st >> 59));
+    }
+    u32 blk[16];
+    u64 counter = 0;
+    int pos = 16, n = 0;
+    while (n < 360) {
+        u32 w[2];
+        for (int k = 0; k < 2; k++) {
+            if (pos == 16) { chacha8_block(key, counter++, blk); pos = 0; }
+            w[k] = blk[pos++];
+        }
+        u64 v = (u64)w[0] | ((u64)w[1] << 32);
+        /* UniformInt<u64>::sample_single(0, p): widening multiply, zone = (p << clz(p)) - 1 = p - 1 */
+        u128 m = (u128)v * P;
+        if ((u64)m <= P - 1) out[n++] = (u64)(m >> 64);
+    }
+}
+
+static u64 RC[360];
+static int rc_ready = 0;
+static const u64 MDS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const u64 MDS_DIAG0 = 8;
+
+static void ensure_rc(void) {
+    if (!rc_ready) {
+#pragma omp critical(glo_rc)
+        {
+            if (!rc_ready) {
+                glo_poseidon_round_constants(RC);
+                rc_ready = 1;
+            }
+        }
+    }
+}
+
+static inline u64 sbox7(u64 x) {
+    u64 x2 = f_mul(x, x), x4 = f_mul(x2, x2), x3 = f_mul(x, x2);
+    return f_mul(x3, x4);
+}
+
+/* Poseidon::mds_layer: out[r] = sum_i state[(i+r)%12]*CIRC[i] + state[r]*DIAG[r]  (literal form) */
+static inline void mds_layer_naive(u64 s[12]) {
+    u64 o[12];
+    for (int r = 0; r < 12; r++) {
+        u128 acc = 0;
+        for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_CIRC[i];
+        if (r == 0) acc += (u128)s[0] * MDS_DIAG0;
+        o[r] = reduce128(acc);
+    }
+    memcpy(s, o, sizeof o);
+}
+
+/* Same map, arranged like upstream's mds_row_shf on 32-bit halves: the circulant entries sum to
+ * 256, so the low-half and high-half dot products stay below 2^41 and need no carries. */
+static inline void mds_layer(u64 s[12]) {
+    u64 lo[24], hi[24], ol[12], oh[12];
+    for (int i = 0; i < 12; i++) {
+        lo[i] = lo[i + 12] = s[i] & EPS;
+        hi[i] = hi[i + 12] = s[i] >> 32;
+    }
+    for (int r = 0; r < 12; r++) {
+        u64 al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) {
+            al += lo[r + i] * MDS_CIRC[i];
+            ah += hi[r + i] * MDS_CIRC[i];
+        }
+        ol[r] = al;
+        oh[r] = ah;
+    }
+    ol[0] += lo[0] * MDS_DIAG0;
+    oh[0] += hi[0] * MDS_DIAG0;
+    for (int r = 0; r < 12; r++) s[r] = reduce128((u128)ol[r] + ((u128)oh[r] << 32));
+}
+
+static void permute_with(u64 s[12], void (*mds)(u64 *)) {
+    ensure_rc();
+    int rc = 0;
+    for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
+    for (int r = 0; r < 30; r++) {
+        for (int i = 0; i < 12; i++) s[i] = f_add(s[i], RC[rc++]);
+        if (r < 4 || r >= 26) {
+            for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+        } else {
+            s[0] = sbox7(s[0]);
+        }
+        mds(s);
+    }
+}
+
+/* Poseidon::poseidon (naive schedule: 4 full, 22 partial, 4 full; x^7).  Reached from
+ * PoseidonHash::two_to_one (src/smt/goldilocks_poseidon/mod.rs:165, src/zkdsa/account.rs:165,
+ * src/zkdsa/circuits/mod.rs:66-67) and PoseidonHash::hash_pad (src/smt/goldilocks_poseidon/mod.rs:170). */
+void glo_poseidon_permute_naive(u64 s[12]) { permute_with(s, mds_layer_naive); }
+
+/* The permutation every other oracle routine uses; identical results, faster MDS (CPU baseline). */
+void glo_poseidon_permute(u64 s[12]) {
+    ensure_rc();
+    const u64 *rc = RC;
+    for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
+    for (int r = 0; r < 30; r++, rc += 12) {
+        for (int i = 0; i < 12; i++) {
+            u64 t = s[i] + rc[i]; /* s canonical, rc canonical: at most one wrap of 2^64 */
+            if (t < rc[i]) t += EPS;
+            s[i] = t;
+        }
+        if (r < 4 || r >= 26) {
+            for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+        } else {
+            s[0] = sbox7(s[0]);
+        }
+        mds_layer(s);
+    }
+}
+
+/* hashing::hash_n_to_m_no_pad with overwrite-mode absorption, RATE = 8, 4 outputs */
+void glo_hash_no_pad(const u64 *in, size_t len, u64 out[4]) {
+    u64 s[12] = {0};
+    for (size_t off = 0; off < len; off += 8) {
+        size_t k = len - off < 8 ? len - off : 8;
+        for (size_t i = 0; i < k; i++) s[i] = canon(in[off + i]);
+        glo_poseidon_permute(s);
+    }
+    memcpy(out, s, 4 * sizeof(u64));
+}
+
+/* Hasher::hash_pad: push 1, zeros until (len+1) % WIDTH == 0, push 1.  WIDTH = 12 is forced by
+ * src/smt/gadgets/common.rs:87-101 == src/smt/goldilocks_poseidon/mod.rs:167-181. */
+void glo_hash_pad(const u64 *in, size_t len, u64 out[4]) {
+    size_t n = len + 1;
+    while ((n + 1) % 12 != 0) n++;
+    n++;
+    u64 *buf = (u64 *)calloc(n, sizeof(u64));
+    memcpy(buf, in, len * sizeof(u64));
+    buf[len] = 1;
+    buf[n - 1] = 1;
+    glo_hash_no_pad(buf, n, out);
+    free(buf);
+}
+
+/* Hasher::hash_or_noop: <= 4 elements are copied (zero padded), longer inputs hashed */
+void glo_hash_or_noop(const u64 *in, size_t len, u64 out[4]) {
+    if (len <= 4) {
+        for (size_t i = 0; i < 4; i++) out[i] = i < len ? canon(in[i]) : 0;
+    } else {
+        glo_hash_no_pad(in, len, out);
+    }
+}
+
+/* hashing::compress = PoseidonHash::two_to_one */
+void glo_two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
+    u64 s[12] = {0};
+    for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; }
+    glo_poseidon_permute(s);
+    memcpy(out, s, 4 * sizeof(u64));
+}
+
+void glo_permute_batch(u64 *states, size_t m) {
+    ensure_rc();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < m; i++) glo_poseidon_permute(states + 12 * i);
+}
+void glo_two_to_one_batch(const u64 *l, const u64 *r, u64 *out, size_t m) {
+    ensure_rc();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < m; i++) glo_two_to_one(l + 4 * i, r + 4 * i, out + 4 * i);
+}
+void glo_hash_no_pad_batch(const u64 *in, size_t len_each, size_t m, u64 *out) {
+    ensure_rc();
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < m; i++) glo_hash_no_pad(in + len_each * i, len_each, out + 4 * i);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P1/P2/P9  plonky2_field::fft  (fft_classic: bit-reverse, then decimation-in-time butterflies
+ *           with a table of roots; natural order in and out).
+ * ---------------------------------------------------------------------------------------------- */
+size_t glo_reverse_bits(size_t x, unsigned bits) {
+    size_t r = 0;
+    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
+    return r;
+}
+
+static void reverse_index_bits_u64(u64 *a, unsigned lg_n) {
+    size_t n = (size_t)1 << lg_n;
+    for (size_t i = 0; i < n; i++) {
+        size_t j = glo_reverse_bits(i, lg_n);
+        if (i < j) { u64 t = a[i]; a[i] = a[j]; a[j] = t; }
+    }
+}
+
+/* roots[j] = w_n^j for j < n/2; level m uses stride n/m (same numbers as FftRootTable row lg_m-1) */
+static u64 *root_cache[33];
+static const u64 *roots_for(unsigned lg_n) {
+    if (lg_n == 0) return NULL;
+    if (!root_cache[lg_n]) {
+#pragma omp critical(glo_roots)
+        {
+            if (!root_cache[lg_n]) {
+                size_t half = (size_t)1 << (lg_n - 1);
+                u64 *t = (u64 *)malloc(half * sizeof(u64));
+                u64 w = glo_primitive_root_of_unity(lg_n), cur = 1;
+                for (size_t j = 0; j < half; j++) { t[j] = cur; cur = f_mul(cur, w); }
+                root_cache[lg_n] = t;
+            }
+        }
+    }
+    return root_cache[lg_n];
+}
+
+/* fft_with_options(poly, zero_factor, root_table): out[j] = sum_i a[i] * w_n^(i*j).
+ * zero_factor = r promises the last n - n/2^r inputs are zero (PolynomialCoeffs::lde); the first r
+ * butterfly layers then degenerate to copies, which is what upstream does; results are identical. */
+void glo_fft(u64 *a, unsigned lg_n, unsigned zero_factor) {
+    size_t n = (size_t)1 << lg_n;
+    if (lg_n == 0) { a[0] = canon(a[0]); return; }
+    const u64 *roots = roots_for(lg_n);
+    for (size_t i = 0; i < n; i++) a[i] = canon(a[i]);
+    reverse_index_bits_u64(a, lg_n);
+    unsigned r = zero_factor > lg_n ? lg_n : zero_factor;
+    if (r > 0) {
+        size_t mask = ~(((size_t)1 << r) - 1);
+        for (size_t i = 0; i < n; i++) a[i] = a[i & mask];
+    }
+    for (unsigned lg_half = r; lg_half < lg_n; lg_half++) {
+        size_t half = (size_t)1 << lg_half, m = half << 1, stride = n / m;
+        for (size_t k = 0; k < n; k += m) {
+            for (size_t j = 0; j < half; j++) {
+                u64 t = f_mul(roots[j * stride], a[k + half + j]);
+                u64 u = a[k + j];
+                a[k + j] = f_add(u, t);
+                a[k + half + j] = f_sub(u, t);
+            }
+        }
+    }
+}
+
+/* ifft_with_options: forward FFT, then out[0],out[n/2] *= 1/n and out[i] <-> out[n-i] scaled by 1/n */
+void glo_ifft(u64 *a, unsigned lg_n) {
+    size_t n = (size_t)1 << lg_n;
+    glo_fft(a, lg_n, 0);
+    u64 n_inv = glo_inv((u64)n % P);
+    a[0] = f_mul(a[0], n_inv);
+    if (n > 1) a[n / 2] = f_mul(a[n / 2], n_inv);
+    for (size_t i = 1; i < n / 2; i++) {
+        size_t j = n - i;
+        u64 ci = f_mul(a[j], n_inv), cj = f_mul(a[i], n_inv);
+        a[i] = ci;
+        a[j] = cj;
+    }
+}
+
+/* PolynomialCoeffs::coset_fft_with_options: coeffs[i] *= shift^i, then fft */
+void glo_coset_fft(u64 *a, unsigned lg_n, u64 shift, unsigned zero_factor) {
+    size_t n = (size_t)1 << lg_n;
+    u64 cur = 1;
+    for (size_t i = 0; i < n; i++) { a[i] = f_mul(a[i], cur); cur = f_mul(cur, shift); }
+    glo_fft(a, lg_n, zero_factor);
+}
+
+/* PolynomialValues::coset_ifft: ifft, then coeffs[i] *= shift^-i */
+void glo_coset_ifft(u64 *a, unsigned lg_n, u64 shift) {
+    size_t n = (size_t)1 << lg_n;
+    glo_ifft(a, lg_n);
+    u64 sinv = glo_inv(shift), cur = 1;
+    for (size_t i = 0; i < n; i++) { a[i] = f_mul(a[i], cur); cur = f_mul(cur, sinv); }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P4/P11  plonky2::hash::merkle_tree::MerkleTree::new / prove, merkle_proofs::verify_merkle_proof_to_cap
+ * ---------------------------------------------------------------------------------------------- */
+static unsigned log2_strict(size_t n) {
+    unsigned k = 0;
+    while (((size_t)1 << k) < n) k++;
+    return k;
+}
+
+/* fill_subtree: digests_buf has 2*(num_leaves-1) entries, recursive in-order layout
+ * [left subtree digests | left child | right child | right subtree digests]; returns the root. */
+static void fill_subtree(u64 *buf, size_t buf_len, const u64 *leaves, size_t num_leaves, size_t leaf_len,
+                         u64 root[4]) {
+    if (buf_len == 0) {
+        glo_hash_or_noop(leaves, leaf_len, root);
+        return;
+    }
+    size_t half_buf = buf_len / 2, half_leaves = num_leaves / 2;
+    u64 *left_slot = buf + 4 * (half_buf - 1);
+    u64 *right_slot = buf + 4 * half_buf;
+    u64 ld[4], rd[4];
+    int par = num_leaves >= 1024; /* rayon::join upstream */
+#pragma omp task shared(ld) if (par)
+    fill_subtree(buf, half_buf - 1, leaves, half_leaves, leaf_len, ld);
+#pragma omp task shared(rd) if (par)
+    fill_subtree(buf + 4 * (half_buf + 1), half_buf - 1, leaves + half_leaves * leaf_len, half_leaves,
+                 leaf_len, rd);
+#pragma omp taskwait
+    memcpy(left_slot, ld, sizeof ld);
+    memcpy(right_slot, rd, sizeof rd);
+    glo_two_to_one(ld, rd, root);
+}
+
+int glo_merkle_tree(const u64 *leaves, size_t num_leaves, size_t leaf_len, unsigned cap_height,
+                    u64 *digests, u64 *cap) {
+    if (num_leaves == 0 || (num_leaves & (num_leaves - 1))) return 1; /* log2_strict panics */
+    unsigned lg = log2_strict(num_leaves);
+    if (cap_height > lg) return 2; /* assert!(cap_height <= log2_leaves_len) */
+    ensure_rc();
+    size_t num_caps = (size_t)1 << cap_height;
+    size_t num_digests = 2 * (num_leaves - num_caps);
+    size_t sub_leaves = num_leaves / num_caps, sub_digests = num_digests / num_caps;
+#pragma omp parallel
+#pragma omp single
+    {
+        for (size_t s = 0; s < num_caps; s++) {
+#pragma omp task firstprivate(s)
+            fill_subtree(digests ? digests + 4 * s * sub_digests : NULL, sub_digests,
+                         leaves + s * sub_leaves * leaf_len, sub_leaves, leaf_len, cap + 4 * s);
+        }
+#pragma omp taskwait
+    }
+    return 0;
+}
+
+void glo_merkle_prove(const u64 *digests, size_t num_leaves, unsigned cap_height, size_t leaf_index,
+                      u64 *siblings) {
+    unsigned lg = log2_strict(num_leaves);
+    unsigned L = lg - cap_height;
+    size_t num_caps = (size_t)1 << cap_height;
+    size_t sub_digests = 2 * (num_leaves - num_caps) / num_caps;
+    size_t subtree = leaf_index >> L;
+    const u64 *buf = digests + 4 * subtree * sub_digests;
+    size_t pair = leaf_index & (((size_t)1 << L) - 1);
+    for (unsigned i = 0; i < L; i++) {
+        size_t parity = pair & 1;
+        pair >>= 1;
+        size_t sib = 2 * ((pair << (i + 1)) + ((size_t)1 << i) - 1) + (1 - parity);
+        memcpy(siblings + 4 * i, buf + 4 * sib, 4 * sizeof(u64));
+    }
+}
+
+int glo_merkle_verify(const u64 *leaf, size_t leaf_len, size_t leaf_index, const u64 *siblings,
+                      unsigned num_siblings, const u64 *cap, unsigned cap_height) {
+    u64 d[4];
+    (void)cap_height;
+    glo_hash_or_noop(leaf, leaf_len, d);
+    size_t idx = leaf_index;
+    for (unsigned i = 0; i < num_siblings; i++) {
+        u64 nd[4];
+        if (idx & 1) glo_two_to_one(siblings + 4 * i, d, nd);
+        else glo_two_to_one(d, siblings + 4 * i, nd);
+        memcpy(d, nd, sizeof d);
+        idx >>= 1;
+    }
+    return memcmp(d, cap + 4 * idx, sizeof d) == 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P*  plonky2::fri::oracle::PolynomialBatch::from_values / from_coeffs
+ *     reached from data.prove(pw) (44 sites, e.g. src/ecdsa/gadgets/ecdsa.rs:349) and
+ *     builder.build::<C>() (41 sites, e.g. src/ecdsa/gadgets/ecdsa.rs:298)
+ * ---------------------------------------------------------------------------------------------- */
+int glo_commit_from_coeffs(const u64 *coeffs, unsigned lg_n, unsigned c, unsigned rate_bits,
+                           unsigned cap_height, u64 *leaves_out, u64 *digests_out, u64 *cap_out) {
+    size_t n = (size_t)1 << lg_n, N = n << rate_bits;
+    unsigned lg_N = lg_n + rate_bits;
+    if (cap_height > lg_N) return 2;
+    roots_for(lg_N);
+    /* "FFT + blinding": lde_values[col] = coeffs[col].lde(rate_bits).coset_fft(7); blinding = false */
+    u64 *lde = (u64 *)malloc((size_t)c * N * sizeof(u64));
+    if (!lde) return 3;
+#pragma omp parallel for schedule(dynamic)
+    for (unsigned col = 0; col < c; col++) {
+        u64 *v = lde + (size_t)col * N;
+        memcpy(v, coeffs + (size_t)col * n, n * sizeof(u64));
+        memset(v + n, 0, (N - n) * sizeof(u64));
+        glo_coset_fft(v, lg_N, 7, rate_bits);
+    }
+    /* "transpose LDEs" + reverse_index_bits_in_place(leaves) */
+    u64 *leaves = leaves_out ? leaves_out : (u64 *)malloc((size_t)c * N * sizeof(u64));
+    if (!leaves) { free(lde); return 3; }
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < N; i++) {
+        size_t src = glo_reverse_bits(i, lg_N);
+        for (unsigned col = 0; col < c; col++) leaves[i * c + col] = lde[(size_t)col * N + src];
+    }
+    free(lde);
+    /* "build Merkle tree" */
+    size_t num_digests = 2 * (N - ((size_t)1 << cap_height));
+    u64 *digests = digests_out ? digests_out : (u64 *)malloc((num_digests ? num_digests : 1) * 4 * sizeof(u64));
+    u64 cap_local[4 * 64];
+    u64 *cap = cap_out ? cap_out : (cap_height <= 6 ? cap_local : (u64 *)malloc(((size_t)4 << cap_height) * sizeof(u64)));
+    int rc = glo_merkle_tree(leaves, N, c, cap_height, digests, cap);
+    if (!leaves_out) free(leaves);
+    if (!digests_out) free(digests);
+    if (!cap_out && cap_height > 6) free(cap);
+    return rc;
+}
+
+int glo_commit_from_values(const u64 *values, unsigned lg_n, unsigned c, unsigned rate_bits,
+                           unsigned cap_height, u64 *coeffs_out, u64 *leaves_out, u64 *digests_out,
+                           u64 *cap_out) {
+    size_t n = (size_t)1 << lg_n;
+    u64 *coeffs = coeffs_out ? coeffs_out : (u64 *)malloc((size_t)c * n * sizeof(u64));
+    if (!coeffs) return 3;
+    roots_for(lg_n);
+    /* "IFFT": values.into_par_iter().map(|v| v.ifft()) */
+#pragma omp parallel for schedule(dynamic)
+    for (unsigned col = 0; col < c; col++) {
+        u64 *v = coeffs + (size_t)col * n;
+        if (v != values + (size_t)col * n) memcpy(v, values + (size_t)col * n, n * sizeof(u64));
+        glo_ifft(v, lg_n);
+    }
+    int rc = glo_commit_from_coeffs(coeffs, lg_n, c, rate_bits, cap_height, leaves_out, digests_out, cap_out);
+    if (!coeffs_out) free(coeffs);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P6  PoseidonNodeHash::calc_node_hash  (src/smt/goldilocks_poseidon/mod.rs:158-184)
+ * ---------------------------------------------------------------------------------------------- */
+void glo_smt_leaf_hash(const u64 key[4], const u64 value[4], u64 out[4]) {
+    u64 in[9];
+    memcpy(in, key, 32);
+    memcpy(in + 4, value, 32);
+    in[8] = 1;
+    glo_hash_pad(in, 9, out); /* = hash_no_pad([k, v, 1, 1, 0, 1]), src/smt/gadgets/common.rs:87-101 */
+}
+void glo_smt_internal_hash(const u64 l[4], const u64 r[4], u64 out[4]) { glo_two_to_one(l, r, out); }
+
+/* ------------------------------------------------------------------------------------------------
+ * P7  verify_smt_process_proof  (src/smt/proof/process.rs:153-257), calc_old_new_root (:260-337),
+ *     smt_processor_sm (:340-370), smt_lev_ins (src/smt/proof/common.rs:8-44).
+ *     Key bits: HashOut::to_bytes (4 x u64 LE) -> LSB-first bits
+ *     (src/smt/goldilocks_poseidon/mod.rs:27-48, src/smt/proof/common.rs:47-58).
+ *     Returns 0 when no assert fires, else the ordinal of the first assert that would panic.
+ * ---------------------------------------------------------------------------------------------- */
+enum { ST_TOP = 0, ST_BOT = 1, ST_OLD0 = 2, ST_NEW1 = 3, ST_UPD = 4, ST_NA = 5 };
+
+static inline int key_bit(const u64 k[4], unsigned i) { return (int)((k[i >> 6] >> (i & 63)) & 1); }
+static inline int is_zero4(const u64 h[4]) { return (h[0] | h[1] | h[2] | h[3]) == 0; }
+static inline int eq4(const u64 a[4], const u64 b[4]) { return memcmp(a, b, 32) == 0; }
+
+static int processor_sm(int prev, int diff_bit, int is_old0, int lev_ins, int ins_or_rem) {
+    if (prev == ST_TOP) {
+        if (!lev_ins) return ST_TOP;
+        if (!ins_or_rem) return ST_UPD;
+        if (is_old0) return ST_OLD0;
+        return diff_bit ? ST_NEW1 : ST_BOT;
+    }
+    if (prev == ST_BOT) return diff_bit ? ST_NEW1 : ST_BOT;
+    return ST_NA;
+}
+
+int glo_smt_verify_process_proof(const glo_smt_process_proof *pf) {
+    enum { LEVELS = 256 };
+    int enabled = pf->fnc != 0;
+    u32 fnc = pf->fnc;
+    const u64 *old_key = pf->old_key, *old_value = pf->old_value, *old_root = pf->old_root;
+    const u64 *new_key = pf->new_key, *new_value = pf->new_value, *new_root = pf->new_root;
+    if (fnc == 3) { /* a remove proof is an insert proof with old and new flipped */
+        fnc = 2;
+        old_key = pf->new_key; old_value = pf->new_value; old_root = pf->new_root;
+        new_key = pf->old_key; new_value = pf->old_value; new_root = pf->old_root;
+    }
+    if (pf->num_siblings >= LEVELS) return 1; /* assert!(siblings.len() < n2b_new.len()) */
+    /* siblings.resize(256, default) : the struct is already zero padded */
+    u64 sib[LEVELS][4];
+    for (unsigned i = 0; i < LEVELS; i++) {
+        if (i < pf->num_siblings) memcpy(sib[i], pf->siblings[i], 32);
+        else memset(sib[i], 0, 32);
+    }
+    /* smt_lev_ins */
+    if (enabled && !is_zero4(sib[LEVELS - 1])) return 2; /* assert!(is_zeros.last()) */
+    unsigned char lev_ins[LEVELS];
+    {
+        /* is_zeros reversed with a trailing false; scan from the bottom of the path upwards */
+        int last_done = 0;
+        for (unsigned i = 0; i < LEVELS; i++) {
+            /* reversed index i+1 is original index LEVELS-2-i; beyond the top -> pushed `false` */
+            int zero_next = (i + 1 < LEVELS) ? is_zero4(sib[LEVELS - 2 - i]) : 0;
+            int v = !zero_next && !last_done;
+            last_done = last_done || !zero_next;
+            lev_ins[LEVELS - 1 - i] = (unsigned char)v;
+        }
+    }
+    int sm[LEVELS];
+    int prev = enabled ? ST_TOP : ST_NA;
+    int ins_or_rem = fnc == 2;
+    for (unsigned i = 0; i < LEVELS; i++) {
+        int st = processor_sm(prev, key_bit(old_key, i) ^ key_bit(new_key, i), (int)pf->is_old0, lev_ins[i],
+                              ins_or_rem);
+        sm[i] = st;
+        prev = st;
+    }
+    if (sm[LEVELS - 1] == ST_TOP || sm[LEVELS - 1] == ST_BOT) return 3;
+    /* calc_old_new_root */
+    u64 zero[4] = {0, 0, 0, 0};
+    u64 old1_leaf[4], new1_leaf[4];
+    glo_smt_leaf_hash(old_key, old_value, old1_leaf);
+    glo_smt_leaf_hash(new_key, new_value, new1_leaf);
+    u64 prev_old[4] = {0, 0, 0, 0}, prev_new[4] = {0, 0, 0, 0};
+    for (int i = LEVELS - 1; i >= 0; i--) {
+        int pos = key_bit(new_key, (unsigned)i);
+        u64 old_hash[4], new_hash[4];
+        if (pos) glo_two_to_one(sib[i], prev_old, old_hash);
+        else glo_two_to_one(prev_old, sib[i], old_hash);
+        const u64 *o_root, *n_left, *n_right, *n_root;
+        switch (sm[i]) {
+            case ST_TOP:  o_root = old_hash;  n_left = prev_new;  n_right = sib[i];    break;
+            case ST_BOT:  o_root = old1_leaf; n_left = prev_new;  n_right = zero;      break;
+            case ST_NEW1: o_root = old1_leaf; n_left = new1_leaf; n_right = old1_leaf; break;
+            case ST_UPD:  o_root = old1_leaf; n_left = zero;      n_right = zero;      break;
+            default:      o_root = zero;      n_left = zero;      n_right = zero;      break;
+        }
+        if (pos) glo_two_to_one(n_right, n_left, new_hash);
+        else glo_two_to_one(n_left, n_right, new_hash);
+        switch (sm[i]) {
+            case ST_TOP: case ST_BOT: case ST_NEW1: n_root = new_hash; break;
+            case ST_OLD0: case ST_UPD: n_root = new1_leaf; break;
+            default: n_root = zero; break;
+        }
+        u64 t_old[4], t_new[4];
+        memcpy(t_old, o_root, 32);
+        memcpy(t_new, n_root, 32);
+        memcpy(prev_old, t_old, 32);
+        memcpy(prev_new, t_new, 32);
+    }
+    if (enabled) {
+        if (!eq4(prev_old, old_root)) return 4;
+        if (!eq4(prev_new, new_root)) return 5;
+    } else {
+        if (!eq4(old_root, new_root)) return 6;
+        if (!eq4(old_value, new_value)) return 7;
+    }
+    if (fnc == 1 || !enabled) {
+        if (!eq4(old_key, new_key)) return 8;
+    }
+    return 0;
+}
+
+void glo_smt_verify_process_batch(const glo_smt_process_proof *proofs, size_t m, int32_t *status) {
+    ensure_rc();
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t i = 0; i < m; i++) status[i] = glo_smt_verify_process_proof(proofs + i);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * In-memory sparse Merkle tree: src/smt/tree.rs (find :588-676, update :174-253, insert :255-387,
+ * remove :390-533, noop :536-559, calc_process_proof :561-586) over NodeDataMemory
+ * (src/smt/goldilocks_poseidon/mod.rs:58-94: nodes are never deleted).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct { u64 hash[4]; u64 a[4]; u64 b[4]; unsigned char used, is_leaf; } smt_node;
+struct glo_smt { smt_node *tab; size_t cap, count; u64 root[4]; };
+
+static size_t h4(const u64 h[4]) { return (size_t)(h[0] ^ (h[1] * 0x9E3779B97F4A7C15ULL) ^ (h[2] << 7) ^ (h[3] >> 3)); }
+
+static smt_node *smt_lookup(const glo_smt *t, const u64 h[4]) {
+    size_t i = h4(h) & (t->cap - 1);
+    while (t->tab[i].used) {
+        if (eq4(t->tab[i].hash, h)) return &t->tab[i];
+        i = (i + 1) & (t->cap - 1);
+    }
+    return NULL;
+}
+static void smt_put(glo_smt *t, const u64 h[4], int is_leaf, const u64 a[4], const u64 b[4]);
+static void smt_grow(glo_smt *t) {
+    smt_node *old = t->tab;
+    size_t oc = t->cap;
+    t->cap *= 2;
+    t->tab = (smt_node *)calloc(t->cap, sizeof(smt_node));
+    t->count = 0;
+    for (size_t i = 0; i < oc; i++)
+        if (old[i].used) smt_put(t, old[i].hash, old[i].is_leaf, old[i].a, old[i].b);
+    free(old);
+}
+static void smt_put(glo_smt *t, const u64 h[4], int is_leaf, const u64 a[4], const u64 b[4]) {
+    if ((t->count + 1) * 2 > t->cap) smt_grow(t);
+    size_t i = h4(h) & (t->cap - 1);
+    while (t->tab[i].used && !eq4(t->tab[i].hash, h)) i = (i + 1) & (t->cap - 1);
+    if (!t->tab[i].used) t->count++;
+    t->tab[i].used = 1;
+    t->tab[i].is_leaf = (unsigned char)is_leaf;
+    memcpy(t->tab[i].hash, h, 32);
+    memcpy(t->tab[i].a, a, 32);
+    memcpy(t->tab[i].b, b, 32);
+}
+
+glo_smt *glo_smt_new(void) {
+    glo_smt *t = (glo_smt *)calloc(1, sizeof(glo_smt));
+    t->cap = 1024;
+    t->tab = (smt_node *)calloc(t->cap, sizeof(smt_node));
+    return t;
+}
+void glo_smt_free(glo_smt *t) { if (t) { free(t->tab); free(t); } }
+void glo_smt_root(const glo_smt *t, u64 out[4]) { memcpy(out, t->root, 32); }
+
+typedef struct {
+    int found, is_old0;
+    u32 ns;
+    u64 sib[256][4];
+    u64 value[4], nf_key[4], nf_value[4];
+} find_res;
+
+/* find_rec, iteratively: siblings[level] is the other child at that level, top first */
+static int smt_find_i(const glo_smt *t, const u64 key[4], find_res *r) {
+    memset(r, 0, sizeof *r);
+    u64 cur[4];
+    memcpy(cur, t->root, 32);
+    for (unsigned level = 0;; level++) {
+        if (is_zero4(cur)) { r->found = 0; r->is_old0 = 1; return 0; }
+        const smt_node *nd = smt_lookup(t, cur);
+        if (!nd) return -1; /* "searching node is not found" */
+        if (nd->is_leaf) {
+            if (eq4(nd->a, key)) { r->found = 1; memcpy(r->value, nd->b, 32); r->is_old0 = 0; }
+            else { r->found = 0; memcpy(r->nf_key, nd->a, 32); memcpy(r->nf_value, nd->b, 32); r->is_old0 = 0; }
+            return 0;
+        }
+        if (level >= 256) return -1;
+        if (key_bit(key, level)) { memcpy(r->sib[r->ns++], nd->a, 32); memcpy(cur, nd->b, 32); }
+        else { memcpy(r->sib[r->ns++], nd->b, 32); memcpy(cur, nd->a, 32); }
+    }
+}
+
+int glo_smt_find(const glo_smt *t, const u64 key[4], u64 *siblings, u32 *num_siblings, u64 not_found_key[4],
+                 u64 value[4], u32 *is_old0) {
+    find_res r;
+    if (smt_find_i(t, key, &r) < 0) return -1;
+    if (siblings) memcpy(siblings, r.sib, (size_t)r.ns * 32);
+    if (num_siblings) *num_siblings = r.ns;
+    if (not_found_key) memcpy(not_found_key, r.nf_key, 32);
+    if (value) memcpy(value, r.found ? r.value : r.nf_value, 32);
+    if (is_old0) *is_old0 = (u32)r.is_old0;
+    return r.found;
+}
+
+static void proof_set_siblings(glo_smt_process_proof *pf, u64 sib[][4], u32 ns) {
+    memset(pf->siblings, 0, sizeof pf->siblings);
+    memcpy(pf->siblings, sib, (size_t)ns * 32);
+    pf->num_siblings = ns;
+}
+
+/* calc_process_proof: value == 0 ? (found ? remove : noop) : (found ? update : insert) */
+int glo_smt_set(glo_smt *t, const u64 key[4], const u64 value[4], glo_smt_process_proof *pf) {
+    find_res r;
+    u64 zero[4] = {0, 0, 0, 0};
+    if (smt_find_i(t, key, &r) < 0) return -1;
+    memset(pf, 0, sizeof *pf);
+    if (is_zero4(value) && !r.found) { /* noop */
+        memcpy(pf->old_root, t->root, 32); memcpy(pf->new_root, t->root, 32);
+        memcpy(pf->old_key, key, 32); memcpy(pf->new_key, key, 32);
+        pf->is_old0 = 1; pf->fnc = 0;
+        return 0;
+    }
+    if (!is_zero4(value) && r.found) { /* update */
+        u64 rt_old[4], rt_new[4];
+        glo_smt_leaf_hash(key, r.value, rt_old);
+        glo_smt_leaf_hash(key, value, rt_new);
+        smt_put(t, rt_new, 1, key, value);
+        for (int lvl = (int)r.ns - 1; lvl >= 0; lvl--) {
+            u64 no[4], nn[4];
+            if (key_bit(key, (unsigned)lvl)) {
+                glo_two_to_one(r.sib[lvl], rt_old, no); glo_two_to_one(r.sib[lvl], rt_new, nn);
+                smt_put(t, nn, 0, r.sib[lvl], rt_new);
+            } else {
+                glo_two_to_one(rt_old, r.sib[lvl], no); glo_two_to_one(rt_new, r.sib[lvl], nn);
+                smt_put(t, nn, 0, rt_new, r.sib[lvl]);
+            }
+            memcpy(rt_old, no, 32); memcpy(rt_new, nn, 32);
+        }
+        memcpy(pf->old_root, t->root, 32); memcpy(pf->old_key, key, 32); memcpy(pf->old_value, r.value, 32);
+        memcpy(pf->new_root, rt_new, 32); memcpy(pf->new_key, key, 32); memcpy(pf->new_value, value, 32);
+        proof_set_siblings(pf, r.sib, r.ns);
+        pf->is_old0 = 0; pf->fnc = 1;
+        memcpy(t->root, rt_new, 32);
+        return 0;
+    }
+    if (!is_zero4(value)) { /* insert */
+        u32 ns = r.ns;
+        int mixed, added_one;
+        u64 rt_old[4];
+        if (!r.is_old0) {
+            for (unsigned i = ns; i < 256; i++) {
+                if (key_bit(r.nf_key, i) != key_bit(key, i)) break;
+                memset(r.sib[ns++], 0, 32);
+            }
+            glo_smt_leaf_hash(r.nf_key, r.nf_value, rt_old);
+            memcpy(r.sib[ns++], rt_old, 32);
+            added_one = 1; mixed = 0;
+        } else {
+            mixed = r.ns != 0; added_one = 0;
+            memset(rt_old, 0, 32);
+        }
+        u64 rt[4];
+        glo_smt_leaf_hash(key, value, rt);
+        smt_put(t, rt, 1, key, value);
+        for (int lvl = (int)ns - 1, level = 0; lvl >= 0; lvl--, level++) {
+            if (level != 0 && !is_zero4(r.sib[lvl])) mixed = 1;
+            int bit = key_bit(key, (unsigned)lvl);
+            if (mixed) {
+                u64 no[4];
+                if (bit) glo_two_to_one(r.sib[lvl], rt_old, no); else glo_two_to_one(rt_old, r.sib[lvl], no);
+                memcpy(rt_old, no, 32);
+            }
+            u64 nn[4];
+            if (bit) { glo_two_to_one(r.sib[lvl], rt, nn); smt_put(t, nn, 0, r.sib[lvl], rt); }
+            else { glo_two_to_one(rt, r.sib[lvl], nn); smt_put(t, nn, 0, rt, r.sib[lvl]); }
+            memcpy(rt, nn, 32);
+        }
+        if (added_one) ns--;
+        while (ns > 0 && is_zero4(r.sib[ns - 1])) ns--;
+        memcpy(pf->old_root, t->root, 32); memcpy(pf->old_key, r.nf_key, 32); memcpy(pf->old_value, r.nf_value, 32);
+        memcpy(pf->new_root, rt, 32); memcpy(pf->new_key, key, 32); memcpy(pf->new_value, value, 32);
+        proof_set_siblings(pf, r.sib, ns);
+        pf->is_old0 = (u32)r.is_old0; pf->fnc = 2;
+        memcpy(t->root, rt, 32);
+        return 0;
+    }
+    /* remove */
+    {
+        u64 rt_old[4], rt_new[4], res_old_key[4], res_old_value[4];
+        int mixed, res_is_old0;
+        glo_smt_leaf_hash(key, r.value, rt_old);
+        if (r.ns > 0) {
+            const smt_node *nx = smt_lookup(t, r.sib[r.ns - 1]);
+            if (nx && nx->is_leaf) {
+                mixed = 0; memcpy(res_old_key, nx->a, 32); memcpy(res_old_value, nx->b, 32);
+                res_is_old0 = 0; memcpy(rt_new, r.sib[r.ns - 1], 32);
+            } else if (nx) {
+                mixed = 1; memcpy(res_old_key, key, 32); memset(res_old_value, 0, 32);
+                res_is_old0 = 1; memset(rt_new, 0, 32);
+            } else if (is_zero4(r.sib[r.ns - 1])) {
+                /* upstream: nodes_db.get(zero) -> None -> unreachable!(); cannot occur in a tree built by set() */
+                return -2;
+            } else return -2;
+        } else {
+            mixed = 0; memcpy(res_old_key, key, 32); memset(res_old_value, 0, 32);
+            res_is_old0 = 1; memset(rt_new, 0, 32);
+        }
+        u64 res_sib[256][4];
+        u32 rns = 0;
+        for (int lvl = (int)r.ns - 1, level = 0; lvl >= 0; lvl--, level++) {
+            const u64 *new_sibling = (level == 0 && !res_is_old0) ? zero : r.sib[lvl];
+            int bit = key_bit(key, (unsigned)lvl);
+            u64 no[4];
+            if (bit) glo_two_to_one(r.sib[lvl], rt_old, no); else glo_two_to_one(rt_old, r.sib[lvl], no);
+            memcpy(rt_old, no, 32);
+            if (!is_zero4(new_sibling)) mixed = 1;
+            if (mixed) {
+                memmove(res_sib[1], res_sib[0], (size_t)rns * 32); /* push front */
+                memcpy(res_sib[0], r.sib[lvl], 32);
+                rns++;
+                u64 nn[4];
+                if (bit) { glo_two_to_one(new_sibling, rt_new, nn); smt_put(t, nn, 0, new_sibling, rt_new); }
+                else { glo_two_to_one(rt_new, new_sibling, nn); smt_put(t, nn, 0, rt_new, new_sibling); }
+                memcpy(rt_new, nn, 32);
+            }
+        }
+        memcpy(pf->old_root, rt_old, 32); memcpy(pf->old_key, key, 32); memcpy(pf->old_value, r.value, 32);
+        memcpy(pf->new_root, rt_new, 32); memcpy(pf->new_key, res_old_key, 32); memcpy(pf->new_value, res_old_value, 32);
+        proof_set_siblings(pf, res_sib, rns);
+        pf->is_old0 = (u32)res_is_old0; pf->fnc = 3;
+        memcpy(t->root, rt_new, 32);
+        return 0;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * P8/P10  plonky2::fri::prover::fri_committed_trees (one layer) and fri_proof_of_work
+ * ---------------------------------------------------------------------------------------------- */
+/* reverse_index_bits_in_place(values); leaves = values.chunks(arity).map(flatten); MerkleTree::new */
+int glo_fri_layer_tree(const u64 *values_ext, size_t len, unsigned arity_bits, unsigned cap_height,
+                       u64 *leaves_out, u64 *digests_out, u64 *cap_out) {
+    unsigned lg = log2_strict(len);
+    size_t arity = (size_t)1 << arity_bits;
+    size_t num_leaves = len >> arity_bits, leaf_len = 2 * arity;
+    u64 *leaves = leaves_out ? leaves_out : (u64 *)malloc(len * 2 * sizeof(u64));
+    for (size_t i = 0; i < len; i++) {
+        size_t src = glo_reverse_bits(i, lg);
+        leaves[2 * i] = canon(values_ext[2 * src]);
+        leaves[2 * i + 1] = canon(values_ext[2 * src + 1]);
+    }
+    int rc = glo_merkle_tree(leaves, num_leaves, leaf_len, cap_height, digests_out, cap_out);
+    if (!leaves_out) free(leaves);
+    return rc;
+}
+
+/* coeffs.chunks_exact(arity).map(|chunk| reduce_with_powers(chunk, beta)) */
+void glo_fri_fold(const u64 *coeffs_ext, size_t len, unsigned arity_bits, const u64 beta[2], u64 *folded) {
+    size_t arity = (size_t)1 << arity_bits;
+    for (size_t k = 0; k < len >> arity_bits; k++) {
+        u64 acc[2] = {0, 0};
+        for (size_t j = arity; j-- > 0;) {
+            u64 t[2];
+            glo_ext_mul(acc, beta, t);
+            ext_add(t, coeffs_ext + 2 * (k * arity + j), acc);
+        }
+        folded[2 * k] = acc[0];
+        folded[2 * k + 1] = acc[1];
+    }
+}
+
+/* PolynomialCoeffs<F::Extension>::coset_fft(shift.into()): roots and shift are base-field, so the two
+ * coordinates transform independently */
+void glo_ext_coset_fft(u64 *a_ext, unsigned lg_n, u64 shift) {
+    size_t n = (size_t)1 << lg_n;
+    u64 *t = (u64 *)malloc(n * sizeof(u64));
+    for (int k = 0; k < 2; k++) {
+        for (size_t i = 0; i < n; i++) t[i] = a_ext[2 * i + k];
+        glo_coset_fft(t, lg_n, shift, 0);
+        for (size_t i = 0; i < n; i++) a_ext[2 * i + k] = t[i];
+    }
+    free(t);
+}
+
+/* fri_proof_of_work: upstream uses rayon find_any (nondeterministic); the deterministic restatement
+ * returns the SMALLEST satisfying candidate in [start, start+count), or UINT64_MAX if none. */
+u64 glo_pow_grind(const u64 state[12], unsigned pos, unsigned out_pos, unsigned min_lz, u64 start, u64 count) {
+    ensure_rc();
+    u64 best = UINT64_MAX;
+#pragma omp parallel for schedule(static) reduction(min : best)
+    for (u64 k = 0; k < count; k++) {
+        u64 cand = start + k;
+        if (cand >= best) continue;
+        u64 s[12];
+        memcpy(s, state, sizeof s);
+        s[pos] = cand;
+        glo_poseidon_permute(s);
+        unsigned lz = s[out_pos] ? (unsigned)__builtin_clzll(s[out_pos]) : 64;
+        if (lz >= min_lz && cand < best) best = cand;
+    }
+    return best;
+}
+
+int glo_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void glo_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
