@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- LDE + Merkle commit throughput (BASELINE.json metric "LDE+Merkle commit cells/s").
+
+Workload (BASELINE.json configs[1]): PolynomialBatch::from_values on 2^20 rows x 135 Goldilocks columns,
+rate_bits = 3, cap_height = 4, Poseidon leaves.  A cell = one input trace element (n * c per commit).
+A step = one commit.
+
+  value   : inputs resident in HBM (GL_DEVICE), outputs left on the device, cap to the host.
+  e2e     : the same call through the C ABI with HOST (pinned) buffers: values H2D, coefficients + cap D2H
+            inside the timed region.
+  roofline: the dominant kernel (Poseidon leaf hashing) timed with the library's own CUDA events.
+  cpu_baseline: the CPU oracle (a port of plonky2 v0.1.4 semantics, oracle/) on a bounded sample, rank 0, N=1.
+
+N > 1 (torchrun, one rank per GPU): one commit sharded by LDE coset = top-level Merkle subtree
+(SURVEY 8e).  Rank r inverse-transforms its column slice, NCCL all-gathers the coefficients, builds
+its leaf blocks + subtrees, NCCL all-gathers the cap: total work fixed => "strong" scaling.
+
+--impl reference: the reference's CPU implementation of the path is Rust in an un-vendored crate and
+cannot be built here (no cargo); the reference arm times the oracle port on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lde_merkle_commit_cells_per_s"
+UNIT = "cells/s"
+LOG_N, COLS, RATE_BITS, CAP_HEIGHT = 20, 135, 3, 4
+IMAD_PER_PERMUTATION = 6700  # plonky2's own schedule, 32x32 multiply(-add)s per permutation
+
+
+def workload_name(log_n, cols):
+    return f"commit 2^{log_n} rows x {cols} Goldilocks cols, rate_bits={RATE_BITS}, cap_height={CAP_HEIGHT}, Poseidon leaves"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        hi = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(log_n_sample: int, cols: int, repeat: int = 1):
+    """The oracle port of the path on the host cores (bounded sample of the workload)."""
+    from oracle import pyoracle as o
+
+    o.lib()
+    v = o.synthetic_values(cols, 1 << log_n_sample)
+    o.commit_from_values(o.synthetic_values(4, 256), RATE_BITS, CAP_HEIGHT, want_leaves=False)  # warm tables
+    best = None
+    for _ in range(repeat):
+        t = time.perf_counter()
+        o.commit_from_values(v, RATE_BITS, CAP_HEIGHT, want_leaves=True)
+        dt = time.perf_counter() - t
+        best = dt if best is None else min(best, dt)
+    cells = cols << log_n_sample
+    return {
+        "value": cells / best, "unit": UNIT, "cores": int(o.lib().glo_num_threads()), "kind": "port",
+        "sample": f"one commit of 2^{log_n_sample} rows x {cols} cols (rate_bits={RATE_BITS}, cap_height={CAP_HEIGHT}) = "
+                  f"1/{1 << (LOG_N - log_n_sample)} of the workload rows, {best:.2f} s; oracle/gl_oracle.c (OpenMP port of plonky2 v0.1.4 semantics)",
+    }, best
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation is un-buildable here (Rust, un-vendored
+    plonky2 fork, no cargo) so the oracle port stands in, on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as o
+
+    o.lib()
+    lg = args.ref_log_n
+    v = o.synthetic_values(args.cols, 1 << lg)
+    for _ in range(max(args.warmup, 0)):
+        o.commit_from_values(o.synthetic_values(args.cols, 1 << 10), RATE_BITS, CAP_HEIGHT, want_leaves=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.commit_from_values(v, RATE_BITS, CAP_HEIGHT, want_leaves=True)
+    dt = time.perf_counter() - t0
+    cells = args.cols << lg
+    val = cells * args.steps / dt
+    cores = int(o.lib().glo_num_threads())
+    sample = (f"each step = one commit of 2^{lg} rows x {args.cols} cols (1/{1 << (args.log_n - lg)} of the workload rows); "
+              f"oracle port of plonky2 v0.1.4 (the Rust reference cannot be built: no cargo, plonky2 fork not vendored)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_n, args.cols), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def synthetic_values_device(torch, cols, n, device, col0=0):
+    """values[col][row] = splitmix64(seed ^ ((col << 32) + row)) mod p, generated on the device (int64 wraps)."""
+    def c64(x):
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    col = (torch.arange(col0, col0 + cols, dtype=torch.int64, device=device) << 32)[:, None]
+    row = torch.arange(n, dtype=torch.int64, device=device)[None, :]
+    z = (col + row) ^ c64(0x706C6F6E6B7932)
+    z = z + c64(0x9E3779B97F4A7C15)
+
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    z = (z ^ lsr(z, 30)) * c64(0xBF58476D1CE4E5B9)
+    z = (z ^ lsr(z, 27)) * c64(0x94D049BB133111EB)
+    z = z ^ lsr(z, 31)
+    # canonical: z >= p (unsigned)  <=>  z in [-2^32 + 1, -1] as signed
+    ge = (z < 0) & (z >= -(1 << 32) + 1)
+    return torch.where(ge, z + ((1 << 32) - 1), z).contiguous()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=LOG_N)
+    ap.add_argument("--cols", type=int, default=COLS)
+    ap.add_argument("--ref-log-n", type=int, default=16, help="rows (log2) of the reference arm's per-step sample")
+    ap.add_argument("--cpu-log-n", type=int, default=17, help="rows (log2) of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    glb = importlib.import_module("plonky2-lib_b200")
+    ctx = glb.Context(local)
+    lib, N = ctx._lib, glb._native
+    import ctypes as C
+
+    log_n, cols = args.log_n, args.cols
+    n = 1 << log_n
+    cells = n * cols
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    values = synthetic_values_device(torch, cols, n, dev)
+    torch.cuda.synchronize()
+    cap_dev = torch.zeros((1 << CAP_HEIGHT, 4), dtype=torch.int64, device=dev)
+    phases = []
+
+    if world == 1:
+        coeffs_dev = torch.empty_like(values)
+
+        def step():
+            h = C.c_void_p()
+            ctx.check(lib.gl_commit_from_values(ctx._h, values.data_ptr(), log_n, cols, RATE_BITS, CAP_HEIGHT,
+                                                coeffs_dev.data_ptr(), cap_dev.data_ptr(), C.byref(h), N.GL_DEVICE))
+            phases.append(ctx.commit_phase_ms())
+            lib.gl_commit_free(h)
+            return cap_dev
+    else:
+        # column slice of this rank for the IFFT; ragged split, padded to equal size for the all-gather
+        per = (cols + world - 1) // world
+        c0, c1 = min(rank * per, cols), min((rank + 1) * per, cols)
+        ctx.set_shard(rank, world)
+        slice_buf = torch.zeros((per, n), dtype=torch.int64, device=dev)
+        gathered = torch.empty((world * per, n), dtype=torch.int64, device=dev)
+        cap_all = torch.zeros((1 << CAP_HEIGHT, 4), dtype=torch.int64, device=dev)
+        cap_per = (1 << CAP_HEIGHT) // world
+
+        def step():
+            if c1 > c0:
+                slice_buf[: c1 - c0].copy_(values[c0:c1])
+                ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf.data_ptr(), log_n, c1 - c0, N.GL_DEVICE))
+            dist.all_gather_into_tensor(gathered, slice_buf)  # coefficients of every column on every rank
+            torch.cuda.current_stream().synchronize()
+            h = C.c_void_p()
+            ctx.check(lib.gl_commit_from_coeffs(ctx._h, gathered.data_ptr(), log_n, cols, RATE_BITS, CAP_HEIGHT,
+                                                cap_dev.data_ptr(), C.byref(h), N.GL_DEVICE))
+            phases.append(ctx.commit_phase_ms())
+            lib.gl_commit_free(h)
+            mine = cap_dev[rank * cap_per:(rank + 1) * cap_per].contiguous()
+            dist.all_gather_into_tensor(cap_all, mine)  # MerkleCap: 2^cap_height digests
+            torch.cuda.current_stream().synchronize()
+            return cap_all
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # torch ops and NCCL collectives of a step are issued on the library's stream
+    torch.cuda.set_stream(stream)
+    for _ in range(args.warmup):
+        step()
+    launches0 = ctx.kernel_launches
+    phases.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        cap = step()
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    # the C ABI blocks at return, so device time == wall time up to launch latency; report the device clock
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches - launches0
+    ms_per_step = dev_ms / args.steps
+    value = cells * args.steps / (dev_ms * 1e-3)
+    cap_host = cap.cpu().numpy().view(np.uint64)
+
+    # ---- e2e: HOST (pinned) buffers through the same C-ABI call -------------------------------------
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        hv = glb.pinned_empty((cols, n))
+        hc = glb.pinned_empty((cols, n))
+        hcap = np.zeros((1 << CAP_HEIGHT, 4), dtype=np.uint64)
+        hv[:] = values.cpu().numpy().view(np.uint64)
+
+        def estep():
+            h = C.c_void_p()
+            ctx.check(lib.gl_commit_from_values(ctx._h, hv.ctypes.data, log_n, cols, RATE_BITS, CAP_HEIGHT,
+                                                hc.ctypes.data, hcap.ctypes.data, C.byref(h), N.GL_HOST))
+            lib.gl_commit_free(h)
+
+        for _ in range(2):
+            estep()
+        torch.cuda.synchronize()
+        ksteps = max(2, min(args.steps, 5))
+        e0.record(stream)
+        for _ in range(ksteps):
+            estep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1) / ksteps
+        assert np.array_equal(hcap, cap_host), "e2e cap differs from the device-resident run"
+        e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(cells * 8),
+               "d2h_bytes_per_step": int(cells * 8 + hcap.nbytes), "ms_per_step": ems,
+               "api": "gl_commit_from_values(space=GL_HOST), pinned host buffers"}
+        del hv, hc
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: k_leaf_hash_cols, timed by the library's CUDA events -------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    leaf_ms = float(np.mean([p["leaf_hash"] for p in phases]))
+    N_local = (n << RATE_BITS) // world
+    leaf_bytes = N_local * cols * 8 + N_local * 32
+    perms_leaf = N_local * ((cols + 7) // 8)
+    achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9
+    phase_mean = {k: float(np.mean([p[k] for p in phases])) for k in phases[0]}
+    roofline = {
+        "bound": "hbm", "kernel": "k_leaf_hash_cols (Poseidon hash_no_pad of every LDE row)",
+        "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+        "traffic": None, "kernel_ms": leaf_ms, "algorithmic_bytes_per_launch": leaf_bytes,
+        "note": "integer-pipe bound kernel (17 Poseidon permutations per 1080-byte leaf): see roofline_int",
+    }
+    roofline_int = {
+        "bound": "imad", "kernel": "k_leaf_hash_cols",
+        "achieved": perms_leaf * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e12,
+        "unit": "T 32x32 multiply-adds/s (6700 per permutation, SURVEY 8d)",
+        "permutations_per_s": perms_leaf / (leaf_ms * 1e-3),
+        "peak": 148 * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
+        "peak_source": "148 SMs x 64 IMAD lanes/clk x median SM clock under load (B300_MICROARCH: IMAD rt_SMSP = 2)",
+    }
+    if roofline_int["peak"]:
+        roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"]
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {
+            "workload": workload_name(log_n, cols), "cells_per_step": cells,
+            "l2": "inputs (1.13 GB) and LDE (9.06 GB) are larger than the 126 MB L2; no flush needed",
+            "parallelism": "single GPU" if world == 1 else f"{world} GPUs: IFFT by column slice + NCCL all-gather of coefficients, LDE/Merkle by coset block, NCCL all-gather of the cap",
+        },
+        "phases_ms": phase_mean, "wall_ms_per_step": wall / args.steps * 1e3,
+        "roofline": roofline, "roofline_int": roofline_int, "clocks": clocks, "gpu_launches": int(launches),
+        "cap0": [f"{int(x):016x}" for x in cap_host[0]],
+    }
+    if e2e:
+        out["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(min(args.cpu_log_n, log_n), cols)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,171 @@
+/*
+ * gl_b200.h -- C ABI of libgl_b200.so: the B200-native Goldilocks NTT/LDE + Poseidon Merkle commit
+ * core that sits underneath every `data.prove(pw)` / `builder.build::<C>()` / `PoseidonHash::*`
+ * call of Orbiter-Finance/Plonky2-lib.
+ *
+ * The reference itself has no FFI: the path lives in its un-vendored dependency plonky2 0.1.4
+ * (ZeroKPunk fork, /root/reference/Cargo.toml:10-11,32-34).  Each entry point below names the
+ * upstream Rust interface it replaces AND the reference call sites (paths relative to
+ * /root/reference) that reach it; INTEGRATION.md shows the Rust `extern "C"` shim a maintainer of
+ * the fork would add.
+ *
+ * Conventions
+ *  - field elements are u64, little-endian host order; inputs may be any u64 (taken mod p),
+ *    outputs are canonical (< p = 2^64 - 2^32 + 1), so byte-compare with HashOut::to_bytes works.
+ *  - `space` says where the caller's buffers live: GL_HOST (pageable or pinned host memory; the
+ *    library stages the copies) or GL_DEVICE (device pointers on the ctx's device; used by callers
+ *    that keep data resident, e.g. bench.py's `value` leg).
+ *  - every function returns 0 on success or a GL_E_* code; gl_last_error() gives the text.  The
+ *    upstream functions are infallible and panic on contract violation (log2_strict on a
+ *    non-power-of-two, `cap_height <= log2(leaves.len())`, inconsistent polynomial degrees): those
+ *    violations return GL_E_ARG and the Rust shim turns any non-zero code into panic!.
+ *  - a gl_ctx owns one device, one stream and its scratch; calls on one ctx are stream-ordered and
+ *    blocking at return.  One ctx per GPU; multi-GPU sharding is set with gl_ctx_set_shard().
+ *  - no CPU fallback exists: without a CUDA device gl_ctx_create fails with GL_E_CUDA.
+ */
+#ifndef GL_B200_H
+#define GL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GL_OK 0
+#define GL_E_ARG 1   /* upstream would panic: bad sizes / non power of two / cap_height too large */
+#define GL_E_CUDA 2  /* CUDA runtime error (no device, launch failure, ...) */
+#define GL_E_OOM 3   /* device or pinned host allocation failed */
+#define GL_E_STATE 4 /* handle used on the wrong ctx / after free */
+
+#define GL_HOST 0
+#define GL_DEVICE 1
+
+typedef struct gl_ctx gl_ctx;
+typedef struct gl_commit gl_commit;
+
+/* ---- context --------------------------------------------------------------------------------- */
+int gl_ctx_create(int device, gl_ctx **out);
+void gl_ctx_destroy(gl_ctx *ctx);
+const char *gl_last_error(const gl_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+void *gl_ctx_stream(gl_ctx *ctx);             /* the ctx's cudaStream_t, for CUDA-event timing */
+int gl_ctx_sync(gl_ctx *ctx);
+/* Multi-GPU: this ctx computes only leaf block [index*N/count, (index+1)*N/count) of every commit
+ * (= LDE cosets k with bitrev_r(k) in that range = whole top-level Merkle subtrees).
+ * count must divide 2^rate_bits and 2^cap_height.  Default (0, 1). */
+int gl_ctx_set_shard(gl_ctx *ctx, uint32_t index, uint32_t count);
+uint64_t gl_ctx_kernel_launches(const gl_ctx *ctx); /* kernels launched so far by this process */
+/* Device time of the phases of the last gl_commit_from_* call on this ctx, in ms (CUDA events on the
+ * ctx stream): [0] copy-in, [1] IFFT, [2] coefficients out, [3] LDE NTT, [4] leaf hashing, [5] tree levels. */
+int gl_ctx_commit_phase_ms(const gl_ctx *ctx, float *out6);
+/* Return pooled device memory (freed commits keep their blocks for the next commit) to the driver. */
+int gl_ctx_trim(gl_ctx *ctx);
+/* Page-locked host memory for callers that want full-speed PCIe copies of their GL_HOST buffers
+ * (the Rust shim backs the Vec<F> of a PolynomialBatch with it); plain malloc memory also works. */
+int gl_host_alloc(size_t bytes, void **out);
+void gl_host_free(void *p);
+
+/* ---- P5/P6: PoseidonHash (plonky2::hash::poseidon) ------------------------------------------- */
+/* Poseidon::poseidon over m states [m][12], in place. */
+int gl_poseidon_permute_batch(gl_ctx *ctx, uint64_t *states, uint64_t m, int space);
+/* PoseidonHash::two_to_one (src/smt/goldilocks_poseidon/mod.rs:165, src/zkdsa/account.rs:165,
+ * src/zkdsa/circuits/mod.rs:66-67): l, r, out are [m][4]. */
+int gl_poseidon_two_to_one_batch(gl_ctx *ctx, const uint64_t *l, const uint64_t *r, uint64_t *out,
+                                 uint64_t m, int space);
+/* PoseidonHash::hash_no_pad over m inputs of len_each elements, in [m][len_each], out [m][4]. */
+int gl_poseidon_hash_no_pad_batch(gl_ctx *ctx, const uint64_t *in, uint32_t len_each, uint64_t m,
+                                  uint64_t *out, int space);
+/* PoseidonNodeHash::calc_node_hash(Node::Leaf(k, v)) = hash_pad([k, v, 1])
+ * (src/smt/goldilocks_poseidon/mod.rs:167-181): keys, values, out are [m][4]. */
+int gl_smt_leaf_hash_batch(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t *out,
+                           uint64_t m, int space);
+
+/* ---- P7: SparseMerkleProcessProof::check over a batch (src/smt/proof/process.rs:47-51,153-337) -- */
+typedef struct {
+    uint64_t old_root[4], old_key[4], old_value[4];
+    uint64_t new_root[4], new_key[4], new_value[4];
+    uint32_t is_old0;
+    uint32_t fnc; /* ProcessMerkleProofRole: 0 NoOp, 1 Update, 2 Insert, 3 Delete */
+} gl_smt_proof_hdr;
+/* proofs [m]; siblings of proof t are sib_pool[sib_off[t] .. sib_off[t+1]) (each 4 x u64), top level
+ * first, exactly `proof.siblings`; status[t] = 0 when every assert of verify_smt_process_proof
+ * holds, else the ordinal of the first assert that would panic (1..8). */
+int gl_smt_verify_process_batch(gl_ctx *ctx, const gl_smt_proof_hdr *proofs, const uint64_t *sib_pool,
+                                const uint64_t *sib_off, uint64_t m, int32_t *status, int space);
+
+/* ---- P4: MerkleTree::new(leaves: Vec<Vec<F>>, cap_height) (plonky2::hash::merkle_tree) --------- */
+/* leaves [num_leaves][leaf_len] row-major; digests_out [2*(num_leaves - 2^cap_height)][4] in
+ * plonky2's recursive in-order layout (what MerkleTree::prove indexes); cap_out [2^cap_height][4].
+ * digests_out may be NULL. */
+int gl_merkle_build(gl_ctx *ctx, const uint64_t *leaves, uint64_t num_leaves, uint32_t leaf_len,
+                    uint32_t cap_height, uint64_t *digests_out, uint64_t *cap_out, int space);
+
+/* ---- P1/P2/P9: plonky2_field::fft on batches of columns ----------------------------------------- */
+/* In place on [c][2^log_n] (column after column), natural order in and out.
+ * gl_fft_batch      = PolynomialCoeffs::fft            (coeffs -> values on <w_n>)
+ * gl_ifft_batch     = PolynomialValues::ifft           ("IFFT" stage of from_values)
+ * gl_coset_fft_batch / gl_coset_ifft_batch = coset_fft(shift) / coset_ifft(shift) */
+int gl_fft_batch(gl_ctx *ctx, uint64_t *data, uint32_t log_n, uint32_t c, int space);
+int gl_ifft_batch(gl_ctx *ctx, uint64_t *data, uint32_t log_n, uint32_t c, int space);
+int gl_coset_fft_batch(gl_ctx *ctx, uint64_t *data, uint32_t log_n, uint32_t c, uint64_t shift, int space);
+int gl_coset_ifft_batch(gl_ctx *ctx, uint64_t *data, uint32_t log_n, uint32_t c, uint64_t shift, int space);
+
+/* ---- P*: PolynomialBatch::from_values / from_coeffs (plonky2::fri::oracle) --------------------- */
+/* Reached from data.prove(pw) (44 sites, e.g. src/ecdsa/gadgets/ecdsa.rs:349,
+ * src/hash/keccak256.rs:248, src/smt/gadgets/process/mod.rs:82, src/zkdsa/circuits/mod.rs:326) and
+ * builder.build::<C>() (41 sites, e.g. src/ecdsa/gadgets/ecdsa.rs:298).
+ * values / coeffs: [c][2^log_n], one contiguous column after another (Vec<PolynomialValues<F>>).
+ * blinding is always false for the reference's configs (zero_knowledge: false) and is not taken.
+ * coeffs_out [c][2^log_n] (PolynomialBatch.polynomials; may be NULL), cap_out [2^cap_height][4]
+ * (with a shard set: only this shard's 2^cap_height/count entries, written at their global index).
+ * The LDE leaves and the digests stay on the device behind *handle ("resident mode"). */
+int gl_commit_from_values(gl_ctx *ctx, const uint64_t *values, uint32_t log_n, uint32_t c,
+                          uint32_t rate_bits, uint32_t cap_height, uint64_t *coeffs_out,
+                          uint64_t *cap_out, gl_commit **handle, int space);
+int gl_commit_from_coeffs(gl_ctx *ctx, const uint64_t *coeffs, uint32_t log_n, uint32_t c,
+                          uint32_t rate_bits, uint32_t cap_height, uint64_t *cap_out,
+                          gl_commit **handle, int space);
+/* PolynomialBatch.polynomials: the coefficients [c][2^log_n] kept on the device behind the handle. */
+int gl_commit_coeffs(gl_commit *h, uint64_t *coeffs_out, int space);
+/* "mirror mode": fill the upstream structs.  leaves_out [N_local][c] row-major in leaf order
+ * (= MerkleTree.leaves after transpose + reverse_index_bits), digests_out [2*(N_local - caps_local)][4]
+ * (= MerkleTree.digests).  Either may be NULL. */
+int gl_commit_download(gl_commit *h, uint64_t *leaves_out, uint64_t *digests_out, int space);
+/* MerkleTree::get(i) + MerkleTree::prove(i) for k leaf indices (global indices; must be owned by
+ * this shard): rows_out [k][c], paths_out [k][log2(N) - cap_height][4] (siblings, leaf level first). */
+int gl_commit_open(gl_commit *h, const uint64_t *leaf_indices, uint32_t k, uint64_t *rows_out,
+                   uint64_t *paths_out, int space);
+/* PolynomialBatch::get_lde_values(index, step) = leaves[reverse_bits(index*step, log2 N)] for k indices. */
+int gl_commit_get_lde_values(gl_commit *h, const uint64_t *indices, uint32_t k, uint64_t step,
+                             uint64_t *rows_out, int space);
+/* geometry of a handle */
+int gl_commit_info(const gl_commit *h, uint32_t *log_n, uint32_t *c, uint32_t *rate_bits,
+                   uint32_t *cap_height, uint64_t *leaf_begin, uint64_t *leaf_end);
+/* device pointers of the resident data (column-major leaves [c][ld], digests), for device callers */
+int gl_commit_device_ptrs(const gl_commit *h, const uint64_t **lde_cols, uint64_t *ld,
+                          const uint64_t **digests);
+void gl_commit_free(gl_commit *h);
+
+/* ---- P8: one reduction layer of fri_committed_trees (plonky2::fri::prover) ---------------------- */
+/* values_ext: len extension elements [len][2] in natural order of their coset.  Builds the layer
+ * tree: reverse_index_bits(values), leaves = chunks of 2^arity_bits ext elements flattened,
+ * MerkleTree::new(leaves, cap_height).  digests_out may be NULL. */
+int gl_fri_layer_tree(gl_ctx *ctx, const uint64_t *values_ext, uint64_t len, uint32_t arity_bits,
+                      uint32_t cap_height, uint64_t *digests_out, uint64_t *cap_out, int space);
+/* coeffs.chunks_exact(2^arity_bits).map(|c| reduce_with_powers(c, beta)) then coset_fft(shift) over
+ * F::Extension: coeffs_ext [len][2] -> folded_coeffs_out [len >> arity_bits][2] and
+ * next_values_out [len >> arity_bits][2] (either may be NULL). */
+int gl_fri_fold(gl_ctx *ctx, const uint64_t *coeffs_ext, uint64_t len, uint32_t arity_bits,
+                const uint64_t beta[2], uint64_t shift, uint64_t *folded_coeffs_out,
+                uint64_t *next_values_out, int space);
+
+/* ---- P10: fri_proof_of_work ------------------------------------------------------------------- */
+/* Smallest w >= 0 such that permute(state with state[input_pos] = w)[7] (the last rate lane, as
+ * `duplex_state.squeeze().last()`) has >= min_leading_zeros leading zero bits.  Upstream's rayon
+ * find_any returns an arbitrary satisfying w; "smallest" makes the proof deterministic. */
+int gl_pow_grind(gl_ctx *ctx, const uint64_t state[12], uint32_t input_pos, uint32_t min_leading_zeros,
+                 uint64_t *witness_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""ctypes binding of libgl_b200.so (the C ABI of include/gl_b200.h).
+
+The library is the product; this module only declares its signatures.  There is deliberately no
+fallback: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgl_b200.so")
+
+GL_OK, GL_E_ARG, GL_E_CUDA, GL_E_OOM, GL_E_STATE = 0, 1, 2, 3, 4
+GL_HOST, GL_DEVICE = 0, 1
+
+u64p = C.POINTER(C.c_uint64)
+vp = C.c_void_p
+u32 = C.c_uint32
+u64 = C.c_uint64
+cint = C.c_int
+
+
+class SmtProofHdr(C.Structure):
+    """gl_smt_proof_hdr == SparseMerkleProcessProof minus siblings (src/smt/proof/process.rs:12-23)."""
+
+    _fields_ = [
+        ("old_root", u64 * 4), ("old_key", u64 * 4), ("old_value", u64 * 4),
+        ("new_root", u64 * 4), ("new_key", u64 * 4), ("new_value", u64 * 4),
+        ("is_old0", u32), ("fnc", u32),
+    ]
+
+
+# name -> (restype, argtypes); must list EVERY symbol include/gl_b200.h declares (tests check this)
+SIGNATURES = {
+    "gl_ctx_create": (cint, [cint, C.POINTER(vp)]),
+    "gl_ctx_destroy": (None, [vp]),
+    "gl_last_error": (C.c_char_p, [vp]),
+    "gl_ctx_stream": (vp, [vp]),
+    "gl_ctx_sync": (cint, [vp]),
+    "gl_ctx_set_shard": (cint, [vp, u32, u32]),
+    "gl_ctx_kernel_launches": (u64, [vp]),
+    "gl_ctx_commit_phase_ms": (cint, [vp, C.POINTER(C.c_float)]),
+    "gl_ctx_trim": (cint, [vp]),
+    "gl_host_alloc": (cint, [C.c_size_t, C.POINTER(vp)]),
+    "gl_host_free": (None, [vp]),
+    "gl_poseidon_permute_batch": (cint, [vp, vp, u64, cint]),
+    "gl_poseidon_two_to_one_batch": (cint, [vp, vp, vp, vp, u64, cint]),
+    "gl_poseidon_hash_no_pad_batch": (cint, [vp, vp, u32, u64, vp, cint]),
+    "gl_smt_leaf_hash_batch": (cint, [vp, vp, vp, vp, u64, cint]),
+    "gl_smt_verify_process_batch": (cint, [vp, vp, vp, vp, u64, vp, cint]),
+    "gl_merkle_build": (cint, [vp, vp, u64, u32, u32, vp, vp, cint]),
+    "gl_fft_batch": (cint, [vp, vp, u32, u32, cint]),
+    "gl_ifft_batch": (cint, [vp, vp, u32, u32, cint]),
+    "gl_coset_fft_batch": (cint, [vp, vp, u32, u32, u64, cint]),
+    "gl_coset_ifft_batch": (cint, [vp, vp, u32, u32, u64, cint]),
+    "gl_commit_from_values": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(vp), cint]),
+    "gl_commit_from_coeffs": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp), cint]),
+    "gl_commit_coeffs": (cint, [vp, vp, cint]),
+    "gl_commit_download": (cint, [vp, vp, vp, cint]),
+    "gl_commit_open": (cint, [vp, vp, u32, vp, vp, cint]),
+    "gl_commit_get_lde_values": (cint, [vp, vp, u32, u64, vp, cint]),
+    "gl_commit_info": (cint, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
+    "gl_commit_device_ptrs": (cint, [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]),
+    "gl_commit_free": (None, [vp]),
+    "gl_fri_layer_tree": (cint, [vp, vp, u64, u32, u32, vp, vp, cint]),
+    "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
+    "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (build it first with plonky2-lib_b200/build.py or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: run `python plonky2-lib_b200/build.py` (nvcc, sm_100a). "
+                "There is no CPU or PyTorch fallback for this path."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -1,0 +1,988 @@
+// libgl_b200.so -- the C ABI declared in include/gl_b200.h (host orchestration; kernels live in
+// ntt_kernels.cu and hash_kernels.cu).
+//
+// Device data layout:
+//   polynomials      [c][n]        column after column (what Vec<PolynomialValues<F>> flattens to)
+//   LDE "leaves"     [c][N_local]  COLUMN-major, leaf order along the fast axis: element (leaf i, col j)
+//                                  at lde[j * N_local + i].  Leaf order = reverse_index_bits of the
+//                                  natural coset order, which is exactly what a decimation-in-frequency
+//                                  NTT leaves behind, so "transpose LDEs" + reverse_index_bits_in_place
+//                                  of PolynomialBatch::from_coeffs never run as separate passes.
+//   digests          [2*(N_local - caps_local)][4]  plonky2's recursive in-order layout
+//   cap              [caps_local][4]
+// There is no CPU fallback anywhere in this file: every entry point needs a live CUDA context.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/gl_b200.h"
+#include "gl_field.cuh"
+#include "hash_kernels.h"
+#include "ntt_kernels.h"
+#include "poseidon_constants.h"
+
+std::atomic<unsigned long long> g_gl_launches{0};
+
+#define GL_PHASES 6  // copy-in, IFFT, coefficients out, LDE NTT, leaf hashing, tree levels
+
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct gl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint32_t shard_index = 0, shard_count = 1;
+    std::map<std::tuple<int, uint64_t, uint64_t, uint64_t>, u64*> tables;
+    DevBuf scratch[6];
+    std::mutex mu;
+    int live_commits = 0;
+    // freed commit buffers, kept for the next commit of the same geometry (cudaMalloc/cudaFree of
+    // multi-GB blocks cost milliseconds and serialise the device)
+    std::multimap<size_t, void*> pool;
+    size_t pool_bytes = 0;
+    // phase boundaries of the last commit (CUDA events on `stream`)
+    cudaEvent_t ev[GL_PHASES + 1] = {};
+    bool ev_valid = false;
+    float phase_ms[GL_PHASES] = {};
+};
+
+struct gl_commit {
+    gl_ctx* ctx = nullptr;
+    uint32_t log_n = 0, c = 0, rate_bits = 0, cap_height = 0;
+    uint32_t shard_index = 0, shard_count = 1;
+    uint64_t n_local = 0;      // leaves held here
+    uint64_t leaf_begin = 0;   // global index of the first local leaf
+    uint32_t cap_local_bits = 0;
+    u64* coeffs = nullptr;     // [c][n]
+    u64* lde = nullptr;        // [c][n_local]
+    u64* digests = nullptr;    // [2*(n_local - 2^cap_local_bits)][4]
+    u64* cap = nullptr;        // [2^cap_local_bits][4]
+    uint64_t num_digests = 0;
+    size_t coeffs_bytes = 0, lde_bytes = 0, digests_bytes = 0, cap_bytes = 0;
+};
+
+static int fail(gl_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+static int cuda_fail(gl_ctx* ctx, cudaError_t e, const char* what) {
+    std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+    cudaGetLastError();
+    return fail(ctx, e == cudaErrorMemoryAllocation ? GL_E_OOM : GL_E_CUDA, msg);
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+    } while (0)
+#define TRY(expr)             \
+    do {                      \
+        int rc__ = (expr);    \
+        if (rc__) return rc__; \
+    } while (0)
+
+static inline unsigned ilog2(uint64_t x) { return 63u - (unsigned)__builtin_clzll(x); }
+static inline bool is_pow2(uint64_t x) { return x && !(x & (x - 1)); }
+static inline uint64_t bitrev(uint64_t x, unsigned bits) {
+    uint64_t r = 0;
+    for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+
+struct Guard {  // binds the ctx's device for the duration of a call and serialises calls on one ctx
+    std::unique_lock<std::mutex> lk;
+    int prev = -1;
+    explicit Guard(gl_ctx* ctx) : lk(ctx->mu) {
+        cudaGetDevice(&prev);
+        if (prev != ctx->device) cudaSetDevice(ctx->device);
+        else prev = -1;
+    }
+    ~Guard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static int scratch_get(gl_ctx* ctx, int slot, size_t bytes, void** out) {
+    DevBuf& b = ctx->scratch[slot];
+    if (b.cap < bytes) {
+        if (b.p) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            cudaFree(b.p);
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&b.p, want);
+        }
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc(scratch)");
+        b.cap = want;
+    }
+    *out = b.p;
+    return GL_OK;
+}
+
+static void pool_trim(gl_ctx* ctx) {
+    for (auto& kv : ctx->pool) cudaFree(kv.second);
+    ctx->pool.clear();
+    ctx->pool_bytes = 0;
+}
+static int dev_alloc(gl_ctx* ctx, size_t bytes, u64** out) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 8;
+    auto it = ctx->pool.find(bytes);
+    if (it != ctx->pool.end()) {
+        *out = (u64*)it->second;
+        ctx->pool.erase(it);
+        ctx->pool_bytes -= bytes;
+        return GL_OK;
+    }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation && !ctx->pool.empty()) {
+        cudaGetLastError();
+        cudaStreamSynchronize(ctx->stream);
+        pool_trim(ctx);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaMalloc");
+    *out = (u64*)p;
+    return GL_OK;
+}
+// stream-ordered reuse: every consumer of a pooled block runs on ctx->stream
+static void dev_release(gl_ctx* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    if (bytes == 0) bytes = 8;
+    if (ctx->pool_bytes + bytes > ((size_t)48 << 30)) {
+        cudaFree(p);
+        return;
+    }
+    ctx->pool.emplace(bytes, p);
+    ctx->pool_bytes += bytes;
+}
+
+// caller buffer -> device pointer (no copy when the caller already is on the device)
+static int stage_in(gl_ctx* ctx, const void* src, size_t bytes, int space, int slot, const u64** out) {
+    if (space == GL_DEVICE) {
+        *out = (const u64*)src;
+        return GL_OK;
+    }
+    void* d;
+    TRY(scratch_get(ctx, slot, bytes ? bytes : 8, &d));
+    if (bytes) CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *out = (const u64*)d;
+    return GL_OK;
+}
+static int copy_out(gl_ctx* ctx, void* dst, const void* dsrc, size_t bytes, int space) {
+    if (!dst || !bytes || dst == dsrc) return GL_OK;
+    CK(cudaMemcpyAsync(dst, dsrc, bytes, space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                       ctx->stream));
+    return GL_OK;
+}
+static int finish(gl_ctx* ctx) {
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tables (built on the host with exact 128-bit arithmetic, cached on the device)
+// ------------------------------------------------------------------------------------------------
+enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3 };
+
+static void fill_pow_table(u64* t, u64 base) {  // [3][1024]: base^e, base^(1024 e), base^(2^20 e)
+    u64 b = glh::canon(base);
+    for (int lvl = 0; lvl < 3; lvl++) {
+        u64 acc = 1;
+        for (int e = 0; e < 1024; e++) {
+            t[lvl * 1024 + e] = acc;
+            acc = glh::mul(acc, b);
+        }
+        b = acc;  // base^(1024)
+    }
+}
+
+static int table_upload(gl_ctx* ctx, std::tuple<int, uint64_t, uint64_t, uint64_t> key, const std::vector<u64>& host,
+                        const u64** out) {
+    u64* d;
+    TRY(dev_alloc(ctx, host.size() * sizeof(u64), &d));
+    CK(cudaMemcpyAsync(d, host.data(), host.size() * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // `host` dies with the caller
+    ctx->tables[key] = d;
+    *out = d;
+    return GL_OK;
+}
+
+// w_{2^m}^x for x < 2^(m-1)  (inverse: w^-x)
+static int small_table(gl_ctx* ctx, unsigned m, bool inverse, const u64** out) {
+    auto key = std::make_tuple((int)TAB_SMALL, (uint64_t)m, (uint64_t)inverse, (uint64_t)0);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    size_t len = m ? ((size_t)1 << (m - 1)) : 1;
+    std::vector<u64> h(len);
+    u64 w = glh::root_of_unity(m);
+    if (inverse) w = glh::inv(w);
+    u64 acc = 1;
+    for (size_t i = 0; i < len; i++) {
+        h[i] = acc;
+        acc = glh::mul(acc, w);
+    }
+    return table_upload(ctx, key, h, out);
+}
+
+static int pow_table(gl_ctx* ctx, u64 base, const u64** out) {
+    auto key = std::make_tuple((int)TAB_POW, (uint64_t)glh::canon(base), (uint64_t)0, (uint64_t)0);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    std::vector<u64> h(3072);
+    fill_pow_table(h.data(), base);
+    return table_upload(ctx, key, h, out);
+}
+
+// one pow table per local leaf block b: shift_b = 7 * w_N^k, k = bitrev_r(global block)
+static int coset_tables(gl_ctx* ctx, unsigned lg_n, unsigned r, uint32_t shard_index, uint32_t shard_count,
+                        const u64** out) {
+    auto key = std::make_tuple((int)TAB_COSETS, (uint64_t)lg_n, (uint64_t)r,
+                               ((uint64_t)shard_index << 32) | shard_count);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    uint32_t blocks = (1u << r) / shard_count;
+    std::vector<u64> h((size_t)blocks * 3072);
+    u64 wN = glh::root_of_unity(lg_n + r);
+    for (uint32_t b = 0; b < blocks; b++) {
+        uint64_t k = bitrev((uint64_t)shard_index * blocks + b, r);
+        u64 shift = glh::mul(7, glh::pow(wN, k));
+        fill_pow_table(h.data() + (size_t)b * 3072, shift);
+    }
+    return table_upload(ctx, key, h, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NTT driver: natural order in, bit-reversed order out (decimation in frequency), 1..3 passes
+// ------------------------------------------------------------------------------------------------
+struct NttJob {
+    const u64* in = nullptr;
+    u64 in_ld = 0, in_coset_stride = 0;
+    u64* out = nullptr;
+    u64 out_ld = 0, out_coset_stride = 0;
+    unsigned L = 0;
+    uint32_t columns = 1, cosets = 1;
+    bool inverse = false;
+    const u64* pre_tab = nullptr;
+    u64 final_scale = 1;
+    int canonical_out = 0;
+};
+
+static int run_dif(gl_ctx* ctx, const NttJob& j) {
+    if (j.columns == 0) return GL_OK;
+    const u64 n = (u64)1 << j.L;
+    unsigned np = j.L == 0 ? 1 : (j.L + 9) / 10;
+    unsigned ms[4];
+    for (unsigned i = 0; i < np; i++) ms[i] = j.L / np + (i < j.L % np ? 1 : 0);
+    unsigned done = 0;
+    for (unsigned i = 0; i < np; i++) {
+        ntt_pass_args a;
+        memset(&a, 0, sizeof a);
+        a.m = ms[i];
+        done += ms[i];
+        a.s = j.L - done;
+        bool first = i == 0, last = i == np - 1;
+        a.in = first ? j.in : j.out;
+        a.in_ld = first ? j.in_ld : j.out_ld;
+        a.in_coset_stride = first ? j.in_coset_stride : j.out_coset_stride;
+        a.out = j.out;
+        a.out_ld = j.out_ld;
+        a.out_coset_stride = j.out_coset_stride;
+        a.pre_tab = first ? j.pre_tab : nullptr;
+        TRY(small_table(ctx, a.m, j.inverse, &a.small_tab));
+        if (a.s) {
+            u64 w = glh::root_of_unity(a.s + a.m);
+            if (j.inverse) w = glh::inv(w);
+            TRY(pow_table(ctx, w, &a.post_tab));
+            a.T = a.s >= 3 ? 8 : (1u << a.s);
+            a.rows = (u64)1 << a.m;
+        } else {
+            a.post_tab = nullptr;
+            a.T = 1;
+            u64 blk = (u64)1 << a.m;
+            a.rows = n < 4096 ? n : 4096;
+            if (a.rows < blk) a.rows = blk;
+        }
+        a.final_scale = last ? j.final_scale : 1;
+        a.canonical_out = last ? j.canonical_out : 0;
+        launch_ntt_pass(a, n, j.columns, j.cosets, ctx->stream);
+    }
+    return GL_OK;
+}
+
+// natural -> natural transform of [c][n] columns at `data` (device), through scratch slot 1
+static int transform_natural(gl_ctx* ctx, u64* data, unsigned L, uint32_t c, bool inverse, const u64* pre_tab,
+                             const u64* post_scale_tab) {
+    const u64 n = (u64)1 << L;
+    void* tmp;
+    TRY(scratch_get(ctx, 1, (size_t)c * n * sizeof(u64), &tmp));
+    NttJob j;
+    j.in = data; j.in_ld = n; j.out = (u64*)tmp; j.out_ld = n;
+    j.L = L; j.columns = c; j.cosets = 1; j.inverse = inverse; j.pre_tab = pre_tab;
+    TRY(run_dif(ctx, j));
+    u64 scale = inverse ? glh::inv(glh::canon(n % GL_P)) : 1;
+    launch_bitrev_permute((const u64*)tmp, n, data, n, L, c, scale, ctx->stream);
+    if (post_scale_tab) launch_scale_powers(data, n, n, c, post_scale_tab, ctx->stream);
+    return GL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context API
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_ctx_create(int device, gl_ctx** out) {
+    if (!out) return fail(nullptr, GL_E_ARG, "gl_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, GL_E_CUDA,
+                    std::string("gl_ctx_create: no CUDA device (this library has no CPU fallback): ") +
+                        cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= count) return fail(nullptr, GL_E_ARG, "gl_ctx_create: bad device index");
+    gl_ctx* ctx = new (std::nothrow) gl_ctx();
+    if (!ctx) return fail(nullptr, GL_E_OOM, "gl_ctx_create: host allocation failed");
+    ctx->device = device;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "gl_ctx_create");
+        delete ctx;
+        return rc;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    uint64_t rc360[360];
+    if (!poseidon_constants::generate(rc360)) {
+        delete ctx;
+        return fail(nullptr, GL_E_STATE, "gl_ctx_create: derived Poseidon round constants fail their fingerprint");
+    }
+    int up = gl_poseidon_upload_constants(rc360);
+    if (up != 0) {
+        int rc = cuda_fail(nullptr, (cudaError_t)up, "upload Poseidon constants");
+        delete ctx;
+        return rc;
+    }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    *out = ctx;
+    return GL_OK;
+}
+
+extern "C" void gl_ctx_destroy(gl_ctx* ctx) {
+    if (!ctx) return;
+    {
+        Guard g(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->tables) cudaFree(kv.second);
+        for (auto& b : ctx->scratch)
+            if (b.p) cudaFree(b.p);
+        pool_trim(ctx);
+        for (auto& ev : ctx->ev)
+            if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+extern "C" const char* gl_last_error(const gl_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+extern "C" void* gl_ctx_stream(gl_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int gl_ctx_sync(gl_ctx* ctx) {
+    if (!ctx) return GL_E_ARG;
+    Guard g(ctx);
+    return finish(ctx);
+}
+extern "C" int gl_ctx_set_shard(gl_ctx* ctx, uint32_t index, uint32_t count) {
+    if (!ctx) return GL_E_ARG;
+    if (!is_pow2(count) || index >= count) return fail(ctx, GL_E_ARG, "gl_ctx_set_shard: count must be a power of two and index < count");
+    ctx->shard_index = index;
+    ctx->shard_count = count;
+    return GL_OK;
+}
+extern "C" uint64_t gl_ctx_kernel_launches(const gl_ctx*) { return g_gl_launches.load(); }
+
+extern "C" int gl_ctx_commit_phase_ms(const gl_ctx* ctx, float* out6) {
+    if (!ctx || !out6 || !ctx->ev_valid) return GL_E_STATE;
+    for (int i = 0; i < GL_PHASES; i++) out6[i] = ctx->phase_ms[i];
+    return GL_OK;
+}
+extern "C" int gl_ctx_trim(gl_ctx* ctx) {
+    if (!ctx) return GL_E_ARG;
+    Guard g(ctx);
+    CK(cudaStreamSynchronize(ctx->stream));
+    pool_trim(ctx);
+    return GL_OK;
+}
+
+extern "C" int gl_host_alloc(size_t bytes, void** out) {
+    if (!out) return GL_E_ARG;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 8, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = nullptr;
+        return fail(nullptr, GL_E_OOM, std::string("gl_host_alloc: ") + cudaGetErrorString(e));
+    }
+    return GL_OK;
+}
+extern "C" void gl_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Poseidon batches
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_poseidon_permute_batch(gl_ctx* ctx, uint64_t* states, uint64_t m, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (m && !states) return fail(ctx, GL_E_ARG, "gl_poseidon_permute_batch: NULL states");
+    Guard g(ctx);
+    const u64* d;
+    TRY(stage_in(ctx, states, m * 96, space, 0, &d));
+    launch_permute_batch((u64*)d, m, ctx->stream);
+    TRY(copy_out(ctx, states, d, m * 96, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_poseidon_two_to_one_batch(gl_ctx* ctx, const uint64_t* l, const uint64_t* r, uint64_t* out,
+                                            uint64_t m, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (m && (!l || !r || !out)) return fail(ctx, GL_E_ARG, "gl_poseidon_two_to_one_batch: NULL buffer");
+    Guard g(ctx);
+    const u64 *dl, *dr;
+    TRY(stage_in(ctx, l, m * 32, space, 0, &dl));
+    TRY(stage_in(ctx, r, m * 32, space, 1, &dr));
+    u64* dout = out;
+    if (space == GL_HOST) {
+        void* t;
+        TRY(scratch_get(ctx, 2, m * 32 + 8, &t));
+        dout = (u64*)t;
+    }
+    launch_two_to_one_batch(dl, dr, dout, m, ctx->stream);
+    TRY(copy_out(ctx, out, dout, m * 32, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_poseidon_hash_no_pad_batch(gl_ctx* ctx, const uint64_t* in, uint32_t len_each, uint64_t m,
+                                             uint64_t* out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (m && (!out || (len_each && !in))) return fail(ctx, GL_E_ARG, "gl_poseidon_hash_no_pad_batch: NULL buffer");
+    Guard g(ctx);
+    const u64* din;
+    TRY(stage_in(ctx, in, (size_t)m * len_each * 8, space, 0, &din));
+    u64* dout = out;
+    if (space == GL_HOST) {
+        void* t;
+        TRY(scratch_get(ctx, 2, m * 32 + 8, &t));
+        dout = (u64*)t;
+    }
+    launch_hash_no_pad_rows(din, len_each, m, dout, ctx->stream);
+    TRY(copy_out(ctx, out, dout, m * 32, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_smt_leaf_hash_batch(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t* out,
+                                      uint64_t m, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (m && (!keys || !values || !out)) return fail(ctx, GL_E_ARG, "gl_smt_leaf_hash_batch: NULL buffer");
+    Guard g(ctx);
+    const u64 *dk, *dv;
+    TRY(stage_in(ctx, keys, m * 32, space, 0, &dk));
+    TRY(stage_in(ctx, values, m * 32, space, 1, &dv));
+    u64* dout = out;
+    if (space == GL_HOST) {
+        void* t;
+        TRY(scratch_get(ctx, 2, m * 32 + 8, &t));
+        dout = (u64*)t;
+    }
+    launch_smt_leaf_hash_batch(dk, dv, dout, m, ctx->stream);
+    TRY(copy_out(ctx, out, dout, m * 32, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_smt_verify_process_batch(gl_ctx* ctx, const gl_smt_proof_hdr* proofs, const uint64_t* sib_pool,
+                                           const uint64_t* sib_off, uint64_t m, int32_t* status, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (m == 0) return GL_OK;
+    if (!proofs || !sib_off || !status) return fail(ctx, GL_E_ARG, "gl_smt_verify_process_batch: NULL buffer");
+    Guard g(ctx);
+    if (space == GL_DEVICE) {
+        launch_smt_verify_process(proofs, sib_pool, sib_off, m, status, ctx->stream);
+        return finish(ctx);
+    }
+    uint64_t total = sib_off[m];
+    for (uint64_t t = 0; t < m; t++)
+        if (sib_off[t + 1] < sib_off[t]) return fail(ctx, GL_E_ARG, "gl_smt_verify_process_batch: sib_off not monotone");
+    if (total && !sib_pool) return fail(ctx, GL_E_ARG, "gl_smt_verify_process_batch: NULL sib_pool");
+    const u64 *dp, *dpool, *doff;
+    TRY(stage_in(ctx, proofs, m * sizeof(gl_smt_proof_hdr), GL_HOST, 0, &dp));
+    TRY(stage_in(ctx, sib_pool, total * 32, GL_HOST, 1, &dpool));
+    TRY(stage_in(ctx, sib_off, (m + 1) * 8, GL_HOST, 2, &doff));
+    void* dst;
+    TRY(scratch_get(ctx, 3, m * 4, &dst));
+    launch_smt_verify_process((const gl_smt_proof_hdr*)dp, dpool, doff, m, (int*)dst, ctx->stream);
+    TRY(copy_out(ctx, status, dst, m * 4, GL_HOST));
+    return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MerkleTree::new on caller-provided row-major leaves
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_merkle_build(gl_ctx* ctx, const uint64_t* leaves, uint64_t num_leaves, uint32_t leaf_len,
+                               uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!is_pow2(num_leaves)) return fail(ctx, GL_E_ARG, "MerkleTree::new: number of leaves is not a power of two (log2_strict)");
+    unsigned lg = ilog2(num_leaves);
+    if (cap_height > lg)
+        return fail(ctx, GL_E_ARG, "MerkleTree::new: cap_height must be at most log2(leaves.len())");
+    if (!cap_out || (leaf_len && !leaves)) return fail(ctx, GL_E_ARG, "gl_merkle_build: NULL buffer");
+    Guard g(ctx);
+    const u64* dl;
+    TRY(stage_in(ctx, leaves, (size_t)num_leaves * leaf_len * 8, space, 0, &dl));
+    uint64_t nd = 2 * (num_leaves - ((uint64_t)1 << cap_height));
+    void *dd, *dc;
+    TRY(scratch_get(ctx, 1, nd * 32 + 32, &dd));
+    TRY(scratch_get(ctx, 2, ((size_t)32 << cap_height), &dc));
+    launch_merkle_rows(dl, leaf_len, lg, cap_height, (u64*)dd, (u64*)dc, ctx->stream);
+    TRY(copy_out(ctx, digests_out, dd, nd * 32, space));
+    TRY(copy_out(ctx, cap_out, dc, ((size_t)32 << cap_height), space));
+    return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plonky2_field::fft batches
+// ------------------------------------------------------------------------------------------------
+static int fft_entry(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t c, int space, bool inverse, bool coset,
+                     uint64_t shift, const char* name) {
+    if (!ctx) return GL_E_ARG;
+    if (log_n > 30) return fail(ctx, GL_E_ARG, std::string(name) + ": log_n > 30 not supported");
+    if (c == 0) return GL_OK;
+    if (!data) return fail(ctx, GL_E_ARG, std::string(name) + ": NULL data");
+    Guard g(ctx);
+    size_t bytes = ((size_t)c << log_n) * 8;
+    const u64* d;
+    TRY(stage_in(ctx, data, bytes, space, 0, &d));
+    const u64 *pre = nullptr, *post = nullptr;
+    if (coset) {
+        u64 sh = glh::canon(shift);
+        if (sh == 0) return fail(ctx, GL_E_ARG, std::string(name) + ": zero coset shift");
+        if (!inverse) TRY(pow_table(ctx, sh, &pre));
+        else TRY(pow_table(ctx, glh::inv(sh), &post));
+    }
+    TRY(transform_natural(ctx, (u64*)d, log_n, c, inverse, pre, post));
+    TRY(copy_out(ctx, data, d, bytes, space));
+    return finish(ctx);
+}
+extern "C" int gl_fft_batch(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t c, int space) {
+    return fft_entry(ctx, data, log_n, c, space, false, false, 1, "gl_fft_batch");
+}
+extern "C" int gl_ifft_batch(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t c, int space) {
+    return fft_entry(ctx, data, log_n, c, space, true, false, 1, "gl_ifft_batch");
+}
+extern "C" int gl_coset_fft_batch(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t c, uint64_t shift, int space) {
+    return fft_entry(ctx, data, log_n, c, space, false, true, shift, "gl_coset_fft_batch");
+}
+extern "C" int gl_coset_ifft_batch(gl_ctx* ctx, uint64_t* data, uint32_t log_n, uint32_t c, uint64_t shift, int space) {
+    return fft_entry(ctx, data, log_n, c, space, true, true, shift, "gl_coset_ifft_batch");
+}
+
+// ------------------------------------------------------------------------------------------------
+// PolynomialBatch::from_values / from_coeffs
+// ------------------------------------------------------------------------------------------------
+static void commit_release(gl_commit* h) {
+    if (!h) return;
+    dev_release(h->ctx, h->coeffs, h->coeffs_bytes);
+    dev_release(h->ctx, h->lde, h->lde_bytes);
+    dev_release(h->ctx, h->digests, h->digests_bytes);
+    dev_release(h->ctx, h->cap, h->cap_bytes);
+    delete h;
+}
+static void mark(gl_ctx* ctx, int i) { cudaEventRecord(ctx->ev[i], ctx->stream); }
+
+static int commit_check(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height,
+                        const char* name) {
+    if (c == 0) return fail(ctx, GL_E_ARG, std::string(name) + ": empty polynomial batch");
+    if (log_n + rate_bits > 30) return fail(ctx, GL_E_ARG, std::string(name) + ": log_n + rate_bits > 30 not supported");
+    if (cap_height > log_n + rate_bits)
+        return fail(ctx, GL_E_ARG, std::string(name) + ": cap_height must be at most log2(leaves.len())");
+    unsigned lc = ilog2(ctx->shard_count);
+    if (lc > rate_bits || lc > cap_height)
+        return fail(ctx, GL_E_ARG, std::string(name) + ": shard count must divide 2^rate_bits and 2^cap_height");
+    return GL_OK;
+}
+
+// h->coeffs already holds the coefficients on the device
+static int commit_lde_and_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space) {
+    const unsigned lc = ilog2(h->shard_count);
+    const u64 n = (u64)1 << h->log_n;
+    const uint32_t blocks = (1u << h->rate_bits) >> lc;
+    h->n_local = n * blocks;
+    h->leaf_begin = (u64)h->shard_index * h->n_local;
+    h->cap_local_bits = h->cap_height - lc;
+    const unsigned lg_local = h->log_n + h->rate_bits - lc;
+    h->num_digests = 2 * (h->n_local - ((u64)1 << h->cap_local_bits));
+    h->lde_bytes = (size_t)h->c * h->n_local * 8;
+    h->digests_bytes = h->num_digests * 32;
+    h->cap_bytes = (size_t)32 << h->cap_local_bits;
+    TRY(dev_alloc(ctx, h->lde_bytes, &h->lde));
+    TRY(dev_alloc(ctx, h->digests_bytes, &h->digests));
+    TRY(dev_alloc(ctx, h->cap_bytes, &h->cap));
+    const u64* pre;
+    TRY(coset_tables(ctx, h->log_n, h->rate_bits, h->shard_index, h->shard_count, &pre));
+    NttJob j;
+    j.in = h->coeffs; j.in_ld = n; j.in_coset_stride = 0;
+    j.out = h->lde; j.out_ld = h->n_local; j.out_coset_stride = n;
+    j.L = h->log_n; j.columns = h->c; j.cosets = blocks; j.inverse = false; j.pre_tab = pre;
+    j.canonical_out = 1;
+    TRY(run_dif(ctx, j));
+    mark(ctx, 4);
+    launch_leaf_hash_cols(h->lde, h->n_local, h->c, lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
+    mark(ctx, 5);
+    launch_merkle_levels(lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
+    mark(ctx, 6);
+    if (cap_out) {
+        size_t cap_bytes = (size_t)32 << h->cap_local_bits;
+        uint64_t* dst = cap_out + 4 * ((size_t)h->shard_index << h->cap_local_bits);
+        TRY(copy_out(ctx, dst, h->cap, cap_bytes, space));
+    }
+    return GL_OK;
+}
+
+static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uint32_t log_n, uint32_t c,
+                         uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_out, uint64_t* cap_out,
+                         gl_commit** handle, int space, const char* name) {
+    if (!ctx) return GL_E_ARG;
+    if (!handle || !input) return fail(ctx, GL_E_ARG, std::string(name) + ": NULL argument");
+    *handle = nullptr;
+    TRY(commit_check(ctx, log_n, c, rate_bits, cap_height, name));
+    Guard g(ctx);
+    gl_commit* h = new (std::nothrow) gl_commit();
+    if (!h) return fail(ctx, GL_E_OOM, "host allocation failed");
+    h->ctx = ctx; h->log_n = log_n; h->c = c; h->rate_bits = rate_bits; h->cap_height = cap_height;
+    h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
+    const u64 n = (u64)1 << log_n;
+    const size_t poly_bytes = (size_t)c * n * 8;
+    h->coeffs_bytes = poly_bytes;
+    int rc = dev_alloc(ctx, poly_bytes, &h->coeffs);
+    mark(ctx, 0);
+    if (rc == GL_OK) {
+        cudaError_t e = cudaMemcpyAsync(h->coeffs, input, poly_bytes,
+                                        space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials to the device");
+    }
+    mark(ctx, 1);
+    if (rc == GL_OK && is_values) {
+        rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr);  // "IFFT"
+        mark(ctx, 2);
+        if (rc == GL_OK) rc = copy_out(ctx, coeffs_out, h->coeffs, poly_bytes, space);
+    } else {
+        mark(ctx, 2);
+    }
+    mark(ctx, 3);
+    if (rc == GL_OK) rc = commit_lde_and_tree(ctx, h, cap_out, space);
+    if (rc == GL_OK) rc = finish(ctx);
+    if (rc == GL_OK) {
+        for (int i = 0; i < GL_PHASES; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+        ctx->ev_valid = true;
+    }
+    if (rc != GL_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        commit_release(h);
+        return rc;
+    }
+    ctx->live_commits++;
+    *handle = h;
+    return GL_OK;
+}
+
+extern "C" int gl_commit_from_values(gl_ctx* ctx, const uint64_t* values, uint32_t log_n, uint32_t c,
+                                     uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_out, uint64_t* cap_out,
+                                     gl_commit** handle, int space) {
+    return commit_common(ctx, values, true, log_n, c, rate_bits, cap_height, coeffs_out, cap_out, handle, space,
+                         "PolynomialBatch::from_values");
+}
+extern "C" int gl_commit_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint32_t c,
+                                     uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out, gl_commit** handle,
+                                     int space) {
+    return commit_common(ctx, coeffs, false, log_n, c, rate_bits, cap_height, nullptr, cap_out, handle, space,
+                         "PolynomialBatch::from_coeffs");
+}
+
+extern "C" void gl_commit_free(gl_commit* h) {
+    if (!h) return;
+    gl_ctx* ctx = h->ctx;
+    Guard g(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->live_commits--;
+    commit_release(h);
+}
+
+extern "C" int gl_commit_info(const gl_commit* h, uint32_t* log_n, uint32_t* c, uint32_t* rate_bits,
+                              uint32_t* cap_height, uint64_t* leaf_begin, uint64_t* leaf_end) {
+    if (!h) return GL_E_ARG;
+    if (log_n) *log_n = h->log_n;
+    if (c) *c = h->c;
+    if (rate_bits) *rate_bits = h->rate_bits;
+    if (cap_height) *cap_height = h->cap_height;
+    if (leaf_begin) *leaf_begin = h->leaf_begin;
+    if (leaf_end) *leaf_end = h->leaf_begin + h->n_local;
+    return GL_OK;
+}
+
+extern "C" int gl_commit_device_ptrs(const gl_commit* h, const uint64_t** lde_cols, uint64_t* ld,
+                                     const uint64_t** digests) {
+    if (!h) return GL_E_ARG;
+    if (lde_cols) *lde_cols = h->lde;
+    if (ld) *ld = h->n_local;
+    if (digests) *digests = h->digests;
+    return GL_OK;
+}
+
+extern "C" int gl_commit_coeffs(gl_commit* h, uint64_t* coeffs_out, int space) {
+    if (!h || !coeffs_out) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    Guard g(ctx);
+    TRY(copy_out(ctx, coeffs_out, h->coeffs, ((size_t)h->c << h->log_n) * 8, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* digests_out, int space) {
+    if (!h) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    Guard g(ctx);
+    if (digests_out) TRY(copy_out(ctx, digests_out, h->digests, h->num_digests * 32, space));
+    if (leaves_out) {
+        if (space == GL_DEVICE) {
+            launch_transpose_to_rows(h->lde, h->n_local, h->c, 0, h->n_local, leaves_out, ctx->stream);
+        } else {
+            const u64 chunk = h->n_local < ((u64)1 << 16) ? h->n_local : ((u64)1 << 16);
+            void* stage;
+            TRY(scratch_get(ctx, 0, (size_t)chunk * h->c * 8, &stage));
+            for (u64 r0 = 0; r0 < h->n_local; r0 += chunk) {
+                launch_transpose_to_rows(h->lde, h->n_local, h->c, r0, chunk, (u64*)stage, ctx->stream);
+                TRY(copy_out(ctx, leaves_out + (size_t)r0 * h->c, stage, (size_t)chunk * h->c * 8, GL_HOST));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+        }
+    }
+    return finish(ctx);
+}
+
+// local leaf indices on the device in scratch slot 3
+static int upload_indices(gl_ctx* ctx, const gl_commit* h, const std::vector<u64>& local, const u64** d_idx) {
+    (void)h;
+    void* d;
+    TRY(scratch_get(ctx, 3, local.size() * 8 + 8, &d));
+    CK(cudaMemcpyAsync(d, local.data(), local.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *d_idx = (const u64*)d;
+    return GL_OK;
+}
+
+static int fetch_indices(gl_ctx* ctx, const uint64_t* idx, uint32_t k, int space, std::vector<u64>& host) {
+    host.resize(k);
+    if (space == GL_DEVICE) {
+        CK(cudaMemcpyAsync(host.data(), idx, (size_t)k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        memcpy(host.data(), idx, (size_t)k * 8);
+    }
+    return GL_OK;
+}
+
+extern "C" int gl_commit_open(gl_commit* h, const uint64_t* leaf_indices, uint32_t k, uint64_t* rows_out,
+                              uint64_t* paths_out, int space) {
+    if (!h) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    if (k == 0) return GL_OK;
+    if (!leaf_indices) return fail(ctx, GL_E_ARG, "gl_commit_open: NULL indices");
+    Guard g(ctx);
+    std::vector<u64> idx;
+    TRY(fetch_indices(ctx, leaf_indices, k, space, idx));
+    for (auto& v : idx) {
+        if (v < h->leaf_begin || v >= h->leaf_begin + h->n_local)
+            return fail(ctx, GL_E_ARG, "MerkleTree::get / prove: leaf index out of range for this shard");
+        v -= h->leaf_begin;
+    }
+    const u64* d_idx;
+    TRY(upload_indices(ctx, h, idx, &d_idx));
+    const unsigned sub_bits = h->log_n + h->rate_bits - h->cap_height;
+    if (rows_out) {
+        u64* d_rows = rows_out;
+        if (space == GL_HOST) {
+            void* t;
+            TRY(scratch_get(ctx, 0, (size_t)k * h->c * 8, &t));
+            d_rows = (u64*)t;
+        }
+        launch_gather_rows(h->lde, h->n_local, h->c, d_idx, k, d_rows, ctx->stream);
+        TRY(copy_out(ctx, rows_out, d_rows, (size_t)k * h->c * 8, space));
+    }
+    if (paths_out && sub_bits) {
+        u64* d_paths = paths_out;
+        if (space == GL_HOST) {
+            void* t;
+            TRY(scratch_get(ctx, 1, (size_t)k * sub_bits * 32, &t));
+            d_paths = (u64*)t;
+        }
+        launch_gather_paths(h->digests, sub_bits, d_idx, k, d_paths, ctx->stream);
+        TRY(copy_out(ctx, paths_out, d_paths, (size_t)k * sub_bits * 32, space));
+    }
+    return finish(ctx);
+}
+
+extern "C" int gl_commit_get_lde_values(gl_commit* h, const uint64_t* indices, uint32_t k, uint64_t step,
+                                        uint64_t* rows_out, int space) {
+    if (!h) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    if (k == 0) return GL_OK;
+    if (!indices || !rows_out) return fail(ctx, GL_E_ARG, "gl_commit_get_lde_values: NULL buffer");
+    Guard g(ctx);
+    std::vector<u64> idx;
+    TRY(fetch_indices(ctx, indices, k, space, idx));
+    const unsigned lgN = h->log_n + h->rate_bits;
+    for (auto& v : idx) {
+        unsigned __int128 prod = (unsigned __int128)v * step;
+        if (prod >= ((unsigned __int128)1 << lgN)) return fail(ctx, GL_E_ARG, "get_lde_values: index * step out of range");
+        u64 leaf = bitrev((u64)prod, lgN);
+        if (leaf < h->leaf_begin || leaf >= h->leaf_begin + h->n_local)
+            return fail(ctx, GL_E_ARG, "get_lde_values: row not held by this shard");
+        v = leaf - h->leaf_begin;
+    }
+    const u64* d_idx;
+    TRY(upload_indices(ctx, h, idx, &d_idx));
+    u64* d_rows = rows_out;
+    if (space == GL_HOST) {
+        void* t;
+        TRY(scratch_get(ctx, 0, (size_t)k * h->c * 8, &t));
+        d_rows = (u64*)t;
+    }
+    launch_gather_rows(h->lde, h->n_local, h->c, d_idx, k, d_rows, ctx->stream);
+    TRY(copy_out(ctx, rows_out, d_rows, (size_t)k * h->c * 8, space));
+    return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FRI layer commit / fold / proof of work
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_fri_layer_tree(gl_ctx* ctx, const uint64_t* values_ext, uint64_t len, uint32_t arity_bits,
+                                 uint32_t cap_height, uint64_t* digests_out, uint64_t* cap_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!is_pow2(len)) return fail(ctx, GL_E_ARG, "fri_committed_trees: length is not a power of two");
+    unsigned lg = ilog2(len);
+    if (arity_bits > lg) return fail(ctx, GL_E_ARG, "fri_committed_trees: arity larger than the layer");
+    if (cap_height > lg - arity_bits)
+        return fail(ctx, GL_E_ARG, "MerkleTree::new: cap_height must be at most log2(leaves.len())");
+    if (!values_ext || !cap_out) return fail(ctx, GL_E_ARG, "gl_fri_layer_tree: NULL buffer");
+    Guard g(ctx);
+    const u64* dv;
+    TRY(stage_in(ctx, values_ext, len * 16, space, 0, &dv));
+    const u64 nl = len >> arity_bits;
+    const uint32_t cols = 2u << arity_bits;
+    void *dcols, *dd, *dc;
+    TRY(scratch_get(ctx, 1, len * 16, &dcols));
+    uint64_t nd = 2 * (nl - ((uint64_t)1 << cap_height));
+    TRY(scratch_get(ctx, 2, nd * 32 + 32, &dd));
+    TRY(scratch_get(ctx, 3, (size_t)32 << cap_height, &dc));
+    launch_fri_leaves(dv, lg, arity_bits, (u64*)dcols, ctx->stream);
+    launch_merkle_cols((const u64*)dcols, nl, cols, lg - arity_bits, cap_height, (u64*)dd, (u64*)dc, ctx->stream);
+    TRY(copy_out(ctx, digests_out, dd, nd * 32, space));
+    TRY(copy_out(ctx, cap_out, dc, (size_t)32 << cap_height, space));
+    return finish(ctx);
+}
+
+extern "C" int gl_fri_fold(gl_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,
+                           const uint64_t beta[2], uint64_t shift, uint64_t* folded_coeffs_out,
+                           uint64_t* next_values_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!is_pow2(len)) return fail(ctx, GL_E_ARG, "fri fold: length is not a power of two");
+    unsigned lg = ilog2(len);
+    if (arity_bits > lg) return fail(ctx, GL_E_ARG, "fri fold: arity larger than the polynomial");
+    if (!coeffs_ext || !beta) return fail(ctx, GL_E_ARG, "gl_fri_fold: NULL buffer");
+    Guard g(ctx);
+    const u64* dcf;
+    TRY(stage_in(ctx, coeffs_ext, len * 16, space, 0, &dcf));
+    const u64 out_len = len >> arity_bits;
+    const unsigned out_lg = lg - arity_bits;
+    void *dcols, *dext;
+    TRY(scratch_get(ctx, 2, out_len * 16, &dcols));
+    TRY(scratch_get(ctx, 3, out_len * 16, &dext));
+    launch_fri_fold(dcf, out_len, arity_bits, beta[0], beta[1], (u64*)dcols, out_len, ctx->stream);
+    if (folded_coeffs_out) {
+        u64* dst = space == GL_DEVICE ? folded_coeffs_out : (u64*)dext;
+        launch_interleave2((const u64*)dcols, out_len, out_len, dst, ctx->stream);
+        TRY(copy_out(ctx, folded_coeffs_out, dst, out_len * 16, space));
+    }
+    if (next_values_out) {
+        u64 sh = glh::canon(shift);
+        if (sh == 0) return fail(ctx, GL_E_ARG, "gl_fri_fold: zero coset shift");
+        const u64* pre;
+        TRY(pow_table(ctx, sh, &pre));
+        TRY(transform_natural(ctx, (u64*)dcols, out_lg, 2, false, pre, nullptr));
+        u64* dst = space == GL_DEVICE ? next_values_out : (u64*)dext;
+        launch_interleave2((const u64*)dcols, out_len, out_len, dst, ctx->stream);
+        TRY(copy_out(ctx, next_values_out, dst, out_len * 16, space));
+    }
+    return finish(ctx);
+}
+
+extern "C" int gl_pow_grind(gl_ctx* ctx, const uint64_t state[12], uint32_t input_pos, uint32_t min_leading_zeros,
+                            uint64_t* witness_out) {
+    if (!ctx) return GL_E_ARG;
+    if (!state || !witness_out || input_pos >= 12 || min_leading_zeros > 64)
+        return fail(ctx, GL_E_ARG, "gl_pow_grind: bad argument");
+    Guard g(ctx);
+    void* d;
+    TRY(scratch_get(ctx, 0, 13 * 8, &d));
+    u64* dstate = (u64*)d;
+    unsigned long long* dbest = (unsigned long long*)(dstate + 12);
+    unsigned long long none = ~0ULL;
+    CK(cudaMemcpyAsync(dstate, state, 96, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dbest, &none, 8, cudaMemcpyHostToDevice, ctx->stream));
+    const u64 chunk = (u64)1 << 22;
+    // witnesses are field elements: upstream searches 0 .. p-1
+    for (u64 start = 0; start < GL_P; start += chunk) {
+        u64 count = GL_P - start < chunk ? GL_P - start : chunk;
+        launch_pow_grind(dstate, input_pos, 7, min_leading_zeros, start, count, dbest, ctx->stream);
+        unsigned long long best;
+        CK(cudaMemcpyAsync(&best, dbest, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (best != none) {
+            *witness_out = best;
+            return GL_OK;
+        }
+        if (start >= ((u64)1 << 40)) break;  // 2^40 failed candidates: min_leading_zeros is unreasonable
+    }
+    return fail(ctx, GL_E_STATE, "gl_pow_grind: no witness found");
+}

@@ -1,0 +1,138 @@
+// Goldilocks field p = 2^64 - 2^32 + 1 on the B200 integer pipes.
+//
+// plonky2_field::goldilocks_field::GoldilocksField (the type the reference imports at
+// src/smt/goldilocks_poseidon/mod.rs:9 and src/zkdsa/circuits/mod.rs:81-100).
+//
+// Representation: a u64 in [0, 2^64) that may be non-canonical (>= p), exactly like upstream keeps
+// it internally; every value that leaves the device goes through gl_canon().  Arithmetic is exact,
+// so results are bit-identical with the CPU whatever the evaluation order.
+//
+// 64x64->128 products are four IMAD.WIDE.U32 (32x32+64) on the FMA pipe; the reduction uses
+// 2^64 = 2^32 - 1 and 2^96 = -1 (mod p), one more IMAD plus carry-chain adds on the ALU pipe.
+#pragma once
+#include <cstdint>
+
+#ifndef GL_HD
+#ifdef __CUDACC__
+#define GL_HD __host__ __device__ __forceinline__
+#define GL_D __device__ __forceinline__
+#else
+#define GL_HD inline
+#define GL_D inline
+#endif
+#endif
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define GL_P 0xFFFFFFFF00000001ULL
+#define GL_EPS 0xFFFFFFFFULL
+
+// ------------------------------------------------------------------------------------------------
+// host-side exact arithmetic (twiddle / constant tables are generated on the host at ctx creation)
+// ------------------------------------------------------------------------------------------------
+namespace glh {
+typedef unsigned __int128 u128;
+inline u64 canon(u64 x) { return x >= GL_P ? x - GL_P : x; }
+inline u64 reduce(u128 x) { return (u64)(x % GL_P); }
+inline u64 add(u64 a, u64 b) { return reduce((u128)a + b); }
+inline u64 sub(u64 a, u64 b) { return reduce((u128)canon(a) + GL_P - canon(b)); }
+inline u64 mul(u64 a, u64 b) { return reduce((u128)a * b); }
+inline u64 pow(u64 a, u64 e) {
+    u64 r = 1;
+    a = canon(a);
+    while (e) {
+        if (e & 1) r = mul(r, a);
+        a = mul(a, a);
+        e >>= 1;
+    }
+    return r;
+}
+inline u64 inv(u64 a) { return pow(a, GL_P - 2); }
+// Field::primitive_root_of_unity(k) = POWER_OF_TWO_GENERATOR^(2^(32-k)), generator 7^((p-1)/2^32)
+inline u64 root_of_unity(unsigned lg) {
+    u64 g = pow(7, (GL_P - 1) >> 32);
+    for (unsigned i = lg; i < 32; i++) g = mul(g, g);
+    return g;
+}
+}  // namespace glh
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// device arithmetic
+// ------------------------------------------------------------------------------------------------
+GL_D u64 gl_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+
+// x (128 bit) -> [0, 2^64), x = lo + 2^64 * hi.
+//   s = lo + hi_lo * (2^32 - 1)             (carry c)
+//   s = s - hi_hi                           (borrow b)
+//   s += (c - b) * (2^32 - 1)               (cannot wrap again)
+GL_D u64 gl_reduce128(u64 lo, u64 hi) {
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32), s0, s1;
+    asm("{\n\t"
+        ".reg .u32 c, bm, e0;\n\t"
+        "mad.lo.cc.u32 %0, %4, 0xffffffff, %2;\n\t"
+        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"
+        "addc.u32 c, 0, 0;\n\t"         // c = carry (0/1)
+        "sub.cc.u32 %0, %0, %5;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 bm, 0, 0;\n\t"        // bm = borrow ? 0xffffffff : 0
+        "sub.u32 e0, 0, bm;\n\t"        // b
+        "sub.u32 e0, e0, c;\n\t"        // low word of (c-b)*EPS  = b - c   (mod 2^32)
+        "add.u32 c, c, 0xffffffff;\n\t" // c ? 0 : 0xffffffff
+        "and.b32 bm, bm, c;\n\t"        // high word of (c-b)*EPS = (b && !c) ? 0xffffffff : 0
+        "add.cc.u32 %0, %0, e0;\n\t"
+        "addc.u32 %1, %1, bm;\n\t"
+        "}"
+        : "=&r"(s0), "=&r"(s1)
+        : "r"(r0), "r"(r1), "r"(h0), "r"(h1));
+    return gl_pack(s0, s1);
+}
+
+GL_D u64 gl_mul(u64 a, u64 b) {
+    unsigned __int128 p = (unsigned __int128)a * b;
+    return gl_reduce128((u64)p, (u64)(p >> 64));
+}
+GL_D u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+
+// a + b where b is canonical (< p): one wrap correction suffices
+GL_D u64 gl_add_c(u64 a, u64 b_canonical) {
+    u64 s = a + b_canonical;
+    return s + ((s < a) ? GL_EPS : 0ULL);
+}
+// general a + b, both possibly non-canonical: a second wrap can happen (only if both >= p - 2^32)
+GL_D u64 gl_add(u64 a, u64 b) {
+    u64 s = a + b;
+    u64 t = s + ((s < a) ? GL_EPS : 0ULL);
+    return t + ((t < s) ? GL_EPS : 0ULL);
+}
+// general a - b
+GL_D u64 gl_sub(u64 a, u64 b) {
+    u64 d = a - b;
+    u64 t = d - ((a < b) ? GL_EPS : 0ULL);
+    return t - ((t > d) ? GL_EPS : 0ULL);
+}
+GL_D u64 gl_canon(u64 x) { return x >= GL_P ? x - GL_P : x; }
+GL_D u64 gl_neg(u64 a) { return gl_sub(0, a); }
+
+GL_D u64 gl_pow(u64 a, u64 e) {
+    u64 r = 1;
+    while (e) {
+        if (e & 1) r = gl_mul(r, a);
+        a = gl_sqr(a);
+        e >>= 1;
+    }
+    return r;
+}
+
+// QuadraticExtension<GoldilocksField>: F[X]/(X^2 - 7)
+struct gl_ext {
+    u64 a, b;
+};
+GL_D gl_ext gl_ext_add(gl_ext x, gl_ext y) { return {gl_add(x.a, y.a), gl_add(x.b, y.b)}; }
+GL_D gl_ext gl_ext_mul(gl_ext x, gl_ext y) {
+    u64 c0 = gl_add(gl_mul(x.a, y.a), gl_mul(7, gl_mul(x.b, y.b)));
+    u64 c1 = gl_add(gl_mul(x.a, y.b), gl_mul(x.b, y.a));
+    return {c0, c1};
+}
+#endif  // __CUDACC__

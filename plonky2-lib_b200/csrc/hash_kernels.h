@@ -1,0 +1,28 @@
+// Internal launcher interface of hash_kernels.cu (host side; streams are plain cudaStream_t).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/gl_b200.h"
+
+// kernels launched by this process (gl_ctx_kernel_launches); bumped at every launch site
+extern std::atomic<unsigned long long> g_gl_launches;
+
+int gl_poseidon_upload_constants(const uint64_t* rc360);
+void launch_permute_batch(uint64_t* states, uint64_t m, cudaStream_t st);
+void launch_two_to_one_batch(const uint64_t* l, const uint64_t* r, uint64_t* out, uint64_t m, cudaStream_t st);
+void launch_hash_no_pad_rows(const uint64_t* in, uint32_t len, uint64_t m, uint64_t* out, cudaStream_t st);
+void launch_smt_leaf_hash_batch(const uint64_t* k, const uint64_t* v, uint64_t* out, uint64_t m, cudaStream_t st);
+void launch_smt_verify_process(const gl_smt_proof_hdr* p, const uint64_t* sib_pool, const uint64_t* sib_off,
+                               uint64_t m, int* status, cudaStream_t st);
+void launch_pow_grind(const uint64_t* state12, unsigned pos, unsigned out_pos, unsigned min_lz, uint64_t start,
+                      uint64_t count, unsigned long long* best, cudaStream_t st);
+void launch_leaf_hash_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned lg_leaves, unsigned cap_height,
+                           uint64_t* digests, uint64_t* cap, cudaStream_t st);
+void launch_merkle_levels(unsigned lg_leaves, unsigned cap_height, uint64_t* digests, uint64_t* cap, cudaStream_t st);
+void launch_merkle_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned lg_leaves, unsigned cap_height,
+                        uint64_t* digests, uint64_t* cap, cudaStream_t st);
+void launch_merkle_rows(const uint64_t* leaves, uint32_t leaf_len, unsigned lg_leaves, unsigned cap_height,
+                        uint64_t* digests, uint64_t* cap, cudaStream_t st);

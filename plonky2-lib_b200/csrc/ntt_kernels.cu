@@ -1,0 +1,284 @@
+// Batched Goldilocks NTT passes (8a rows P1, P2, P3, P9).
+//
+// A size-2^L transform of one column is done as up to three decimation-in-frequency passes over
+// disjoint groups of index bits, each pass = shared-memory radix-2 stages over 2^m points followed
+// by the "four-step" twiddle.  Natural order in, bit-reversed order out, in place per index bits:
+//
+//     pass (m, s):  for every (outer, j_lo):  x[outer][.][j_lo]  <-  DFT_{2^m}(x[outer][.][j_lo])
+//                   stored at bit-reversed position, then times w_{2^(s+m)}^(k * j_lo)
+//
+// A strided pass (s > 0) gives one CTA a tile of T adjacent j_lo so that every global access is a
+// T*8-byte segment; the last pass (s = 0) gives one CTA consecutive 2^m-blocks (fully coalesced).
+// Bit-reversed output is exactly the leaf order PolynomialBatch needs (leaves[i] = lde[bitrev(i)]),
+// so the LDE never runs a separate "transpose + reverse_index_bits" over the 9 GB of leaves.
+#include <cuda_runtime.h>
+
+#include "gl_field.cuh"
+#include "ntt_kernels.h"
+
+// base^e from a 3 x 1024 table (e < 2^30)
+GL_D u64 powtab_eval(const u64* __restrict__ tab, u64 e) {
+    u64 r = __ldg(tab + (e & 1023));
+    if (e >> 10) {
+        r = gl_mul(r, __ldg(tab + 1024 + ((e >> 10) & 1023)));
+        if (e >> 20) r = gl_mul(r, __ldg(tab + 2048 + ((e >> 20) & 1023)));
+    }
+    return r;
+}
+
+// One pass.  grid = (tiles per column, columns, cosets).  Dynamic smem: rows * T elements + 2^(m-1) twiddles.
+__global__ void __launch_bounds__(NTT_THREADS)
+k_ntt_pass(ntt_pass_args a) {
+    extern __shared__ u64 sm[];
+    const unsigned m = a.m, s = a.s, T = a.T;
+    const u64 rows = a.rows;                   // rows per CTA (multiple of 2^m)
+    const u64 E = rows * T;
+    u64* tw = sm + E;                          // w_{2^m}^x, x < 2^(m-1)
+    const unsigned coset = blockIdx.z;
+    const u64 col = blockIdx.y;
+    // position of this CTA's tile inside the column
+    u64 tile = blockIdx.x, base;
+    if (s == 0) {
+        base = tile * rows;                    // consecutive 2^m blocks
+    } else {
+        u64 tiles_per_block = ((u64)1 << s) / T;        // tiles along j_lo
+        u64 outer = tile / tiles_per_block, jt = tile % tiles_per_block;
+        base = (outer << (s + m)) + jt * T;
+    }
+    const u64 rowstride = (u64)1 << s;
+    const u64* in = a.in + col * a.in_ld + (u64)coset * a.in_coset_stride;
+    u64* out = a.out + col * a.out_ld + (u64)coset * a.out_coset_stride;
+    const u64* pre = a.pre_tab ? a.pre_tab + (u64)coset * 3072 : nullptr;
+
+    for (u64 x = threadIdx.x; x < ((u64)1 << m) / 2; x += NTT_THREADS) tw[x] = __ldg(a.small_tab + x);
+    for (u64 e = threadIdx.x; e < E; e += NTT_THREADS) {
+        u64 row = e / T, t = e % T;
+        u64 pos = base + row * rowstride + t;
+        u64 v = in[pos];
+        if (pre) v = gl_mul(v, powtab_eval(pre, pos));   // coset_fft: coeffs[i] * shift^i
+        sm[e] = v;
+    }
+    __syncthreads();
+    // DIF stages over the low m bits of the row index
+    for (unsigned st = 0; st < m; st++) {
+        const unsigned lh = m - 1 - st;                  // log2(half)
+        const u64 half = (u64)1 << lh;
+        for (u64 b = threadIdx.x; b < E / 2; b += NTT_THREADS) {
+            u64 t = b % T, bb = b / T;
+            u64 j = bb & (half - 1), blk = bb >> lh;
+            u64 i0 = ((blk << (lh + 1)) + j) * T + t, i1 = i0 + half * T;
+            u64 u = sm[i0], v = sm[i1];
+            sm[i0] = gl_add(u, v);
+            u64 d = gl_sub(u, v);
+            sm[i1] = st == m - 1 ? d : gl_mul(d, tw[j << st]);
+        }
+        __syncthreads();
+    }
+    // store (in-place positions) with the four-step twiddle w_{2^(s+m)}^(k * j_lo), k = bitrev_m(row)
+    for (u64 e = threadIdx.x; e < E; e += NTT_THREADS) {
+        u64 row = e / T, t = e % T;
+        u64 pos = base + row * rowstride + t;
+        u64 v = sm[e];
+        if (s != 0 && a.post_tab) {
+            u64 k = m ? (__brevll(row & (((u64)1 << m) - 1)) >> (64 - m)) : 0;
+            u64 jlo = pos & (rowstride - 1);
+            v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
+        }
+        if (a.final_scale != 1) v = gl_mul(v, a.final_scale);
+        if (a.canonical_out) v = gl_canon(v);
+        out[pos] = v;
+    }
+}
+
+void launch_ntt_pass(const ntt_pass_args& a, u64 n, u32 columns, u32 cosets, cudaStream_t st) {
+    u64 E = a.rows * a.T;
+    size_t smem = (E + (((u64)1 << a.m) / 2)) * sizeof(u64);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(n / E), columns, cosets);
+    { k_ntt_pass<<<grid, NTT_THREADS, smem, st>>>(a); ++g_gl_launches; }
+}
+
+// out[col][bitrev_L(i)] = in[col][i] * scale  (canonical).  Tiled through shared memory so both sides
+// move 32-element (256 B) runs: i = (hi | mid | lo) with |hi| = |lo| = 5 bits swaps hi and lo blocks.
+__global__ void __launch_bounds__(256)
+k_bitrev_permute(const u64* __restrict__ in, u64 in_ld, u64* __restrict__ out, u64 out_ld, unsigned L, u64 scale) {
+    const u64 col = blockIdx.y;
+    const u64* src = in + col * in_ld;
+    u64* dst = out + col * out_ld;
+    if (L < 10) {  // small: direct
+        u64 n = (u64)1 << L;
+        for (u64 i = blockIdx.x * (u64)256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+            u64 j = L ? (__brevll(i) >> (64 - L)) : 0;
+            u64 v = src[i];
+            if (scale != 1) v = gl_mul(v, scale);
+            dst[j] = gl_canon(v);
+        }
+        return;
+    }
+    __shared__ u64 tile[32][33];
+    const unsigned midbits = L - 10;
+    for (u64 mid = blockIdx.x; mid < ((u64)1 << midbits); mid += gridDim.x) {
+        u64 rmid = midbits ? (__brevll(mid) >> (64 - midbits)) : 0;
+        unsigned lo = threadIdx.x & 31, hi0 = threadIdx.x >> 5;
+        for (unsigned hi = hi0; hi < 32; hi += 8) {
+            u64 v = src[((u64)hi << (L - 5)) | (mid << 5) | lo];
+            if (scale != 1) v = gl_mul(v, scale);
+            tile[hi][lo] = gl_canon(v);
+        }
+        __syncthreads();
+        // destination index: (rev(lo) | rev(mid) | rev(hi)); let thread's fast index run over rev(hi)
+        unsigned a = threadIdx.x & 31, b0 = threadIdx.x >> 5;   // a = rev5(hi) position, b = rev5(lo)
+        for (unsigned b = b0; b < 32; b += 8) {
+            unsigned hi = __brev(a) >> 27, lo2 = __brev(b) >> 27;
+            dst[((u64)b << (L - 5)) | (rmid << 5) | a] = tile[hi][lo2];
+        }
+        __syncthreads();
+    }
+}
+
+void launch_bitrev_permute(const u64* in, u64 in_ld, u64* out, u64 out_ld, unsigned L, u32 columns, u64 scale,
+                           cudaStream_t st) {
+    u64 blocks = L < 10 ? 1 : ((u64)1 << (L - 10));
+    if (blocks > 4096) blocks = 4096;
+    dim3 grid((unsigned)blocks, columns);
+    { k_bitrev_permute<<<grid, 256, 0, st>>>(in, in_ld, out, out_ld, L, scale); ++g_gl_launches; }
+}
+
+// ifft_with_options epilogue done directly: plonky2 runs the forward FFT and then maps
+// out[i] <-> out[n-i] * n^-1; that is the inverse DFT, which the passes above compute with inverse roots.
+
+// Elementwise helpers ------------------------------------------------------------------------------
+// data[col][i] *= base^i (coset scaling for natural-order coset_fft / coset_ifft)
+__global__ void __launch_bounds__(256)
+k_scale_powers(u64* __restrict__ data, u64 ld, u64 n, const u64* __restrict__ tab) {
+    u64 col = blockIdx.y;
+    for (u64 i = blockIdx.x * (u64)256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+        u64* p = data + col * ld + i;
+        *p = gl_canon(gl_mul(*p, powtab_eval(tab, i)));
+    }
+}
+void launch_scale_powers(u64* data, u64 ld, u64 n, u32 columns, const u64* tab, cudaStream_t st) {
+    u64 blocks = (n + 255) / 256;
+    if (blocks > 2048) blocks = 2048;
+    dim3 grid((unsigned)blocks, columns);
+    { k_scale_powers<<<grid, 256, 0, st>>>(data, ld, n, tab); ++g_gl_launches; }
+}
+
+// Column-major [c][ld] (rows r0 .. r0+nrows) -> row-major [nrows][c]  ("transpose LDEs" for mirror mode)
+__global__ void __launch_bounds__(256)
+k_transpose_to_rows(const u64* __restrict__ cols, u64 ld, u32 c, u64 r0, u64 nrows, u64* __restrict__ rows) {
+    __shared__ u64 tile[32][33];
+    u64 rb = (u64)blockIdx.x * 32, cb = (u64)blockIdx.y * 32;
+    unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (unsigned j = ty; j < 32; j += 8) {
+        u64 col = cb + j, row = rb + tx;
+        tile[j][tx] = (col < c && row < nrows) ? cols[col * ld + r0 + row] : 0;
+    }
+    __syncthreads();
+    for (unsigned j = ty; j < 32; j += 8) {
+        u64 row = rb + j, col = cb + tx;
+        if (row < nrows && col < c) rows[row * c + col] = tile[tx][j];
+    }
+}
+void launch_transpose_to_rows(const u64* cols, u64 ld, u32 c, u64 r0, u64 nrows, u64* rows, cudaStream_t st) {
+    dim3 grid((unsigned)((nrows + 31) / 32), (c + 31) / 32);
+    { k_transpose_to_rows<<<grid, 256, 0, st>>>(cols, ld, c, r0, nrows, rows); ++g_gl_launches; }
+}
+
+// Gather k rows (leaf indices local to the buffer) into [k][c]
+__global__ void k_gather_rows(const u64* __restrict__ cols, u64 ld, u32 c, const u64* __restrict__ idx, u32 k,
+                              u64* __restrict__ rows) {
+    u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (g >= (u64)k * c) return;
+    u64 q = g / c, col = g % c;
+    rows[g] = cols[col * ld + idx[q]];
+}
+void launch_gather_rows(const u64* cols, u64 ld, u32 c, const u64* idx, u32 k, u64* rows, cudaStream_t st) {
+    u64 total = (u64)k * c;
+    if (total) { k_gather_rows<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cols, ld, c, idx, k, rows); ++g_gl_launches; }
+}
+
+// MerkleTree::prove for k local leaf indices: paths [k][sub_bits][4]
+__global__ void k_gather_paths(const u64* __restrict__ digests, unsigned sub_bits, const u64* __restrict__ idx, u32 k,
+                               u64* __restrict__ paths) {
+    u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (g >= (u64)k * sub_bits) return;
+    u64 q = g / sub_bits;
+    unsigned layer = (unsigned)(g % sub_bits);
+    u64 leaf = idx[q];
+    u64 subtree = leaf >> sub_bits;
+    u64 pair = (leaf & (((u64)1 << sub_bits) - 1)) >> layer;   // node index at `layer`
+    u64 parity = pair & 1;
+    pair >>= 1;
+    u64 sib = 2 * ((pair << (layer + 1)) + ((u64)1 << layer) - 1) + (1 - parity);
+    u64 per_subtree = 2 * (((u64)1 << sub_bits) - 1);
+    const u64* src = digests + 4 * (subtree * per_subtree + sib);
+    u64* dst = paths + 4 * g;
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+void launch_gather_paths(const u64* digests, unsigned sub_bits, const u64* idx, u32 k, u64* paths, cudaStream_t st) {
+    u64 total = (u64)k * sub_bits;
+    if (total) { k_gather_paths<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(digests, sub_bits, idx, k, paths); ++g_gl_launches; }
+}
+
+// FRI layer leaves, column-major: element (leaf j, column 2a+e) = values_ext[bitrev(j * arity + a)][e]
+__global__ void __launch_bounds__(256)
+k_fri_leaves(const u64* __restrict__ values_ext, unsigned lg_len, unsigned arity_bits, u64* __restrict__ cols) {
+    u64 len = (u64)1 << lg_len, nl = len >> arity_bits;
+    u64 g = blockIdx.x * (u64)256 + threadIdx.x;
+    if (g >= len) return;
+    u64 a = g / nl, j = g % nl;           // consecutive threads -> consecutive leaves of one column pair
+    u64 src = lg_len ? (__brevll((j << arity_bits) + a) >> (64 - lg_len)) : 0;
+    cols[(2 * a) * nl + j] = gl_canon(values_ext[2 * src]);
+    cols[(2 * a + 1) * nl + j] = gl_canon(values_ext[2 * src + 1]);
+}
+void launch_fri_leaves(const u64* values_ext, unsigned lg_len, unsigned arity_bits, u64* cols, cudaStream_t st) {
+    u64 len = (u64)1 << lg_len;
+    { k_fri_leaves<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(values_ext, lg_len, arity_bits, cols); ++g_gl_launches; }
+}
+
+// reduce_with_powers over chunks of 2^arity_bits extension coefficients; output split into two base
+// columns out[0][k], out[1][k] (ready for the two base-field NTTs of the extension coset_fft)
+__global__ void __launch_bounds__(256)
+k_fri_fold(const u64* __restrict__ coeffs_ext, u64 out_len, unsigned arity_bits, u64 b0, u64 b1,
+           u64* __restrict__ out_cols, u64 out_ld) {
+    u64 k = blockIdx.x * (u64)256 + threadIdx.x;
+    if (k >= out_len) return;
+    unsigned arity = 1u << arity_bits;
+    gl_ext beta = {b0, b1}, acc = {0, 0};
+    const u64* p = coeffs_ext + 2 * (k << arity_bits);
+    for (int j = (int)arity - 1; j >= 0; j--) {
+        gl_ext cj = {p[2 * j], p[2 * j + 1]};
+        acc = gl_ext_add(gl_ext_mul(acc, beta), cj);
+    }
+    out_cols[k] = gl_canon(acc.a);
+    out_cols[out_ld + k] = gl_canon(acc.b);
+}
+void launch_fri_fold(const u64* coeffs_ext, u64 out_len, unsigned arity_bits, u64 b0, u64 b1, u64* out_cols,
+                     u64 out_ld, cudaStream_t st) {
+    { k_fri_fold<<<(unsigned)((out_len + 255) / 256), 256, 0, st>>>(coeffs_ext, out_len, arity_bits, b0, b1, out_cols, out_ld); ++g_gl_launches; }
+}
+
+// [2][n] base columns <-> [n][2] interleaved extension elements
+__global__ void k_interleave2(const u64* __restrict__ cols, u64 ld, u64 n, u64* __restrict__ ext) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ext[2 * i] = cols[i];
+    ext[2 * i + 1] = cols[ld + i];
+}
+__global__ void k_deinterleave2(const u64* __restrict__ ext, u64 n, u64* __restrict__ cols, u64 ld) {
+    u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cols[i] = ext[2 * i];
+    cols[ld + i] = ext[2 * i + 1];
+}
+void launch_interleave2(const u64* cols, u64 ld, u64 n, u64* ext, cudaStream_t st) {
+    if (n) { k_interleave2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cols, ld, n, ext); ++g_gl_launches; }
+}
+void launch_deinterleave2(const u64* ext, u64 n, u64* cols, u64 ld, cudaStream_t st) {
+    if (n) { k_deinterleave2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ext, n, cols, ld); ++g_gl_launches; }
+}

@@ -1,0 +1,43 @@
+// Internal launcher interface of ntt_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+extern std::atomic<unsigned long long> g_gl_launches;
+
+#define NTT_THREADS 512
+
+struct ntt_pass_args {
+    const uint64_t* in;        // column 0 of the input
+    uint64_t in_ld;            // elements between columns
+    uint64_t in_coset_stride;  // elements between coset blocks of the input (0: every coset reads the same data)
+    uint64_t* out;
+    uint64_t out_ld;
+    uint64_t out_coset_stride;
+    const uint64_t* pre_tab;   // [cosets][3][1024] power tables of the coset shifts, or null
+    const uint64_t* post_tab;  // [3][1024] power table of w_{2^(s+m)} (direction already applied), or null
+    const uint64_t* small_tab; // w_{2^m}^x, x < 2^(m-1)
+    uint64_t rows;             // rows per CTA (multiple of 2^m)
+    uint64_t final_scale;      // multiply every output (1 = none)
+    unsigned m, s, T;
+    int canonical_out;
+};
+
+void launch_ntt_pass(const ntt_pass_args& a, uint64_t n, uint32_t columns, uint32_t cosets, cudaStream_t st);
+void launch_bitrev_permute(const uint64_t* in, uint64_t in_ld, uint64_t* out, uint64_t out_ld, unsigned L,
+                           uint32_t columns, uint64_t scale, cudaStream_t st);
+void launch_scale_powers(uint64_t* data, uint64_t ld, uint64_t n, uint32_t columns, const uint64_t* tab,
+                         cudaStream_t st);
+void launch_transpose_to_rows(const uint64_t* cols, uint64_t ld, uint32_t c, uint64_t r0, uint64_t nrows,
+                              uint64_t* rows, cudaStream_t st);
+void launch_gather_rows(const uint64_t* cols, uint64_t ld, uint32_t c, const uint64_t* idx, uint32_t k,
+                        uint64_t* rows, cudaStream_t st);
+void launch_gather_paths(const uint64_t* digests, unsigned sub_bits, const uint64_t* idx, uint32_t k,
+                         uint64_t* paths, cudaStream_t st);
+void launch_fri_leaves(const uint64_t* values_ext, unsigned lg_len, unsigned arity_bits, uint64_t* cols,
+                       cudaStream_t st);
+void launch_fri_fold(const uint64_t* coeffs_ext, uint64_t out_len, unsigned arity_bits, uint64_t b0, uint64_t b1,
+                     uint64_t* out_cols, uint64_t out_ld, cudaStream_t st);
+void launch_interleave2(const uint64_t* cols, uint64_t ld, uint64_t n, uint64_t* ext, cudaStream_t st);
+void launch_deinterleave2(const uint64_t* ext, uint64_t n, uint64_t* cols, uint64_t ld, cudaStream_t st);

@@ -1,0 +1,651 @@
+"""Host-side mirror of the plonky2 plugin surface that Plonky2-lib reaches, over the
+C ABI of include/gl_b200.h.
+
+Names, argument meaning and error behaviour follow the upstream Rust interface so the parity tests
+read like the reference's own: `PolynomialBatch.from_values / from_coeffs`, `MerkleTree.new /
+prove / get`, `PoseidonHash.hash_no_pad / two_to_one / hash_pad / hash_or_noop`, `FriConfig`,
+`PoseidonNodeHash.calc_node_hash` (src/smt/goldilocks_poseidon/mod.rs:158-184) and
+`SparseMerkleProcessProof.check` (src/smt/proof/process.rs:47-51).  Upstream functions are infallible
+and panic on contract violations; here a violation raises `GlPanic` carrying the library's message.
+
+Buffers: numpy uint64 arrays are host memory (GL_HOST); torch CUDA tensors with an 8-byte dtype are
+device memory (GL_DEVICE) and are used in place.  Nothing in this module computes field arithmetic:
+every result comes from libgl_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+
+P = 0xFFFFFFFF00000001
+
+
+class GlPanic(RuntimeError):
+    """What `panic!` is upstream: a contract violation or a CUDA failure (code in .code)."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[GL_E {code}] {msg}")
+        self.code = code
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class _Buf:
+    """pointer + space of a caller buffer (numpy host array or torch CUDA tensor)."""
+
+    __slots__ = ("ptr", "space", "keep", "nbytes")
+
+    def __init__(self, x, writable: bool = False):
+        if x is None:
+            self.ptr, self.space, self.keep, self.nbytes = None, None, None, 0
+            return
+        if _is_torch(x):
+            if not x.is_cuda:
+                x = x.numpy()
+            else:
+                if not x.is_contiguous() or x.element_size() != 8:
+                    raise TypeError("device buffers must be contiguous tensors of an 8-byte dtype")
+                self.ptr, self.space, self.keep = x.data_ptr(), N.GL_DEVICE, x
+                self.nbytes = x.numel() * 8
+                return
+        if not isinstance(x, np.ndarray) or x.dtype != np.uint64 or not x.flags.c_contiguous:
+            raise TypeError("host buffers must be C-contiguous numpy uint64 arrays")
+        if writable and not x.flags.writeable:
+            raise TypeError("output buffer is read-only")
+        self.ptr, self.space, self.keep, self.nbytes = x.ctypes.data, N.GL_HOST, x, x.nbytes
+
+
+def _h(x) -> np.ndarray:
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+def _same_space(*bufs: _Buf) -> int:
+    spaces = {b.space for b in bufs if b.space is not None}
+    if len(spaces) > 1:
+        raise TypeError("all buffers of one call must live in the same space (all host or all device)")
+    return spaces.pop() if spaces else N.GL_HOST
+
+
+class Context:
+    """gl_ctx: one device, one stream.  `Context.default()` is what the mirror classes use."""
+
+    _default: Optional["Context"] = None
+
+    def __init__(self, device: int = 0):
+        self._lib = N.load()
+        h = C.c_void_p()
+        rc = self._lib.gl_ctx_create(device, C.byref(h))
+        if rc:
+            raise GlPanic(rc, (self._lib.gl_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    @classmethod
+    def default(cls) -> "Context":
+        if cls._default is None:
+            cls._default = Context(0)
+        return cls._default
+
+    def check(self, rc: int):
+        if rc:
+            raise GlPanic(rc, (self._lib.gl_last_error(self._h) or b"").decode())
+
+    def set_shard(self, index: int, count: int):
+        self.check(self._lib.gl_ctx_set_shard(self._h, index, count))
+
+    def sync(self):
+        self.check(self._lib.gl_ctx_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._lib.gl_ctx_stream(self._h) or 0)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._lib.gl_ctx_kernel_launches(self._h))
+
+    PHASES = ("copy_in", "ifft", "coeffs_out", "lde_ntt", "leaf_hash", "tree_levels")
+
+    def commit_phase_ms(self) -> dict:
+        """Device time (ms) of each phase of the last PolynomialBatch.from_* call."""
+        out = (C.c_float * 6)()
+        self.check(self._lib.gl_ctx_commit_phase_ms(self._h, out))
+        return dict(zip(self.PHASES, [float(x) for x in out]))
+
+    def trim(self):
+        self.check(self._lib.gl_ctx_trim(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gl_ctx_destroy(self._h)
+            self._h = None
+            if Context._default is self:
+                Context._default = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ctx(ctx: Optional[Context]) -> Context:
+    return ctx if ctx is not None else Context.default()
+
+
+def pinned_empty(shape, ctx: Optional[Context] = None) -> np.ndarray:
+    """uint64 array in page-locked host memory (gl_host_alloc); freed when the array is collected."""
+    lib = N.load()
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    rc = lib.gl_host_alloc(n * 8, C.byref(p))
+    if rc:
+        raise GlPanic(rc, (lib.gl_last_error(None) or b"").decode())
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            lib.gl_host_free(self.ptr)
+
+    owner = _Owner(p)
+    buf = (C.c_uint64 * n).from_address(p.value)
+    return _PinnedArray(np.frombuffer(buf, dtype=np.uint64).reshape(shape), owner)
+
+
+class _PinnedArray(np.ndarray):
+    """ndarray view that keeps its pinned allocation alive."""
+
+    def __new__(cls, arr, owner):
+        obj = np.asarray(arr).view(cls)
+        obj._owner = owner
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
+# ------------------------------------------------------------------------------------------------
+# plonky2::hash::poseidon::PoseidonHash (Hasher<F>)
+# ------------------------------------------------------------------------------------------------
+class PoseidonHash:
+    HASH_SIZE = 32
+    SPONGE_WIDTH = 12
+    SPONGE_RATE = 8
+
+    @staticmethod
+    def permute(states, ctx: Optional[Context] = None):
+        """PoseidonPermutation::permute over a batch [m][12]; returns a new array (host) / in place (device)."""
+        ctx = _ctx(ctx)
+        if not _is_torch(states):
+            states = _h(states).copy()
+        single = states.ndim == 1
+        s2 = states.reshape(-1, 12)
+        b = _Buf(s2, writable=True)
+        ctx.check(ctx._lib.gl_poseidon_permute_batch(ctx._h, b.ptr, s2.shape[0], b.space))
+        return s2.reshape(12) if single else s2
+
+    @staticmethod
+    def two_to_one(left, right, out=None, ctx: Optional[Context] = None):
+        """Hasher::two_to_one (src/smt/goldilocks_poseidon/mod.rs:165, src/zkdsa/account.rs:165); [m][4] or [4]."""
+        ctx = _ctx(ctx)
+        dev = _is_torch(left) and left.is_cuda
+        if not dev:
+            left, right = _h(left), _h(right)
+        single = left.ndim == 1
+        l2, r2 = left.reshape(-1, 4), right.reshape(-1, 4)
+        if l2.shape != r2.shape:
+            raise GlPanic(N.GL_E_ARG, "two_to_one: shape mismatch")
+        if out is None:
+            if dev:
+                import torch
+
+                out = torch.empty_like(l2)
+            else:
+                out = np.empty_like(l2)
+        bl, br, bo = _Buf(l2), _Buf(r2), _Buf(out, writable=True)
+        ctx.check(ctx._lib.gl_poseidon_two_to_one_batch(ctx._h, bl.ptr, br.ptr, bo.ptr, l2.shape[0], _same_space(bl, br, bo)))
+        return out.reshape(4) if single else out
+
+    @staticmethod
+    def hash_no_pad(inputs, out=None, ctx: Optional[Context] = None):
+        """Hasher::hash_no_pad; [m][len] -> [m][4], or [len] -> [4]."""
+        ctx = _ctx(ctx)
+        dev = _is_torch(inputs) and inputs.is_cuda
+        if not dev:
+            inputs = _h(inputs)
+        single = inputs.ndim == 1
+        x2 = inputs.reshape(1, -1) if single else inputs
+        m, ln = x2.shape
+        if out is None:
+            if dev:
+                import torch
+
+                out = torch.empty((m, 4), dtype=x2.dtype, device=x2.device)
+            else:
+                out = np.empty((m, 4), dtype=np.uint64)
+        bi, bo = _Buf(x2), _Buf(out, writable=True)
+        ctx.check(ctx._lib.gl_poseidon_hash_no_pad_batch(ctx._h, bi.ptr, ln, m, bo.ptr, _same_space(bi, bo)))
+        return out.reshape(4) if single else out
+
+    @staticmethod
+    def hash_pad(inputs, ctx: Optional[Context] = None):
+        """Hasher::hash_pad: append 1, zeros, 1 up to a multiple of SPONGE_WIDTH, then hash_no_pad
+        (this fork generation pads to the width: src/smt/goldilocks_poseidon/mod.rs:167-181 must equal
+        src/smt/gadgets/common.rs:87-101).  Host inputs only (the padding is a host-side reshape)."""
+        x = _h(inputs)
+        single = x.ndim == 1
+        x2 = x.reshape(1, -1) if single else x
+        m, ln = x2.shape
+        total = ln + 2
+        while total % PoseidonHash.SPONGE_WIDTH:
+            total += 1
+        padded = np.zeros((m, total), dtype=np.uint64)
+        padded[:, :ln] = x2
+        padded[:, ln] = 1
+        padded[:, total - 1] = 1
+        out = PoseidonHash.hash_no_pad(padded, ctx=ctx)
+        return out.reshape(4) if single else out
+
+    @staticmethod
+    def hash_or_noop(inputs, ctx: Optional[Context] = None):
+        """Hasher::hash_or_noop: rows of at most 4 elements are zero-padded copies, else hash_no_pad."""
+        x = _h(inputs)
+        single = x.ndim == 1
+        x2 = x.reshape(1, -1) if single else x
+        if x2.shape[1] <= 4:
+            out = np.zeros((x2.shape[0], 4), dtype=np.uint64)
+            out[:, : x2.shape[1]] = x2 % np.uint64(P)
+        else:
+            out = PoseidonHash.hash_no_pad(x2, ctx=ctx)
+        return out.reshape(4) if single else out
+
+
+# ------------------------------------------------------------------------------------------------
+# plonky2::hash::merkle_tree::MerkleTree
+# ------------------------------------------------------------------------------------------------
+def _prove_from_digests(digests: np.ndarray, num_leaves: int, cap_height: int, leaf_index: int) -> np.ndarray:
+    """MerkleTree::prove's index walk over the in-order digest buffer."""
+    L = num_leaves.bit_length() - 1 - cap_height
+    if L <= 0:
+        return np.zeros((0, 4), dtype=np.uint64)
+    per = 2 * ((1 << L) - 1)
+    sub = leaf_index >> L
+    buf = digests[sub * per : (sub + 1) * per]
+    pair = leaf_index & ((1 << L) - 1)
+    sib = np.empty((L, 4), dtype=np.uint64)
+    for i in range(L):
+        parity = pair & 1
+        pair >>= 1
+        sib[i] = buf[2 * ((pair << (i + 1)) + (1 << i) - 1) + (1 - parity)]
+    return sib
+
+
+class MerkleTree:
+    """MerkleTree<F, PoseidonHash>{leaves, digests, cap}."""
+
+    def __init__(self, leaves: np.ndarray, digests: np.ndarray, cap: np.ndarray, cap_height: int):
+        self.leaves, self.digests, self.cap, self.cap_height = leaves, digests, cap, cap_height
+
+    @classmethod
+    def new(cls, leaves, cap_height: int, ctx: Optional[Context] = None) -> "MerkleTree":
+        ctx = _ctx(ctx)
+        leaves = _h(leaves)
+        if leaves.ndim != 2:
+            raise GlPanic(N.GL_E_ARG, "MerkleTree::new: leaves must be [num_leaves][leaf_len]")
+        n, ll = leaves.shape
+        nd = max(2 * (n - (1 << cap_height)), 0)
+        digests = np.empty((nd, 4), dtype=np.uint64)
+        cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        bl, bd, bc = _Buf(leaves), _Buf(digests, True), _Buf(cap, True)
+        ctx.check(ctx._lib.gl_merkle_build(ctx._h, bl.ptr, n, ll, cap_height, bd.ptr, bc.ptr, N.GL_HOST))
+        return cls(leaves, digests, cap, cap_height)
+
+    def get(self, i: int) -> np.ndarray:
+        return self.leaves[i]
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        """MerkleProof.siblings, leaf level first: [log2(num_leaves) - cap_height][4]."""
+        return _prove_from_digests(self.digests, self.leaves.shape[0], self.cap_height, leaf_index)
+
+
+class ResidentMerkleTree:
+    """The merkle_tree of a device-resident PolynomialBatch: cap on the host, leaves and digests behind
+    the gl_commit handle.  `.leaves` / `.digests` download the mirror on first use ("mirror mode")."""
+
+    def __init__(self, batch: "PolynomialBatch", cap: np.ndarray):
+        self._b = batch
+        self.cap = cap
+        self.cap_height = batch.cap_height
+        self._leaves = None
+        self._digests = None
+
+    def _mirror(self, want_leaves: bool, want_digests: bool):
+        b = self._b
+        lib, ctx = b._ctx._lib, b._ctx
+        if want_leaves and self._leaves is None:
+            self._leaves = np.empty((b.num_local_leaves, b.num_columns), dtype=np.uint64)
+            ctx.check(lib.gl_commit_download(b._h, self._leaves.ctypes.data, None, N.GL_HOST))
+        if want_digests and self._digests is None:
+            nd = 2 * (b.num_local_leaves - (1 << b.cap_local_bits))
+            self._digests = np.empty((nd, 4), dtype=np.uint64)
+            ctx.check(lib.gl_commit_download(b._h, None, self._digests.ctypes.data, N.GL_HOST))
+
+    @property
+    def leaves(self) -> np.ndarray:
+        self._mirror(True, False)
+        return self._leaves
+
+    @property
+    def digests(self) -> np.ndarray:
+        self._mirror(False, True)
+        return self._digests
+
+    def get(self, i: int) -> np.ndarray:
+        return self._b.open([i])[0][0]
+
+    def prove(self, leaf_index: int) -> np.ndarray:
+        return self._b.open([leaf_index])[1][0]
+
+
+# ------------------------------------------------------------------------------------------------
+# plonky2::fri::oracle::PolynomialBatch
+# ------------------------------------------------------------------------------------------------
+class PolynomialBatch:
+    """PolynomialBatch{polynomials, merkle_tree, degree_log, rate_bits, blinding}, LDE resident on the device."""
+
+    def __init__(self):
+        raise TypeError("use PolynomialBatch.from_values / from_coeffs")
+
+    @classmethod
+    def _make(cls, inputs, is_values: bool, rate_bits: int, blinding: bool, cap_height: int, ctx, want_coeffs):
+        if blinding:
+            raise GlPanic(N.GL_E_ARG, "blinding (zero_knowledge) is not supported: every reference config uses zero_knowledge = false")
+        ctx = _ctx(ctx)
+        dev = _is_torch(inputs) and inputs.is_cuda
+        if not dev:
+            inputs = _h(inputs)
+        if inputs.ndim != 2:
+            raise GlPanic(N.GL_E_ARG, "polynomials must be [columns][n]")
+        c, n = int(inputs.shape[0]), int(inputs.shape[1])
+        if n == 0 or n & (n - 1):
+            raise GlPanic(N.GL_E_ARG, "log2_strict: polynomial length is not a power of two")
+        lg = n.bit_length() - 1
+        self = object.__new__(cls)
+        self._ctx = ctx
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, False, cap_height
+        self.num_columns = c
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        bi = _Buf(inputs)
+        self._polys = None
+        if dev:
+            import torch
+
+            cap_dev = torch.zeros((1 << cap_height, 4), dtype=inputs.dtype, device=inputs.device)
+            bc = _Buf(cap_dev, True)
+        else:
+            bc = _Buf(cap, True)
+        if is_values:
+            co = None
+            if want_coeffs:
+                if dev:
+                    import torch
+
+                    co = torch.empty_like(inputs)
+                else:
+                    co = np.empty_like(inputs)
+            bo = _Buf(co, True)
+            rc = ctx._lib.gl_commit_from_values(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bo.ptr, bc.ptr, C.byref(h), bi.space)
+            self._polys = co
+        else:
+            rc = ctx._lib.gl_commit_from_coeffs(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bc.ptr, C.byref(h), bi.space)
+            self._polys = inputs
+        ctx.check(rc)
+        if dev:
+            cap = cap_dev.cpu().numpy().view(np.uint64)
+        self._h = h
+        lb, le = C.c_uint64(), C.c_uint64()
+        ctx.check(ctx._lib.gl_commit_info(h, None, None, None, None, C.byref(lb), C.byref(le)))
+        self.leaf_begin, self.leaf_end = lb.value, le.value
+        self.num_local_leaves = le.value - lb.value
+        total = n << rate_bits
+        self.cap_local_bits = cap_height - ((total // self.num_local_leaves).bit_length() - 1)
+        self.merkle_tree = ResidentMerkleTree(self, cap)
+        return self
+
+    @classmethod
+    def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None, fft_root_table=None,
+                    ctx: Optional[Context] = None, want_coeffs: bool = True) -> "PolynomialBatch":
+        """values: [columns][n] evaluations on the subgroup (Vec<PolynomialValues<F>>).  `timing` and
+        `fft_root_table` are accepted for signature parity and ignored (the device keeps its own tables)."""
+        return cls._make(values, True, rate_bits, blinding, cap_height, ctx, want_coeffs)
+
+    @classmethod
+    def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
+                    fft_root_table=None, ctx: Optional[Context] = None) -> "PolynomialBatch":
+        return cls._make(polynomials, False, rate_bits, blinding, cap_height, ctx, False)
+
+    @property
+    def polynomials(self):
+        """Vec<PolynomialCoeffs<F>> as [columns][n]."""
+        if self._polys is None:
+            self._polys = np.empty((self.num_columns, 1 << self.degree_log), dtype=np.uint64)
+            self._ctx.check(self._ctx._lib.gl_commit_coeffs(self._h, self._polys.ctypes.data, N.GL_HOST))
+        return self._polys
+
+    def get_lde_values(self, index, step: int) -> np.ndarray:
+        """PolynomialBatch::get_lde_values(index, step) for one index or a list: [k][columns]."""
+        idx = _h(np.atleast_1d(index))
+        out = np.empty((idx.shape[0], self.num_columns), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.gl_commit_get_lde_values(self._h, idx.ctypes.data, idx.shape[0], step, out.ctypes.data, N.GL_HOST))
+        return out[0] if np.ndim(index) == 0 else out
+
+    def open(self, leaf_indices: Sequence[int]):
+        """(rows [k][columns], paths [k][L][4]) = (tree.get(i), tree.prove(i).siblings) for every i."""
+        idx = _h(np.asarray(leaf_indices))
+        k = idx.shape[0]
+        L = self.degree_log + self.rate_bits - self.cap_height
+        rows = np.empty((k, self.num_columns), dtype=np.uint64)
+        paths = np.empty((k, L, 4), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.gl_commit_open(self._h, idx.ctypes.data, k, rows.ctypes.data, paths.ctypes.data, N.GL_HOST))
+        return rows, paths
+
+    def device_ptrs(self):
+        """(lde pointer, leading dimension, digests pointer) of the resident data (column-major leaves)."""
+        a, b, ld = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._ctx.check(self._ctx._lib.gl_commit_device_ptrs(self._h, C.byref(a), C.byref(ld), C.byref(b)))
+        return a.value, ld.value, b.value
+
+    def free(self):
+        if getattr(self, "_h", None) and self._ctx._h:
+            self._ctx._lib.gl_commit_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
+# plonky2_field::fft / polynomial
+# ------------------------------------------------------------------------------------------------
+def _fft_call(name, data, shift, ctx):
+    ctx = _ctx(ctx)
+    dev = _is_torch(data) and data.is_cuda
+    if not dev:
+        data = _h(data).copy()
+    single = data.ndim == 1
+    d2 = data.reshape(1, -1) if single else data
+    c, n = d2.shape
+    if n == 0 or n & (n - 1):
+        raise GlPanic(N.GL_E_ARG, "log2_strict: length is not a power of two")
+    b = _Buf(d2, True)
+    fn = getattr(ctx._lib, name)
+    if shift is None:
+        ctx.check(fn(ctx._h, b.ptr, n.bit_length() - 1, c, b.space))
+    else:
+        ctx.check(fn(ctx._h, b.ptr, n.bit_length() - 1, c, shift, b.space))
+    return d2.reshape(-1) if single else d2
+
+
+def fft(coeffs, ctx=None):
+    """PolynomialCoeffs::fft over [c][n] (or [n])."""
+    return _fft_call("gl_fft_batch", coeffs, None, ctx)
+
+
+def ifft(values, ctx=None):
+    """PolynomialValues::ifft."""
+    return _fft_call("gl_ifft_batch", values, None, ctx)
+
+
+def coset_fft(coeffs, shift: int = 7, ctx=None):
+    return _fft_call("gl_coset_fft_batch", coeffs, shift, ctx)
+
+
+def coset_ifft(values, shift: int = 7, ctx=None):
+    return _fft_call("gl_coset_ifft_batch", values, shift, ctx)
+
+
+# ------------------------------------------------------------------------------------------------
+# plonky2::fri  (configuration + the data-parallel pieces of fri_committed_trees / fri_proof_of_work)
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class FriReductionStrategy:
+    """ConstantArityBits(arity_bits, final_poly_bits)."""
+
+    arity_bits: int = 4
+    final_poly_bits: int = 5
+
+    def reduction_arity_bits(self, degree_bits: int, rate_bits: int, cap_height: int) -> list:
+        out = []
+        d = degree_bits
+        while d > self.final_poly_bits and d + rate_bits - self.arity_bits >= cap_height:
+            out.append(self.arity_bits)
+            d -= self.arity_bits
+        return out
+
+
+@dataclasses.dataclass(frozen=True)
+class FriConfig:
+    rate_bits: int = 3
+    cap_height: int = 4
+    proof_of_work_bits: int = 16
+    reduction_strategy: FriReductionStrategy = FriReductionStrategy()
+    num_query_rounds: int = 28
+
+
+@dataclasses.dataclass(frozen=True)
+class CircuitConfig:
+    num_wires: int = 135
+    num_routed_wires: int = 80
+    num_constants: int = 2
+    num_challenges: int = 2
+    zero_knowledge: bool = False
+    max_quotient_degree_factor: int = 8
+    fri_config: FriConfig = FriConfig()
+
+    @staticmethod
+    def standard_recursion_config() -> "CircuitConfig":
+        return CircuitConfig()
+
+    @staticmethod
+    def standard_ecc_config() -> "CircuitConfig":
+        return CircuitConfig(num_wires=136)
+
+    @staticmethod
+    def wide_ecc_config() -> "CircuitConfig":
+        return CircuitConfig(num_wires=234)
+
+
+def fri_layer_tree(values_ext, arity_bits: int, cap_height: int, want_digests: bool = True, ctx=None):
+    """One layer of fri_committed_trees: (digests, cap) of MerkleTree::new over the bit-reversed,
+    arity-chunked extension values [len][2]."""
+    ctx = _ctx(ctx)
+    v = _h(values_ext)
+    ln = v.shape[0]
+    nl = ln >> arity_bits
+    nd = max(2 * (nl - (1 << cap_height)), 0)
+    digests = np.empty((nd, 4), dtype=np.uint64) if want_digests else None
+    cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+    ctx.check(ctx._lib.gl_fri_layer_tree(ctx._h, v.ctypes.data, ln, arity_bits, cap_height,
+                                          digests.ctypes.data if want_digests else None, cap.ctypes.data, N.GL_HOST))
+    return digests, cap
+
+
+def fri_fold(coeffs_ext, arity_bits: int, beta, shift: int, ctx=None):
+    """(folded coefficients, their values on shift * <w>) for one FRI reduction."""
+    ctx = _ctx(ctx)
+    cf = _h(coeffs_ext)
+    ln = cf.shape[0]
+    out_len = ln >> arity_bits
+    folded = np.empty((out_len, 2), dtype=np.uint64)
+    nxt = np.empty((out_len, 2), dtype=np.uint64)
+    b = (C.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+    ctx.check(ctx._lib.gl_fri_fold(ctx._h, cf.ctypes.data, ln, arity_bits, b, shift, folded.ctypes.data, nxt.ctypes.data, N.GL_HOST))
+    return folded, nxt
+
+
+def fri_proof_of_work(state12, input_pos: int, min_leading_zeros: int, ctx=None) -> int:
+    """Deterministic fri_proof_of_work: the smallest witness."""
+    ctx = _ctx(ctx)
+    s = (C.c_uint64 * 12)(*[int(x) for x in state12])
+    w = C.c_uint64()
+    ctx.check(ctx._lib.gl_pow_grind(ctx._h, s, input_pos, min_leading_zeros, C.byref(w)))
+    return w.value
+
+
+# ------------------------------------------------------------------------------------------------
+# src/smt: PoseidonNodeHash + SparseMerkleProcessProof::check over batches
+# ------------------------------------------------------------------------------------------------
+class PoseidonNodeHash:
+    """NodeHash for the Poseidon SMT (src/smt/goldilocks_poseidon/mod.rs:158-184), batched."""
+
+    @staticmethod
+    def calc_leaf_hash(keys, values, ctx=None):
+        ctx = _ctx(ctx)
+        k, v = _h(keys), _h(values)
+        single = k.ndim == 1
+        k2, v2 = k.reshape(-1, 4), v.reshape(-1, 4)
+        out = np.empty_like(k2)
+        ctx.check(ctx._lib.gl_smt_leaf_hash_batch(ctx._h, k2.ctypes.data, v2.ctypes.data, out.ctypes.data, k2.shape[0], N.GL_HOST))
+        return out.reshape(4) if single else out
+
+    @staticmethod
+    def calc_internal_hash(left, right, ctx=None):
+        return PoseidonHash.two_to_one(left, right, ctx=ctx)
+
+
+PROCESS_NOOP, PROCESS_UPDATE, PROCESS_INSERT, PROCESS_DELETE = 0, 1, 2, 3
+
+SMT_HDR_DTYPE = np.dtype(
+    [("old_root", "<u8", 4), ("old_key", "<u8", 4), ("old_value", "<u8", 4),
+     ("new_root", "<u8", 4), ("new_key", "<u8", 4), ("new_value", "<u8", 4),
+     ("is_old0", "<u4"), ("fnc", "<u4")]
+)
+assert SMT_HDR_DTYPE.itemsize == C.sizeof(N.SmtProofHdr)
+
+
+def smt_check_process_proofs(headers: np.ndarray, sib_pool: np.ndarray, sib_off: np.ndarray, ctx=None) -> np.ndarray:
+    """SparseMerkleProcessProof::check for a batch.  status 0 = verify_smt_process_proof would return
+    normally; k > 0 = its k-th assert would panic (DESIGN.md lists them)."""
+    ctx = _ctx(ctx)
+    hd = np.ascontiguousarray(headers, dtype=SMT_HDR_DTYPE)
+    pool = _h(sib_pool).reshape(-1, 4)
+    off = _h(sib_off)
+    m = hd.shape[0]
+    if off.shape[0] != m + 1:
+        raise GlPanic(N.GL_E_ARG, "sib_off must have m + 1 entries")
+    status = np.empty(m, dtype=np.int32)
+    ctx.check(ctx._lib.gl_smt_verify_process_batch(ctx._h, hd.ctypes.data, pool.ctypes.data, off.ctypes.data, m, status.ctypes.data, N.GL_HOST))
+    return status

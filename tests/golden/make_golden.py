@@ -1,0 +1,45 @@
+"""Generates the fixtures in tests/golden/.
+
+poseidon_kat.json : the permutation vectors of SURVEY.md 8c.  The all-zero vector's first four lanes are
+                    the reference's own KAT (src/zkdsa/circuits/mod.rs:85-105); the others were PROBED with
+                    the constants recipe and match upstream plonky2's poseidon_goldilocks test_vectors.
+commit_caps.json  : Merkle caps of PolynomialBatch::from_values on the synthetic input of SURVEY 8d,
+                    produced by the oracle itself ("parity unpinned" rows: regression fixtures only).
+Run from the repo root:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as o  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+P = o.P
+
+perm = []
+for name, vec in [("zeros", [0] * 12), ("iota", list(range(12))), ("p_minus_1", [P - 1] * 12)]:
+    out = o.permute(np.array(vec, dtype=np.uint64))
+    perm.append({"name": name, "in": [f"{x:016x}" for x in vec], "out": [f"{int(x):016x}" for x in out]})
+expected = {
+    "zeros": "3c18a9786cb0b359 c4055e3364a246c3 7953db0ab48808f4 c71603f33a1144ca d7709673896996dc 46a84e87642f44ed d032648251ee0b3c 1c687363b207df62 df8565563e8045fe 40f5b37ff4254dae d070f637b431067c 1792b1c4342109d7",
+    "iota": "d64e1e3efc5b8e9e 53666633020aaa47 d40285597c6a8825 613a4f81e81231d2 414754bfebd051f0 cb1f8980294a023f 6eb2a9e4d54a9d0f 1902bc3af467e056 f045d5eafdc6021f e4150f77caaa3be5 c9bfd01d39b50cce 5c0a27fcb0e1459b",
+    "p_minus_1": "be0085cfc57a8357 d95af71847d05c09 cf55a13d33c1c953 95803a74f4530e82 fcd99eb30a135df1 e095905e913a3029 de0392461b42919b 7d3260e24e81d031 10d3d0465d9deaa0 a87571083dfc2a47 e18263681e9958f8 e28e96f1ae5e60d3",
+}
+for p_ in perm:
+    assert p_["out"] == expected[p_["name"]].split(), p_["name"]
+json.dump({"source": "SURVEY.md 8c; zeros[0:4] = src/zkdsa/circuits/mod.rs:85-105", "permutation": perm},
+          open(os.path.join(HERE, "poseidon_kat.json"), "w"), indent=1)
+
+cases = []
+for lg_n, c, r, h in [(3, 5, 3, 4), (6, 20, 3, 4), (8, 135, 3, 4), (10, 16, 3, 4), (12, 136, 3, 4), (14, 135, 3, 4)]:
+    v = o.synthetic_values(c, 1 << lg_n)
+    res = o.commit_from_values(v, r, h, want_leaves=False)
+    cases.append({"lg_n": lg_n, "c": c, "rate_bits": r, "cap_height": h,
+                  "cap": [f"{int(x):016x}" for x in res["cap"].reshape(-1)]})
+json.dump({"source": "oracle/gl_oracle.c glo_commit_from_values on pyoracle.synthetic_values (seed 0x706C6F6E6B7932)",
+           "cases": cases}, open(os.path.join(HERE, "commit_caps.json"), "w"), indent=1)
+print("wrote", HERE)

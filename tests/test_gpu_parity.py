@@ -1,0 +1,320 @@
+"""GPU parity tests: every result of libgl_b200.so (through the C ABI) against the CPU oracle on the
+same seeded inputs, plus the reference's own known-answer vectors.  Integer work: bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import P, adversarial_columns, rand_field
+
+pytestmark = pytest.mark.gpu
+
+# src/zkdsa/circuits/mod.rs:85-105 (test_default_simple_signature): PoseidonHash::two_to_one(0, 0)
+KAT_TWO_TO_ONE_ZERO = [4330397376401421145, 14124799381142128323, 8742572140681234676, 14345658006221440202]
+
+
+# ---- P5 Poseidon ---------------------------------------------------------------------------------
+def test_reference_kat_two_to_one_zero(glb, ctx):
+    out = glb.PoseidonHash.two_to_one(np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.uint64))
+    assert out.tolist() == KAT_TWO_TO_ONE_ZERO
+
+
+def test_permutation_vectors(glb, ctx):
+    v = glb.PoseidonHash.permute(np.arange(12, dtype=np.uint64))
+    assert [hex(int(x)) for x in v[:4]] == ["0xd64e1e3efc5b8e9e", "0x53666633020aaa47", "0xd40285597c6a8825", "0x613a4f81e81231d2"]
+    v = glb.PoseidonHash.permute(np.full(12, P - 1, dtype=np.uint64))
+    assert [hex(int(x)) for x in v[:2]] == ["0xbe0085cfc57a8357", "0xd95af71847d05c09"]
+
+
+def test_permute_batch_matches_oracle(glb, ctx, oracle, rng):
+    states = rand_field(rng, (4099, 12))
+    states[0] = 0
+    states[1] = P - 1
+    states[2] = np.uint64(0xFFFFFFFFFFFFFFFF)  # non-canonical input: taken mod p
+    states[3] = np.uint64(0xFFFFFFFF)
+    got = glb.PoseidonHash.permute(states)
+    want = oracle.permute_batch(states)
+    assert np.array_equal(got, want)
+    assert (got < np.uint64(P)).all()
+
+
+@pytest.mark.parametrize("length", [0, 1, 4, 5, 7, 8, 9, 12, 16, 20, 32, 85, 135, 136, 234])
+def test_hash_no_pad_lengths(glb, ctx, oracle, rng, length):
+    x = rand_field(rng, (257, length))
+    got = glb.PoseidonHash.hash_no_pad(x)
+    want = oracle.hash_no_pad_batch(x) if length else np.tile(oracle.hash_no_pad(np.zeros(0, dtype=np.uint64)), (257, 1))
+    assert np.array_equal(got, want)
+
+
+def test_two_to_one_batch(glb, ctx, oracle, rng):
+    l, r = rand_field(rng, (1000, 4)), rand_field(rng, (1000, 4))
+    assert np.array_equal(glb.PoseidonHash.two_to_one(l, r), oracle.two_to_one_batch(l, r))
+
+
+def test_hash_pad_and_smt_leaf_consistency(glb, ctx, oracle):
+    """src/smt/goldilocks_poseidon/mod.rs:167-181 (hash_pad([k, v, 1])) == src/smt/gadgets/common.rs:87-101
+    (hash_no_pad([k, v, 1, 1, 0, 1])), inputs of test_calc_node_hash (common.rs:67-71)."""
+    k, v = oracle.from_u128(1), oracle.from_u128(2)
+    a = glb.PoseidonHash.hash_pad(np.concatenate([k, v, [np.uint64(1)]]))
+    b = glb.PoseidonHash.hash_no_pad(np.concatenate([k, v, np.array([1, 1, 0, 1], dtype=np.uint64)]))
+    c = glb.PoseidonNodeHash.calc_leaf_hash(k, v)
+    want = [9613647271972624781, 17898244898336278454, 17153022918269186278, 8190762674233093240]
+    assert a.tolist() == want and b.tolist() == want and c.tolist() == want
+    assert oracle.smt_leaf_hash(k, v).tolist() == want
+    assert glb.PoseidonNodeHash.calc_internal_hash(k, v).tolist() == [
+        17484264305055072364, 557184275190569619, 7427655570849746255, 2765125522432587977]
+
+
+def test_device_resident_buffers(glb, ctx, oracle, rng):
+    import torch
+
+    x = rand_field(rng, (513, 12))
+    t = torch.from_numpy(x.view(np.int64)).cuda()
+    glb.PoseidonHash.permute(t)
+    assert np.array_equal(t.cpu().numpy().view(np.uint64), oracle.permute_batch(x))
+
+
+# ---- P4 MerkleTree::new --------------------------------------------------------------------------
+@pytest.mark.parametrize("lg,leaf_len,cap_height", [(0, 7, 0), (1, 3, 0), (1, 3, 1), (3, 4, 1), (5, 5, 0), (5, 9, 5),
+                                                    (6, 135, 4), (10, 32, 4), (9, 20, 0), (7, 1, 2)])
+def test_merkle_tree_new(glb, ctx, oracle, rng, lg, leaf_len, cap_height):
+    leaves = rand_field(rng, (1 << lg, leaf_len))
+    t = glb.MerkleTree.new(leaves, cap_height)
+    digests, cap = oracle.merkle_tree(leaves, cap_height)
+    assert np.array_equal(t.cap, cap)
+    assert np.array_equal(t.digests, digests)
+    for i in {0, (1 << lg) - 1, (1 << lg) // 3}:
+        sib = t.prove(i)
+        assert np.array_equal(sib, oracle.merkle_prove(digests, 1 << lg, cap_height, i))
+        assert oracle.merkle_verify(leaves[i], i, sib, cap, cap_height)
+
+
+def test_merkle_tree_panics_like_upstream(glb, ctx, rng):
+    with pytest.raises(glb.GlPanic):
+        glb.MerkleTree.new(rand_field(rng, (8, 5)), 4)  # cap_height > log2(len)
+    with pytest.raises(glb.GlPanic):
+        glb.MerkleTree.new(rand_field(rng, (6, 5)), 1)  # log2_strict
+
+
+# ---- P1/P2/P9 FFT family -------------------------------------------------------------------------
+@pytest.mark.parametrize("lg", [0, 1, 2, 3, 5, 8, 10, 11, 13, 16])
+def test_fft_family(glb, ctx, oracle, rng, lg):
+    n = 1 << lg
+    a = rand_field(rng, (3, n))
+    if n >= 8:
+        a[1] = adversarial_columns(n)[4]
+    assert np.array_equal(glb.fft(a), np.stack([oracle.fft(r) for r in a]))
+    assert np.array_equal(glb.ifft(a), np.stack([oracle.ifft(r) for r in a]))
+    assert np.array_equal(glb.coset_fft(a, 7), np.stack([oracle.coset_fft(r, 7) for r in a]))
+    assert np.array_equal(glb.coset_ifft(a, 7), np.stack([oracle.coset_ifft(r, 7) for r in a]))
+    assert np.array_equal(glb.ifft(glb.fft(a)), a)
+
+
+@pytest.mark.parametrize("lg", [21, 22])
+def test_fft_three_pass_sizes(glb, ctx, oracle, rng, lg):
+    a = rand_field(rng, (1, 1 << lg))
+    assert np.array_equal(glb.coset_fft(a, 7)[0], oracle.coset_fft(a[0], 7))
+    assert np.array_equal(glb.coset_ifft(glb.coset_fft(a, 7), 7), a)
+
+
+# ---- P* PolynomialBatch --------------------------------------------------------------------------
+COMMIT_CASES = [
+    # lg_n, c, rate_bits, cap_height
+    (0, 1, 0, 0), (0, 3, 3, 0), (1, 2, 1, 1), (2, 4, 3, 4), (3, 5, 3, 4), (4, 9, 2, 0), (5, 16, 3, 4), (6, 20, 3, 4),
+    (8, 135, 3, 4), (10, 136, 3, 4), (11, 7, 3, 4), (12, 85, 3, 4), (7, 234, 3, 4), (9, 2, 1, 10), (12, 33, 0, 3),
+]
+
+
+@pytest.mark.parametrize("lg_n,c,rate_bits,cap_height", COMMIT_CASES)
+def test_commit_from_values_matches_oracle(glb, ctx, oracle, lg_n, c, rate_bits, cap_height):
+    n = 1 << lg_n
+    values = oracle.synthetic_values(c, n)
+    if n >= 8 and c >= 7:
+        values[:5] = adversarial_columns(n)
+    want = oracle.commit_from_values(values, rate_bits, cap_height)
+    b = glb.PolynomialBatch.from_values(values, rate_bits, False, cap_height)
+    assert np.array_equal(b.merkle_tree.cap, want["cap"])
+    assert np.array_equal(b.polynomials, want["coeffs"])
+    assert np.array_equal(b.merkle_tree.leaves, want["leaves"])
+    assert np.array_equal(b.merkle_tree.digests, want["digests"])
+    N = n << rate_bits
+    idx = sorted({0, N - 1, N // 2, (N * 5) // 7})
+    rows, paths = b.open(idx)
+    for q, i in enumerate(idx):
+        assert np.array_equal(rows[q], want["leaves"][i])
+        assert np.array_equal(paths[q], oracle.merkle_prove(want["digests"], N, cap_height, i))
+        assert oracle.merkle_verify(rows[q], i, paths[q], want["cap"], cap_height)
+    # get_lde_values(i, step) = leaves[reverse_bits(i * step, lg N)]
+    step = 1 << rate_bits
+    for i in {0, n - 1, n // 2}:
+        r = oracle.lib().glo_reverse_bits(i * step, lg_n + rate_bits)
+        assert np.array_equal(b.get_lde_values(i, step), want["leaves"][r])
+    b.free()
+
+
+def test_commit_from_coeffs_matches_oracle(glb, ctx, oracle, rng):
+    coeffs = rand_field(rng, (21, 512))
+    want = oracle.commit_from_coeffs(coeffs, 3, 4)
+    b = glb.PolynomialBatch.from_coeffs(coeffs, 3, False, 4)
+    assert np.array_equal(b.merkle_tree.cap, want["cap"])
+    assert np.array_equal(b.merkle_tree.leaves, want["leaves"])
+    assert np.array_equal(b.merkle_tree.digests, want["digests"])
+
+
+def test_commit_panics_like_upstream(glb, ctx, rng):
+    with pytest.raises(glb.GlPanic):
+        glb.PolynomialBatch.from_values(rand_field(rng, (3, 12)), 3, False, 4)  # log2_strict
+    with pytest.raises(glb.GlPanic):
+        glb.PolynomialBatch.from_values(rand_field(rng, (3, 2)), 1, False, 4)  # cap_height > log2(N)
+    with pytest.raises(glb.GlPanic):
+        glb.PolynomialBatch.from_values(rand_field(rng, (3, 8)), 3, True, 4)  # blinding unsupported
+
+
+@pytest.mark.parametrize("count", [2, 4, 8])
+def test_sharded_commit_equals_whole(glb, oracle, count):
+    """shard s computes leaf block s = whole top-level subtrees; caps concatenate."""
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    values = oracle.synthetic_values(19, 256)
+    want = oracle.commit_from_values(values, 3, 4)
+    N = 256 << 3
+    cap = np.zeros((16, 4), dtype=np.uint64)
+    for s in range(count):
+        c = glb.Context(0)
+        c.set_shard(s, count)
+        b = glb.PolynomialBatch.from_values(values, 3, False, 4, ctx=c)
+        lo, hi = b.leaf_begin, b.leaf_end
+        assert (lo, hi) == (s * N // count, (s + 1) * N // count)
+        assert np.array_equal(b.merkle_tree.leaves, want["leaves"][lo:hi])
+        per = 16 // count
+        cap[s * per:(s + 1) * per] = b.merkle_tree.cap[s * per:(s + 1) * per]
+        rows, paths = b.open([lo, hi - 1])
+        assert oracle.merkle_verify(rows[1], hi - 1, paths[1], want["cap"], 4)
+        with pytest.raises(glb.GlPanic):
+            b.open([hi % N if count > 1 else N])
+        b.free()
+        c.close()
+    assert np.array_equal(cap, want["cap"])
+
+
+def test_lde_linearity_and_low_degree_at_scale(glb, ctx, oracle):
+    """Size-independent properties at a size the oracle does not run in seconds: commit(a)+commit(b) rows
+    = commit(a+b) rows, and every opened path verifies against the cap."""
+    n, c = 1 << 16, 24
+    a = oracle.synthetic_values(c, n, seed=1)
+    b = oracle.synthetic_values(c, n, seed=2)
+    s = ((a.astype(object) + b.astype(object)) % P).astype(np.uint64)
+    ba = glb.PolynomialBatch.from_values(a, 3, False, 4)
+    bb = glb.PolynomialBatch.from_values(b, 3, False, 4)
+    bs = glb.PolynomialBatch.from_values(s, 3, False, 4)
+    idx = [0, 1, 12345, (n << 3) - 1, 77777]
+    ra, pa = ba.open(idx)
+    rb, _ = bb.open(idx)
+    rs, _ = bs.open(idx)
+    assert np.array_equal(((ra.astype(object) + rb.astype(object)) % P).astype(np.uint64), rs)
+    for q, i in enumerate(idx):
+        assert oracle.merkle_verify(ra[q], i, pa[q], ba.merkle_tree.cap, 4)
+    # the n-coset restriction: leaves of block 0 are the values on 7<w_n> in bit-reversed order
+    coef = ba.polynomials
+    lde0 = ba.get_lde_values(np.arange(4), 8)
+    col = oracle.coset_fft(coef[3], 7)
+    assert [int(lde0[i][3]) for i in range(4)] == [int(col[i]) for i in range(4)]
+
+
+# ---- P8/P10 FRI pieces ---------------------------------------------------------------------------
+@pytest.mark.parametrize("lg,arity_bits,cap_height", [(4, 4, 0), (8, 4, 4), (12, 4, 4), (7, 3, 2), (10, 1, 0)])
+def test_fri_layer_tree(glb, ctx, oracle, rng, lg, arity_bits, cap_height):
+    v = rand_field(rng, (1 << lg, 2))
+    _, digests, cap = oracle.fri_layer_tree(v, arity_bits, cap_height)
+    d, c = glb.fri_layer_tree(v, arity_bits, cap_height)
+    assert np.array_equal(c, cap) and np.array_equal(d, digests)
+
+
+@pytest.mark.parametrize("lg,arity_bits", [(4, 4), (8, 4), (13, 4), (9, 3)])
+def test_fri_fold(glb, ctx, oracle, rng, lg, arity_bits):
+    cf = rand_field(rng, (1 << lg, 2))
+    beta = rand_field(rng, (2,))
+    shift = pow(7, 1 << arity_bits, P)
+    folded, nxt = glb.fri_fold(cf, arity_bits, beta, shift)
+    want = oracle.fri_fold(cf, arity_bits, beta)
+    assert np.array_equal(folded, want)
+    assert np.array_equal(nxt, oracle.ext_coset_fft(want, shift))
+
+
+def test_pow_grind_smallest_witness(glb, ctx, oracle, rng):
+    state = rand_field(rng, (12,))
+    for bits in (4, 10, 16):
+        w = glb.fri_proof_of_work(state, 0, bits)
+        assert w == oracle.pow_grind(state, 0, bits, 0, 1 << 20)
+        s = state.copy()
+        s[0] = w
+        assert int(oracle.permute(s)[7]) >> (64 - bits) == 0
+
+
+# ---- P7 SparseMerkleProcessProof::check over batches ---------------------------------------------
+def _smt_proofs(oracle, rng, n_ops=60):
+    t = oracle.Smt()
+    recs = []
+    keys = [rand_field(rng, (4,)) for _ in range(n_ops // 2)]
+    # inserts, updates, deletes (value 0 removes: src/smt/tree.rs:143-155), and noops
+    for k in keys:
+        recs.append(t.set(k, rand_field(rng, (4,))))
+    for k in keys[::3]:
+        recs.append(t.set(k, rand_field(rng, (4,))))
+    for k in keys[1::4]:
+        recs.append(t.set(k, np.zeros(4, dtype=np.uint64)))
+    recs.append(t.set(rand_field(rng, (4,)), np.zeros(4, dtype=np.uint64)))
+    return np.array(recs, dtype=oracle.SMT_PROOF_DTYPE)
+
+
+def _pack(glb, recs):
+    hd = np.zeros(recs.shape[0], dtype=glb.host.SMT_HDR_DTYPE)
+    for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "is_old0", "fnc"):
+        hd[f] = recs[f]
+    off = np.zeros(recs.shape[0] + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(recs["num_siblings"])
+    pool = np.concatenate([r["siblings"][: r["num_siblings"]] for r in recs] + [np.zeros((0, 4), dtype=np.uint64)])
+    return hd, pool, off
+
+
+def test_smt_process_proofs(glb, ctx, oracle, rng):
+    recs = _smt_proofs(oracle, rng)
+    assert set(recs["fnc"].tolist()) == {0, 1, 2, 3}
+    want = oracle.smt_verify_process_batch(recs)
+    assert (want == 0).all()
+    hd, pool, off = _pack(glb, recs)
+    assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
+    # corrupt: wrong new_root, wrong sibling, wrong key on update -> same assert ordinal as the oracle
+    bad = recs.copy()
+    bad["new_root"][0][0] ^= np.uint64(1)
+    bad["old_value"][3][1] ^= np.uint64(5)
+    for i in range(5, len(bad), 7):
+        if bad["num_siblings"][i]:
+            bad["siblings"][i][0][2] ^= np.uint64(9)
+    want = oracle.smt_verify_process_batch(bad)
+    assert (want != 0).any()
+    hd, pool, off = _pack(glb, bad)
+    assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
+
+
+def test_smt_fixture_root_three_inserts(glb, ctx, oracle):
+    """(1->2), (12->1), (5->51) as in src/smt/gadgets/verify/mod.rs:24-34."""
+    t = oracle.Smt()
+    recs = [t.set(oracle.from_u128(k), oracle.from_u128(v)) for k, v in [(1, 2), (12, 1), (5, 51)]]
+    assert t.root().tolist() == [16994558480514381166, 8559105504417206749, 13458782878755336329, 17099432696459526118]
+    recs = np.array(recs, dtype=oracle.SMT_PROOF_DTYPE)
+    hd, pool, off = _pack(glb, recs)
+    assert (glb.smt_check_process_proofs(hd, pool, off) == 0).all()
+
+
+def test_golden_commit_caps(glb, ctx, oracle):
+    """Committed fixtures (tests/golden/commit_caps.json, made by tests/golden/make_golden.py)."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "commit_caps.json")))
+    for case in g["cases"]:
+        v = oracle.synthetic_values(case["c"], 1 << case["lg_n"])
+        b = glb.PolynomialBatch.from_values(v, case["rate_bits"], False, case["cap_height"])
+        assert [f"{int(x):016x}" for x in b.merkle_tree.cap.reshape(-1)] == case["cap"]
+        b.free()
