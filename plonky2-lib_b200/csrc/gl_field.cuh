@@ -63,30 +63,30 @@ inline u64 root_of_unity(unsigned lg) {
 // ------------------------------------------------------------------------------------------------
 GL_D u64 gl_pack(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
 
-// x (128 bit) -> [0, 2^64), x = lo + 2^64 * hi.
-//   s = lo + hi_lo * (2^32 - 1)             (carry c)
-//   s = s - hi_hi                           (borrow b)
-//   s += (c - b) * (2^32 - 1)               (cannot wrap again)
+// x (128 bit) -> [0, 2^64), x = r0 + 2^32 r1 + 2^64 r2 + 2^96 r3.  2^64 = 2^32 - 1, 2^96 = -1 (mod p):
+//   x = (r0 + 2^32 r1) + 2^32 r2 - (r2 + r3)
+// One 64-bit add (carry K1), one 64-bit subtract of the 33-bit g = r2 + r3 (borrow K2), then the net
+// wrap k = K1 - K2 in {-1, 0, 1} is folded back as k * (2^32 - 1).  All on the ALU pipe, no multiply
+// (IMAD.HI runs at a third of the IMAD rate on B200: profiles/r1_pipe_peaks.json).
 GL_D u64 gl_reduce128(u64 lo, u64 hi) {
-    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), h0 = (u32)hi, h1 = (u32)(hi >> 32), s0, s1;
+    u32 r0 = (u32)lo, r1 = (u32)(lo >> 32), r2 = (u32)hi, r3 = (u32)(hi >> 32), w0, w1;
     asm("{\n\t"
-        ".reg .u32 c, bm, e0;\n\t"
-        "mad.lo.cc.u32 %0, %4, 0xffffffff, %2;\n\t"
-        "madc.hi.cc.u32 %1, %4, 0xffffffff, %3;\n\t"
-        "addc.u32 c, 0, 0;\n\t"         // c = carry (0/1)
-        "sub.cc.u32 %0, %0, %5;\n\t"
-        "subc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 bm, 0, 0;\n\t"        // bm = borrow ? 0xffffffff : 0
-        "sub.u32 e0, 0, bm;\n\t"        // b
-        "sub.u32 e0, e0, c;\n\t"        // low word of (c-b)*EPS  = b - c   (mod 2^32)
-        "add.u32 c, c, 0xffffffff;\n\t" // c ? 0 : 0xffffffff
-        "and.b32 bm, bm, c;\n\t"        // high word of (c-b)*EPS = (b && !c) ? 0xffffffff : 0
-        "add.cc.u32 %0, %0, e0;\n\t"
-        "addc.u32 %1, %1, bm;\n\t"
+        ".reg .u32 k, g0, g1, nk, sg;\n\t"
+        "add.cc.u32 %1, %3, %4;\n\t"     // w1 = r1 + r2
+        "addc.u32 k, 0, 0;\n\t"          // K1
+        "add.cc.u32 g0, %4, %5;\n\t"     // g = r2 + r3
+        "addc.u32 g1, 0, 0;\n\t"
+        "sub.cc.u32 %0, %2, g0;\n\t"     // w -= g
+        "subc.cc.u32 %1, %1, g1;\n\t"
+        "subc.u32 k, k, 0;\n\t"          // k = K1 - K2
+        "sub.u32 nk, 0, k;\n\t"          // low word of k * (2^32 - 1)
+        "shr.s32 sg, k, 31;\n\t"         // high word: -1 when k = -1
+        "add.cc.u32 %0, %0, nk;\n\t"
+        "addc.u32 %1, %1, sg;\n\t"
         "}"
-        : "=&r"(s0), "=&r"(s1)
-        : "r"(r0), "r"(r1), "r"(h0), "r"(h1));
-    return gl_pack(s0, s1);
+        : "=&r"(w0), "=&r"(w1)
+        : "r"(r0), "r"(r1), "r"(r2), "r"(r3));
+    return gl_pack(w0, w1);
 }
 
 GL_D u64 gl_mul(u64 a, u64 b) {

@@ -5,12 +5,18 @@
 // src/zkdsa/account.rs:165, src/zkdsa/circuits/mod.rs:66-67), PoseidonHash::hash_pad
 // (src/smt/goldilocks_poseidon/mod.rs:170) and, through data.prove(pw), from MerkleTree::new.
 //
-// B200 mapping: the 12-lane state lives in 24 registers of one thread; round constants sit in
-// __constant__ memory (every lane of a warp reads the same word -> one broadcast).  The MDS layer
-// uses that the circulant row sums to 256 (+8 on the diagonal): each 64-bit lane is split into two
-// 32-bit halves, the two half-dot-products are 12 carry-free IMAD.WIDE.U32 each (< 2^42), and one
-// more IMAD.WIDE folds them back into [0, 2^64).  The S-box is four 64x64 products (4 IMAD.WIDE
-// each) with the Goldilocks shift-reduction on the ALU pipe.
+// B200 mapping (measured pipe rates: profiles/r1_pipe_peaks.json).  IMAD.WIDE.U32 issues at ~51
+// lanes/clk/SM and does not overlap with ALU work, so the two halves of a round go to different
+// pipes:
+//   * S-box x^7: four 64x64 products = IMAD.WIDE.U32 on the FMA-heavy pipe + shift-reduction on ALU.
+//   * MDS layer: on the FP64 pipe (B200 keeps full-rate DFMA).  A 32-bit half x of a lane is
+//     reinterpreted as the double with bit pattern (hi = 0, lo = x), i.e. the denormal x * 2^-1074.
+//     The circulant entries are <= 41 and each row sums to 264, so sum_i c_i * x_i < 2^42 stays below
+//     2^52: every DFMA is exact and the accumulator's BIT PATTERN is the integer sum.  No int<->fp
+//     conversion instruction is ever issued, in either direction.
+//   * The next round's constants are the addend of the first DFMA of each row (a constant-bank
+//     operand), so "add round constants" costs nothing.
+// The 12-lane state lives in 24 registers of one thread.
 #pragma once
 #include "gl_field.cuh"
 
@@ -23,6 +29,9 @@
 // ALL_ROUND_CONSTANTS[round * 12 + lane]; filled by gl_poseidon_upload_constants() at ctx creation.
 // Defined here (not extern): include this header from exactly one translation unit (hash_kernels.cu).
 __constant__ u64 c_poseidon_rc[POSEIDON_ROUNDS * POSEIDON_WIDTH];
+// The same constants split for the FP64 MDS: [round][lane] -> (double with bits rc & 0xffffffff,
+// double with bits rc >> 32); one extra all-zero round so the last MDS adds nothing.
+__constant__ double2 c_poseidon_rc_split[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH];
 
 #ifdef __CUDACC__
 GL_D u64 poseidon_sbox(u64 x) {
@@ -32,54 +41,55 @@ GL_D u64 poseidon_sbox(u64 x) {
     return gl_mul(x3, x4);
 }
 
-// out[r] = sum_i s[(i + r) % 12] * CIRC[i] + s[r] * DIAG[r],  CIRC = 17 15 41 16 2 28 13 13 39 18 34 20, DIAG = 8 0 ...
-GL_D void poseidon_mds(u64 s[12]) {
-    constexpr u32 C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
-    u32 lo[12], hi[12];
+GL_D double u32_as_denormal(u32 x) { return __hiloint2double(0, (int)x); }
+GL_D u64 double_bits(double d) { return (u64)__double_as_longlong(d); }
+
+// out[r] = sum_i s[(i + r) % 12] * CIRC[i] + s[r] * DIAG[r] + rc[r]
+// CIRC = 17 15 41 16 2 28 13 13 39 18 34 20, DIAG = 8 0 ... 0
+GL_D void poseidon_mds_rc(u64 s[12], const double2* __restrict__ rc) {
+    constexpr double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
+    double dl[12], dh[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        lo[i] = (u32)s[i];
-        hi[i] = (u32)(s[i] >> 32);
+        dl[i] = u32_as_denormal((u32)s[i]);
+        dh[i] = u32_as_denormal((u32)(s[i] >> 32));
     }
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
+        double2 k = rc[r];
+        double al = k.x, ah = k.y;
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            al += (u64)lo[(i + r) % 12] * C[i];
-            ah += (u64)hi[(i + r) % 12] * C[i];
+            al = __fma_rn(C[i], dl[(i + r) % 12], al);
+            ah = __fma_rn(C[i], dh[(i + r) % 12], ah);
         }
         if (r == 0) {
-            al += (u64)lo[0] * 8u;
-            ah += (u64)hi[0] * 8u;
+            al = __fma_rn(8., dl[0], al);
+            ah = __fma_rn(8., dh[0], ah);
         }
-        // value = al + 2^32 * ah, al, ah < 2^42.  2^64 = 2^32 - 1:
-        u64 x = al + (u64)(u32)(ah >> 32) * GL_EPS;  // < 2^43
-        u64 y = x + (ah << 32);
-        s[r] = y + ((y < x) ? GL_EPS : 0ULL);        // true value < 2^64 + 2^43: one wrap at most
+        // value = A + 2^32 * B with A, B < 2^43 (integer bit patterns).  2^64 = 2^32 - 1 (mod p):
+        u64 A = double_bits(al), B = double_bits(ah);
+        u64 t = A + (u64)(u32)(B >> 32) * GL_EPS;   // < 2^44
+        u64 y = t + (B << 32);
+        s[r] = y + ((y < t) ? GL_EPS : 0ULL);        // true value < 2^64 + 2^44: one wrap at most
     }
 }
 
 GL_D void poseidon_permute(u64 s[12]) {
-    const u64* rc = c_poseidon_rc;
-#pragma unroll 1
-    for (int r = 0; r < POSEIDON_FULL_HALF; r++, rc += 12) {
+    const double2* rc = c_poseidon_rc_split + 12;   // constants of round r + 1 go into the MDS of round r
 #pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add_c(s[i], rc[i]));
-        poseidon_mds(s);
-    }
+    for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_poseidon_rc[i]);
+    // One loop body for all 30 rounds (the branch is warp-uniform): the S-box of lanes 1..11 is skipped in
+    // the 22 partial rounds.  Keeping a single copy of the round keeps the kernel inside the instruction
+    // cache (three unrolled copies measured ~1.4 "no instruction" stall cycles per issued instruction).
 #pragma unroll 1
-    for (int r = 0; r < POSEIDON_PARTIAL; r++, rc += 12) {
+    for (int r = 0; r < POSEIDON_ROUNDS; r++, rc += 12) {
+        s[0] = poseidon_sbox(s[0]);
+        if (r < POSEIDON_FULL_HALF || r >= POSEIDON_FULL_HALF + POSEIDON_PARTIAL) {
 #pragma unroll
-        for (int i = 1; i < 12; i++) s[i] = gl_add_c(s[i], rc[i]);
-        s[0] = poseidon_sbox(gl_add_c(s[0], rc[0]));
-        poseidon_mds(s);
-    }
-#pragma unroll 1
-    for (int r = 0; r < POSEIDON_FULL_HALF; r++, rc += 12) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = poseidon_sbox(gl_add_c(s[i], rc[i]));
-        poseidon_mds(s);
+            for (int i = 1; i < 12; i++) s[i] = poseidon_sbox(s[i]);
+        }
+        poseidon_mds_rc(s, rc);
     }
 }
 
