@@ -57,6 +57,8 @@ struct gl_ctx {
     std::multimap<size_t, void*> pool;
     size_t pool_bytes = 0;
     // phase boundaries of the last commit (CUDA events on `stream`)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // PCIe copies of the host-buffer commit pipeline
+    std::vector<cudaEvent_t> pipe_ev;
     cudaEvent_t ev[GL_PHASES + 1] = {};
     bool ev_valid = false;
     float phase_ms[GL_PHASES] = {};
@@ -381,6 +383,8 @@ extern "C" int gl_ctx_create(int device, gl_ctx** out) {
     cudaGetDevice(&prev);
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "gl_ctx_create");
         delete ctx;
@@ -414,6 +418,9 @@ extern "C" void gl_ctx_destroy(gl_ctx* ctx) {
         pool_trim(ctx);
         for (auto& ev : ctx->ev)
             if (ev) cudaEventDestroy(ev);
+        for (auto& ev : ctx->pipe_ev) cudaEventDestroy(ev);
+        if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+        if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -644,14 +651,14 @@ static int commit_check(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_b
 }
 
 // h->coeffs already holds the coefficients on the device
-static int commit_lde_and_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space) {
+// geometry + device buffers of the LDE / digests / cap
+static int commit_prepare(gl_ctx* ctx, gl_commit* h) {
     const unsigned lc = ilog2(h->shard_count);
     const u64 n = (u64)1 << h->log_n;
     const uint32_t blocks = (1u << h->rate_bits) >> lc;
     h->n_local = n * blocks;
     h->leaf_begin = (u64)h->shard_index * h->n_local;
     h->cap_local_bits = h->cap_height - lc;
-    const unsigned lg_local = h->log_n + h->rate_bits - lc;
     h->num_digests = 2 * (h->n_local - ((u64)1 << h->cap_local_bits));
     h->lde_bytes = (size_t)h->c * h->n_local * 8;
     h->digests_bytes = h->num_digests * 32;
@@ -659,23 +666,72 @@ static int commit_lde_and_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int
     TRY(dev_alloc(ctx, h->lde_bytes, &h->lde));
     TRY(dev_alloc(ctx, h->digests_bytes, &h->digests));
     TRY(dev_alloc(ctx, h->cap_bytes, &h->cap));
+    return GL_OK;
+}
+
+// "FFT + blinding" for columns [col0, col0 + ncols): every local coset of those columns, written in leaf order
+static int commit_lde_columns(gl_ctx* ctx, gl_commit* h, uint32_t col0, uint32_t ncols) {
+    const u64 n = (u64)1 << h->log_n;
+    const uint32_t blocks = (1u << h->rate_bits) >> ilog2(h->shard_count);
     const u64* pre;
     TRY(coset_tables(ctx, h->log_n, h->rate_bits, h->shard_index, h->shard_count, &pre));
     NttJob j;
-    j.in = h->coeffs; j.in_ld = n; j.in_coset_stride = 0;
-    j.out = h->lde; j.out_ld = h->n_local; j.out_coset_stride = n;
-    j.L = h->log_n; j.columns = h->c; j.cosets = blocks; j.inverse = false; j.pre_tab = pre;
+    j.in = h->coeffs + (size_t)col0 * n; j.in_ld = n; j.in_coset_stride = 0;
+    j.out = h->lde + (size_t)col0 * h->n_local; j.out_ld = h->n_local; j.out_coset_stride = n;
+    j.L = h->log_n; j.columns = ncols; j.cosets = blocks; j.inverse = false; j.pre_tab = pre;
     j.canonical_out = 1;
-    TRY(run_dif(ctx, j));
+    return run_dif(ctx, j);
+}
+
+// "build Merkle tree"
+static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space) {
+    const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
     mark(ctx, 4);
     launch_leaf_hash_cols(h->lde, h->n_local, h->c, lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 5);
     launch_merkle_levels(lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 6);
     if (cap_out) {
-        size_t cap_bytes = (size_t)32 << h->cap_local_bits;
         uint64_t* dst = cap_out + 4 * ((size_t)h->shard_index << h->cap_local_bits);
-        TRY(copy_out(ctx, dst, h->cap, cap_bytes, space));
+        TRY(copy_out(ctx, dst, h->cap, h->cap_bytes, space));
+    }
+    return GL_OK;
+}
+
+// Host buffers: the H2D copy of column block b+1, the IFFT + LDE of block b and the D2H copy of block b's
+// coefficients run on three streams, so PCIe traffic hides behind the transforms (PCIe is full duplex).
+static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const uint64_t* input, bool is_values,
+                                uint64_t* coeffs_out) {
+    const u64 n = (u64)1 << h->log_n;
+    const size_t col_bytes = n * 8;
+    uint32_t cb = (uint32_t)(((size_t)96 << 20) / col_bytes);
+    if (cb < 1) cb = 1;
+    if (cb > h->c) cb = h->c;
+    const uint32_t nb = (h->c + cb - 1) / cb;
+    while (ctx->pipe_ev.size() < 2 * (size_t)nb) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    cudaEvent_t start = ctx->ev[1];   // recorded by the caller on the main stream
+    CK(cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
+    CK(cudaStreamWaitEvent(ctx->d2h_stream, start, 0));
+    for (uint32_t b = 0; b < nb; b++) {
+        const uint32_t col0 = b * cb, nc = (col0 + cb <= h->c) ? cb : h->c - col0;
+        u64* dcol = h->coeffs + (size_t)col0 * n;
+        CK(cudaMemcpyAsync(dcol, input + (size_t)col0 * n, nc * col_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CK(cudaEventRecord(ctx->pipe_ev[2 * b], ctx->h2d_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * b], 0));
+        if (is_values) {
+            TRY(transform_natural(ctx, dcol, h->log_n, nc, true, nullptr, nullptr));  // "IFFT"
+            if (coeffs_out) {
+                CK(cudaEventRecord(ctx->pipe_ev[2 * b + 1], ctx->stream));
+                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_ev[2 * b + 1], 0));
+                CK(cudaMemcpyAsync(coeffs_out + (size_t)col0 * n, dcol, nc * col_bytes, cudaMemcpyDeviceToHost,
+                                   ctx->d2h_stream));
+            }
+        }
+        TRY(commit_lde_columns(ctx, h, col0, nc));
     }
     return GL_OK;
 }
@@ -696,29 +752,43 @@ static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uin
     const size_t poly_bytes = (size_t)c * n * 8;
     h->coeffs_bytes = poly_bytes;
     int rc = dev_alloc(ctx, poly_bytes, &h->coeffs);
+    if (rc == GL_OK) rc = commit_prepare(ctx, h);
     mark(ctx, 0);
-    if (rc == GL_OK) {
-        cudaError_t e = cudaMemcpyAsync(h->coeffs, input, poly_bytes,
-                                        space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials to the device");
-    }
-    mark(ctx, 1);
-    if (rc == GL_OK && is_values) {
-        rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr);  // "IFFT"
+    if (rc == GL_OK && space == GL_HOST) {
+        // phases 1..3 overlap in this mode: their sum is reported as "lde_ntt" (phase 3)
+        mark(ctx, 1);
         mark(ctx, 2);
-        if (rc == GL_OK) rc = copy_out(ctx, coeffs_out, h->coeffs, poly_bytes, space);
-    } else {
-        mark(ctx, 2);
+        mark(ctx, 3);
+        rc = commit_pipeline_host(ctx, h, input, is_values, coeffs_out);
+    } else if (rc == GL_OK) {
+        cudaError_t e = cudaMemcpyAsync(h->coeffs, input, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials");
+        mark(ctx, 1);
+        if (rc == GL_OK && is_values) {
+            rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr);  // "IFFT"
+            mark(ctx, 2);
+            if (rc == GL_OK) rc = copy_out(ctx, coeffs_out, h->coeffs, poly_bytes, space);
+        } else {
+            mark(ctx, 2);
+        }
+        mark(ctx, 3);
+        if (rc == GL_OK) rc = commit_lde_columns(ctx, h, 0, c);
     }
-    mark(ctx, 3);
-    if (rc == GL_OK) rc = commit_lde_and_tree(ctx, h, cap_out, space);
+    if (rc == GL_OK) rc = commit_tree(ctx, h, cap_out, space);
     if (rc == GL_OK) rc = finish(ctx);
+    if (rc == GL_OK && space == GL_HOST) {
+        cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
+        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "coefficient download");
+    }
     if (rc == GL_OK) {
         for (int i = 0; i < GL_PHASES; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
         ctx->ev_valid = true;
     }
     if (rc != GL_OK) {
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamSynchronize(ctx->d2h_stream);
+        cudaGetLastError();
         commit_release(h);
         return rc;
     }
