@@ -223,27 +223,27 @@ def main():
             return cap_dev
     else:
         # column slice of this rank for the IFFT; ragged split, padded to equal size for the all-gather
-        per = (cols + world - 1) // world
-        c0, c1 = min(rank * per, cols), min((rank + 1) * per, cols)
+        par = importlib.import_module("plonky2-lib_b200.parallel")
+        par.check_shardable(world, RATE_BITS, CAP_HEIGHT)
+        c0, c1, per = par.column_slice(rank, world, cols)
         ctx.set_shard(rank, world)
         slice_buf = torch.zeros((per, n), dtype=torch.int64, device=dev)
         gathered = torch.empty((world * per, n), dtype=torch.int64, device=dev)
         cap_all = torch.zeros((1 << CAP_HEIGHT, 4), dtype=torch.int64, device=dev)
-        cap_per = (1 << CAP_HEIGHT) // world
+        k0, k1 = par.cap_range(rank, world, CAP_HEIGHT)
 
         def step():
             if c1 > c0:
                 slice_buf[: c1 - c0].copy_(values[c0:c1])
                 ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf.data_ptr(), log_n, c1 - c0, N.GL_DEVICE))
-            dist.all_gather_into_tensor(gathered, slice_buf)  # coefficients of every column on every rank
+            par.all_gather_coefficients(dist, slice_buf, gathered, cols)  # every column's coefficients on every rank
             torch.cuda.current_stream().synchronize()
             h = C.c_void_p()
             ctx.check(lib.gl_commit_from_coeffs(ctx._h, gathered.data_ptr(), log_n, cols, RATE_BITS, CAP_HEIGHT,
                                                 cap_dev.data_ptr(), C.byref(h), N.GL_DEVICE))
             phases.append(ctx.commit_phase_ms())
             lib.gl_commit_free(h)
-            mine = cap_dev[rank * cap_per:(rank + 1) * cap_per].contiguous()
-            dist.all_gather_into_tensor(cap_all, mine)  # MerkleCap: 2^cap_height digests
+            par.all_gather_cap(dist, cap_dev[k0:k1].contiguous(), cap_all)  # MerkleCap: 2^cap_height digests
             torch.cuda.current_stream().synchronize()
             return cap_all
 

@@ -1,0 +1,53 @@
+"""Multi-GPU plan of one sharded commit: who owns what, and the two exchanges.
+
+One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  A commit of c polynomials
+of n coefficients with N = n * 2^rate_bits leaves is split over `world` ranks:
+
+  * the IFFT by column slice (`column_slice`), followed by ONE all-gather of the coefficients;
+  * the LDE + Merkle tree by leaf block: rank r owns leaves [r * N / world, (r + 1) * N / world)
+    = LDE cosets k with bitrev_r(k) in that range = whole top-level subtrees and their cap entries
+    (`gl_ctx_set_shard`); no exchange;
+  * the cap by ONE all-gather of 2^cap_height / world digests per rank;
+  * query openings are answered by `owner_of_leaf`.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+
+def column_slice(rank: int, world: int, cols: int) -> Tuple[int, int, int]:
+    """(first column, one-past-last column, padded slice width) of the IFFT slice of `rank`."""
+    per = (cols + world - 1) // world
+    return min(rank * per, cols), min((rank + 1) * per, cols), per
+
+
+def leaf_range(rank: int, world: int, num_leaves: int) -> Tuple[int, int]:
+    per = num_leaves // world
+    return rank * per, (rank + 1) * per
+
+
+def owner_of_leaf(leaf_index: int, world: int, num_leaves: int) -> int:
+    return leaf_index // (num_leaves // world)
+
+
+def cap_range(rank: int, world: int, cap_height: int) -> Tuple[int, int]:
+    per = (1 << cap_height) // world
+    return rank * per, (rank + 1) * per
+
+
+def check_shardable(world: int, rate_bits: int, cap_height: int) -> None:
+    if world & (world - 1) or world > (1 << rate_bits) or world > (1 << cap_height):
+        raise ValueError("the rank count must be a power of two dividing 2^rate_bits and 2^cap_height")
+
+
+def all_gather_coefficients(dist, slice_buf, gathered, cols: int):
+    """slice_buf [per][n] (this rank's IFFT output, zero padded) -> gathered [world * per][n]; the first
+    `cols` rows of `gathered` are the coefficients of every column, in order, on every rank."""
+    dist.all_gather_into_tensor(gathered, slice_buf)
+    return gathered[:cols]
+
+
+def all_gather_cap(dist, local_cap, cap_all):
+    """local_cap [2^cap_height / world][4] -> cap_all [2^cap_height][4] (MerkleCap) on every rank."""
+    dist.all_gather_into_tensor(cap_all, local_cap)
+    return cap_all

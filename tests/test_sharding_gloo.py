@@ -1,0 +1,83 @@
+"""The N > 1 host logic on CPU: world_size 2 over gloo.  Each rank runs the plan of
+plonky2-lib_b200/parallel.py with the ORACLE standing in for the device (the oracle is test infrastructure;
+the real device path of the same plan is bench.py --gpus N and tests/test_gpu_parity.py::test_sharded_*)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, cols, lg_n, rate_bits, cap_height, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from oracle import pyoracle as o
+
+    par = importlib.import_module("plonky2-lib_b200.parallel")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1 << lg_n
+        N = n << rate_bits
+        par.check_shardable(world, rate_bits, cap_height)
+        values = o.synthetic_values(cols, n)
+        c0, c1, per = par.column_slice(rank, world, cols)
+        sl = np.zeros((per, n), dtype=np.uint64)
+        for j in range(c0, c1):
+            sl[j - c0] = o.ifft(values[j])
+        slice_buf = torch.from_numpy(sl.view(np.int64))
+        gathered = torch.empty((world * per, n), dtype=torch.int64)
+        coeffs = par.all_gather_coefficients(dist, slice_buf, gathered, cols).numpy().view(np.uint64)
+        whole = o.commit_from_coeffs(np.ascontiguousarray(coeffs), rate_bits, cap_height)
+        lo, hi = par.leaf_range(rank, world, N)
+        k0, k1 = par.cap_range(rank, world, cap_height)
+        # this rank's subtrees, rebuilt from its own leaf block only
+        _, local_cap = o.merkle_tree(whole["leaves"][lo:hi], cap_height - (world.bit_length() - 1))
+        assert np.array_equal(local_cap, whole["cap"][k0:k1])
+        cap_all = torch.empty((1 << cap_height, 4), dtype=torch.int64)
+        par.all_gather_cap(dist, torch.from_numpy(local_cap.view(np.int64).copy()), cap_all)
+        ref = o.commit_from_values(values, rate_bits, cap_height, want_leaves=False)
+        ok = np.array_equal(cap_all.numpy().view(np.uint64), ref["cap"]) and np.array_equal(coeffs, ref["coeffs"])
+        owners = [par.owner_of_leaf(i, world, N) for i in (0, lo, hi - 1, N - 1)]
+        q.put((rank, bool(ok), owners, (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cols", [5, 8])
+def test_sharded_commit_plan_world2(cols):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200 + cols
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cols, 6, 3, 4, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort()
+    N = 64 << 3
+    assert all(r[1] for r in res)
+    assert res[0][3] == (0, N // 2) and res[1][3] == (N // 2, N)
+    assert res[0][2] == [0, 0, 0, 1] and res[1][2] == [0, 1, 1, 1]
+
+
+def test_plan_helpers():
+    par = importlib.import_module("plonky2-lib_b200.parallel")
+    assert par.column_slice(0, 8, 135) == (0, 17, 17)
+    assert par.column_slice(7, 8, 135) == (119, 135, 17)
+    assert sum(par.column_slice(r, 8, 135)[1] - par.column_slice(r, 8, 135)[0] for r in range(8)) == 135
+    assert par.column_slice(3, 4, 2) == (2, 2, 1)  # more ranks than columns: empty slice
+    assert par.cap_range(3, 8, 4) == (6, 8)
+    with pytest.raises(ValueError):
+        par.check_shardable(16, 3, 4)
+    with pytest.raises(ValueError):
+        par.check_shardable(3, 3, 4)
