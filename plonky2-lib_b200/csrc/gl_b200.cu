@@ -209,7 +209,7 @@ static int finish(gl_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------
 // tables (built on the host with exact 128-bit arithmetic, cached on the device)
 // ------------------------------------------------------------------------------------------------
-enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3 };
+enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3, TAB_FULL = 4 };
 
 static void fill_pow_table(u64* t, u64 base) {  // [3][1024]: base^e, base^(1024 e), base^(2^20 e)
     u64 b = glh::canon(base);
@@ -303,20 +303,73 @@ struct NttJob {
     int canonical_out = 0;
 };
 
+// w_{2^m}^e for e < 2^m (inverse: w^-e): twiddle table of the fast pass
+static int full_table(gl_ctx* ctx, unsigned m, bool inverse, const u64** out) {
+    auto key = std::make_tuple((int)TAB_FULL, (uint64_t)m, (uint64_t)inverse, (uint64_t)0);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    std::vector<u64> h((size_t)1 << m);
+    u64 w = glh::root_of_unity(m);
+    if (inverse) w = glh::inv(w);
+    u64 acc = 1;
+    for (auto& v : h) {
+        v = acc;
+        acc = glh::mul(acc, w);
+    }
+    return table_upload(ctx, key, h, out);
+}
+
+// split of a size-2^L transform into passes; fast[i] says the radix-16 register kernel (m = 8..10) runs it
+static unsigned plan_passes(unsigned L, unsigned ms[4], bool fast[4]) {
+    auto set = [&](unsigned i, unsigned m, bool f) { ms[i] = m; fast[i] = f; };
+    if (L <= 7) { set(0, L, false); return 1; }
+    if (L <= 10) { set(0, L, true); return 1; }
+    if (L <= 15) { set(0, 8, true); set(1, L - 8, false); return 2; }
+    if (L <= 20) { set(0, (L + 1) / 2, true); set(1, L / 2, true); return 2; }
+    if (L <= 23) { set(0, 8, true); set(1, 8, true); set(2, L - 16, false); return 3; }
+    for (unsigned i = 0; i < 3; i++) set(i, L / 3 + (i < L % 3 ? 1 : 0), true);
+    return 3;
+}
+
 static int run_dif(gl_ctx* ctx, const NttJob& j) {
     if (j.columns == 0) return GL_OK;
     const u64 n = (u64)1 << j.L;
-    unsigned np = j.L == 0 ? 1 : (j.L + 9) / 10;
     unsigned ms[4];
-    for (unsigned i = 0; i < np; i++) ms[i] = j.L / np + (i < j.L % np ? 1 : 0);
+    bool fast[4];
+    const unsigned np = plan_passes(j.L, ms, fast);
     unsigned done = 0;
     for (unsigned i = 0; i < np; i++) {
+        const unsigned m = ms[i];
+        done += m;
+        const unsigned s = j.L - done;
+        const bool first = i == 0, last = i == np - 1;
+        const u64* post = nullptr;
+        if (s) {
+            u64 w = glh::root_of_unity(s + m);
+            if (j.inverse) w = glh::inv(w);
+            TRY(pow_table(ctx, w, &post));
+        }
+        if (fast[i] && (!last || j.final_scale == 1)) {
+            ntt16_args f;
+            memset(&f, 0, sizeof f);
+            f.in = first ? j.in : j.out;
+            f.in_ld = first ? j.in_ld : j.out_ld;
+            f.in_coset_stride = first ? j.in_coset_stride : j.out_coset_stride;
+            f.out = j.out; f.out_ld = j.out_ld; f.out_coset_stride = j.out_coset_stride;
+            f.pre_tab = first ? j.pre_tab : nullptr;
+            f.post_tab = post;
+            TRY(full_table(ctx, m, j.inverse, &f.wtab));
+            f.s = s;
+            f.canonical_out = last ? j.canonical_out : 0;
+            if (launch_ntt16(f, m, j.inverse, n, j.columns, j.cosets, ctx->stream)) continue;
+        }
         ntt_pass_args a;
         memset(&a, 0, sizeof a);
-        a.m = ms[i];
-        done += ms[i];
-        a.s = j.L - done;
-        bool first = i == 0, last = i == np - 1;
+        a.m = m;
+        a.s = s;
         a.in = first ? j.in : j.out;
         a.in_ld = first ? j.in_ld : j.out_ld;
         a.in_coset_stride = first ? j.in_coset_stride : j.out_coset_stride;
@@ -326,9 +379,7 @@ static int run_dif(gl_ctx* ctx, const NttJob& j) {
         a.pre_tab = first ? j.pre_tab : nullptr;
         TRY(small_table(ctx, a.m, j.inverse, &a.small_tab));
         if (a.s) {
-            u64 w = glh::root_of_unity(a.s + a.m);
-            if (j.inverse) w = glh::inv(w);
-            TRY(pow_table(ctx, w, &a.post_tab));
+            a.post_tab = post;
             a.T = a.s >= 3 ? 8 : (1u << a.s);
             a.rows = (u64)1 << a.m;
         } else {

@@ -282,3 +282,184 @@ void launch_interleave2(const u64* cols, u64 ld, u64 n, u64* ext, cudaStream_t s
 void launch_deinterleave2(const u64* ext, u64 n, u64* cols, u64 ld, cudaStream_t st) {
     if (n) { k_deinterleave2<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ext, n, cols, ld); ++g_gl_launches; }
 }
+
+// ================================================================================================
+// Fast pass.  One CTA transforms W independent 2^M-point DFTs (W adjacent j_lo for a strided pass, W
+// consecutive blocks for the last pass), 16 elements per thread:
+//   round 1: radix-16 over the top 4 index bits, in registers (loaded straight from HBM), then the
+//            twiddle w_{2^M}^(k1 * low) from a shared-memory table;
+//   round 2: after one exchange through shared memory, radix-16 over the next 4 bits, twiddle
+//            w_{2^(M-4)}^(k2 * low);
+//   round 3: the last M-8 <= 2 bits are warp-shuffle butterflies; results go straight to HBM with
+//            the four-step twiddle w_{2^(s+M)}^(k * j_lo).
+// 2^192 = 1 (mod p): every root of unity of order <= 64 is a power of two (plonky2's w_16 is 2^156),
+// so the 17 twiddles inside a radix-16 block are compile-time constants with one or two set bits per
+// 32-bit half and their products compile to shifts.
+// ================================================================================================
+__host__ __device__ constexpr u64 pow2_mod_p(int e) {  // 2^e for 0 <= e < 96
+    return e < 64 ? ((u64)1 << e) : (((u64)1 << (e - 32)) - ((u64)1 << (e - 64)));
+}
+
+// (u - v) * w_16^(J * STEP), w_16 = 2^156 (forward) or 2^36 (inverse); 2^96 = -1 flips the subtraction
+template <bool INV, int J>
+GL_D u64 diff_times_w16(u64 u, u64 v) {
+    constexpr int E = ((INV ? 36 : 156) * J) % 192;
+    if (E == 0) return gl_sub(u, v);
+    if (E >= 96) return gl_mul(gl_sub(v, u), pow2_mod_p(E - 96));
+    return gl_mul(gl_sub(u, v), pow2_mod_p(E));
+}
+
+template <bool INV>
+GL_D void radix16_dif(u64 x[16]) {
+#define BF(i, j, J)                               \
+    {                                             \
+        u64 u_ = x[i], v_ = x[j];                 \
+        x[i] = gl_add(u_, v_);                    \
+        x[j] = diff_times_w16<INV, J>(u_, v_);    \
+    }
+    BF(0, 8, 0) BF(1, 9, 1) BF(2, 10, 2) BF(3, 11, 3) BF(4, 12, 4) BF(5, 13, 5) BF(6, 14, 6) BF(7, 15, 7)
+    BF(0, 4, 0) BF(1, 5, 2) BF(2, 6, 4) BF(3, 7, 6) BF(8, 12, 0) BF(9, 13, 2) BF(10, 14, 4) BF(11, 15, 6)
+    BF(0, 2, 0) BF(1, 3, 4) BF(4, 6, 0) BF(5, 7, 4) BF(8, 10, 0) BF(9, 11, 4) BF(12, 14, 0) BF(13, 15, 4)
+    BF(0, 1, 0) BF(2, 3, 0) BF(4, 5, 0) BF(6, 7, 0) BF(8, 9, 0) BF(10, 11, 0) BF(12, 13, 0) BF(14, 15, 0)
+#undef BF
+}
+
+GL_D unsigned brev4(unsigned x) { return __brev(x) >> 28; }
+
+template <int M, bool INV, bool STRIDED>
+__global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
+    extern __shared__ u64 sm[];
+    constexpr unsigned Q = 1u << (M - 4);          // threads per DFT
+    const unsigned logW = a.logW, W = 1u << logW;
+    u64* wt = sm + ((size_t)W << M);
+    const unsigned tid = threadIdx.x;
+    const unsigned d = STRIDED ? (tid & (W - 1)) : (tid >> (M - 4));
+    const unsigned q = STRIDED ? (tid >> logW) : (tid & (Q - 1));
+    const unsigned s = a.s;
+    const unsigned coset = blockIdx.z;
+    const u64 col = blockIdx.y;
+    u64 base;
+    if (STRIDED) {
+        u64 tiles_per_block = ((u64)1 << s) >> logW;
+        u64 outer = blockIdx.x / tiles_per_block, jt = blockIdx.x % tiles_per_block;
+        base = (outer << (s + M)) + (jt << logW) + d;
+    } else {
+        base = ((u64)blockIdx.x << (M + logW)) + ((u64)d << M);
+    }
+    const u64* in = a.in + col * a.in_ld + (u64)coset * a.in_coset_stride + base;
+    u64* out = a.out + col * a.out_ld + (u64)coset * a.out_coset_stride + base;
+    const unsigned rs = STRIDED ? s : 0;          // log2 of the row stride in HBM
+
+    for (unsigned e = tid; e < (1u << M); e += blockDim.x) wt[e] = __ldg(a.wtab + e);
+
+    u64 x[16];
+    // ---- round 1: rows a * Q + q -----------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = in[(u64)(i * Q + q) << rs];
+    if (a.pre_tab) {
+        const u64* pre = a.pre_tab + (u64)coset * 3072;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = gl_mul(x[i], powtab_eval(pre, base + ((u64)(i * Q + q) << rs)));
+    }
+    radix16_dif<INV>(x);
+    __syncthreads();   // twiddle table ready
+#pragma unroll
+    for (int i = 1; i < 16; i++) x[i] = gl_mul(x[i], wt[brev4(i) * q]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned p = i * Q + q;
+        unsigned idx = STRIDED ? ((p << logW) + d) : ((d << M) + (p ^ (((p >> (M - 4)) & 15u) << (M - 8))));
+        sm[idx] = x[i];
+    }
+    __syncthreads();
+    // ---- round 2: rows phigh * Q + r * 2^(M-8) + plow ------------------------------------------------
+    constexpr unsigned LB = M - 8;                 // bits left for round 3
+    const unsigned plow = q & ((1u << LB) - 1), phigh = q >> LB;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned p = phigh * Q + ((unsigned)i << LB) + plow;
+        unsigned idx = STRIDED ? ((p << logW) + d) : ((d << M) + (p ^ (((p >> (M - 4)) & 15u) << (M - 8))));
+        x[i] = sm[idx];
+    }
+    radix16_dif<INV>(x);
+    if (LB > 0) {
+#pragma unroll
+        for (int i = 1; i < 16; i++) x[i] = gl_mul(x[i], wt[(brev4(i) * plow) << 4]);
+        // ---- round 3: butterflies across lanes ------------------------------------------------------
+#pragma unroll
+        for (int b = (int)LB - 1; b >= 0; b--) {
+            const unsigned lane_mask = STRIDED ? (1u << (logW + b)) : (1u << b);
+            const bool hi = (plow >> b) & 1;
+            // the only non-trivial twiddle left is w_4 = 2^48 (inverse: -2^48), on the odd element of the b = 1 stage
+            const bool tw = (b == 1) && hi && (plow & 1);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                u64 mine = x[i];
+                u64 other = __shfl_xor_sync(0xffffffffu, mine, lane_mask);
+                u64 sum = gl_add(mine, other);
+                u64 dif = (INV && b == 1) ? (tw ? gl_sub(mine, other) : gl_sub(other, mine)) : gl_sub(other, mine);
+                if (b == 1) {
+                    u64 dt = gl_mul(dif, pow2_mod_p(48));
+                    dif = tw ? dt : dif;
+                }
+                x[i] = hi ? dif : sum;
+            }
+        }
+    }
+    // ---- store: in-place position p holds output index brev_M(p) ---------------------------------------
+    const u64 jlo = STRIDED ? (base & (((u64)1 << s) - 1)) : 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned p = phigh * Q + ((unsigned)i << LB) + plow;
+        u64 v = x[i];
+        if (STRIDED && a.post_tab) {
+            u64 k = __brev(p) >> (32 - M);
+            v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
+        }
+        if (a.canonical_out) v = gl_canon(v);
+        out[(u64)p << rs] = v;
+    }
+}
+
+template <int M>
+static void launch_ntt16_m(const ntt16_args& a, bool inverse, bool strided, dim3 grid, unsigned threads, size_t smem,
+                           cudaStream_t st) {
+    auto set = [&](void (*kern)(ntt16_args)) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        kern<<<grid, threads, smem, st>>>(a);
+        ++g_gl_launches;
+    };
+    if (inverse) {
+        if (strided) set(k_ntt16<M, true, true>);
+        else set(k_ntt16<M, true, false>);
+    } else {
+        if (strided) set(k_ntt16<M, false, true>);
+        else set(k_ntt16<M, false, false>);
+    }
+}
+
+bool launch_ntt16(const ntt16_args& a0, unsigned M, bool inverse, u64 n, u32 columns, u32 cosets, cudaStream_t st) {
+    if (M < 8 || M > 10) return false;
+    ntt16_args a = a0;
+    const bool strided = a.s != 0;
+    unsigned logW = 13 - M;
+    if (strided) {
+        if (logW > a.s) logW = a.s;
+        if (logW + (M - 8) > 5) logW = 5 - (M - 8);
+    } else {
+        u64 blocks = n >> M;
+        while (((u64)1 << logW) > blocks) logW--;
+    }
+    unsigned threads = (1u << (M - 4)) << logW;
+    if (threads < 32) return false;
+    a.logW = logW;
+    u64 tiles = n >> (M + logW);
+    dim3 grid((unsigned)tiles, columns, cosets);
+    size_t smem = (((size_t)1 << (M + logW)) + ((size_t)1 << M)) * sizeof(u64);
+    switch (M) {
+        case 8: launch_ntt16_m<8>(a, inverse, strided, grid, threads, smem, st); break;
+        case 9: launch_ntt16_m<9>(a, inverse, strided, grid, threads, smem, st); break;
+        default: launch_ntt16_m<10>(a, inverse, strided, grid, threads, smem, st); break;
+    }
+    return true;
+}

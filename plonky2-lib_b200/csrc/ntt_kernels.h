@@ -41,3 +41,19 @@ void launch_fri_fold(const uint64_t* coeffs_ext, uint64_t out_len, unsigned arit
                      uint64_t* out_cols, uint64_t out_ld, cudaStream_t st);
 void launch_interleave2(const uint64_t* cols, uint64_t ld, uint64_t n, uint64_t* ext, cudaStream_t st);
 void launch_deinterleave2(const uint64_t* ext, uint64_t n, uint64_t* cols, uint64_t ld, cudaStream_t st);
+
+// ---- fast pass: 2^M-point DFTs (M = 8, 9, 10) as two radix-16 register rounds + warp-shuffle stages ----
+struct ntt16_args {
+    const uint64_t* in;
+    uint64_t in_ld, in_coset_stride;
+    uint64_t* out;
+    uint64_t out_ld, out_coset_stride;
+    const uint64_t* pre_tab;   // [cosets][3][1024] or null
+    const uint64_t* post_tab;  // [3][1024] power table of w_{2^(s+M)} (direction applied) or null (s == 0)
+    const uint64_t* wtab;      // w_{2^M}^e, e < 2^M (direction applied)
+    unsigned s, logW;
+    int canonical_out;
+};
+// returns false when (M, s, n) is not handled by the fast kernel
+bool launch_ntt16(const ntt16_args& a, unsigned M, bool inverse, uint64_t n, uint32_t columns, uint32_t cosets,
+                  cudaStream_t st);

@@ -108,7 +108,17 @@ def test_fft_family(glb, ctx, oracle, rng, lg):
     assert np.array_equal(glb.ifft(glb.fft(a)), a)
 
 
-@pytest.mark.parametrize("lg", [21, 22])
+@pytest.mark.parametrize("lg", [9, 12, 14, 15, 17, 18, 19, 20])
+def test_fft_fast_pass_sizes(glb, ctx, oracle, rng, lg):
+    """Every split of the radix-16 register kernel (m = 8, 9, 10; strided and contiguous) and its mix with the
+    generic pass: forward, inverse and coset variants against the oracle."""
+    a = rand_field(rng, (2, 1 << lg))
+    assert np.array_equal(glb.fft(a), np.stack([oracle.fft(r) for r in a]))
+    assert np.array_equal(glb.coset_ifft(a, 7), np.stack([oracle.coset_ifft(r, 7) for r in a]))
+    assert np.array_equal(glb.coset_fft(a, 7)[1], oracle.coset_fft(a[1], 7))
+
+
+@pytest.mark.parametrize("lg", [21, 22, 24])
 def test_fft_three_pass_sizes(glb, ctx, oracle, rng, lg):
     a = rand_field(rng, (1, 1 << lg))
     assert np.array_equal(glb.coset_fft(a, 7)[0], oracle.coset_fft(a[0], 7))
