@@ -21,7 +21,24 @@ int gl_poseidon_upload_constants(const u64* rc360) {
         split[2 * i + 1] = rc360[i] >> 32;
     }
     for (int i = POSEIDON_ROUNDS * POSEIDON_WIDTH * 2; i < (POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH * 2; i++) split[i] = 0;
-    return (int)cudaMemcpyToSymbol(c_poseidon_rc_split, split, sizeof(split));
+    e = cudaMemcpyToSymbol(c_poseidon_rc_split, split, sizeof(split));
+    if (e != cudaSuccess) return (int)e;
+    // fused partial pairs: K[pair][lane] half sums (exact integers < 2^41)
+    static u64 pk[(POSEIDON_PARTIAL / 2) * POSEIDON_WIDTH * 2];
+    for (int pair = 0; pair < POSEIDON_PARTIAL / 2; pair++) {
+        const u64* r1 = rc360 + (POSEIDON_FULL_HALF + 2 * pair + 1) * 12;
+        const u64* r2 = rc360 + (POSEIDON_FULL_HALF + 2 * pair + 2) * 12;
+        for (int lane = 0; lane < 12; lane++) {
+            u64 lo = r2[lane] & 0xFFFFFFFFULL, hi = r2[lane] >> 32;
+            for (int i = 1; i < 12; i++) {
+                lo += (u64)poseidon_mds_entry(lane, i) * (r1[i] & 0xFFFFFFFFULL);
+                hi += (u64)poseidon_mds_entry(lane, i) * (r1[i] >> 32);
+            }
+            pk[(pair * 12 + lane) * 2] = lo;
+            pk[(pair * 12 + lane) * 2 + 1] = hi;
+        }
+    }
+    return (int)cudaMemcpyToSymbol(c_poseidon_pair_k, pk, sizeof(pk));
 }
 
 // ---- position of node q of layer i inside one subtree's digest buffer (plonky2 in-order layout) ----
