@@ -337,16 +337,35 @@ def main():
         "traffic": None, "kernel_ms": leaf_ms, "algorithmic_bytes_per_launch": leaf_bytes,
         "note": "integer-pipe bound kernel (17 Poseidon permutations per 1080-byte leaf): see roofline_int",
     }
+    # integer roofline: algorithmic work in 32x32->64 multiply-add equivalents against the MEASURED
+    # mad.wide.u32 issue rate of this GPU (tools/pipe_peaks.cu -> profiles/r1_pipe_peaks.json)
+    imad_peak, imad_src = 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1965 MHz"
+    try:
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")))
+        imad_peak = float(pk["imad_wide"]["ops_per_s"])
+        imad_src = "measured mad.wide.u32 rate, profiles/r1_pipe_peaks.json (tools/pipe_peaks.cu)"
+    except Exception:
+        pass
+    perms_commit = N_local * ((cols + 7) // 8) + (N_local - (1 << CAP_HEIGHT) // world)
+    ntt_bfly = (cols * n * log_n // 2 if world == 1 else 0) + cols * N_local * log_n // 2
+    imad_commit = perms_commit * IMAD_PER_PERMUTATION + ntt_bfly * 4 + cols * N_local * 4
     roofline_int = {
         "bound": "imad", "kernel": "k_leaf_hash_cols",
         "achieved": perms_leaf * IMAD_PER_PERMUTATION / (leaf_ms * 1e-3) / 1e12,
-        "unit": "T 32x32 multiply-adds/s (6700 per permutation, SURVEY 8d)",
+        "unit": "T 32x32->64 multiply-add equivalents/s (6700 per permutation, 4 per butterfly: SURVEY 8d)",
         "permutations_per_s": perms_leaf / (leaf_ms * 1e-3),
-        "peak": 148 * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12 if clocks else None,
-        "peak_source": "148 SMs x 64 IMAD lanes/clk x median SM clock under load (B300_MICROARCH: IMAD rt_SMSP = 2)",
+        "peak": imad_peak / 1e12, "peak_source": imad_src,
+        "whole_commit_achieved": imad_commit / (ms_per_step * 1e-3) / 1e12,
     }
-    if roofline_int["peak"]:
-        roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"]
+    roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"]
+    roofline_int["whole_commit_frac"] = roofline_int["whole_commit_achieved"] / roofline_int["peak"]
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_leaf_hash_traffic.json")))
+        if tr.get("cols") == cols:
+            roofline["traffic"] = tr["dram_bytes_per_leaf"] * N_local
+            roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -105,35 +105,51 @@ GL_D u64 poseidon_fold(double al, double ah) {
 //   z  = N x~ + K + M[.][0] * sigma                 (N = M M' without the lane-0 path)
 // 336 DFMA instead of 576, 13 folds instead of 24; every partial sum stays below 2^50 (exact).
 GL_D void poseidon_partial_pair(u64 s[12], int pair) {
-    s[0] = poseidon_sbox(s[0]);
+    // Everything that does not depend on lane 0 is issued first, so the FP64 pipe works through lanes 1..11
+    // while the two serial S-boxes of lane 0 run on the integer pipes.
     double dl[12], dh[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
+    for (int i = 1; i < 12; i++) {
         dl[i] = u32_as_denormal((u32)s[i]);
         dh[i] = u32_as_denormal((u32)(s[i] >> 32));
     }
     const double2 ky = c_poseidon_rc_split[(POSEIDON_FULL_HALF + 2 * pair + 1) * 12];
     double yl = ky.x, yh = ky.y;
 #pragma unroll
-    for (int j = 0; j < 12; j++) {
+    for (int j = 1; j < 12; j++) {
         yl = __fma_rn((double)poseidon_mds_entry(0, j), dl[j], yl);
         yh = __fma_rn((double)poseidon_mds_entry(0, j), dh[j], yh);
     }
-    const u64 sigma = poseidon_sbox(poseidon_fold(yl, yh));
-    const double gl = u32_as_denormal((u32)sigma), gh = u32_as_denormal((u32)(sigma >> 32));
     const double2* kk = c_poseidon_pair_k + pair * 12;
+    double al[12], ah[12];
 #pragma unroll
     for (int r = 0; r < 12; r++) {
         double2 k = kk[r];
-        double al = k.x, ah = k.y;
+        al[r] = k.x;
+        ah[r] = k.y;
 #pragma unroll
-        for (int j = 0; j < 12; j++) {
-            al = __fma_rn((double)poseidon_pair_entry(r, j), dl[j], al);
-            ah = __fma_rn((double)poseidon_pair_entry(r, j), dh[j], ah);
+        for (int j = 1; j < 12; j++) {
+            al[r] = __fma_rn((double)poseidon_pair_entry(r, j), dl[j], al[r]);
+            ah[r] = __fma_rn((double)poseidon_pair_entry(r, j), dh[j], ah[r]);
         }
-        al = __fma_rn((double)poseidon_mds_entry(r, 0), gl, al);
-        ah = __fma_rn((double)poseidon_mds_entry(r, 0), gh, ah);
-        s[r] = poseidon_fold(al, ah);
+    }
+    const u64 x0 = poseidon_sbox(s[0]);
+    dl[0] = u32_as_denormal((u32)x0);
+    dh[0] = u32_as_denormal((u32)(x0 >> 32));
+    yl = __fma_rn((double)poseidon_mds_entry(0, 0), dl[0], yl);
+    yh = __fma_rn((double)poseidon_mds_entry(0, 0), dh[0], yh);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        al[r] = __fma_rn((double)poseidon_pair_entry(r, 0), dl[0], al[r]);
+        ah[r] = __fma_rn((double)poseidon_pair_entry(r, 0), dh[0], ah[r]);
+    }
+    const u64 sigma = poseidon_sbox(poseidon_fold(yl, yh));
+    const double gl = u32_as_denormal((u32)sigma), gh = u32_as_denormal((u32)(sigma >> 32));
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        al[r] = __fma_rn((double)poseidon_mds_entry(r, 0), gl, al[r]);
+        ah[r] = __fma_rn((double)poseidon_mds_entry(r, 0), gh, ah[r]);
+        s[r] = poseidon_fold(al[r], ah[r]);
     }
 }
 

@@ -328,3 +328,43 @@ def test_golden_commit_caps(glb, ctx, oracle):
         b = glb.PolynomialBatch.from_values(v, case["rate_bits"], False, case["cap_height"])
         assert [f"{int(x):016x}" for x in b.merkle_tree.cap.reshape(-1)] == case["cap"]
         b.free()
+
+
+def _horner(coeffs, x):
+    acc = 0
+    for c in coeffs[::-1].tolist():
+        acc = (acc * x + c) % P
+    return acc
+
+
+def test_config2_full_size_properties(glb, ctx, oracle):
+    """BASELINE.json configs[1] at full size (2^20 rows x 135 columns, rate_bits 3, cap_height 4), checked through
+    size-independent properties: coefficients interpolate the values, opened LDE rows are the polynomial
+    evaluated at 7 * w_N^bitrev(i), every opened Merkle path verifies against the cap, and the sub-sampled
+    coset (get_lde_values) agrees with the opened rows."""
+    lg_n, c, r, h = 20, 135, 3, 4
+    n, N = 1 << lg_n, 1 << (lg_n + r)
+    values = oracle.synthetic_values(c, n)
+    b = glb.PolynomialBatch.from_values(values, r, False, h)
+    coeffs = b.polynomials
+    w_n = oracle.lib().glo_primitive_root_of_unity(lg_n)
+    w_N = oracle.lib().glo_primitive_root_of_unity(lg_n + r)
+    rng = np.random.default_rng(7)
+    for col in (0, 134):
+        j = int(rng.integers(0, n))
+        assert _horner(coeffs[col], pow(w_n, j, P)) == int(values[col][j])
+    idx = sorted(set(int(x) for x in rng.integers(0, N, size=6)) | {0, N - 1})
+    rows, paths = b.open(idx)
+    cap = b.merkle_tree.cap
+    for q, i in enumerate(idx):
+        assert oracle.merkle_verify(rows[q], i, paths[q], cap, h)
+    for q in (0, len(idx) // 2):
+        i = idx[q]
+        x = 7 * pow(w_N, oracle.lib().glo_reverse_bits(i, lg_n + r), P) % P
+        for col in (3, 77):
+            assert _horner(coeffs[col], x) == int(rows[q][col])
+    i = 123457
+    leaf = oracle.lib().glo_reverse_bits(i * 8, lg_n + r)
+    assert np.array_equal(b.get_lde_values(i, 8), b.open([leaf])[0][0])
+    b.free()
+    ctx.trim()
