@@ -121,9 +121,11 @@ GL_D void smt_leaf_hash(const u64 k[4], const u64 v[4], u64 out[4]) {
         s[4 + i] = v[i];
         s[8 + i] = 0;
     }
-    poseidon_permute(s);
-    s[0] = 1; s[1] = 1; s[2] = 0; s[3] = 1;  // second chunk overwrites lanes 0..3 only
-    poseidon_permute(s);
+#pragma unroll 1
+    for (int chunk = 0; chunk < 2; chunk++) {
+        if (chunk) { s[0] = 1; s[1] = 1; s[2] = 0; s[3] = 1; }  // second chunk overwrites lanes 0..3 only
+        poseidon_permute(s);
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
 }
@@ -168,20 +170,15 @@ k_leaf_hash_cols(const u64* __restrict__ lde, u64 ld, u32 c, u64 num_leaves, uns
 #pragma unroll
         for (int k = 0; k < 12; k++) s[k] = 0;
         const u64* p = lde + i;
-        u32 full = c / 8;
-        for (u32 ch = 0; ch < full; ch++, p += 8 * ld) {
-            u64 t[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) t[j] = p[(u64)j * ld];
-#pragma unroll
-            for (int j = 0; j < 8; j++) s[j] = t[j];
-            poseidon_permute(s);
-        }
-        u32 rem = c - full * 8;
-        if (rem) {
+        // one call site for the permutation (a second inlined copy pushes the kernel past the instruction
+        // cache): the ragged last chunk is handled by predicated loads
+        const u32 chunks = (c + 7) / 8;
+#pragma unroll 1
+        for (u32 ch = 0; ch < chunks; ch++, p += 8 * ld) {
+            const u32 k = c - 8 * ch;   // elements left (>= 1)
 #pragma unroll
             for (int j = 0; j < 8; j++)
-                if (j < rem) s[j] = p[(u64)j * ld];
+                if (j < k) s[j] = p[(u64)j * ld];
             poseidon_permute(s);
         }
 #pragma unroll
@@ -259,6 +256,35 @@ k_pow_grind(const u64* __restrict__ state12, unsigned pos, unsigned out_pos, uns
 // P7 verify_smt_process_proof over a batch (src/smt/proof/process.rs:153-337): one proof per thread,
 // 256 levels x 2 compressions + 2 leaf hashes = 516 permutations, no divergence in the hash count.
 // ------------------------------------------------------------------------------------------------
+// Out-of-line permutation for kernels with several hash sites (one copy of the 33 KB round code; the state
+// travels through local memory, 24 accesses against ~17k instructions).
+__device__ __noinline__ void poseidon_permute_call(u64* state) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = state[i];
+    poseidon_permute(s);
+#pragma unroll
+    for (int i = 0; i < 12; i++) state[i] = s[i];
+}
+GL_D void two_to_one_call(const u64 l[4], const u64 r[4], u64 out[4]) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s[i] = l[i]; s[4 + i] = r[i]; s[8 + i] = 0; }
+    poseidon_permute_call(s);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
+}
+GL_D void smt_leaf_hash_call(const u64 k[4], const u64 v[4], u64 out[4]) {
+    u64 s[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { s[i] = k[i]; s[4 + i] = v[i]; s[8 + i] = 0; }
+    poseidon_permute_call(s);
+    s[0] = 1; s[1] = 1; s[2] = 0; s[3] = 1;
+    poseidon_permute_call(s);
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
+}
+
 enum { ST_TOP = 0, ST_BOT = 1, ST_OLD0 = 2, ST_NEW1 = 3, ST_UPD = 4, ST_NA = 5 };
 
 GL_D bool is_zero4(const u64 h[4]) { return (h[0] | h[1] | h[2] | h[3]) == 0; }
@@ -337,8 +363,8 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
     }
     if (prev == ST_TOP || prev == ST_BOT) { status[t] = 3; return; }
     u64 old1_leaf[4], new1_leaf[4];
-    smt_leaf_hash(old_key, old_value, old1_leaf);
-    smt_leaf_hash(new_key, new_value, new1_leaf);
+    smt_leaf_hash_call(old_key, old_value, old1_leaf);
+    smt_leaf_hash_call(new_key, new_value, new1_leaf);
     u64 prev_old[4] = {0, 0, 0, 0}, prev_new[4] = {0, 0, 0, 0};
     const u64 zero[4] = {0, 0, 0, 0};
 #pragma unroll 1
@@ -351,7 +377,7 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
         u64 l[4], r[4], old_hash[4], new_hash[4];
         sel4(l, sb, pos, prev_old);
         sel4(r, prev_old, pos, sb);
-        poseidon_two_to_one(l, r, old_hash);
+        two_to_one_call(l, r, old_hash);
         u64 n_left[4], n_right[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -360,7 +386,7 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
         }
         sel4(l, n_right, pos, n_left);
         sel4(r, n_left, pos, n_right);
-        poseidon_two_to_one(l, r, new_hash);
+        two_to_one_call(l, r, new_hash);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             prev_old[j] = st == ST_TOP ? old_hash[j]
