@@ -100,17 +100,44 @@ GL_D u64 gl_add_c(u64 a, u64 b_canonical) {
     u64 s = a + b_canonical;
     return s + ((s < a) ? GL_EPS : 0ULL);
 }
-// general a + b, both possibly non-canonical: a second wrap can happen (only if both >= p - 2^32)
+// general a + b, both possibly non-canonical: a second wrap can happen (only if both >= p).  Carry-flag
+// chains: 8 ALU instructions (the C form with 64-bit compares compiles to 12).
 GL_D u64 gl_add(u64 a, u64 b) {
-    u64 s = a + b;
-    u64 t = s + ((s < a) ? GL_EPS : 0ULL);
-    return t + ((t < s) ? GL_EPS : 0ULL);
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "add.cc.u32 %0, %2, %4;\n\t"
+        "addc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // 0 + ~0 + CF = carry - 1  (ptxas: CF is always "carry", never "borrow")
+        "not.b32 m, m;\n\t"              // carry ? 0xffffffff : 0  = carry * (2^32 - 1)
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "not.b32 m, m;\n\t"
+        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl_pack(r0, r1);
 }
 // general a - b
 GL_D u64 gl_sub(u64 a, u64 b) {
-    u64 d = a - b;
-    u64 t = d - ((a < b) ? GL_EPS : 0ULL);
-    return t - ((t > d) ? GL_EPS : 0ULL);
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32), r0, r1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "sub.cc.u32 %0, %2, %4;\n\t"
+        "subc.cc.u32 %1, %3, %5;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // 0 + ~0 + CF = (no borrow) - 1 = borrow ? 0xffffffff : 0
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.cc.u32 %1, %1, 0;\n\t"
+        "subc.u32 m, 0, 0;\n\t"
+        "sub.cc.u32 %0, %0, m;\n\t"
+        "subc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(r0), "=&r"(r1)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1));
+    return gl_pack(r0, r1);
 }
 GL_D u64 gl_canon(u64 x) { return x >= GL_P ? x - GL_P : x; }
 GL_D u64 gl_neg(u64 a) { return gl_sub(0, a); }

@@ -93,10 +93,21 @@ GL_D u64 poseidon_fold(double al, double ah);
 GL_D u64 poseidon_fold_fwd(double al, double ah) { return poseidon_fold(al, ah); }
 GL_D u64 poseidon_fold(double al, double ah) {
     // value = A + 2^32 * B with A, B < 2^50 (integer bit patterns).  2^64 = 2^32 - 1 (mod p):
+    //   t = A + (B >> 32) * (2^32 - 1)  (< 2^51, one IMAD.WIDE);  y = t + (B mod 2^32) * 2^32 wraps at most once
     u64 A = double_bits(al), B = double_bits(ah);
-    u64 t = A + (u64)(u32)(B >> 32) * GL_EPS;   // < 2^51
-    u64 y = t + (B << 32);
-    return y + ((y < t) ? GL_EPS : 0ULL);        // true value < 2^64 + 2^51: one wrap at most
+    u64 t = A + (u64)(u32)(B >> 32) * GL_EPS;
+    u32 t0 = (u32)t, t1 = (u32)(t >> 32), b0 = (u32)B, y0, y1;
+    asm("{\n\t"
+        ".reg .u32 m;\n\t"
+        "add.cc.u32 %1, %3, %4;\n\t"
+        "subc.u32 m, 0, 0;\n\t"          // carry - 1
+        "not.b32 m, m;\n\t"              // carry * (2^32 - 1)
+        "add.cc.u32 %0, %2, m;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        "}"
+        : "=&r"(y0), "=&r"(y1)
+        : "r"(t0), "r"(t1), "r"(b0));
+    return gl_pack(y0, y1);
 }
 
 // Two consecutive partial rounds a, a + 1 in one pass over the FP64 pipe.  On entry the state holds the input
