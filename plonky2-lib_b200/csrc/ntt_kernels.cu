@@ -382,42 +382,88 @@ __global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
         x[i] = sm[idx];
     }
     radix16_dif<INV>(x);
-    if (LB > 0) {
+    if (LB == 0) {
+        // ---- store: in-place position p holds output index brev_M(p) -----------------------------------
+        const u64 jlo = STRIDED ? (base & (((u64)1 << s) - 1)) : 0;
 #pragma unroll
-        for (int i = 1; i < 16; i++) x[i] = gl_mul(x[i], wt[(brev4(i) * plow) << 4]);
-        // ---- round 3: butterflies across lanes ------------------------------------------------------
-#pragma unroll
-        for (int b = (int)LB - 1; b >= 0; b--) {
-            const unsigned lane_mask = STRIDED ? (1u << (logW + b)) : (1u << b);
-            const bool hi = (plow >> b) & 1;
-            // the only non-trivial twiddle left is w_4 = 2^48 (inverse: -2^48), on the odd element of the b = 1 stage
-            const bool tw = (b == 1) && hi && (plow & 1);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                u64 mine = x[i];
-                u64 other = __shfl_xor_sync(0xffffffffu, mine, lane_mask);
-                u64 sum = gl_add(mine, other);
-                u64 dif = (INV && b == 1) ? (tw ? gl_sub(mine, other) : gl_sub(other, mine)) : gl_sub(other, mine);
-                if (b == 1) {
-                    u64 dt = gl_mul(dif, pow2_mod_p(48));
-                    dif = tw ? dt : dif;
-                }
-                x[i] = hi ? dif : sum;
+        for (int i = 0; i < 16; i++) {
+            unsigned p = phigh * Q + (unsigned)i;
+            u64 v = x[i];
+            if (STRIDED && a.post_tab) {
+                u64 k = __brev(p) >> (32 - M);
+                v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
             }
+            if (a.canonical_out) v = gl_canon(v);
+            out[(u64)p << rs] = v;
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 1; i < 16; i++) x[i] = gl_mul(x[i], wt[(brev4(i) * plow) << 4]);
+    // ---- round 3: the last LB <= 2 bits.  Second exchange (its own swizzle), then each thread holds the LB-bit
+    // field f = p[LB-1..0] for 2^(4-LB) values g of the TOP bits of p, i.e. 2^(4-LB) independent radix-2^LB blocks.
+    constexpr unsigned GB = 4 - LB;                      // bits of g
+    __syncthreads();                                     // everyone is done reading the first exchange
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned p = phigh * Q + ((unsigned)i << LB) + plow;
+        unsigned idx = STRIDED ? (((p << logW) + d) ^ (LB == 2 ? (((p >> 2) & 3u) << logW) : 0u))
+                               : ((d << M) + (p ^ ((p >> 4) & 15u)));
+        sm[idx] = x[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        unsigned g = (unsigned)i >> LB, f = (unsigned)i & ((1u << LB) - 1);
+        unsigned p = (g << (M - GB)) | (q << LB) | f;
+        unsigned idx = STRIDED ? (((p << logW) + d) ^ (LB == 2 ? (((p >> 2) & 3u) << logW) : 0u))
+                               : ((d << M) + (p ^ ((p >> 4) & 15u)));
+        x[i] = sm[idx];
+    }
+    if (LB == 2) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            u64 a0 = x[4 * g], a1 = x[4 * g + 1], a2 = x[4 * g + 2], a3 = x[4 * g + 3];
+            u64 s02 = gl_add(a0, a2), d02 = gl_sub(a0, a2);
+            u64 s13 = gl_add(a1, a3);
+            // (a1 - a3) * w_4, w_4 = 2^48 (inverse: 2^144 = -2^48)
+            u64 d13 = gl_mul(INV ? gl_sub(a3, a1) : gl_sub(a1, a3), pow2_mod_p(48));
+            x[4 * g] = gl_add(s02, s13);
+            x[4 * g + 1] = gl_sub(s02, s13);
+            x[4 * g + 2] = gl_add(d02, d13);
+            x[4 * g + 3] = gl_sub(d02, d13);
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            u64 a0 = x[2 * g], a1 = x[2 * g + 1];
+            x[2 * g] = gl_add(a0, a1);
+            x[2 * g + 1] = gl_sub(a0, a1);
         }
     }
     // ---- store: in-place position p holds output index brev_M(p) ---------------------------------------
     const u64 jlo = STRIDED ? (base & (((u64)1 << s) - 1)) : 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        unsigned p = phigh * Q + ((unsigned)i << LB) + plow;
+        unsigned g = (unsigned)i >> LB, f = (unsigned)i & ((1u << LB) - 1);
+        unsigned p = (g << (M - GB)) | (q << LB) | f;
         u64 v = x[i];
         if (STRIDED && a.post_tab) {
             u64 k = __brev(p) >> (32 - M);
             v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
         }
         if (a.canonical_out) v = gl_canon(v);
-        out[(u64)p << rs] = v;
+        x[i] = v;
+        if (STRIDED) out[(u64)p << rs] = v;
+    }
+    if (!STRIDED) {
+        // f is the low bits of p: a thread owns 2^LB consecutive outputs per g -> 16-byte stores
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            unsigned g = (unsigned)i >> LB, f = (unsigned)i & ((1u << LB) - 1);
+            unsigned p = (g << (M - GB)) | (q << LB) | f;
+            *reinterpret_cast<ulonglong2*>(out + p) = make_ulonglong2(x[i], x[i + 1]);
+        }
     }
 }
 
