@@ -299,9 +299,12 @@ class Smt:
         self._h = lib().glo_smt_new()
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().glo_smt_free(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                lib().glo_smt_free(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def root(self) -> np.ndarray:
         out = np.zeros(4, dtype=np.uint64)

@@ -1,0 +1,112 @@
+#!/usr/bin/env python
+"""Throughput of the secondary entry points of the C ABI (device-resident buffers, blocking calls, wall clock):
+Poseidon batches, row-major MerkleTree::new, SMT process-proof batches (BASELINE config 4), FRI layer pieces.
+Prints one JSON object; numbers quoted in DESIGN.md come from here (profiles/r1_bench_aux.json)."""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+glb = importlib.import_module("plonky2-lib_b200")
+from oracle import pyoracle as o  # noqa: E402  (only to generate valid SMT proofs)
+
+ctx = glb.Context(0)
+lib, N = ctx._lib, glb._native
+import ctypes as C  # noqa: E402
+
+dev = torch.device("cuda", 0)
+P = glb.host.P
+out = {}
+
+
+def timeit(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        t = time.perf_counter()
+        fn()
+        best = min(best, time.perf_counter() - t)
+    return best
+
+
+def rand_dev(shape):
+    return torch.randint(0, 2**62, shape, dtype=torch.int64, device=dev)
+
+
+m = 1 << 22
+st = rand_dev((m, 12))
+t = timeit(lambda: ctx.check(lib.gl_poseidon_permute_batch(ctx._h, st.data_ptr(), m, N.GL_DEVICE)))
+out["permute_batch"] = {"states": m, "ms": t * 1e3, "perms_per_s": m / t}
+l, r, d = rand_dev((m, 4)), rand_dev((m, 4)), torch.empty((m, 4), dtype=torch.int64, device=dev)
+t = timeit(lambda: ctx.check(lib.gl_poseidon_two_to_one_batch(ctx._h, l.data_ptr(), r.data_ptr(), d.data_ptr(), m, N.GL_DEVICE)))
+out["two_to_one_batch"] = {"pairs": m, "ms": t * 1e3, "perms_per_s": m / t}
+
+nl, ll = 1 << 20, 135
+leaves = rand_dev((nl, ll))
+dig = torch.empty((2 * (nl - 16), 4), dtype=torch.int64, device=dev)
+cap = torch.empty((16, 4), dtype=torch.int64, device=dev)
+t = timeit(lambda: ctx.check(lib.gl_merkle_build(ctx._h, leaves.data_ptr(), nl, ll, 4, dig.data_ptr(), cap.data_ptr(), N.GL_DEVICE)), 3)
+out["merkle_build_rows"] = {"leaves": nl, "leaf_len": ll, "ms": t * 1e3, "perms_per_s": (nl * 17 + nl - 16) / t}
+hd = torch.empty((nl, 4), dtype=torch.int64, device=dev)
+t = timeit(lambda: ctx.check(lib.gl_poseidon_hash_no_pad_batch(ctx._h, leaves.data_ptr(), ll, nl, hd.data_ptr(), N.GL_DEVICE)), 3)
+out["hash_no_pad_rows"] = {"rows": nl, "len": ll, "ms": t * 1e3, "perms_per_s": nl * 17 / t}
+del leaves, dig
+
+# BASELINE config 4 (i): SparseMerkleProcessProof::check over a batch; 2^13 real proofs tiled to 2^20
+rng = np.random.default_rng(4)
+tree = o.Smt()
+recs = []
+for _ in range(1 << 13):
+    recs.append(tree.set(rng.integers(0, P, 4, dtype=np.uint64), rng.integers(0, P, 4, dtype=np.uint64)))
+recs = np.array(recs, dtype=o.SMT_PROOF_DTYPE)
+hdr = np.zeros(recs.shape[0], dtype=glb.host.SMT_HDR_DTYPE)
+for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "is_old0", "fnc"):
+    hdr[f] = recs[f]
+ns = recs["num_siblings"].astype(np.uint64)
+pool = np.concatenate([r["siblings"][: r["num_siblings"]] for r in recs])
+reps = (1 << 20) // recs.shape[0]
+hdr_all = np.tile(hdr, reps)
+off_all = np.zeros(hdr_all.shape[0] + 1, dtype=np.uint64)
+off_one = np.concatenate([[0], np.cumsum(ns)]).astype(np.uint64)
+# every replica points at the same sibling pool
+off_all = None
+d_hdr = torch.from_numpy(hdr_all.view(np.uint8)).to(dev)
+d_pool = torch.from_numpy(pool.view(np.int64)).to(dev)
+# offsets must be monotone per proof pair (t, t+1): lay the replicas out as one long pool instead
+pool_all = np.tile(pool, (reps, 1))
+off_all = np.concatenate([[0], np.cumsum(np.tile(ns, reps))]).astype(np.uint64)
+d_pool = torch.from_numpy(pool_all.view(np.int64)).to(dev)
+d_off = torch.from_numpy(off_all.view(np.int64)).to(dev)
+d_status = torch.empty(hdr_all.shape[0], dtype=torch.int32, device=dev)
+mm = hdr_all.shape[0]
+t = timeit(lambda: ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr.data_ptr(), d_pool.data_ptr(), d_off.data_ptr(), mm,
+                                                            d_status.data_ptr(), N.GL_DEVICE)), 3)
+assert int(d_status.abs().sum().item()) == 0
+out["smt_verify_process_batch"] = {"proofs": mm, "avg_siblings": float(ns.mean()), "ms": t * 1e3, "proofs_per_s": mm / t,
+                                   "perms_per_s": mm * 516 / t}
+del d_pool, d_hdr
+
+# FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
+ln = 1 << 23
+vals = rand_dev((ln, 2))
+fd = torch.empty((2 * ((ln >> 4) - 16), 4), dtype=torch.int64, device=dev)
+t = timeit(lambda: ctx.check(lib.gl_fri_layer_tree(ctx._h, vals.data_ptr(), ln, 4, 4, fd.data_ptr(), cap.data_ptr(), N.GL_DEVICE)), 3)
+out["fri_layer_tree"] = {"ext_values": ln, "arity_bits": 4, "ms": t * 1e3}
+fo = torch.empty((ln >> 4, 2), dtype=torch.int64, device=dev)
+nx = torch.empty((ln >> 4, 2), dtype=torch.int64, device=dev)
+beta = (C.c_uint64 * 2)(12345678901234567, 7654321987654321)
+t = timeit(lambda: ctx.check(lib.gl_fri_fold(ctx._h, vals.data_ptr(), ln, 4, beta, pow(7, 16, P), fo.data_ptr(), nx.data_ptr(), N.GL_DEVICE)), 3)
+out["fri_fold"] = {"ext_coeffs": ln, "ms": t * 1e3}
+state = (C.c_uint64 * 12)(*[int(x) for x in rng.integers(0, P, 12, dtype=np.uint64)])
+w = C.c_uint64()
+t = timeit(lambda: ctx.check(lib.gl_pow_grind(ctx._h, state, 0, 16, C.byref(w))), 3)
+out["pow_grind_16_bits"] = {"ms": t * 1e3, "witness": w.value}
+print(json.dumps(out))
