@@ -209,7 +209,7 @@ static int finish(gl_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------
 // tables (built on the host with exact 128-bit arithmetic, cached on the device)
 // ------------------------------------------------------------------------------------------------
-enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3, TAB_FULL = 4 };
+enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3, TAB_FULL = 4, TAB_DIRECT = 5, TAB_COSETS_DIRECT = 6 };
 
 static void fill_pow_table(u64* t, u64 base) {  // [3][1024]: base^e, base^(1024 e), base^(2^20 e)
     u64 b = glh::canon(base);
@@ -299,6 +299,7 @@ struct NttJob {
     uint32_t columns = 1, cosets = 1;
     bool inverse = false;
     const u64* pre_tab = nullptr;
+    bool pre_direct_ok = false;   // pre_tab is the head of a cached coset_tables() block (stable key for the expanded copy)
     u64 final_scale = 1;
     int canonical_out = 0;
 };
@@ -320,6 +321,38 @@ static int full_table(gl_ctx* ctx, unsigned m, bool inverse, const u64** out) {
         acc = glh::mul(acc, w);
     }
     return table_upload(ctx, key, h, out);
+}
+
+// base^i for i < 2^lg, expanded on the device from the 3 x 1024 power table `pow` (key = the table's pointer)
+static int direct_table(gl_ctx* ctx, const u64* pow, unsigned lg, const u64** out) {
+    auto key = std::make_tuple((int)TAB_DIRECT, (uint64_t)(uintptr_t)pow, (uint64_t)lg, (uint64_t)0);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    u64* d;
+    TRY(dev_alloc(ctx, sizeof(u64) << lg, &d));
+    launch_fill_powers(d, (u64)1 << lg, pow, ctx->stream);
+    ctx->tables[key] = d;
+    *out = d;
+    return GL_OK;
+}
+// [blocks][2^lg]: shift_b^i for every local coset block b (expanded from coset_tables' power tables)
+static int coset_direct_tables(gl_ctx* ctx, const u64* coset_pow, unsigned lg, uint32_t blocks, const u64** out) {
+    auto key = std::make_tuple((int)TAB_COSETS_DIRECT, (uint64_t)(uintptr_t)coset_pow, (uint64_t)lg, (uint64_t)blocks);
+    auto it = ctx->tables.find(key);
+    if (it != ctx->tables.end()) {
+        *out = it->second;
+        return GL_OK;
+    }
+    u64* d;
+    TRY(dev_alloc(ctx, ((size_t)blocks * sizeof(u64)) << lg, &d));
+    for (uint32_t b = 0; b < blocks; b++)
+        launch_fill_powers(d + ((size_t)b << lg), (u64)1 << lg, coset_pow + (size_t)b * 3072, ctx->stream);
+    ctx->tables[key] = d;
+    *out = d;
+    return GL_OK;
 }
 
 // split of a size-2^L transform into passes; fast[i] says the radix-16 register kernel (m = 8..10) runs it
@@ -361,6 +394,11 @@ static int run_dif(gl_ctx* ctx, const NttJob& j) {
             f.out = j.out; f.out_ld = j.out_ld; f.out_coset_stride = j.out_coset_stride;
             f.pre_tab = first ? j.pre_tab : nullptr;
             f.post_tab = post;
+            // large transforms: one table load instead of two lookups and a multiply per element
+            if (j.L >= 16 && j.L <= 22 && j.columns >= 8) {
+                if (post && s + m <= 22) TRY(direct_table(ctx, post, s + m, &f.post_direct));
+                if (f.pre_tab && j.pre_direct_ok) TRY(coset_direct_tables(ctx, j.pre_tab, j.L, j.cosets, &f.pre_direct));
+            }
             TRY(full_table(ctx, m, j.inverse, &f.wtab));
             f.s = s;
             f.canonical_out = last ? j.canonical_out : 0;
@@ -730,6 +768,7 @@ static int commit_lde_columns(gl_ctx* ctx, gl_commit* h, uint32_t col0, uint32_t
     j.in = h->coeffs + (size_t)col0 * n; j.in_ld = n; j.in_coset_stride = 0;
     j.out = h->lde + (size_t)col0 * h->n_local; j.out_ld = h->n_local; j.out_coset_stride = n;
     j.L = h->log_n; j.columns = ncols; j.cosets = blocks; j.inverse = false; j.pre_tab = pre;
+    j.pre_direct_ok = true;
     j.canonical_out = 1;
     return run_dif(ctx, j);
 }

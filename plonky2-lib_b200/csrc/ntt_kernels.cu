@@ -356,7 +356,11 @@ __global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
     // ---- round 1: rows a * Q + q -----------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < 16; i++) x[i] = in[(u64)(i * Q + q) << rs];
-    if (a.pre_tab) {
+    if (a.pre_direct) {
+        const u64* pre = a.pre_direct + (u64)coset * a.n + base;
+#pragma unroll
+        for (int i = 0; i < 16; i++) x[i] = gl_mul(x[i], __ldg(pre + ((u64)(i * Q + q) << rs)));
+    } else if (a.pre_tab) {
         const u64* pre = a.pre_tab + (u64)coset * 3072;
 #pragma unroll
         for (int i = 0; i < 16; i++) x[i] = gl_mul(x[i], powtab_eval(pre, base + ((u64)(i * Q + q) << rs)));
@@ -389,7 +393,10 @@ __global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
         for (int i = 0; i < 16; i++) {
             unsigned p = phigh * Q + (unsigned)i;
             u64 v = x[i];
-            if (STRIDED && a.post_tab) {
+            if (STRIDED && a.post_direct) {
+                u64 k = __brev(p) >> (32 - M);
+                v = gl_mul(v, __ldg(a.post_direct + k * jlo));
+            } else if (STRIDED && a.post_tab) {
                 u64 k = __brev(p) >> (32 - M);
                 v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
             }
@@ -448,7 +455,10 @@ __global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
         unsigned g = (unsigned)i >> LB, f = (unsigned)i & ((1u << LB) - 1);
         unsigned p = (g << (M - GB)) | (q << LB) | f;
         u64 v = x[i];
-        if (STRIDED && a.post_tab) {
+        if (STRIDED && a.post_direct) {
+            u64 k = __brev(p) >> (32 - M);
+            v = gl_mul(v, __ldg(a.post_direct + k * jlo));
+        } else if (STRIDED && a.post_tab) {
             u64 k = __brev(p) >> (32 - M);
             v = gl_mul(v, powtab_eval(a.post_tab, k * jlo));
         }
@@ -465,6 +475,16 @@ __global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
             *reinterpret_cast<ulonglong2*>(out + p) = make_ulonglong2(x[i], x[i + 1]);
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_fill_powers(u64* __restrict__ out, u64 len, const u64* __restrict__ tab) {
+    for (u64 i = blockIdx.x * (u64)256 + threadIdx.x; i < len; i += (u64)gridDim.x * 256)
+        out[i] = gl_canon(powtab_eval(tab, i));
+}
+void launch_fill_powers(u64* out, u64 len, const u64* powtab, cudaStream_t st) {
+    u64 blocks = (len + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    { k_fill_powers<<<(unsigned)blocks, 256, 0, st>>>(out, len, powtab); ++g_gl_launches; }
 }
 
 template <int M>
@@ -499,6 +519,7 @@ bool launch_ntt16(const ntt16_args& a0, unsigned M, bool inverse, u64 n, u32 col
     unsigned threads = (1u << (M - 4)) << logW;
     if (threads < 32) return false;
     a.logW = logW;
+    a.n = n;
     u64 tiles = n >> (M + logW);
     dim3 grid((unsigned)tiles, columns, cosets);
     size_t smem = (((size_t)1 << (M + logW)) + ((size_t)1 << M)) * sizeof(u64);

@@ -51,9 +51,14 @@ struct ntt16_args {
     const uint64_t* pre_tab;   // [cosets][3][1024] or null
     const uint64_t* post_tab;  // [3][1024] power table of w_{2^(s+M)} (direction applied) or null (s == 0)
     const uint64_t* wtab;      // w_{2^M}^e, e < 2^M (direction applied)
+    const uint64_t* pre_direct;   // [cosets][n]: shift_coset^i, replaces pre_tab's two lookups + multiply (or null)
+    const uint64_t* post_direct;  // [2^(s+M)]: w_{2^(s+M)}^e, replaces post_tab's lookups + multiply (or null)
+    uint64_t n;
     unsigned s, logW;
     int canonical_out;
 };
 // returns false when (M, s, n) is not handled by the fast kernel
+// out[i] = base^i for i < len, from a 3 x 1024 power table (fills the direct twiddle tables once per geometry)
+void launch_fill_powers(uint64_t* out, uint64_t len, const uint64_t* powtab, cudaStream_t st);
 bool launch_ntt16(const ntt16_args& a, unsigned M, bool inverse, uint64_t n, uint32_t columns, uint32_t cosets,
                   cudaStream_t st);
