@@ -327,7 +327,7 @@ GL_D void radix16_dif(u64 x[16]) {
 GL_D unsigned brev4(unsigned x) { return __brev(x) >> 28; }
 
 template <int M, bool INV, bool STRIDED>
-__global__ void __launch_bounds__(512) k_ntt16(ntt16_args a) {
+__global__ void __launch_bounds__(512, 2) k_ntt16(ntt16_args a) {
     extern __shared__ u64 sm[];
     constexpr unsigned Q = 1u << (M - 4);          // threads per DFT
     const unsigned logW = a.logW, W = 1u << logW;
