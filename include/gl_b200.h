@@ -151,6 +151,11 @@ void gl_commit_free(gl_commit *h);
  * MerkleTree::new(leaves, cap_height).  digests_out may be NULL. */
 int gl_fri_layer_tree(gl_ctx *ctx, const uint64_t *values_ext, uint64_t len, uint32_t arity_bits,
                       uint32_t cap_height, uint64_t *digests_out, uint64_t *cap_out, int space);
+/* The same layer tree, kept RESIDENT for the query phase (fri_prover_query_round reads tree.get(x >> arity_bits)
+ * and tree.prove(x >> arity_bits) from every layer): *handle behaves like a commit of 2 * 2^arity_bits columns
+ * over len >> arity_bits leaves (gl_commit_open returns the flattened evals and the sibling path). */
+int gl_fri_layer_commit(gl_ctx *ctx, const uint64_t *values_ext, uint64_t len, uint32_t arity_bits,
+                        uint32_t cap_height, uint64_t *cap_out, gl_commit **handle, int space);
 /* coeffs.chunks_exact(2^arity_bits).map(|c| reduce_with_powers(c, beta)) then coset_fft(shift) over
  * F::Extension: coeffs_ext [len][2] -> folded_coeffs_out [len >> arity_bits][2] and
  * next_values_out [len >> arity_bits][2] (either may be NULL). */

@@ -64,6 +64,7 @@ SIGNATURES = {
     "gl_commit_device_ptrs": (cint, [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(vp)]),
     "gl_commit_free": (None, [vp]),
     "gl_fri_layer_tree": (cint, [vp, vp, u64, u32, u32, vp, vp, cint]),
+    "gl_fri_layer_commit": (cint, [vp, vp, u64, u32, u32, vp, C.POINTER(vp), cint]),
     "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
     "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
 }

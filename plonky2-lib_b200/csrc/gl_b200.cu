@@ -933,6 +933,7 @@ extern "C" int gl_commit_device_ptrs(const gl_commit* h, const uint64_t** lde_co
 extern "C" int gl_commit_coeffs(gl_commit* h, uint64_t* coeffs_out, int space) {
     if (!h || !coeffs_out) return GL_E_ARG;
     gl_ctx* ctx = h->ctx;
+    if (!h->coeffs) return fail(ctx, GL_E_STATE, "gl_commit_coeffs: this handle has no polynomials (FRI layer tree)");
     Guard g(ctx);
     TRY(copy_out(ctx, coeffs_out, h->coeffs, ((size_t)h->c << h->log_n) * 8, space));
     return finish(ctx);
@@ -1080,6 +1081,52 @@ extern "C" int gl_fri_layer_tree(gl_ctx* ctx, const uint64_t* values_ext, uint64
     TRY(copy_out(ctx, digests_out, dd, nd * 32, space));
     TRY(copy_out(ctx, cap_out, dc, (size_t)32 << cap_height, space));
     return finish(ctx);
+}
+
+extern "C" int gl_fri_layer_commit(gl_ctx* ctx, const uint64_t* values_ext, uint64_t len, uint32_t arity_bits,
+                                   uint32_t cap_height, uint64_t* cap_out, gl_commit** handle, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!handle) return fail(ctx, GL_E_ARG, "gl_fri_layer_commit: NULL handle");
+    *handle = nullptr;
+    if (!is_pow2(len)) return fail(ctx, GL_E_ARG, "fri_committed_trees: length is not a power of two");
+    unsigned lg = ilog2(len);
+    if (arity_bits > lg || arity_bits > 8) return fail(ctx, GL_E_ARG, "fri_committed_trees: bad arity");
+    if (cap_height > lg - arity_bits)
+        return fail(ctx, GL_E_ARG, "MerkleTree::new: cap_height must be at most log2(leaves.len())");
+    if (!values_ext) return fail(ctx, GL_E_ARG, "gl_fri_layer_commit: NULL buffer");
+    Guard g(ctx);
+    gl_commit* h = new (std::nothrow) gl_commit();
+    if (!h) return fail(ctx, GL_E_OOM, "host allocation failed");
+    h->ctx = ctx;
+    h->log_n = lg - arity_bits;
+    h->c = 2u << arity_bits;
+    h->rate_bits = 0;
+    h->cap_height = cap_height;
+    h->n_local = len >> arity_bits;
+    h->cap_local_bits = cap_height;
+    h->num_digests = 2 * (h->n_local - ((u64)1 << cap_height));
+    h->lde_bytes = len * 16;
+    h->digests_bytes = h->num_digests * 32;
+    h->cap_bytes = (size_t)32 << cap_height;
+    int rc = dev_alloc(ctx, h->lde_bytes, &h->lde);
+    if (rc == GL_OK) rc = dev_alloc(ctx, h->digests_bytes, &h->digests);
+    if (rc == GL_OK) rc = dev_alloc(ctx, h->cap_bytes, &h->cap);
+    const u64* dv = nullptr;
+    if (rc == GL_OK) rc = stage_in(ctx, values_ext, len * 16, space, 0, &dv);
+    if (rc == GL_OK) {
+        launch_fri_leaves(dv, lg, arity_bits, h->lde, ctx->stream);
+        launch_merkle_cols(h->lde, h->n_local, h->c, h->log_n, cap_height, h->digests, h->cap, ctx->stream);
+        rc = copy_out(ctx, cap_out, h->cap, h->cap_bytes, space);
+    }
+    if (rc == GL_OK) rc = finish(ctx);
+    if (rc != GL_OK) {
+        cudaStreamSynchronize(ctx->stream);
+        commit_release(h);
+        return rc;
+    }
+    ctx->live_commits++;
+    *handle = h;
+    return GL_OK;
 }
 
 extern "C" int gl_fri_fold(gl_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len, uint32_t arity_bits,

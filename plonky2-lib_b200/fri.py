@@ -1,0 +1,205 @@
+"""plonky2::fri::prover on top of the C ABI: `fri_proof` = commit phase + proof of work + query
+phase, with the data-parallel work on the device and the serial Fiat-Shamir transcript (`Challenger`,
+plonky2::iop::challenger) on the host.
+
+Every layer tree stays resident (`gl_fri_layer_commit`); the 28 query rounds of a proof are answered with one
+`gl_commit_open` per tree.  The Challenger's permutations are single-state `gl_poseidon_permute_batch` calls
+(there is no CPU Poseidon in the product).  Upstream's `fri_proof_of_work` takes any satisfying witness found
+by rayon `find_any`; here it is the smallest one (`gl_pow_grind`), which makes proofs deterministic.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from .host import Context, FriConfig, GlPanic, PoseidonHash, _ctx, _h, fri_fold
+
+P = 0xFFFFFFFF00000001
+SPONGE_RATE, SPONGE_WIDTH = 8, 12
+
+
+class Challenger:
+    """plonky2::iop::challenger::Challenger<F, PoseidonHash>: overwrite-mode duplex sponge."""
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self._ctx = _ctx(ctx)
+        self.sponge_state = np.zeros(SPONGE_WIDTH, dtype=np.uint64)
+        self.input_buffer: List[int] = []
+        self.output_buffer: List[int] = []
+
+    def observe_element(self, e: int):
+        self.output_buffer = []           # any buffered outputs are now invalid
+        self.input_buffer.append(int(e) % P)
+        if len(self.input_buffer) == SPONGE_RATE:
+            self._duplexing()
+
+    def observe_elements(self, es):
+        for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist():
+            self.observe_element(e)
+
+    def observe_hash(self, h):
+        self.observe_elements(h)
+
+    def observe_cap(self, cap):
+        self.observe_elements(cap)
+
+    def observe_extension_elements(self, es):
+        self.observe_elements(es)         # [a0, a1] per element, in order
+
+    def get_challenge(self) -> int:
+        if self.input_buffer or not self.output_buffer:
+            self._duplexing()
+        return self.output_buffer.pop()
+
+    def get_n_challenges(self, n: int) -> List[int]:
+        return [self.get_challenge() for _ in range(n)]
+
+    def get_extension_challenge(self) -> List[int]:
+        return self.get_n_challenges(2)
+
+    def _duplexing(self):
+        assert len(self.input_buffer) <= SPONGE_RATE
+        for i, v in enumerate(self.input_buffer):
+            self.sponge_state[i] = v
+        self.input_buffer = []
+        self.sponge_state = PoseidonHash.permute(self.sponge_state, ctx=self._ctx)
+        self.output_buffer = [int(x) for x in self.sponge_state[:SPONGE_RATE]]
+
+
+@dataclasses.dataclass
+class FriParams:
+    config: FriConfig
+    degree_bits: int
+    hiding: bool = False
+    reduction_arity_bits: Sequence[int] = ()
+
+    @staticmethod
+    def for_degree(config: FriConfig, degree_bits: int) -> "FriParams":
+        ab = config.reduction_strategy.reduction_arity_bits(degree_bits, config.rate_bits, config.cap_height)
+        return FriParams(config, degree_bits, False, tuple(ab))
+
+    def lde_bits(self) -> int:
+        return self.degree_bits + self.config.rate_bits
+
+
+class FriLayerTree:
+    """One resident layer tree of fri_committed_trees (MerkleTree over bit-reversed, arity-chunked values)."""
+
+    def __init__(self, values_ext: np.ndarray, arity_bits: int, cap_height: int, ctx: Context):
+        import ctypes as C
+
+        v = _h(values_ext)
+        self._ctx, self.arity_bits, self.cap_height = ctx, arity_bits, cap_height
+        self.num_leaves = v.shape[0] >> arity_bits
+        self.cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        ctx.check(ctx._lib.gl_fri_layer_commit(ctx._h, v.ctypes.data, v.shape[0], arity_bits, cap_height,
+                                               self.cap.ctypes.data, C.byref(h), N.GL_HOST))
+        self._h = h
+
+    def open(self, leaf_indices):
+        """(flattened evals [k][2 * arity], sibling paths [k][L][4])."""
+        idx = _h(np.asarray(leaf_indices))
+        k = idx.shape[0]
+        L = (self.num_leaves.bit_length() - 1) - self.cap_height
+        rows = np.empty((k, 2 << self.arity_bits), dtype=np.uint64)
+        paths = np.empty((k, L, 4), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.gl_commit_open(self._h, idx.ctypes.data, k, rows.ctypes.data, paths.ctypes.data, N.GL_HOST))
+        return rows, paths
+
+    def free(self):
+        if getattr(self, "_h", None) and self._ctx._h:
+            self._ctx._lib.gl_commit_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fri_committed_trees(coeffs_ext, values_ext, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None):
+    """plonky2::fri::prover::fri_committed_trees -> (layer trees, final polynomial coefficients [len][2])."""
+    ctx = _ctx(ctx)
+    coeffs, values = _h(coeffs_ext), _h(values_ext)
+    trees = []
+    shift = 7  # F::MULTIPLICATIVE_GROUP_GENERATOR
+    for arity_bits in fri_params.reduction_arity_bits:
+        tree = FriLayerTree(values, arity_bits, fri_params.config.cap_height, ctx)
+        challenger.observe_cap(tree.cap)
+        trees.append(tree)
+        beta = challenger.get_extension_challenge()
+        shift = pow(shift, 1 << arity_bits, P)
+        coeffs, values = fri_fold(coeffs, arity_bits, beta, shift, ctx=ctx)
+    # the coefficients being removed here are always zero
+    coeffs = coeffs[: coeffs.shape[0] >> fri_params.config.rate_bits].copy()
+    challenger.observe_extension_elements(coeffs)
+    return trees, coeffs
+
+
+def fri_proof_of_work(challenger: Challenger, config: FriConfig, ctx: Optional[Context] = None) -> int:
+    import ctypes as C
+
+    ctx = _ctx(ctx)
+    min_leading_zeros = config.proof_of_work_bits + (64 - P.bit_length())
+    state = challenger.sponge_state.copy()
+    pos = len(challenger.input_buffer)
+    for i, v in enumerate(challenger.input_buffer):
+        state[i] = v
+    s = (C.c_uint64 * 12)(*[int(x) for x in state])
+    w = C.c_uint64()
+    ctx.check(ctx._lib.gl_pow_grind(ctx._h, s, pos, min_leading_zeros, C.byref(w)))
+    # recompute the response with the normal Challenger code, as upstream does
+    challenger.observe_element(w.value)
+    response = challenger.get_challenge()
+    if min_leading_zeros and response >> (64 - min_leading_zeros):
+        raise GlPanic(N.GL_E_STATE, "fri_proof_of_work: response does not have the required leading zeros")
+    return w.value
+
+
+def fri_prover_query_rounds(initial_batches, trees: Sequence[FriLayerTree], challenger: Challenger, n: int,
+                            fri_params: FriParams):
+    """28 x fri_prover_query_round; the challenger is only read here, so all x_index are drawn first and each
+    tree answers every round with one gather."""
+    rounds = fri_params.config.num_query_rounds
+    xs = [challenger.get_challenge() % n for _ in range(rounds)]
+    initial = [b.open(xs) for b in initial_batches]
+    steps = []
+    idx = list(xs)
+    for tree in trees:
+        idx = [x >> tree.arity_bits for x in idx]
+        steps.append(tree.open(idx))
+    out = []
+    for q in range(rounds):
+        out.append({
+            "x_index": xs[q],
+            "initial_trees_proof": [(rows[q], paths[q]) for rows, paths in initial],
+            "steps": [{"evals": rows[q].reshape(-1, 2), "merkle_proof": paths[q]} for rows, paths in steps],
+        })
+    return out
+
+
+def fri_proof(initial_batches, lde_polynomial_coeffs, lde_polynomial_values, challenger: Challenger,
+              fri_params: FriParams, ctx: Optional[Context] = None) -> dict:
+    """plonky2::fri::prover::fri_proof.  initial_batches: the resident PolynomialBatch oracles (their
+    merkle_tree answers the initial openings)."""
+    ctx = _ctx(ctx)
+    n = _h(lde_polynomial_values).shape[0]
+    if _h(lde_polynomial_coeffs).shape[0] != n:
+        raise GlPanic(N.GL_E_ARG, "assert_eq!(lde_polynomial_coeffs.len(), n)")
+    trees, final_coeffs = fri_committed_trees(lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params, ctx)
+    pow_witness = fri_proof_of_work(challenger, fri_params.config, ctx)
+    query_round_proofs = fri_prover_query_rounds(initial_batches, trees, challenger, n, fri_params)
+    proof = {
+        "commit_phase_merkle_caps": [t.cap for t in trees],
+        "query_round_proofs": query_round_proofs,
+        "final_poly": final_coeffs,
+        "pow_witness": pow_witness,
+    }
+    for t in trees:
+        t.free()
+    return proof

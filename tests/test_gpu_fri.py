@@ -1,0 +1,86 @@
+"""N1: plonky2::fri::prover::fri_proof on the device (resident layer trees, device PoW, gathered
+query openings, host Challenger) against the oracle's fri_proof, field by field, and through the oracle's
+restatement of the upstream verifier."""
+import importlib
+
+import numpy as np
+import pytest
+
+from conftest import rand_field
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_proof(a, b):
+    assert a["pow_witness"] == b["pow_witness"]
+    assert np.array_equal(a["final_poly"], b["final_poly"])
+    assert len(a["commit_phase_merkle_caps"]) == len(b["commit_phase_merkle_caps"])
+    for x, y in zip(a["commit_phase_merkle_caps"], b["commit_phase_merkle_caps"]):
+        assert np.array_equal(x, y)
+    assert len(a["query_round_proofs"]) == len(b["query_round_proofs"])
+    for ra, rb in zip(a["query_round_proofs"], b["query_round_proofs"]):
+        assert ra["x_index"] == rb["x_index"]
+        for (rowa, patha), (rowb, pathb) in zip(ra["initial_trees_proof"], rb["initial_trees_proof"]):
+            assert np.array_equal(rowa, rowb) and np.array_equal(patha, pathb)
+        for sa, sb in zip(ra["steps"], rb["steps"]):
+            assert np.array_equal(sa["evals"], sb["evals"]) and np.array_equal(sa["merkle_proof"], sb["merkle_proof"])
+
+
+@pytest.mark.parametrize("degree_bits,pow_bits,cols", [(6, 4, (3,)), (10, 8, (5, 20)), (12, 16, (135, 20, 16))])
+def test_fri_proof_matches_oracle_and_verifies(glb, ctx, oracle, rng, degree_bits, pow_bits, cols):
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    rate_bits, cap_height, rounds = 3, 4, 28
+    n, lde = 1 << degree_bits, 1 << (degree_bits + rate_bits)
+    coeffs = np.zeros((lde, 2), dtype=np.uint64)
+    coeffs[:n] = rand_field(rng, (n, 2))
+    values = glb.coset_fft(np.ascontiguousarray(coeffs.T), 7)          # extension coset_fft = two base transforms
+    values = np.ascontiguousarray(values.T)
+    assert np.array_equal(values, oracle.ext_coset_fft(coeffs, 7))
+    # the initial oracles: resident commits on the device, mirrored trees on the CPU
+    batches, cpu_trees = [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=900 + k)
+        b = glb.PolynomialBatch.from_values(v, rate_bits, False, cap_height)
+        batches.append(b)
+        cpu_trees.append(fo.MerkleTree(oracle.commit_from_values(v, rate_bits, cap_height)["leaves"], cap_height))
+        assert np.array_equal(b.merkle_tree.cap, cpu_trees[-1].cap)
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+    assert list(params.reduction_arity_bits) == fo.reduction_arity_bits(degree_bits, rate_bits, cap_height)
+    ch = fri.Challenger()
+    och = fo.Challenger()
+    for t in cpu_trees:
+        ch.observe_cap(t.cap)
+        och.observe_cap(t.cap)
+    got = fri.fri_proof(batches, coeffs, values, ch, params)
+    want = fo.fri_proof(cpu_trees, coeffs, values, och, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    _same_proof(got, want)
+    assert ch.get_challenge() == och.get_challenge()                  # transcripts end in the same state
+    vch = fo.Challenger()
+    for t in cpu_trees:
+        vch.observe_cap(t.cap)
+
+    def first_layer_eval(x_index, rows, subgroup_x):
+        return fo.eval_ext_poly(coeffs[:n], (subgroup_x, 0))
+
+    assert fo.verify_fri_proof(got, [t.cap for t in cpu_trees], cap_height, vch, degree_bits, first_layer_eval,
+                               rate_bits, cap_height, pow_bits, rounds)
+    for b in batches:
+        b.free()
+
+
+def test_challenger_matches_oracle(glb, ctx, oracle, rng):
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    a, b = fri.Challenger(), fo.Challenger()
+    for step in range(40):
+        if step % 3 == 0:
+            assert a.get_challenge() == b.get_challenge()
+        else:
+            xs = rand_field(rng, (int(rng.integers(1, 12)),))
+            a.observe_elements(xs)
+            b.observe_elements(xs)
+    assert a.get_extension_challenge() == b.get_extension_challenge()

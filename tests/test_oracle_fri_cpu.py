@@ -1,0 +1,75 @@
+"""The FRI half of the oracle (oracle/fri_oracle.py) checks itself the way the reference's circuit tests do:
+prove, then verify (every reference test is `data.prove(pw)` followed by `data.verify(proof)`,
+e.g. src/ecdsa/gadgets/ecdsa.rs:349-352)."""
+import numpy as np
+import pytest
+
+from conftest import P, rand_field
+
+
+def make_instance(oracle, rng, degree_bits, rate_bits=3, cap_height=4):
+    from oracle import fri_oracle as fo
+
+    n = 1 << degree_bits
+    lde = n << rate_bits
+    coeffs = np.zeros((lde, 2), dtype=np.uint64)
+    coeffs[:n] = rand_field(rng, (n, 2))
+    values = oracle.ext_coset_fft(coeffs, 7)
+    base = oracle.commit_from_values(oracle.synthetic_values(6, n), rate_bits, cap_height)
+    tree = fo.MerkleTree(base["leaves"], cap_height)
+    return coeffs, values, tree
+
+
+def direct_eval(coeffs, degree_bits):
+    from oracle import fri_oracle as fo
+
+    def f(x_index, rows, subgroup_x):
+        return fo.eval_ext_poly(coeffs[: 1 << degree_bits], (subgroup_x, 0))
+
+    return f
+
+
+@pytest.mark.parametrize("degree_bits,pow_bits", [(6, 4), (10, 8), (9, 16)])
+def test_fri_prove_then_verify(oracle, rng, degree_bits, pow_bits):
+    from oracle import fri_oracle as fo
+
+    coeffs, values, tree = make_instance(oracle, rng, degree_bits)
+    ch = fo.Challenger()
+    ch.observe_cap(tree.cap)
+    proof = fo.fri_proof([tree], coeffs, values, ch, degree_bits, pow_bits=pow_bits, num_query_rounds=6)
+    vch = fo.Challenger()
+    vch.observe_cap(tree.cap)
+    assert fo.verify_fri_proof(proof, [tree.cap], 4, vch, degree_bits, direct_eval(coeffs, degree_bits), pow_bits=pow_bits,
+                               num_query_rounds=6)
+    # the verifier rejects a tampered proof
+    bad = dict(proof)
+    bad["final_poly"] = proof["final_poly"].copy()
+    bad["final_poly"][0][0] ^= np.uint64(1)
+    vch = fo.Challenger()
+    vch.observe_cap(tree.cap)
+    with pytest.raises(AssertionError):
+        fo.verify_fri_proof(bad, [tree.cap], 4, vch, degree_bits, direct_eval(coeffs, degree_bits), pow_bits=pow_bits,
+                            num_query_rounds=6)
+
+
+def test_challenger_duplex_semantics(oracle):
+    """Outputs are popped from the back; observing clears pending outputs; 8 inputs trigger a duplex."""
+    from oracle import fri_oracle as fo
+
+    ch = fo.Challenger()
+    for i in range(8):
+        ch.observe_element(i)
+    st = oracle.permute(np.array(list(range(8)) + [0, 0, 0, 0], dtype=np.uint64))
+    assert ch.get_challenge() == int(st[7]) and ch.get_challenge() == int(st[6])
+    ch.observe_element(5)
+    s2 = st.copy()
+    s2[0] = 5
+    assert ch.get_challenge() == int(oracle.permute(s2)[7])
+
+
+def test_reduction_strategy(oracle):
+    from oracle import fri_oracle as fo
+
+    assert fo.reduction_arity_bits(20, 3, 4) == [4, 4, 4, 4]
+    assert fo.reduction_arity_bits(16, 3, 4) == [4, 4, 4]
+    assert fo.reduction_arity_bits(5, 3, 4) == []
