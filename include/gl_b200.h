@@ -163,6 +163,24 @@ int gl_fri_fold(gl_ctx *ctx, const uint64_t *coeffs_ext, uint64_t len, uint32_t 
                 const uint64_t beta[2], uint64_t shift, uint64_t *folded_coeffs_out,
                 uint64_t *next_values_out, int space);
 
+/* ---- N1: PolynomialBatch::prove_openings up to the FRI polynomial (plonky2::fri::oracle) ----------------- */
+/* One FriBatchInfo: the polynomials polys[first_poly .. first_poly + num_polys) are opened at `point`
+ * (an extension element); a polynomial is (oracle_index, polynomial_index) into the resident commits. */
+typedef struct {
+    uint64_t point[2];
+    uint32_t first_poly, num_polys;
+} gl_fri_batch;
+typedef struct {
+    uint32_t oracle_index, polynomial_index;
+} gl_fri_poly;
+/* final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i), F_i = sum_j alpha^j f_ij  (reduce_polys_base,
+ * divide_by_linear, shift_poly), then final_poly.lde(rate_bits) and its coset_fft(7) over the extension.
+ * Every oracle must be a commit of this ctx with the same degree.  Outputs: lde_coeffs_out and lde_values_out,
+ * both [n << rate_bits][2] (natural order) -- the two arguments fri_proof takes.  Either may be NULL. */
+int gl_fri_final_poly(gl_ctx *ctx, gl_commit *const *oracles, uint32_t num_oracles, const gl_fri_batch *batches,
+                      uint32_t num_batches, const gl_fri_poly *polys, const uint64_t alpha[2], uint32_t rate_bits,
+                      uint64_t *lde_coeffs_out, uint64_t *lde_values_out, int space);
+
 /* ---- P10: fri_proof_of_work ------------------------------------------------------------------- */
 /* Smallest w >= 0 such that permute(state with state[input_pos] = w)[7] (the last rate lane, as
  * `duplex_state.squeeze().last()`) has >= min_leading_zeros leading zero bits.  Upstream's rayon

@@ -227,3 +227,74 @@ def verify_fri_proof(proof, initial_caps, initial_cap_height, challenger, degree
             x_index = coset_index
         assert eval_ext_poly(proof["final_poly"], (subgroup_x, 0)) == old_eval, "final polynomial mismatch"
     return True
+
+
+# ---- fri::oracle::PolynomialBatch::prove_openings and the verifier's fri_combine_initial ---------------
+# An instance is a list of batches: (point (a0, a1), [(oracle_index, polynomial_index), ...]); upstream's
+# FriInstanceInfo for a proof has two: every polynomial at zeta, the Z polynomials at g * zeta.
+def ext_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ext_mul(r, a)
+        a = ext_mul(a, a)
+        e >>= 1
+    return r
+
+
+def final_poly_of_openings(oracle_polys, batches, alpha):
+    """final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),  F_i = sum_j alpha^j f_ij."""
+    n = oracle_polys[0].shape[1]
+    final = np.zeros((n, 2), dtype=np.uint64)
+    for point, polys in batches:
+        comp = o.reduce_polys_base([oracle_polys[oi][pi] for oi, pi in polys], alpha)
+        quot = o.divide_by_linear(comp, point)           # remainder dropped, padded back with a zero
+        shift = ext_pow(tuple(int(x) for x in alpha), len(polys))   # ReducingFactor::shift_poly
+        final = o.ext_poly_scale_add(final, shift, quot)
+    return final
+
+
+def prove_openings(oracle_polys, oracle_trees, batches, challenger, degree_bits, rate_bits=3, cap_height=4, pow_bits=16,
+                   num_query_rounds=28):
+    alpha = challenger.get_extension_challenge()
+    final = final_poly_of_openings(oracle_polys, batches, alpha)
+    n = final.shape[0]
+    lde_coeffs = np.zeros((n << rate_bits, 2), dtype=np.uint64)
+    lde_coeffs[:n] = final
+    lde_values = o.ext_coset_fft(lde_coeffs, 7)
+    return fri_proof(oracle_trees, lde_coeffs, lde_values, challenger, degree_bits, rate_bits, cap_height, pow_bits,
+                     num_query_rounds)
+
+
+def opening_set(oracle_polys, batches):
+    """OpeningSet: f_ij(z_i) for every polynomial of every batch (what the proof carries next to the FRI proof)."""
+    return [[o.eval_base_poly_at_ext(oracle_polys[oi][pi], point) for oi, pi in polys] for point, polys in batches]
+
+
+def fri_combine_initial(batches, openings, initial_rows, alpha, subgroup_x):
+    """fri::verifier::fri_combine_initial: sum_i alpha^(k_i) (reduce(evals_i) - reduce(openings_i)) / (x - z_i)."""
+    alpha = tuple(int(x) for x in alpha)
+    total = (0, 0)
+    for (point, polys), opened in zip(batches, openings):
+        red_e, red_o = (0, 0), (0, 0)
+        for (oi, pi), ov in zip(reversed(polys), reversed(opened)):     # ReducingFactor::reduce: Horner from the back
+            red_e = ext_add(ext_mul(red_e, alpha), (int(initial_rows[oi][pi]), 0))
+            red_o = ext_add(ext_mul(red_o, alpha), ov)
+        num = ext_sub(red_e, red_o)
+        den = ext_sub((subgroup_x, 0), (int(point[0]), int(point[1])))
+        total = ext_mul(total, ext_pow(alpha, len(polys)))
+        total = ext_add(total, ext_mul(num, ext_inv(den)))
+    return total
+
+
+def verify_openings(proof, openings, oracle_caps, batches, challenger, degree_bits, rate_bits=3, cap_height=4, pow_bits=16,
+                    num_query_rounds=28):
+    """verify_fri_proof with the real fri_combine_initial: ties the opened rows of the initial trees and the
+    claimed openings to the first FRI layer."""
+    alpha = challenger.get_extension_challenge()
+
+    def first_layer_eval(x_index, rows, subgroup_x):
+        return fri_combine_initial(batches, openings, rows, alpha, subgroup_x)
+
+    return verify_fri_proof(proof, oracle_caps, cap_height, challenger, degree_bits, first_layer_eval, rate_bits, cap_height,
+                            pow_bits, num_query_rounds)

@@ -949,6 +949,74 @@ u64 glo_pow_grind(const u64 state[12], unsigned pos, unsigned out_pos, unsigned 
     return best;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * N1  plonky2::fri::oracle::PolynomialBatch::prove_openings, the part before fri_proof
+ *     (ReducingFactor::reduce_polys_base, PolynomialCoeffs::divide_by_linear, shift_poly) and the
+ *     OpeningSet evaluations the verifier's fri_combine_initial needs.
+ * ---------------------------------------------------------------------------------------------- */
+/* out = sum_j alpha^j * polys[j]   (polys: k base-field coefficient vectors of length n, pointers) */
+void glo_reduce_polys_base(const u64 *const *polys, size_t k, size_t n, const u64 alpha[2], u64 *out_ext) {
+    u64 *pw = (u64 *)malloc(2 * k * sizeof(u64));
+    u64 cur[2] = {1, 0};
+    for (size_t j = 0; j < k; j++) {
+        pw[2 * j] = cur[0];
+        pw[2 * j + 1] = cur[1];
+        u64 t[2];
+        glo_ext_mul(cur, alpha, t);
+        cur[0] = t[0];
+        cur[1] = t[1];
+    }
+#pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        u64 a0 = 0, a1 = 0;
+        for (size_t j = 0; j < k; j++) {
+            u64 c = canon(polys[j][i]);
+            a0 = f_add(a0, f_mul(c, pw[2 * j]));
+            a1 = f_add(a1, f_mul(c, pw[2 * j + 1]));
+        }
+        out_ext[2 * i] = canon(a0);
+        out_ext[2 * i + 1] = canon(a1);
+    }
+    free(pw);
+}
+/* PolynomialCoeffs::divide_by_linear(z) followed by the push(ZERO) of prove_openings: quot has n entries */
+void glo_divide_by_linear(const u64 *poly_ext, size_t n, const u64 z[2], u64 *quot_ext) {
+    u64 acc[2] = {0, 0};
+    for (size_t i = n; i-- > 0;) {
+        u64 t[2];
+        glo_ext_mul(acc, z, t);
+        ext_add(t, poly_ext + 2 * i, acc);      /* acc = b_i = b_{i+1} z + c_i */
+        if (i > 0) {
+            quot_ext[2 * (i - 1)] = canon(acc[0]);
+            quot_ext[2 * (i - 1) + 1] = canon(acc[1]);
+        }
+    }
+    quot_ext[2 * (n - 1)] = 0;
+    quot_ext[2 * (n - 1) + 1] = 0;
+}
+/* acc = acc * scalar + add  (ReducingFactor::shift_poly then +=) */
+void glo_ext_poly_scale_add(u64 *acc_ext, size_t n, const u64 scalar[2], const u64 *add_ext) {
+    for (size_t i = 0; i < n; i++) {
+        u64 t[2];
+        glo_ext_mul(acc_ext + 2 * i, scalar, t);
+        ext_add(t, add_ext + 2 * i, acc_ext + 2 * i);
+        acc_ext[2 * i] = canon(acc_ext[2 * i]);
+        acc_ext[2 * i + 1] = canon(acc_ext[2 * i + 1]);
+    }
+}
+/* PolynomialCoeffs<F>::to_extension().eval(point) */
+void glo_eval_base_poly_at_ext(const u64 *coeffs, size_t n, const u64 point[2], u64 out[2]) {
+    u64 acc[2] = {0, 0};
+    for (size_t i = n; i-- > 0;) {
+        u64 t[2];
+        glo_ext_mul(acc, point, t);
+        acc[0] = f_add(t[0], canon(coeffs[i]));
+        acc[1] = t[1];
+    }
+    out[0] = canon(acc[0]);
+    out[1] = canon(acc[1]);
+}
+
 int glo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

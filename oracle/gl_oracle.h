@@ -117,6 +117,12 @@ void glo_ext_coset_fft(uint64_t *a_ext, unsigned lg_n, uint64_t shift);
 uint64_t glo_pow_grind(const uint64_t state[12], unsigned pos, unsigned out_pos, unsigned min_lz,
                        uint64_t start, uint64_t count);
 
+/* ---- N1: prove_openings before fri_proof ---- */
+void glo_reduce_polys_base(const uint64_t *const *polys, size_t k, size_t n, const uint64_t alpha[2], uint64_t *out_ext);
+void glo_divide_by_linear(const uint64_t *poly_ext, size_t n, const uint64_t z[2], uint64_t *quot_ext);
+void glo_ext_poly_scale_add(uint64_t *acc_ext, size_t n, const uint64_t scalar[2], const uint64_t *add_ext);
+void glo_eval_base_poly_at_ext(const uint64_t *coeffs, size_t n, const uint64_t point[2], uint64_t out[2]);
+
 int glo_num_threads(void);
 void glo_set_num_threads(int n);
 

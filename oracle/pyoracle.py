@@ -115,6 +115,10 @@ def lib():
         "glo_fri_fold": (None, [u64p, sz, u, u64p, u64p]),
         "glo_ext_coset_fft": (None, [u64p, u, C.c_uint64]),
         "glo_pow_grind": (C.c_uint64, [u64p, u, u, u, C.c_uint64, C.c_uint64]),
+        "glo_reduce_polys_base": (None, [C.POINTER(u64p), sz, sz, u64p, u64p]),
+        "glo_divide_by_linear": (None, [u64p, sz, u64p, u64p]),
+        "glo_ext_poly_scale_add": (None, [u64p, sz, u64p, u64p]),
+        "glo_eval_base_poly_at_ext": (None, [u64p, sz, u64p, u64p]),
         "glo_num_threads": (C.c_int, []),
         "glo_set_num_threads": (None, [C.c_int]),
     }
@@ -373,6 +377,39 @@ def ext_coset_fft(a_ext, shift: int) -> np.ndarray:
 def pow_grind(state, pos: int, min_lz: int, start: int = 0, count: int = 1 << 22, out_pos: int = 7) -> int:
     s = _a(state)
     return int(lib().glo_pow_grind(_p(s), pos, out_pos, min_lz, start, count))
+
+
+def reduce_polys_base(polys, alpha) -> np.ndarray:
+    """ReducingFactor::reduce_polys_base: sum_j alpha^j * polys[j] -> [n][2]."""
+    polys = [_a(p) for p in polys]
+    n = polys[0].shape[0]
+    arr = (u64p * len(polys))(*[_p(p) for p in polys])
+    out = np.zeros((n, 2), dtype=np.uint64)
+    a = _a(alpha)
+    lib().glo_reduce_polys_base(arr, len(polys), n, _p(a), _p(out))
+    return out
+
+
+def divide_by_linear(poly_ext, z) -> np.ndarray:
+    p = _a(poly_ext)
+    out = np.zeros_like(p)
+    zz = _a(z)
+    lib().glo_divide_by_linear(_p(p), p.shape[0], _p(zz), _p(out))
+    return out
+
+
+def ext_poly_scale_add(acc_ext, scalar, add_ext) -> np.ndarray:
+    acc = _a(acc_ext).copy()
+    sc, ad = _a(scalar), _a(add_ext)
+    lib().glo_ext_poly_scale_add(_p(acc), acc.shape[0], _p(sc), _p(ad))
+    return acc
+
+
+def eval_base_poly_at_ext(coeffs, point):
+    c, pt = _a(coeffs), _a(point)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().glo_eval_base_poly_at_ext(_p(c), c.shape[0], _p(pt), _p(out))
+    return (int(out[0]), int(out[1]))
 
 
 def synthetic_values(c: int, n: int, seed: int = 0x706C6F6E6B7932, col0: int = 0) -> np.ndarray:

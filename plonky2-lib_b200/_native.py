@@ -31,6 +31,14 @@ class SmtProofHdr(C.Structure):
     ]
 
 
+class FriBatch(C.Structure):
+    _fields_ = [("point", u64 * 2), ("first_poly", u32), ("num_polys", u32)]
+
+
+class FriPoly(C.Structure):
+    _fields_ = [("oracle_index", u32), ("polynomial_index", u32)]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/gl_b200.h declares (tests check this)
 SIGNATURES = {
     "gl_ctx_create": (cint, [cint, C.POINTER(vp)]),
@@ -66,6 +74,7 @@ SIGNATURES = {
     "gl_fri_layer_tree": (cint, [vp, vp, u64, u32, u32, vp, vp, cint]),
     "gl_fri_layer_commit": (cint, [vp, vp, u64, u32, u32, vp, C.POINTER(vp), cint]),
     "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
+    "gl_fri_final_poly": (cint, [vp, vp, u32, vp, u32, vp, u64p, u32, vp, vp, cint]),
     "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
 }
 

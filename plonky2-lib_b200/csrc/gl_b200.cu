@@ -25,6 +25,7 @@
 
 #include "../../include/gl_b200.h"
 #include "gl_field.cuh"
+#include "fri_kernels.h"
 #include "hash_kernels.h"
 #include "ntt_kernels.h"
 #include "poseidon_constants.h"
@@ -1160,6 +1161,80 @@ extern "C" int gl_fri_fold(gl_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len
         u64* dst = space == GL_DEVICE ? next_values_out : (u64*)dext;
         launch_interleave2((const u64*)dcols, out_len, out_len, dst, ctx->stream);
         TRY(copy_out(ctx, next_values_out, dst, out_len * 16, space));
+    }
+    return finish(ctx);
+}
+
+extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num_oracles, const gl_fri_batch* batches,
+                                 uint32_t num_batches, const gl_fri_poly* polys, const uint64_t alpha[2],
+                                 uint32_t rate_bits, uint64_t* lde_coeffs_out, uint64_t* lde_values_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!oracles || !num_oracles || !batches || !num_batches || !polys || !alpha)
+        return fail(ctx, GL_E_ARG, "gl_fri_final_poly: NULL or empty argument");
+    const uint32_t log_n = oracles[0]->log_n;
+    for (uint32_t i = 0; i < num_oracles; i++) {
+        if (!oracles[i] || oracles[i]->ctx != ctx || !oracles[i]->coeffs)
+            return fail(ctx, GL_E_STATE, "gl_fri_final_poly: oracle is not a polynomial commit of this ctx");
+        if (oracles[i]->log_n != log_n) return fail(ctx, GL_E_ARG, "gl_fri_final_poly: oracles of different degree");
+    }
+    if (log_n + rate_bits > 30) return fail(ctx, GL_E_ARG, "gl_fri_final_poly: log_n + rate_bits > 30 not supported");
+    const u64 n = (u64)1 << log_n, N = n << rate_bits;
+    uint32_t total = 0, kmax = 0;
+    for (uint32_t b = 0; b < num_batches; b++) {
+        if (batches[b].first_poly != total) return fail(ctx, GL_E_ARG, "gl_fri_final_poly: batches must tile polys[] in order");
+        total += batches[b].num_polys;
+        if (batches[b].num_polys > kmax) kmax = batches[b].num_polys;
+        if (batches[b].num_polys == 0 || batches[b].num_polys > 2048)
+            return fail(ctx, GL_E_ARG, "gl_fri_final_poly: a batch needs 1..2048 polynomials");
+    }
+    for (uint32_t j = 0; j < total; j++)
+        if (polys[j].oracle_index >= num_oracles || polys[j].polynomial_index >= oracles[polys[j].oracle_index]->c)
+            return fail(ctx, GL_E_ARG, "gl_fri_final_poly: polynomial index out of range");
+    Guard g(ctx);
+    // scratch: 0 = pointer + power tables, 1 = transform scratch (transform_natural), 2 = composition poly,
+    // 3 = final poly, 4 = padded columns, 5 = segment carries + interleaved output
+    void *d_tab, *d_comp, *d_final, *d_cols, *d_misc;
+    const size_t tab_bytes = (size_t)kmax * (sizeof(u64*) + 16);
+    TRY(scratch_get(ctx, 0, tab_bytes, &d_tab));
+    TRY(scratch_get(ctx, 2, n * 16, &d_comp));
+    TRY(scratch_get(ctx, 3, n * 16, &d_final));
+    TRY(scratch_get(ctx, 4, N * 16, &d_cols));
+    const size_t nseg = n / FRI_DIV_SEG + 1;
+    TRY(scratch_get(ctx, 5, nseg * 32 + N * 16, &d_misc));
+    u64* seg_h = (u64*)d_misc;
+    u64* seg_b = seg_h + 2 * nseg;
+    u64* d_ext = seg_b + 2 * nseg;
+    CK(cudaMemsetAsync(d_final, 0, n * 16, ctx->stream));
+    const glh::ext al = {glh::canon(alpha[0]), glh::canon(alpha[1])};
+    std::vector<u64> host_tab;
+    for (uint32_t b = 0; b < num_batches; b++) {
+        const uint32_t k = batches[b].num_polys;
+        host_tab.assign((size_t)k * 3, 0);
+        glh::ext cur = {1, 0};
+        for (uint32_t j = 0; j < k; j++) {
+            const gl_fri_poly& fp = polys[batches[b].first_poly + j];
+            host_tab[j] = (u64)(uintptr_t)(oracles[fp.oracle_index]->coeffs + (size_t)fp.polynomial_index * n);
+            host_tab[k + 2 * j] = cur.a;
+            host_tab[k + 2 * j + 1] = cur.b;
+            cur = glh::ext_mul(cur, al);
+        }
+        CK(cudaMemcpyAsync(d_tab, host_tab.data(), host_tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));   // host_tab is reused by the next batch
+        launch_fri_reduce_polys((const u64* const*)d_tab, k, n, (const u64*)d_tab + k, (u64*)d_comp, ctx->stream);
+        const glh::ext z = {glh::canon(batches[b].point[0]), glh::canon(batches[b].point[1])};
+        const glh::ext zs = glh::ext_pow(z, FRI_DIV_SEG), sh = glh::ext_pow(al, k);
+        const u64 zz[2] = {z.a, z.b}, zt[2] = {zs.a, zs.b}, shv[2] = {sh.a, sh.b};
+        launch_fri_divide_accumulate((const u64*)d_comp, n, zz, zt, shv, seg_h, seg_b, (u64*)d_final, ctx->stream);
+    }
+    // final_poly.lde(rate_bits), then coset_fft(7) over the extension = two base transforms
+    launch_ext_to_padded_cols((const u64*)d_final, n, N, (u64*)d_cols, d_ext, ctx->stream);
+    TRY(copy_out(ctx, lde_coeffs_out, d_ext, N * 16, space));
+    if (lde_values_out) {
+        const u64* pre;
+        TRY(pow_table(ctx, 7, &pre));
+        TRY(transform_natural(ctx, (u64*)d_cols, log_n + rate_bits, 2, false, pre, nullptr));
+        launch_interleave2((const u64*)d_cols, N, N, d_ext, ctx->stream);
+        TRY(copy_out(ctx, lde_values_out, d_ext, N * 16, space));
     }
     return finish(ctx);
 }

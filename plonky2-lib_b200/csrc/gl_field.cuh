@@ -55,6 +55,22 @@ inline u64 root_of_unity(unsigned lg) {
     for (unsigned i = lg; i < 32; i++) g = mul(g, g);
     return g;
 }
+// QuadraticExtension: F[X]/(X^2 - 7)
+struct ext {
+    u64 a, b;
+};
+inline ext ext_mul(ext x, ext y) {
+    return {add(mul(x.a, y.a), mul(7, mul(x.b, y.b))), add(mul(x.a, y.b), mul(x.b, y.a))};
+}
+inline ext ext_pow(ext x, u64 e) {
+    ext r = {1, 0};
+    while (e) {
+        if (e & 1) r = ext_mul(r, x);
+        x = ext_mul(x, x);
+        e >>= 1;
+    }
+    return r;
+}
 }  // namespace glh
 
 #ifdef __CUDACC__

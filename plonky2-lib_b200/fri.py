@@ -203,3 +203,40 @@ def fri_proof(initial_batches, lde_polynomial_coeffs, lde_polynomial_values, cha
     for t in trees:
         t.free()
     return proof
+
+
+def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Context] = None):
+    """reduce_polys_base / divide_by_linear / shift_poly over the resident commits, then lde + extension coset_fft:
+    returns (lde_final_poly coefficients [N][2], lde_final_values [N][2]).
+    batches: [(point (a0, a1), [(oracle_index, polynomial_index), ...]), ...]  (FriInstanceInfo.batches)."""
+    import ctypes as C
+
+    ctx = _ctx(ctx)
+    nb = len(batches)
+    total = sum(len(p) for _, p in batches)
+    cb = (N.FriBatch * nb)()
+    cp = (N.FriPoly * total)()
+    at = 0
+    for i, (point, polys) in enumerate(batches):
+        cb[i].point[0], cb[i].point[1] = int(point[0]) % P, int(point[1]) % P
+        cb[i].first_poly, cb[i].num_polys = at, len(polys)
+        for oi, pi in polys:
+            cp[at].oracle_index, cp[at].polynomial_index = oi, pi
+            at += 1
+    handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
+    n = 1 << oracles[0].degree_log
+    lde = n << rate_bits
+    coeffs = np.empty((lde, 2), dtype=np.uint64)
+    values = np.empty((lde, 2), dtype=np.uint64)
+    al = (C.c_uint64 * 2)(int(alpha[0]) % P, int(alpha[1]) % P)
+    ctx.check(ctx._lib.gl_fri_final_poly(ctx._h, handles, len(oracles), cb, nb, cp, al, rate_bits,
+                                         coeffs.ctypes.data, values.ctypes.data, N.GL_HOST))
+    return coeffs, values
+
+
+def prove_openings(oracles, batches, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None) -> dict:
+    """plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params)."""
+    ctx = _ctx(ctx)
+    alpha = challenger.get_extension_challenge()
+    lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx)
+    return fri_proof(oracles, lde_coeffs, lde_values, challenger, fri_params, ctx)

@@ -84,3 +84,49 @@ def test_challenger_matches_oracle(glb, ctx, oracle, rng):
             a.observe_elements(xs)
             b.observe_elements(xs)
     assert a.get_extension_challenge() == b.get_extension_challenge()
+
+
+@pytest.mark.parametrize("degree_bits,cols", [(5, (3, 2)), (8, (4, 9, 3)), (12, (84, 135, 20, 16))])
+def test_prove_openings_matches_oracle_and_verifies(glb, ctx, oracle, rng, degree_bits, cols):
+    """PolynomialBatch::prove_openings end to end on the device (alpha reduction, division by X - z, LDE, FRI),
+    against the oracle and through its restatement of the upstream verifier (fri_combine_initial included).
+    The last case has the oracle shapes of a real proof: constants+sigmas, wires, Z/partial products, quotient."""
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    rate_bits, cap_height, pow_bits, rounds = 3, 4, 10, 28
+    n = 1 << degree_bits
+    batches_dev, polys, trees = [], [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=700 + k)
+        b = glb.PolynomialBatch.from_values(v, rate_bits, False, cap_height)
+        res = oracle.commit_from_values(v, rate_bits, cap_height)
+        batches_dev.append(b)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], cap_height))
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    g = oracle.lib().glo_primitive_root_of_unity(degree_bits)
+    zs = min(len(cols) - 1, 2)                                    # the oracle holding the Z polynomials
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+                (fo.ext_scalar(zeta, g), [(zs, pi) for pi in range(min(2, cols[zs]))])]
+    # the FRI polynomial itself
+    alpha = tuple(int(x) for x in rand_field(rng, (2,)))
+    want_final = fo.final_poly_of_openings(polys, instance, alpha)
+    got_coeffs, got_values = fri.fri_final_poly(batches_dev, instance, alpha, rate_bits)
+    assert np.array_equal(got_coeffs[:n], want_final) and not got_coeffs[n:].any()
+    assert np.array_equal(got_values, oracle.ext_coset_fft(got_coeffs, 7))
+    # the whole opening proof
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+    ch, och, vch = fri.Challenger(), fo.Challenger(), fo.Challenger()
+    for t in trees:
+        for c in (ch, och, vch):
+            c.observe_cap(t.cap)
+    got = fri.prove_openings(batches_dev, instance, ch, params)
+    want = fo.prove_openings(polys, trees, instance, och, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    _same_proof(got, want)
+    openings = fo.opening_set(polys, instance)
+    assert fo.verify_openings(got, openings, [t.cap for t in trees], instance, vch, degree_bits, rate_bits, cap_height,
+                              pow_bits, rounds)
+    for b in batches_dev:
+        b.free()

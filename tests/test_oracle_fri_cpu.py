@@ -73,3 +73,37 @@ def test_reduction_strategy(oracle):
     assert fo.reduction_arity_bits(20, 3, 4) == [4, 4, 4, 4]
     assert fo.reduction_arity_bits(16, 3, 4) == [4, 4, 4]
     assert fo.reduction_arity_bits(5, 3, 4) == []
+
+
+def test_prove_openings_then_verify(oracle, rng):
+    """PolynomialBatch::prove_openings -> verify_fri_proof with fri_combine_initial: the full opening argument of a
+    proof (two batches: every polynomial at zeta, a few at g * zeta), prove then verify, then a wrong opening."""
+    from oracle import fri_oracle as fo
+
+    degree_bits, rate_bits, cap_height = 8, 3, 4
+    n = 1 << degree_bits
+    cols = (4, 9, 3)
+    polys, trees = [], []
+    for k, c in enumerate(cols):
+        res = oracle.commit_from_values(oracle.synthetic_values(c, n, seed=50 + k), rate_bits, cap_height)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], cap_height))
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    g = oracle.lib().glo_primitive_root_of_unity(degree_bits)
+    batches = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+               (fo.ext_scalar(zeta, g), [(1, pi) for pi in range(4)])]
+    openings = fo.opening_set(polys, batches)
+    ch = fo.Challenger()
+    for t in trees:
+        ch.observe_cap(t.cap)
+    proof = fo.prove_openings(polys, trees, batches, ch, degree_bits, rate_bits, cap_height, pow_bits=6, num_query_rounds=5)
+    vch = fo.Challenger()
+    for t in trees:
+        vch.observe_cap(t.cap)
+    assert fo.verify_openings(proof, openings, [t.cap for t in trees], batches, vch, degree_bits, rate_bits, cap_height, 6, 5)
+    openings[0][2] = fo.ext_add(openings[0][2], (1, 0))
+    vch = fo.Challenger()
+    for t in trees:
+        vch.observe_cap(t.cap)
+    with pytest.raises(AssertionError):
+        fo.verify_openings(proof, openings, [t.cap for t in trees], batches, vch, degree_bits, rate_bits, cap_height, 6, 5)

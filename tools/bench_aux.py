@@ -109,4 +109,37 @@ state = (C.c_uint64 * 12)(*[int(x) for x in rng.integers(0, P, 12, dtype=np.uint
 w = C.c_uint64()
 t = timeit(lambda: ctx.check(lib.gl_pow_grind(ctx._h, state, 0, 16, C.byref(w))), 3)
 out["pow_grind_16_bits"] = {"ms": t * 1e3, "witness": w.value}
+# N1: PolynomialBatch::prove_openings at the shapes of a 2^20-row proof (constants+sigmas 84, wires 135, Z 20, quotient 16)
+del vals, fd, fo, nx
+ctx.trim()
+fri = importlib.import_module("plonky2-lib_b200.fri")
+lg = 20
+batches = []
+for k, c in enumerate((84, 135, 20, 16)):
+    v = rand_dev((c, 1 << lg)).cpu().numpy().view(np.uint64) % np.uint64(P)
+    batches.append(glb.PolynomialBatch.from_values(v, 3, False, 4, want_coeffs=False))
+    del v
+zeta = (1234567890123, 987654321987)
+g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - lg), P)
+cols = (84, 135, 20, 16)
+instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+            ((zeta[0] * g % P, zeta[1] * g % P), [(2, pi) for pi in range(20)])]
+params = fri.FriParams.for_degree(glb.FriConfig(), lg)
+
+
+def run_open():
+    ch = fri.Challenger()
+    for b in batches:
+        ch.observe_cap(b.merkle_tree.cap)
+    return fri.prove_openings(batches, instance, ch, params)
+
+
+t0 = time.perf_counter()
+alpha = (111, 222)
+fc, fv = fri.fri_final_poly(batches, instance, alpha, 3)
+t_final = time.perf_counter() - t0
+t = timeit(run_open, 2)
+out["prove_openings_2^20"] = {"oracles": list(cols), "ms": t * 1e3, "fri_final_poly_ms_incl_d2h": t_final * 1e3,
+                              "note": "alpha reduction of 275 polynomial openings, division, LDE, 4 FRI layers, 16-bit PoW, 28 queries; "
+                                      "final poly and layer values cross PCIe (host Challenger)"}
 print(json.dumps(out))
