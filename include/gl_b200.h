@@ -59,6 +59,11 @@ uint64_t gl_ctx_kernel_launches(const gl_ctx *ctx); /* kernels launched so far b
 int gl_ctx_commit_phase_ms(const gl_ctx *ctx, float *out6);
 /* Return pooled device memory (freed commits keep their blocks for the next commit) to the driver. */
 int gl_ctx_trim(gl_ctx *ctx);
+/* Device memory owned by the caller (host mirrors keep the FRI polynomial and the layer values resident between
+ * calls with it) and a copy between any two spaces, ordered on the ctx stream and blocking at return. */
+int gl_dev_alloc(gl_ctx *ctx, size_t bytes, void **out);
+void gl_dev_free(gl_ctx *ctx, void *p);
+int gl_copy(gl_ctx *ctx, void *dst, int dst_space, const void *src, int src_space, size_t bytes);
 /* Page-locked host memory for callers that want full-speed PCIe copies of their GL_HOST buffers
  * (the Rust shim backs the Vec<F> of a PolynomialBatch with it); plain malloc memory also works. */
 int gl_host_alloc(size_t bytes, void **out);

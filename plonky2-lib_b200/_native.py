@@ -50,6 +50,9 @@ SIGNATURES = {
     "gl_ctx_kernel_launches": (u64, [vp]),
     "gl_ctx_commit_phase_ms": (cint, [vp, C.POINTER(C.c_float)]),
     "gl_ctx_trim": (cint, [vp]),
+    "gl_dev_alloc": (cint, [vp, C.c_size_t, C.POINTER(vp)]),
+    "gl_dev_free": (None, [vp, vp]),
+    "gl_copy": (cint, [vp, vp, cint, vp, cint, C.c_size_t]),
     "gl_host_alloc": (cint, [C.c_size_t, C.POINTER(vp)]),
     "gl_host_free": (None, [vp]),
     "gl_poseidon_permute_batch": (cint, [vp, vp, u64, cint]),

@@ -57,6 +57,7 @@ struct gl_ctx {
     // multi-GB blocks cost milliseconds and serialise the device)
     std::multimap<size_t, void*> pool;
     size_t pool_bytes = 0;
+    std::map<void*, size_t> user_allocs;   // gl_dev_alloc blocks
     // phase boundaries of the last commit (CUDA events on `stream`)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // PCIe copies of the host-buffer commit pipeline
     std::vector<cudaEvent_t> pipe_ev;
@@ -505,6 +506,7 @@ extern "C" void gl_ctx_destroy(gl_ctx* ctx) {
         for (auto& kv : ctx->tables) cudaFree(kv.second);
         for (auto& b : ctx->scratch)
             if (b.p) cudaFree(b.p);
+        for (auto& kv : ctx->user_allocs) cudaFree(kv.first);
         pool_trim(ctx);
         for (auto& ev : ctx->ev)
             if (ev) cudaEventDestroy(ev);
@@ -543,6 +545,34 @@ extern "C" int gl_ctx_trim(gl_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     pool_trim(ctx);
     return GL_OK;
+}
+
+extern "C" int gl_dev_alloc(gl_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return GL_E_ARG;
+    Guard g(ctx);
+    u64* p;
+    TRY(dev_alloc(ctx, bytes, &p));
+    ctx->user_allocs[p] = bytes ? bytes : 8;
+    *out = p;
+    return GL_OK;
+}
+extern "C" void gl_dev_free(gl_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    Guard g(ctx);
+    auto it = ctx->user_allocs.find(p);
+    if (it == ctx->user_allocs.end()) return;
+    cudaStreamSynchronize(ctx->stream);
+    dev_release(ctx, p, it->second);
+    ctx->user_allocs.erase(it);
+}
+extern "C" int gl_copy(gl_ctx* ctx, void* dst, int dst_space, const void* src, int src_space, size_t bytes) {
+    if (!ctx) return GL_E_ARG;
+    if (bytes && (!dst || !src)) return fail(ctx, GL_E_ARG, "gl_copy: NULL buffer");
+    Guard g(ctx);
+    cudaMemcpyKind kind = dst_space == GL_DEVICE ? (src_space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                                 : (src_space == GL_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
+    return finish(ctx);
 }
 
 extern "C" int gl_host_alloc(size_t bytes, void** out) {

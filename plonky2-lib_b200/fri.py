@@ -15,7 +15,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .host import Context, FriConfig, GlPanic, PoseidonHash, _ctx, _h, fri_fold
+from .host import Context, DeviceBuffer, FriConfig, GlPanic, PoseidonHash, _ctx, _h
 
 P = 0xFFFFFFFF00000001
 SPONGE_RATE, SPONGE_WIDTH = 8, 12
@@ -88,16 +88,18 @@ class FriParams:
 class FriLayerTree:
     """One resident layer tree of fri_committed_trees (MerkleTree over bit-reversed, arity-chunked values)."""
 
-    def __init__(self, values_ext: np.ndarray, arity_bits: int, cap_height: int, ctx: Context):
+    def __init__(self, values_ext, length: int, arity_bits: int, cap_height: int, ctx: Context):
+        """values_ext: DeviceBuffer holding `length` extension elements (natural order of their coset)."""
         import ctypes as C
 
-        v = _h(values_ext)
         self._ctx, self.arity_bits, self.cap_height = ctx, arity_bits, cap_height
-        self.num_leaves = v.shape[0] >> arity_bits
-        self.cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        self.num_leaves = length >> arity_bits
+        cap_dev = DeviceBuffer((1 << cap_height, 4), ctx)
         h = C.c_void_p()
-        ctx.check(ctx._lib.gl_fri_layer_commit(ctx._h, v.ctypes.data, v.shape[0], arity_bits, cap_height,
-                                               self.cap.ctypes.data, C.byref(h), N.GL_HOST))
+        ctx.check(ctx._lib.gl_fri_layer_commit(ctx._h, values_ext.ptr, length, arity_bits, cap_height,
+                                               cap_dev.ptr, C.byref(h), N.GL_DEVICE))
+        self.cap = cap_dev.to_host()
+        cap_dev.free()
         self._h = h
 
     def open(self, leaf_indices):
@@ -122,23 +124,48 @@ class FriLayerTree:
             pass
 
 
+def _to_device(x, ctx: Context) -> DeviceBuffer:
+    if isinstance(x, DeviceBuffer):
+        return x
+    a = _h(x)
+    return DeviceBuffer(a.shape, ctx).from_host(a)
+
+
 def fri_committed_trees(coeffs_ext, values_ext, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None):
-    """plonky2::fri::prover::fri_committed_trees -> (layer trees, final polynomial coefficients [len][2])."""
+    """plonky2::fri::prover::fri_committed_trees -> (layer trees, final polynomial coefficients [len][2]).
+    coeffs_ext / values_ext: [len][2] host arrays or DeviceBuffers; everything between the layers stays in HBM,
+    only the caps (to the Challenger) and the final coefficients come back."""
+    import ctypes as C
+
     ctx = _ctx(ctx)
-    coeffs, values = _h(coeffs_ext), _h(values_ext)
+    coeffs, values = _to_device(coeffs_ext, ctx), _to_device(values_ext, ctx)
+    length = coeffs.shape[0]
     trees = []
     shift = 7  # F::MULTIPLICATIVE_GROUP_GENERATOR
     for arity_bits in fri_params.reduction_arity_bits:
-        tree = FriLayerTree(values, arity_bits, fri_params.config.cap_height, ctx)
+        tree = FriLayerTree(values, length, arity_bits, fri_params.config.cap_height, ctx)
         challenger.observe_cap(tree.cap)
         trees.append(tree)
         beta = challenger.get_extension_challenge()
         shift = pow(shift, 1 << arity_bits, P)
-        coeffs, values = fri_fold(coeffs, arity_bits, beta, shift, ctx=ctx)
+        out_len = length >> arity_bits
+        folded, nxt = DeviceBuffer((out_len, 2), ctx), DeviceBuffer((out_len, 2), ctx)
+        b = (C.c_uint64 * 2)(int(beta[0]), int(beta[1]))
+        ctx.check(ctx._lib.gl_fri_fold(ctx._h, coeffs.ptr, length, arity_bits, b, shift, folded.ptr, nxt.ptr, N.GL_DEVICE))
+        if coeffs is not coeffs_ext:
+            coeffs.free()
+        if values is not values_ext:
+            values.free()
+        coeffs, values, length = folded, nxt, out_len
     # the coefficients being removed here are always zero
-    coeffs = coeffs[: coeffs.shape[0] >> fri_params.config.rate_bits].copy()
-    challenger.observe_extension_elements(coeffs)
-    return trees, coeffs
+    final_len = length >> fri_params.config.rate_bits
+    final = coeffs.to_host(final_len * 2).reshape(final_len, 2)
+    if coeffs is not coeffs_ext:
+        coeffs.free()
+    if values is not values_ext:
+        values.free()
+    challenger.observe_extension_elements(final)
+    return trees, final
 
 
 def fri_proof_of_work(challenger: Challenger, config: FriConfig, ctx: Optional[Context] = None) -> int:
@@ -188,8 +215,8 @@ def fri_proof(initial_batches, lde_polynomial_coeffs, lde_polynomial_values, cha
     """plonky2::fri::prover::fri_proof.  initial_batches: the resident PolynomialBatch oracles (their
     merkle_tree answers the initial openings)."""
     ctx = _ctx(ctx)
-    n = _h(lde_polynomial_values).shape[0]
-    if _h(lde_polynomial_coeffs).shape[0] != n:
+    n = int(lde_polynomial_values.shape[0])
+    if int(lde_polynomial_coeffs.shape[0]) != n:
         raise GlPanic(N.GL_E_ARG, "assert_eq!(lde_polynomial_coeffs.len(), n)")
     trees, final_coeffs = fri_committed_trees(lde_polynomial_coeffs, lde_polynomial_values, challenger, fri_params, ctx)
     pow_witness = fri_proof_of_work(challenger, fri_params.config, ctx)
@@ -205,9 +232,10 @@ def fri_proof(initial_batches, lde_polynomial_coeffs, lde_polynomial_values, cha
     return proof
 
 
-def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Context] = None):
+def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Context] = None, resident: bool = False):
     """reduce_polys_base / divide_by_linear / shift_poly over the resident commits, then lde + extension coset_fft:
-    returns (lde_final_poly coefficients [N][2], lde_final_values [N][2]).
+    returns (lde_final_poly coefficients [N][2], lde_final_values [N][2]) as host arrays, or as DeviceBuffers
+    when `resident` (what prove_openings uses: the polynomial never leaves HBM).
     batches: [(point (a0, a1), [(oracle_index, polynomial_index), ...]), ...]  (FriInstanceInfo.batches)."""
     import ctypes as C
 
@@ -226,9 +254,14 @@ def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Contex
     handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
     n = 1 << oracles[0].degree_log
     lde = n << rate_bits
+    al = (C.c_uint64 * 2)(int(alpha[0]) % P, int(alpha[1]) % P)
+    if resident:
+        coeffs, values = DeviceBuffer((lde, 2), ctx), DeviceBuffer((lde, 2), ctx)
+        ctx.check(ctx._lib.gl_fri_final_poly(ctx._h, handles, len(oracles), cb, nb, cp, al, rate_bits, coeffs.ptr, values.ptr,
+                                             N.GL_DEVICE))
+        return coeffs, values
     coeffs = np.empty((lde, 2), dtype=np.uint64)
     values = np.empty((lde, 2), dtype=np.uint64)
-    al = (C.c_uint64 * 2)(int(alpha[0]) % P, int(alpha[1]) % P)
     ctx.check(ctx._lib.gl_fri_final_poly(ctx._h, handles, len(oracles), cb, nb, cp, al, rate_bits,
                                          coeffs.ctypes.data, values.ctypes.data, N.GL_HOST))
     return coeffs, values
@@ -238,5 +271,9 @@ def prove_openings(oracles, batches, challenger: Challenger, fri_params: FriPara
     """plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params)."""
     ctx = _ctx(ctx)
     alpha = challenger.get_extension_challenge()
-    lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx)
-    return fri_proof(oracles, lde_coeffs, lde_values, challenger, fri_params, ctx)
+    lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx, resident=True)
+    try:
+        return fri_proof(oracles, lde_coeffs, lde_values, challenger, fri_params, ctx)
+    finally:
+        lde_coeffs.free()
+        lde_values.free()

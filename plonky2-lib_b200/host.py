@@ -37,14 +37,52 @@ def _is_torch(x) -> bool:
     return type(x).__module__.startswith("torch")
 
 
+class DeviceBuffer:
+    """A block of device memory owned by the host mirror (gl_dev_alloc): `shape` uint64 elements."""
+
+    def __init__(self, shape, ctx: "Context"):
+        self.shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.nbytes = int(np.prod(self.shape)) * 8
+        self._ctx = ctx
+        p = C.c_void_p()
+        ctx.check(ctx._lib.gl_dev_alloc(ctx._h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def to_host(self, count_elems: Optional[int] = None) -> np.ndarray:
+        n = int(np.prod(self.shape)) if count_elems is None else count_elems
+        out = np.empty(n, dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.gl_copy(self._ctx._h, out.ctypes.data, N.GL_HOST, self.ptr, N.GL_DEVICE, n * 8))
+        return out.reshape(self.shape) if count_elems is None else out
+
+    def from_host(self, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=np.uint64)
+        assert a.nbytes <= self.nbytes
+        self._ctx.check(self._ctx._lib.gl_copy(self._ctx._h, self.ptr, N.GL_DEVICE, a.ctypes.data, N.GL_HOST, a.nbytes))
+        return self
+
+    def free(self):
+        if getattr(self, "ptr", None) and self._ctx._h:
+            self._ctx._lib.gl_dev_free(self._ctx._h, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class _Buf:
-    """pointer + space of a caller buffer (numpy host array or torch CUDA tensor)."""
+    """pointer + space of a caller buffer (numpy host array, torch CUDA tensor or DeviceBuffer)."""
 
     __slots__ = ("ptr", "space", "keep", "nbytes")
 
     def __init__(self, x, writable: bool = False):
         if x is None:
             self.ptr, self.space, self.keep, self.nbytes = None, None, None, 0
+            return
+        if isinstance(x, DeviceBuffer):
+            self.ptr, self.space, self.keep, self.nbytes = x.ptr, N.GL_DEVICE, x, x.nbytes
             return
         if _is_torch(x):
             if not x.is_cuda:

@@ -141,5 +141,5 @@ t_final = time.perf_counter() - t0
 t = timeit(run_open, 2)
 out["prove_openings_2^20"] = {"oracles": list(cols), "ms": t * 1e3, "fri_final_poly_ms_incl_d2h": t_final * 1e3,
                               "note": "alpha reduction of 275 polynomial openings, division, LDE, 4 FRI layers, 16-bit PoW, 28 queries; "
-                                      "final poly and layer values cross PCIe (host Challenger)"}
+                                      "the FRI polynomial and every layer stay in HBM; only caps, the final coefficients and the 28 opened rows + paths cross PCIe (host Challenger)"}
 print(json.dumps(out))
