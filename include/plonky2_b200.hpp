@@ -6,12 +6,14 @@
 //   plonky2::hash::merkle_tree::MerkleTree::{new, get, prove}        (MerkleTree::build here: `new` is a keyword)
 //   plonky2::hash::poseidon::PoseidonHash::{hash_no_pad, hash_pad, hash_or_noop, two_to_one}
 //   plonky2::fri::FriConfig / plonk::circuit_data::CircuitConfig presets
+//   plonky2::iop::challenger::Challenger, plonky2::fri::prover::fri_proof, PolynomialBatch::prove_openings (N1)
 //   src/smt/goldilocks_poseidon/mod.rs:158-184  PoseidonNodeHash::calc_node_hash
 //
 // Upstream is infallible and panics on contract violations; here a violation throws plonky2_b200::Panic.
 // Nothing in this header computes field arithmetic: every result comes from libgl_b200.so.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -242,6 +244,7 @@ class PolynomialBatch {
         ctx_->check(gl_commit_download(h_, leaves_row_major ? leaves_row_major->data() : nullptr,
                                        digests && !digests->empty() ? &(*digests)[0].elements[0] : nullptr, GL_HOST));
     }
+    gl_commit* raw_handle() const { return h_; }  // the resident commit (for the FRI functions below)
     PolynomialBatch(PolynomialBatch&& o) noexcept { *this = std::move(o); }
     PolynomialBatch& operator=(PolynomialBatch&& o) noexcept {
         std::swap(polynomials, o.polynomials);
@@ -292,5 +295,230 @@ class PolynomialBatch {
     gl_commit* h_ = nullptr;
     const Context* ctx_ = nullptr;
 };
+
+// ---- plonky2::iop::challenger::Challenger (host side of the Fiat-Shamir transcript) -----------------------------
+class Challenger {
+   public:
+    explicit Challenger(const Context& c) : ctx_(&c) {
+        for (auto& v : sponge_state) v = 0;
+    }
+    F sponge_state[12];
+    std::vector<F> input_buffer, output_buffer;
+
+    void observe_element(F e) {
+        output_buffer.clear();  // any buffered outputs are now invalid
+        input_buffer.push_back(e % 0xFFFFFFFF00000001ULL);
+        if (input_buffer.size() == PoseidonHash::SPONGE_RATE) duplexing();
+    }
+    void observe_elements(const F* es, size_t n) {
+        for (size_t i = 0; i < n; i++) observe_element(es[i]);
+    }
+    void observe_hash(const HashOut& h) { observe_elements(h.elements, 4); }
+    void observe_cap(const MerkleCap& cap) {
+        for (auto& h : cap) observe_hash(h);
+    }
+    void observe_extension_element(const F e[2]) { observe_elements(e, 2); }
+    F get_challenge() {
+        if (!input_buffer.empty() || output_buffer.empty()) duplexing();
+        F v = output_buffer.back();
+        output_buffer.pop_back();
+        return v;
+    }
+    void get_extension_challenge(F out[2]) {
+        out[0] = get_challenge();
+        out[1] = get_challenge();
+    }
+
+   private:
+    void duplexing() {
+        for (size_t i = 0; i < input_buffer.size(); i++) sponge_state[i] = input_buffer[i];  // overwrite mode
+        input_buffer.clear();
+        ctx_->check(gl_poseidon_permute_batch(ctx_->raw(), sponge_state, 1, GL_HOST));
+        output_buffer.assign(sponge_state, sponge_state + PoseidonHash::SPONGE_RATE);
+    }
+    const Context* ctx_;
+};
+
+// ---- plonky2::fri: FriParams, proof structures, fri_proof, PolynomialBatch::prove_openings ----------------------
+struct FriParams {
+    FriConfig config;
+    bool hiding = false;
+    uint32_t degree_bits = 0;
+    std::vector<uint32_t> reduction_arity_bits;
+    static FriParams for_degree(const FriConfig& cfg, uint32_t degree_bits) {
+        FriParams p;
+        p.config = cfg;
+        p.degree_bits = degree_bits;
+        p.reduction_arity_bits = cfg.reduction_strategy.reduction_arity_bits(degree_bits, cfg.rate_bits, cfg.cap_height);
+        return p;
+    }
+};
+struct FriBatchInfo {  // FriBatchInfo: polynomials (oracle_index, polynomial_index) opened at `point`
+    F point[2];
+    std::vector<std::pair<uint32_t, uint32_t>> polynomials;
+};
+struct FriQueryStep {
+    std::vector<F> evals;  // arity extension elements, flattened
+    MerkleProof merkle_proof;
+};
+struct FriQueryRound {
+    uint64_t x_index = 0;
+    std::vector<std::pair<std::vector<F>, MerkleProof>> initial_trees_proof;  // per oracle: (row, path)
+    std::vector<FriQueryStep> steps;
+};
+struct FriProof {
+    std::vector<MerkleCap> commit_phase_merkle_caps;
+    std::vector<FriQueryRound> query_round_proofs;
+    std::vector<F> final_poly;  // extension coefficients, flattened [len][2]
+    F pow_witness = 0;
+};
+
+namespace detail {
+struct DevBuf {  // gl_dev_alloc block
+    const Context* c;
+    void* p = nullptr;
+    DevBuf(const Context& ctx, size_t bytes) : c(&ctx) { ctx.check(gl_dev_alloc(ctx.raw(), bytes, &p)); }
+    ~DevBuf() { gl_dev_free(c->raw(), p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    uint64_t* u64() const { return static_cast<uint64_t*>(p); }
+};
+struct LayerTree {  // resident layer tree of fri_committed_trees
+    gl_commit* h = nullptr;
+    uint32_t arity_bits = 0, lg_leaves = 0;
+    MerkleCap cap;
+};
+inline F pow_mod(F b, uint64_t e) {
+    const unsigned __int128 P = 0xFFFFFFFF00000001ULL;
+    unsigned __int128 r = 1, x = b % (F)P;
+    while (e) {
+        if (e & 1) r = r * x % P;
+        x = x * x % P;
+        e >>= 1;
+    }
+    return (F)r;
+}
+inline std::pair<std::vector<std::vector<F>>, std::vector<MerkleProof>> open_handle(const Context& c, gl_commit* h, uint32_t cols,
+                                                                                   uint32_t path_len,
+                                                                                   const std::vector<uint64_t>& idx) {
+    const uint32_t k = (uint32_t)idx.size();
+    std::vector<F> rows((size_t)k * cols), paths((size_t)k * path_len * 4 + 4);
+    c.check(gl_commit_open(h, idx.data(), k, rows.data(), paths.data(), GL_HOST));
+    std::pair<std::vector<std::vector<F>>, std::vector<MerkleProof>> out;
+    for (uint32_t q = 0; q < k; q++) {
+        out.first.emplace_back(rows.begin() + (size_t)q * cols, rows.begin() + (size_t)(q + 1) * cols);
+        MerkleProof p;
+        for (uint32_t l = 0; l < path_len; l++) {
+            HashOut d;
+            for (int e = 0; e < 4; e++) d.elements[e] = paths[((size_t)q * path_len + l) * 4 + e];
+            p.siblings.push_back(d);
+        }
+        out.second.push_back(std::move(p));
+    }
+    return out;
+}
+}  // namespace detail
+
+// plonky2::fri::prover::fri_proof on device-resident inputs: lde_coeffs / lde_values are gl_dev_alloc blocks of
+// n extension elements ([n][2], natural order); the oracles answer the initial openings.  Commit phase
+// (fri_committed_trees), proof of work (smallest witness; upstream: any) and the query rounds.
+inline FriProof fri_proof_resident(const Context& c, const std::vector<const PolynomialBatch*>& oracles, uint64_t* lde_coeffs,
+                                   uint64_t* lde_values, uint64_t n, Challenger& challenger, const FriParams& fp) {
+    FriProof proof;
+    std::vector<detail::LayerTree> trees;
+    std::vector<std::unique_ptr<detail::DevBuf>> owned;  // folded coefficients / values of the layers
+    uint64_t *coeffs = lde_coeffs, *values = lde_values, len = n;
+    F shift = 7;  // F::MULTIPLICATIVE_GROUP_GENERATOR
+    uint32_t lg = 0;
+    while ((1ull << lg) < n) lg++;
+    for (uint32_t arity_bits : fp.reduction_arity_bits) {
+        detail::LayerTree t;
+        t.arity_bits = arity_bits;
+        t.lg_leaves = lg - arity_bits;
+        t.cap.resize(1ull << fp.config.cap_height);
+        detail::DevBuf cap_dev(c, t.cap.size() * 32);
+        c.check(gl_fri_layer_commit(c.raw(), values, len, arity_bits, fp.config.cap_height, cap_dev.u64(), &t.h, GL_DEVICE));
+        c.check(gl_copy(c.raw(), &t.cap[0].elements[0], GL_HOST, cap_dev.p, GL_DEVICE, t.cap.size() * 32));
+        challenger.observe_cap(t.cap);
+        proof.commit_phase_merkle_caps.push_back(t.cap);
+        trees.push_back(t);
+        F beta[2];
+        challenger.get_extension_challenge(beta);
+        shift = detail::pow_mod(shift, 1ull << arity_bits);
+        const uint64_t out_len = len >> arity_bits;
+        owned.emplace_back(new detail::DevBuf(c, out_len * 16));
+        owned.emplace_back(new detail::DevBuf(c, out_len * 16));
+        uint64_t* folded = owned[owned.size() - 2]->u64();
+        uint64_t* next = owned[owned.size() - 1]->u64();
+        c.check(gl_fri_fold(c.raw(), coeffs, len, arity_bits, beta, shift, folded, next, GL_DEVICE));
+        coeffs = folded;
+        values = next;
+        len = out_len;
+        lg -= arity_bits;
+    }
+    // the coefficients being removed here are always zero
+    const uint64_t final_len = len >> fp.config.rate_bits;
+    proof.final_poly.resize(final_len * 2);
+    c.check(gl_copy(c.raw(), proof.final_poly.data(), GL_HOST, coeffs, GL_DEVICE, final_len * 16));
+    challenger.observe_elements(proof.final_poly.data(), proof.final_poly.size());
+    // fri_proof_of_work
+    {
+        F state[12];
+        for (int i = 0; i < 12; i++) state[i] = challenger.sponge_state[i];
+        const uint32_t pos = (uint32_t)challenger.input_buffer.size();
+        for (uint32_t i = 0; i < pos; i++) state[i] = challenger.input_buffer[i];
+        const uint32_t min_lz = fp.config.proof_of_work_bits;  // + (64 - F::order().bits()) = + 0
+        c.check(gl_pow_grind(c.raw(), state, pos, min_lz, &proof.pow_witness));
+        challenger.observe_element(proof.pow_witness);
+        F response = challenger.get_challenge();
+        if (min_lz && (response >> (64 - min_lz))) throw Panic(GL_E_STATE, "fri_proof_of_work: invalid response");
+    }
+    // fri_prover_query_rounds: the challenger is only read here, so every x_index is drawn first and each tree
+    // answers all rounds with one gather
+    const uint32_t rounds = fp.config.num_query_rounds;
+    std::vector<uint64_t> xs(rounds);
+    for (auto& x : xs) x = challenger.get_challenge() % n;
+    proof.query_round_proofs.resize(rounds);
+    for (uint32_t q = 0; q < rounds; q++) proof.query_round_proofs[q].x_index = xs[q];
+    for (const PolynomialBatch* o : oracles) {
+        auto opened = o->open(xs);
+        for (uint32_t q = 0; q < rounds; q++)
+            proof.query_round_proofs[q].initial_trees_proof.emplace_back(std::move(opened.first[q]), std::move(opened.second[q]));
+    }
+    std::vector<uint64_t> idx = xs;
+    for (auto& t : trees) {
+        for (auto& x : idx) x >>= t.arity_bits;
+        auto opened = detail::open_handle(c, t.h, 2u << t.arity_bits, t.lg_leaves - fp.config.cap_height, idx);
+        for (uint32_t q = 0; q < rounds; q++)
+            proof.query_round_proofs[q].steps.push_back({std::move(opened.first[q]), std::move(opened.second[q])});
+        gl_commit_free(t.h);
+    }
+    return proof;
+}
+
+// plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params)
+inline FriProof prove_openings(const Context& c, const std::vector<FriBatchInfo>& instance,
+                               const std::vector<const PolynomialBatch*>& oracles, Challenger& challenger, const FriParams& fp) {
+    F alpha[2];
+    challenger.get_extension_challenge(alpha);
+    std::vector<gl_fri_batch> batches;
+    std::vector<gl_fri_poly> polys;
+    for (auto& b : instance) {
+        gl_fri_batch gb;
+        gb.point[0] = b.point[0];
+        gb.point[1] = b.point[1];
+        gb.first_poly = (uint32_t)polys.size();
+        gb.num_polys = (uint32_t)b.polynomials.size();
+        for (auto& pr : b.polynomials) polys.push_back({pr.first, pr.second});
+        batches.push_back(gb);
+    }
+    std::vector<gl_commit*> handles;
+    for (auto* o : oracles) handles.push_back(o->raw_handle());
+    const uint64_t n = (1ull << oracles[0]->degree_log) << fp.config.rate_bits;
+    detail::DevBuf coeffs(c, n * 16), values(c, n * 16);
+    c.check(gl_fri_final_poly(c.raw(), handles.data(), (uint32_t)handles.size(), batches.data(), (uint32_t)batches.size(),
+                              polys.data(), alpha, fp.config.rate_bits, coeffs.u64(), values.u64(), GL_DEVICE));
+    return fri_proof_resident(c, oracles, coeffs.u64(), values.u64(), n, challenger, fp);
+}
 
 }  // namespace plonky2_b200
