@@ -97,6 +97,18 @@ typedef struct {
 int gl_smt_verify_process_batch(gl_ctx *ctx, const gl_smt_proof_hdr *proofs, const uint64_t *sib_pool,
                                 const uint64_t *sib_off, uint64_t m, int32_t *status, int space);
 
+/* ---- N2: bulk build of the sparse Merkle tree (src/smt/tree.rs) ------------------------------------------------- */
+/* The root (and optionally every internal node) of the compact sparse Merkle tree holding m DISTINCT keys with
+ * non-default values: what m successive SparseMerkleTree::set calls (src/smt/tree.rs:143-155; insert :255-387) on an
+ * empty PoseidonSparseMerkleTreeMemory leave behind, in any order (insert-only batches are order independent).
+ * keys, values [m][4]; root_out [4]; nodes_out [nodes_cap][12] = (hash, left, right) of every Node::Internal the
+ * NodeData store would hold, unordered (may be NULL); leaf_hashes_out [m][4] in input order (may be NULL);
+ * *num_nodes_out = internal nodes produced (can exceed nodes_cap: only the first nodes_cap are stored).
+ * Duplicate keys return GL_E_ARG ("given key already exists"). */
+int gl_smt_build(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m, uint64_t *root_out,
+                 uint64_t *nodes_out, uint64_t nodes_cap, uint64_t *num_nodes_out, uint64_t *leaf_hashes_out,
+                 int space);
+
 /* ---- P4: MerkleTree::new(leaves: Vec<Vec<F>>, cap_height) (plonky2::hash::merkle_tree) --------- */
 /* leaves [num_leaves][leaf_len] row-major; digests_out [2*(num_leaves - 2^cap_height)][4] in
  * plonky2's recursive in-order layout (what MerkleTree::prove indexes); cap_out [2^cap_height][4].

@@ -29,6 +29,7 @@
 #include "hash_kernels.h"
 #include "ntt_kernels.h"
 #include "poseidon_constants.h"
+#include "smt_kernels.h"
 
 std::atomic<unsigned long long> g_gl_launches{0};
 
@@ -681,6 +682,78 @@ extern "C" int gl_smt_verify_process_batch(gl_ctx* ctx, const gl_smt_proof_hdr* 
     TRY(scratch_get(ctx, 3, m * 4, &dst));
     launch_smt_verify_process((const gl_smt_proof_hdr*)dp, dpool, doff, m, (int*)dst, ctx->stream);
     TRY(copy_out(ctx, status, dst, m * 4, GL_HOST));
+    return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// N2: bulk sparse Merkle tree
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m, uint64_t* root_out,
+                            uint64_t* nodes_out, uint64_t nodes_cap, uint64_t* num_nodes_out, uint64_t* leaf_hashes_out,
+                            int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!root_out || (m && (!keys || !values))) return fail(ctx, GL_E_ARG, "gl_smt_build: NULL buffer");
+    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_build: at most 2^31 - 1 entries");
+    Guard g(ctx);
+    if (m == 0) {
+        if (num_nodes_out) *num_nodes_out = 0;
+        if (space == GL_HOST) memset(root_out, 0, 32);
+        else CK(cudaMemsetAsync(root_out, 0, 32, ctx->stream));
+        return finish(ctx);
+    }
+    smt_build_buffers b;
+    memset(&b, 0, sizeof b);
+    b.m = m;
+    const u64 *dk, *dv;
+    TRY(stage_in(ctx, keys, m * 32, space, 0, &dk));
+    TRY(stage_in(ctx, values, m * 32, space, 1, &dv));
+    b.keys = dk;
+    b.values = dv;
+    b.sort_tmp_bytes = smt_sort_temp_bytes(m);
+    // one scratch block carved into the work arrays (all 8-byte aligned)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
+    const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
+                 o_lcp = take(m * 2), o_vf = take(m * 32), o_vl = take(m * 32), o_end = take(m * 4), o_start = take(m * 4),
+                 o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4), o_cnt = take(8), o_root = take(32),
+                 o_tmp = take(b.sort_tmp_bytes), o_lh = take(leaf_hashes_out && space == GL_HOST ? m * 32 : 0),
+                 o_nodes = take(nodes_out && space == GL_HOST ? nodes_cap * 96 : 0);
+    void* base;
+    TRY(scratch_get(ctx, 2, off, &base));
+    char* p = (char*)base;
+    b.rk = (u64*)(p + o_rk); b.rk_alt = (u64*)(p + o_rka); b.perm = (uint32_t*)(p + o_perm); b.perm_alt = (uint32_t*)(p + o_perma);
+    b.leafh = (u64*)(p + o_leafh); b.lcp = (uint16_t*)(p + o_lcp); b.val_first = (u64*)(p + o_vf); b.val_last = (u64*)(p + o_vl);
+    b.end_of = (uint32_t*)(p + o_end); b.start_of = (uint32_t*)(p + o_start); b.form_depth = (uint16_t*)(p + o_fd);
+    b.last_valid = (uint8_t*)(p + o_lv); b.hist = (uint32_t*)(p + o_hist); b.node_count = (unsigned long long*)(p + o_cnt);
+    b.sort_tmp = p + o_tmp;
+    b.leaf_hashes = leaf_hashes_out ? (space == GL_HOST ? (u64*)(p + o_lh) : leaf_hashes_out) : nullptr;
+    b.nodes = nodes_out ? (space == GL_HOST ? (u64*)(p + o_nodes) : nodes_out) : nullptr;
+    b.nodes_cap = nodes_out ? nodes_cap : 0;
+    u64* d_root = (u64*)(p + o_root);
+    CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 0, ctx->stream));
+    CK(cudaMemsetAsync(b.node_count, 0, 8, ctx->stream));
+    int rc = smt_build_prepare(b, ctx->stream);
+    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_build: sort");
+    uint32_t hist[257];
+    CK(cudaMemcpyAsync(hist, b.hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (hist[256]) return fail(ctx, GL_E_ARG, "SparseMerkleTree::insert: given key already exists (duplicate keys in the batch)");
+    int dmax = -1;
+    for (int d = 255; d >= 0; d--)
+        if (hist[d]) { dmax = d; break; }
+    for (int d = dmax; d >= 0; d--) smt_build_level(b, (unsigned)d, ctx->stream);
+    // m == 1: the single leaf is the root; else the group [0, m-1] climbed to depth 0
+    CK(cudaMemcpyAsync(d_root, m == 1 ? b.leafh : b.val_first, 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    TRY(copy_out(ctx, root_out, d_root, 32, space));
+    unsigned long long count = 0;
+    CK(cudaMemcpyAsync(&count, b.node_count, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (num_nodes_out) *num_nodes_out = count;
+    if (space == GL_HOST) {
+        if (leaf_hashes_out) TRY(copy_out(ctx, leaf_hashes_out, b.leaf_hashes, m * 32, GL_HOST));
+        if (nodes_out) TRY(copy_out(ctx, nodes_out, b.nodes, (count < nodes_cap ? count : nodes_cap) * 96, GL_HOST));
+    }
     return finish(ctx);
 }
 

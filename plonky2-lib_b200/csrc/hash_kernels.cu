@@ -463,3 +463,6 @@ void launch_merkle_rows(const u64* leaves, u32 leaf_len, unsigned lg_leaves, uns
         { k_merkle_level<<<nblk(nodes, HASH_BLOCK), HASH_BLOCK, 0, st>>>(digests, cap, sub_bits, layer, nodes); ++g_gl_launches; }
     }
 }
+
+// N2: SMT bulk build (shares this translation unit's Poseidon constants)
+#include "smt_kernels.cu"

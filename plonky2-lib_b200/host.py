@@ -687,3 +687,34 @@ def smt_check_process_proofs(headers: np.ndarray, sib_pool: np.ndarray, sib_off:
     status = np.empty(m, dtype=np.int32)
     ctx.check(ctx._lib.gl_smt_verify_process_batch(ctx._h, hd.ctypes.data, pool.ctypes.data, off.ctypes.data, m, status.ctypes.data, N.GL_HOST))
     return status
+
+
+def smt_build_tree(keys, values, want_nodes: bool = False, ctx=None):
+    """N2: the sparse Merkle tree of src/smt/tree.rs holding `keys -> values`, built in one pass on the device.
+    Returns root [4] (and, with want_nodes, the internal nodes [(hash, left, right)] as an [k][12] array plus the
+    leaf hashes [m][4]): what m successive `tree.set(key, value)` calls leave in the root and node stores.
+    Entries whose value is all zero are dropped first (`set` with the default value is a removal, tree.rs:143-155)."""
+    ctx = _ctx(ctx)
+    k, v = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4)
+    if k.shape != v.shape:
+        raise GlPanic(N.GL_E_ARG, "smt_build_tree: keys and values differ in shape")
+    keep = v.any(axis=1)
+    k, v = np.ascontiguousarray(k[keep]), np.ascontiguousarray(v[keep])
+    m = k.shape[0]
+    root = np.zeros(4, dtype=np.uint64)
+    count = C.c_uint64(0)
+    if want_nodes:
+        cap = max(4 * m + 1024, 1024)
+        nodes = np.empty((cap, 12), dtype=np.uint64)
+        leaf_hashes = np.empty((m, 4), dtype=np.uint64)
+        while True:
+            ctx.check(ctx._lib.gl_smt_build(ctx._h, k.ctypes.data, v.ctypes.data, m, root.ctypes.data, nodes.ctypes.data, cap,
+                                            C.byref(count), leaf_hashes.ctypes.data, N.GL_HOST))
+            if count.value <= cap:
+                break
+            cap = int(count.value)
+            nodes = np.empty((cap, 12), dtype=np.uint64)
+        return root, nodes[: count.value].copy(), leaf_hashes
+    ctx.check(ctx._lib.gl_smt_build(ctx._h, k.ctypes.data, v.ctypes.data, m, root.ctypes.data, None, 0, C.byref(count), None,
+                                    N.GL_HOST))
+    return root

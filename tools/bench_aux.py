@@ -94,6 +94,14 @@ out["smt_verify_process_batch"] = {"proofs": mm, "avg_siblings": float(ns.mean()
                                    "perms_per_s": mm * 516 / t}
 del d_pool, d_hdr
 
+# N2: bulk build of the sparse Merkle tree over 2^20 entries (BASELINE config 4: "batch of 2^20 native leaf updates")
+mk = 1 << 20
+kk = rng.integers(0, P, (mk, 4), dtype=np.uint64)
+vv = rng.integers(1, P, (mk, 4), dtype=np.uint64)
+t = timeit(lambda: glb.host.smt_build_tree(kk, vv), 2)
+out["smt_build_tree"] = {"entries": mk, "ms": t * 1e3, "entries_per_s": mk / t, "note": "host buffers: 64 MB H2D inside the call"}
+del kk, vv
+
 # FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
 ln = 1 << 23
 vals = rand_dev((ln, 2))
