@@ -12,8 +12,9 @@ A step = one commit.
   cpu_baseline: the CPU oracle (a port of plonky2 v0.1.4 semantics, oracle/) on a bounded sample, rank 0, N=1.
 
 N > 1 (torchrun, one rank per GPU): one commit sharded by LDE coset = top-level Merkle subtree
-(SURVEY 8e).  Rank r inverse-transforms its column slice, NCCL all-gathers the coefficients, builds
-its leaf blocks + subtrees, NCCL all-gathers the cap: total work fixed => "strong" scaling.
+(SURVEY 8e).  Rank r inverse-transforms its share of the columns, the coefficients are NCCL all-gathered in a
+few rounds that overlap the LDE of the previous round, every rank builds its leaf blocks + subtrees, and the
+cap is NCCL all-gathered: total work fixed => "strong" scaling.
 
 --impl reference: the reference's CPU implementation of the path is Rust in an un-vendored crate and
 cannot be built here (no cargo); the reference arm times the oracle port on all host cores.
@@ -223,25 +224,32 @@ def main():
             lib.gl_commit_free(h)
             return cap_dev
     else:
-        # column slice of this rank for the IFFT; ragged split, padded to equal size for the all-gather
+        # Pipelined plan (plonky2-lib_b200/parallel.py round_blocks): the columns are cut into ~5 rounds of W * G
+        # consecutive columns; rank r inverse-transforms G of them per round; round j is all-gathered on NCCL's
+        # stream while the LDE of round j - 1 runs on the library's stream (gl_commit_begin / add_coeffs / finish).
         par = importlib.import_module("plonky2-lib_b200.parallel")
         par.check_shardable(world, RATE_BITS, CAP_HEIGHT)
-        c0, c1, per = par.column_slice(rank, world, cols)
+        G, rounds, mine = par.round_blocks(rank, world, cols)
         ctx.set_shard(rank, world)
-        slice_buf = torch.zeros((per, n), dtype=torch.int64, device=dev)
-        gathered = torch.empty((world * per, n), dtype=torch.int64, device=dev)
+        slice_buf = torch.zeros((rounds, G, n), dtype=torch.int64, device=dev)
+        stage = torch.empty((rounds, world * G, n), dtype=torch.int64, device=dev)
         cap_all = torch.zeros((1 << CAP_HEIGHT, 4), dtype=torch.int64, device=dev)
         k0, k1 = par.cap_range(rank, world, CAP_HEIGHT)
 
         def step():
-            if c1 > c0:
-                slice_buf[: c1 - c0].copy_(values[c0:c1])
-                ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf.data_ptr(), log_n, c1 - c0, N.GL_DEVICE))
-            par.all_gather_coefficients(dist, slice_buf, gathered, cols)  # every column's coefficients on every rank
-            torch.cuda.current_stream().synchronize()
+            for j, (c0, c1) in enumerate(mine):
+                if c1 > c0:
+                    slice_buf[j, : c1 - c0].copy_(values[c0:c1])
+            # one IFFT launch over all of this rank's columns (padding rows are zeros and stay zeros)
+            ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf.data_ptr(), log_n, rounds * G, N.GL_DEVICE))
+            works = [dist.all_gather_into_tensor(stage[j], slice_buf[j], async_op=True) for j in range(rounds)]
             h = C.c_void_p()
-            ctx.check(lib.gl_commit_from_coeffs(ctx._h, gathered.data_ptr(), log_n, cols, RATE_BITS, CAP_HEIGHT,
-                                                cap_dev.data_ptr(), C.byref(h), N.GL_DEVICE))
+            ctx.check(lib.gl_commit_begin(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT, C.byref(h)))
+            for j in range(rounds):
+                works[j].wait()                       # the library's stream waits for round j; the host does not
+                c0 = j * world * G
+                ctx.check(lib.gl_commit_add_coeffs(h, c0, min(world * G, cols - c0), stage[j].data_ptr(), N.GL_DEVICE))
+            ctx.check(lib.gl_commit_finish(h, cap_dev.data_ptr(), N.GL_DEVICE))
             phases.append(ctx.commit_phase_ms())
             lib.gl_commit_free(h)
             par.all_gather_cap(dist, cap_dev[k0:k1].contiguous(), cap_all)  # MerkleCap: 2^cap_height digests
@@ -375,7 +383,7 @@ def main():
         "config": {
             "workload": workload_name(log_n, cols), "cells_per_step": cells,
             "l2": "inputs (1.13 GB) and LDE (9.06 GB) are larger than the 126 MB L2; no flush needed",
-            "parallelism": "single GPU" if world == 1 else f"{world} GPUs: IFFT by column slice + NCCL all-gather of coefficients, LDE/Merkle by coset block, NCCL all-gather of the cap",
+            "parallelism": "single GPU" if world == 1 else f"{world} GPUs: IFFT by column blocks, NCCL all-gather of the coefficients in ~5 rounds overlapped with the LDE of the previous round, LDE/Merkle by coset block, NCCL all-gather of the cap",
         },
         "phases_ms": phase_mean, "wall_ms_per_step": wall / args.steps * 1e3,
         "roofline": roofline, "roofline_int": roofline_int, "clocks": clocks, "gpu_launches": int(launches),

@@ -141,6 +141,13 @@ int gl_commit_from_values(gl_ctx *ctx, const uint64_t *values, uint32_t log_n, u
 int gl_commit_from_coeffs(gl_ctx *ctx, const uint64_t *coeffs, uint32_t log_n, uint32_t c,
                           uint32_t rate_bits, uint32_t cap_height, uint64_t *cap_out,
                           gl_commit **handle, int space);
+/* The same commit fed column block by column block (from_coeffs as a stream): begin allocates the resident buffers,
+ * add_coeffs copies the coefficients of polynomials [col0, col0 + ncols) ([ncols][2^log_n]) behind the handle and runs
+ * their LDE, finish hashes the leaves and builds the tree once every column has arrived.  Lets a caller overlap the
+ * arrival of coefficients (PCIe, or an NCCL all-gather in the multi-GPU plan) with the transforms of earlier blocks. */
+int gl_commit_begin(gl_ctx *ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height, gl_commit **handle);
+int gl_commit_add_coeffs(gl_commit *h, uint32_t col0, uint32_t ncols, const uint64_t *coeffs, int space);
+int gl_commit_finish(gl_commit *h, uint64_t *cap_out, int space);
 /* PolynomialBatch.polynomials: the coefficients [c][2^log_n] kept on the device behind the handle. */
 int gl_commit_coeffs(gl_commit *h, uint64_t *coeffs_out, int space);
 /* "mirror mode": fill the upstream structs.  leaves_out [N_local][c] row-major in leaf order

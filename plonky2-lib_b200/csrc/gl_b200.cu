@@ -80,6 +80,8 @@ struct gl_commit {
     u64* cap = nullptr;        // [2^cap_local_bits][4]
     uint64_t num_digests = 0;
     size_t coeffs_bytes = 0, lde_bytes = 0, digests_bytes = 0, cap_bytes = 0;
+    uint32_t cols_added = 0;   // gl_commit_begin / add_coeffs / finish
+    bool finished = true;
 };
 
 static int fail(gl_ctx* ctx, int code, const std::string& msg) {
@@ -1004,6 +1006,57 @@ extern "C" int gl_commit_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs, uint32
                          "PolynomialBatch::from_coeffs");
 }
 
+extern "C" int gl_commit_begin(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height,
+                               gl_commit** handle) {
+    if (!ctx) return GL_E_ARG;
+    if (!handle) return fail(ctx, GL_E_ARG, "gl_commit_begin: NULL handle");
+    *handle = nullptr;
+    TRY(commit_check(ctx, log_n, c, rate_bits, cap_height, "PolynomialBatch::from_coeffs"));
+    Guard g(ctx);
+    gl_commit* h = new (std::nothrow) gl_commit();
+    if (!h) return fail(ctx, GL_E_OOM, "host allocation failed");
+    h->ctx = ctx; h->log_n = log_n; h->c = c; h->rate_bits = rate_bits; h->cap_height = cap_height;
+    h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
+    h->coeffs_bytes = ((size_t)c << log_n) * 8;
+    h->finished = false;
+    int rc = dev_alloc(ctx, h->coeffs_bytes, &h->coeffs);
+    if (rc == GL_OK) rc = commit_prepare(ctx, h);
+    if (rc != GL_OK) {
+        commit_release(h);
+        return rc;
+    }
+    for (int i = 0; i <= 3; i++) mark(ctx, i);
+    ctx->live_commits++;
+    *handle = h;
+    return GL_OK;
+}
+extern "C" int gl_commit_add_coeffs(gl_commit* h, uint32_t col0, uint32_t ncols, const uint64_t* coeffs, int space) {
+    if (!h) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    if (h->finished) return fail(ctx, GL_E_STATE, "gl_commit_add_coeffs: the commit is already finished");
+    if (!coeffs || ncols == 0 || col0 + (uint64_t)ncols > h->c) return fail(ctx, GL_E_ARG, "gl_commit_add_coeffs: bad column range");
+    Guard g(ctx);
+    const u64 n = (u64)1 << h->log_n;
+    CK(cudaMemcpyAsync(h->coeffs + (size_t)col0 * n, coeffs, (size_t)ncols * n * 8,
+                       space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    TRY(commit_lde_columns(ctx, h, col0, ncols));
+    h->cols_added += ncols;
+    return finish(ctx);
+}
+extern "C" int gl_commit_finish(gl_commit* h, uint64_t* cap_out, int space) {
+    if (!h) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    if (h->finished) return fail(ctx, GL_E_STATE, "gl_commit_finish: the commit is already finished");
+    if (h->cols_added != h->c) return fail(ctx, GL_E_STATE, "gl_commit_finish: not every polynomial has been added");
+    Guard g(ctx);
+    TRY(commit_tree(ctx, h, cap_out, space));
+    TRY(finish(ctx));
+    h->finished = true;
+    for (int i = 0; i < GL_PHASES; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
+    ctx->ev_valid = true;
+    return GL_OK;
+}
+
 extern "C" void gl_commit_free(gl_commit* h) {
     if (!h) return;
     gl_ctx* ctx = h->ctx;
@@ -1046,6 +1099,7 @@ extern "C" int gl_commit_coeffs(gl_commit* h, uint64_t* coeffs_out, int space) {
 extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* digests_out, int space) {
     if (!h) return GL_E_ARG;
     gl_ctx* ctx = h->ctx;
+    if (!h->finished) return fail(ctx, GL_E_STATE, "gl_commit_download: gl_commit_finish has not run yet");
     Guard g(ctx);
     if (digests_out) TRY(copy_out(ctx, digests_out, h->digests, h->num_digests * 32, space));
     if (leaves_out) {
@@ -1091,6 +1145,7 @@ extern "C" int gl_commit_open(gl_commit* h, const uint64_t* leaf_indices, uint32
                               uint64_t* paths_out, int space) {
     if (!h) return GL_E_ARG;
     gl_ctx* ctx = h->ctx;
+    if (!h->finished) return fail(ctx, GL_E_STATE, "gl_commit_open: gl_commit_finish has not run yet");
     if (k == 0) return GL_OK;
     if (!leaf_indices) return fail(ctx, GL_E_ARG, "gl_commit_open: NULL indices");
     Guard g(ctx);
@@ -1131,6 +1186,7 @@ extern "C" int gl_commit_get_lde_values(gl_commit* h, const uint64_t* indices, u
                                         uint64_t* rows_out, int space) {
     if (!h) return GL_E_ARG;
     gl_ctx* ctx = h->ctx;
+    if (!h->finished) return fail(ctx, GL_E_STATE, "gl_commit_get_lde_values: gl_commit_finish has not run yet");
     if (k == 0) return GL_OK;
     if (!indices || !rows_out) return fail(ctx, GL_E_ARG, "gl_commit_get_lde_values: NULL buffer");
     Guard g(ctx);

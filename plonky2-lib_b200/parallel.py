@@ -21,6 +21,20 @@ def column_slice(rank: int, world: int, cols: int) -> Tuple[int, int, int]:
     return min(rank * per, cols), min((rank + 1) * per, cols), per
 
 
+def round_blocks(rank: int, world: int, cols: int, target_rounds: int = 5):
+    """Pipelined plan: the columns are cut into rounds of world * G consecutive columns; inside round j rank r
+    inverse-transforms the G columns [j * world * G + r * G, + G).  An all-gather of the G columns of every rank
+    then yields the round's world * G coefficient columns contiguously, so the LDE of round j can run while
+    round j + 1 is on the wire.  Returns (G, rounds, [(first, last) of this rank's real columns per round])."""
+    G = max(1, -(-cols // (world * target_rounds)))
+    rounds = -(-cols // (world * G))
+    mine = []
+    for j in range(rounds):
+        first = j * world * G + rank * G
+        mine.append((min(first, cols), min(first + G, cols)))
+    return G, rounds, mine
+
+
 def leaf_range(rank: int, world: int, num_leaves: int) -> Tuple[int, int]:
     per = num_leaves // world
     return rank * per, (rank + 1) * per

@@ -368,3 +368,30 @@ def test_config2_full_size_properties(glb, ctx, oracle):
     assert np.array_equal(b.get_lde_values(i, 8), b.open([leaf])[0][0])
     b.free()
     ctx.trim()
+
+
+def test_streaming_commit_equals_from_coeffs(glb, ctx, oracle, rng):
+    """gl_commit_begin / add_coeffs / finish (from_coeffs fed column block by column block, in any order)."""
+    import ctypes as C
+
+    lib, N = ctx._lib, glb._native
+    c, lg = 21, 9
+    coeffs = rand_field(rng, (c, 1 << lg))
+    want = oracle.commit_from_coeffs(coeffs, 3, 4)
+    h = C.c_void_p()
+    ctx.check(lib.gl_commit_begin(ctx._h, lg, c, 3, 4, C.byref(h)))
+    cap = np.zeros((16, 4), dtype=np.uint64)
+    assert lib.gl_commit_finish(h, cap.ctypes.data, N.GL_HOST) == N.GL_E_STATE          # columns missing
+    rows = np.zeros((1, c), dtype=np.uint64)
+    idx = np.zeros(1, dtype=np.uint64)
+    assert lib.gl_commit_open(h, idx.ctypes.data, 1, rows.ctypes.data, None, N.GL_HOST) == N.GL_E_STATE
+    for col0, nc in [(16, 5), (0, 8), (8, 8)]:
+        blk = np.ascontiguousarray(coeffs[col0:col0 + nc])
+        ctx.check(lib.gl_commit_add_coeffs(h, col0, nc, blk.ctypes.data, N.GL_HOST))
+    assert lib.gl_commit_add_coeffs(h, 20, 2, coeffs.ctypes.data, N.GL_HOST) == N.GL_E_ARG
+    ctx.check(lib.gl_commit_finish(h, cap.ctypes.data, N.GL_HOST))
+    assert np.array_equal(cap, want["cap"])
+    leaves = np.zeros(((1 << lg) << 3, c), dtype=np.uint64)
+    ctx.check(lib.gl_commit_download(h, leaves.ctypes.data, None, N.GL_HOST))
+    assert np.array_equal(leaves, want["leaves"])
+    lib.gl_commit_free(h)

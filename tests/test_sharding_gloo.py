@@ -70,7 +70,61 @@ def test_sharded_commit_plan_world2(cols):
     assert res[0][2] == [0, 0, 0, 1] and res[1][2] == [0, 1, 1, 1]
 
 
+def _worker_interleaved(rank, world, port, cols, lg_n, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from oracle import pyoracle as o
+
+    par = importlib.import_module("plonky2-lib_b200.parallel")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = 1 << lg_n
+        values = o.synthetic_values(cols, n)
+        G, rounds, mine = par.round_blocks(rank, world, cols, target_rounds=2)
+        sl = np.zeros((rounds, G, n), dtype=np.uint64)
+        for j, (c0, c1) in enumerate(mine):
+            for col in range(c0, c1):
+                sl[j, col - c0] = o.ifft(values[col])
+        slice_buf = torch.from_numpy(sl.view(np.int64))
+        coeffs = np.zeros((cols, n), dtype=np.uint64)
+        for j in range(rounds):            # round j: G columns from every rank = world * G consecutive global columns
+            stage = torch.empty((world * G, n), dtype=torch.int64)
+            dist.all_gather_into_tensor(stage, slice_buf[j])
+            c0 = j * world * G
+            nc = min(world * G, cols - c0)
+            coeffs[c0: c0 + nc] = stage.numpy().view(np.uint64)[:nc]
+        ref = o.commit_from_values(values, 3, 4, want_leaves=False)
+        q.put((rank, bool(np.array_equal(coeffs, ref["coeffs"]))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_interleaved_column_plan_world2():
+    """The pipelined plan of bench.py --gpus N: round j gathers G columns per rank into consecutive global columns."""
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_worker_interleaved, args=(r, 2, port, 7, 6, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
 def test_plan_helpers():
+    par = importlib.import_module("plonky2-lib_b200.parallel")
+    G, rounds, mine = par.round_blocks(1, 8, 135)
+    assert (G, rounds) == (4, 5) and mine[0] == (4, 8) and mine[4] == (132, 135)
+    assert par.round_blocks(7, 8, 135)[2][4] == (135, 135)            # nothing left for the last rank in the last round
+    assert sum(c1 - c0 for r in range(8) for c0, c1 in par.round_blocks(r, 8, 135)[2]) == 135
     par = importlib.import_module("plonky2-lib_b200.parallel")
     assert par.column_slice(0, 8, 135) == (0, 17, 17)
     assert par.column_slice(7, 8, 135) == (119, 135, 17)
