@@ -1,9 +1,11 @@
 // Poseidon batch / Merkle / SMT kernels (8a rows P4-P7, P10).
 //
-// Every kernel is "one Poseidon state per thread": the work is integer-pipe bound (about 2*10^4
-// SASS instructions per permutation against at most 1 KB of traffic per leaf), so the only memory
-// rule that matters is that a warp's loads coalesce -- leaves are therefore kept COLUMN-major on the
-// device ([column][leaf]) so that 32 consecutive leaves read 256 contiguous bytes per column.
+// Every kernel is "one Poseidon state per thread": the work is issue bound (about 1.7*10^4 SASS
+// instructions per permutation, a third of them DFMA, against at most 1.1 KB of traffic per leaf), so the
+// only memory rule that matters is that a warp's loads coalesce -- leaves are therefore kept
+// COLUMN-major on the device ([column][leaf]) so that 32 consecutive leaves read 256 contiguous bytes
+// per column.  Each kernel has ONE inlined permutation site (a second copy of the 33 KB round code
+// pushes a kernel out of the instruction cache); kernels with several hash sites call it out of line.
 #include <cuda_runtime.h>
 
 #include "hash_kernels.h"

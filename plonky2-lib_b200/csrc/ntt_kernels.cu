@@ -1,8 +1,10 @@
 // Batched Goldilocks NTT passes (8a rows P1, P2, P3, P9).
 //
 // A size-2^L transform of one column is done as up to three decimation-in-frequency passes over
-// disjoint groups of index bits, each pass = shared-memory radix-2 stages over 2^m points followed
-// by the "four-step" twiddle.  Natural order in, bit-reversed order out, in place per index bits:
+// disjoint groups of index bits, each pass = 2^m-point DFTs followed by the "four-step" twiddle.
+// Passes of m = 8..10 bits run in k_ntt16 (radix-16 rounds in registers, second half of this file);
+// k_ntt_pass (shared-memory radix-2 stages, any m <= 10) takes the small leftover pass.
+// Natural order in, bit-reversed order out, in place per index bits:
 //
 //     pass (m, s):  for every (outer, j_lo):  x[outer][.][j_lo]  <-  DFT_{2^m}(x[outer][.][j_lo])
 //                   stored at bit-reversed position, then times w_{2^(s+m)}^(k * j_lo)
@@ -93,11 +95,8 @@ k_ntt_pass(ntt_pass_args a) {
 void launch_ntt_pass(const ntt_pass_args& a, u64 n, u32 columns, u32 cosets, cudaStream_t st) {
     u64 E = a.rows * a.T;
     size_t smem = (E + (((u64)1 << a.m) / 2)) * sizeof(u64);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
+    // per launch (cheap) rather than once per process: the attribute is per device
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     dim3 grid((unsigned)(n / E), columns, cosets);
     { k_ntt_pass<<<grid, NTT_THREADS, smem, st>>>(a); ++g_gl_launches; }
 }
