@@ -141,4 +141,43 @@ t = timeit(run_open, 2)
 out["prove_openings_2^20"] = {"oracles": list(cols), "ms": t * 1e3, "fri_final_poly_ms_incl_d2h": t_final * 1e3,
                               "note": "alpha reduction of 275 polynomial openings, division, LDE, 4 FRI layers, 16-bit PoW, 28 queries; "
                                       "the FRI polynomial and every layer stay in HBM; only caps, the final coefficients and the 28 opened rows + paths cross PCIe (host Challenger)"}
+# "Plonky2 prove ms per circuit" (BASELINE.json metric, first half) as far as this path goes: the commit + opening
+# trace of one data.prove(pw) -- wires, Z/partial products, quotient commits and prove_openings over those three plus
+# the build-time constants+sigmas oracle -- at the row counts SURVEY 8d estimates for BASELINE configs 1, 3, 4(ii), 5.
+# Witness generation and compute_quotient_polys stay on the host in the reference and are not part of this number.
+for b in batches:
+    b.free()
+ctx.trim()
+
+
+def proof_trace(lg):
+    n_ = 1 << lg
+    vals_ = [rand_dev((c, n_)).cpu().numpy().view(np.uint64) % np.uint64(P) for c in (84, 135, 20, 16)]
+    const_sigmas = glb.PolynomialBatch.from_values(vals_[0], 3, False, 4, want_coeffs=False)   # CircuitBuilder::build
+    g_ = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - lg), P)
+    inst = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+            ((zeta[0] * g_ % P, zeta[1] * g_ % P), [(2, pi) for pi in range(20)])]
+    prm = fri.FriParams.for_degree(glb.FriConfig(), lg)
+
+    def once():
+        bs = [const_sigmas] + [glb.PolynomialBatch.from_values(v, 3, False, 4, want_coeffs=True) for v in vals_[1:]]
+        ch = fri.Challenger()
+        for b in bs:
+            ch.observe_cap(b.merkle_tree.cap)
+        fri.prove_openings(bs, inst, ch, prm)
+        for b in bs[1:]:
+            b.free()
+
+    t_ = timeit(once, 3)
+    const_sigmas.free()
+    return t_ * 1e3
+
+
+out["proof_trace_ms"] = {
+    "what": "3 commits (135 + 20 + 16 columns, pageable host buffers in and coefficients out) + prove_openings over 4 oracles",
+    "config1_ecdsa_2^16_rows": proof_trace(16),
+    "config4_smt_256_inclusions_2^15_rows": proof_trace(15),
+    "config3_keccak_64_blocks_2^18_rows": proof_trace(18),
+    "config5_outer_recursion_2^13_rows": proof_trace(13),
+}
 print(json.dumps(out))
