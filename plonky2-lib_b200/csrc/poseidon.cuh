@@ -117,79 +117,123 @@ GL_D u64 poseidon_fold(double al, double ah) {
 //   y0 = M[0] . x~ + rc[a+1][0]                     -> S-box of round a + 1 -> sigma
 //   z  = N x~ + K + M[.][0] * sigma                 (N = M M' without the lane-0 path)
 // 336 DFMA instead of 576, 13 folds instead of 24; every partial sum stays below 2^50 (exact).
+// ------------------------------------------------------------------------------------------------------------
+// Circulant products through a 4 x 3 Good-Thomas FFT (exact, FP64 pipe).
+//
+// y_r = sum_i CIRC[i] x_{(i+r) mod 12} is a cyclic convolution over Z_12 = Z_4 x Z_3 (index n <-> (n mod 4, n mod 3),
+// no twiddles).  A real FFT of length 4 along the Z_4 axis leaves, for the frequencies 0, 1 (complex) and 2, one
+// length-3 cyclic convolution each; the inverse FFT's 1/4 is absorbed into the kernel, which stays integral
+// because plonky2's MDS row was chosen that way: FFT4(row)/4 = {16,32,16}, {(2,1),(-1,4),(-16,1)}/.., {-1,8,2}.
+// 90 FP64 operations per 12-vector instead of 144 multiply-adds; every intermediate is an integer below 2^50 in
+// units of 2^-1074 (signed: differences can be negative denormals), so the arithmetic is exact and the final,
+// non-negative results are again integer bit patterns.  SQ = 1 applies the circulant twice (kernel convolved with
+// itself), which is what the fused partial-round pair needs.
+template <int SQ>
+GL_D void poseidon_circ12(const double x[12], double y[12]) {
+    constexpr double K0[2][3] = {{16., 32., 16.}, {5120., 5120., 6144.}};
+    constexpr double K2[2][3] = {{-1., 8., 2.}, {132., -48., 240.}};
+    constexpr double KR[2][3] = {{2., -1., -16.}, {54., 486., -162.}};
+    constexpr double KI[2][3] = {{1., 4., 1.}, {-252., -36., -72.}};
+    constexpr int IDX[4][3] = {{0, 4, 8}, {9, 1, 5}, {6, 10, 2}, {3, 7, 11}};   // lane with (n mod 4, n mod 3) = (a, b)
+    double U0[3], U2[3], UR[3], UI[3];
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const double p0 = x[IDX[0][b]], p1 = x[IDX[1][b]], p2 = x[IDX[2][b]], p3 = x[IDX[3][b]];
+        const double t0 = p0 + p2, t1 = p1 + p3;
+        U0[b] = t0 + t1;
+        U2[b] = t0 - t1;
+        UR[b] = p0 - p2;      // F1 = (p0 - p2) + i (p3 - p1)
+        UI[b] = p3 - p1;
+    }
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+        const int b1 = (b + 2) % 3, b2 = (b + 1) % 3;        // (b - 1) mod 3, (b - 2) mod 3
+        const double v0 = __fma_rn(K0[SQ][2], U0[b2], __fma_rn(K0[SQ][1], U0[b1], K0[SQ][0] * U0[b]));
+        const double v2 = __fma_rn(K2[SQ][2], U2[b2], __fma_rn(K2[SQ][1], U2[b1], K2[SQ][0] * U2[b]));
+        double vr = KR[SQ][0] * UR[b], vi = KR[SQ][0] * UI[b];
+        vr = __fma_rn(-KI[SQ][0], UI[b], vr);
+        vi = __fma_rn(KI[SQ][0], UR[b], vi);
+        vr = __fma_rn(KR[SQ][1], UR[b1], vr);
+        vi = __fma_rn(KR[SQ][1], UI[b1], vi);
+        vr = __fma_rn(-KI[SQ][1], UI[b1], vr);
+        vi = __fma_rn(KI[SQ][1], UR[b1], vi);
+        vr = __fma_rn(KR[SQ][2], UR[b2], vr);
+        vi = __fma_rn(KR[SQ][2], UI[b2], vi);
+        vr = __fma_rn(-KI[SQ][2], UI[b2], vr);
+        vi = __fma_rn(KI[SQ][2], UR[b2], vi);
+        const double sm = v0 + v2, df = v0 - v2;
+        y[IDX[0][b]] = sm + vr;
+        y[IDX[2][b]] = sm - vr;
+        y[IDX[1][b]] = df - vi;
+        y[IDX[3][b]] = df + vi;
+    }
+}
+
+// One full round: S-box on every lane, then out = CIRC x + 8 x_0 e_0 + rc through the FFT form (206 FP64
+// operations instead of 290).
+GL_D void poseidon_full_round(u64 s[12], const double2* __restrict__ rc) {
+    double dl[12], dh[12], yl[12], yh[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const u64 x = poseidon_sbox(s[j]);
+        dl[j] = u32_as_denormal((u32)x);
+        dh[j] = u32_as_denormal((u32)(x >> 32));
+    }
+    poseidon_circ12<0>(dl, yl);
+    poseidon_circ12<0>(dh, yh);
+#pragma unroll
+    for (int r = 0; r < 12; r++) {
+        const double2 k = rc[r];
+        double al = yl[r] + k.x, ah = yh[r] + k.y;
+        if (r == 0) {
+            al = __fma_rn(8., dl[0], al);
+            ah = __fma_rn(8., dh[0], ah);
+        }
+        s[r] = poseidon_fold(al, ah);
+    }
+}
+
+// Two consecutive partial rounds in FFT form.  With M = CIRC + 8 e0 e0^T and M' = M without its row 0,
+//   N x~ = M M' x~ = CIRC^2 x~ + col0(CIRC) * (8 x~_0 - Yraw),   Yraw = M[0] . x~  (the unfolded y0 without its constant)
+// so z = CIRC^2 x~ (90 operations through poseidon_circ12<1>) + col0(CIRC) * w + M[.][0] * sigma + K: 280 FP64
+// operations per pair instead of 336, 13 folds.
 GL_D void poseidon_partial_pair(u64 s[12], int pair) {
-    // Everything that does not depend on lane 0 is issued first, so the FP64 pipe works through lanes 1..11
-    // while the two serial S-boxes of lane 0 run on the integer pipes.
     double dl[12], dh[12];
 #pragma unroll
     for (int i = 1; i < 12; i++) {
         dl[i] = u32_as_denormal((u32)s[i]);
         dh[i] = u32_as_denormal((u32)(s[i] >> 32));
     }
-    const double2 ky = c_poseidon_rc_split[(POSEIDON_FULL_HALF + 2 * pair + 1) * 12];
-    double yl = ky.x, yh = ky.y;
+    // everything that does not depend on lane 0 first: the FP64 pipe works while lane 0 goes through its S-box
+    double yl = (double)poseidon_mds_entry(0, 1) * dl[1], yh = (double)poseidon_mds_entry(0, 1) * dh[1];
 #pragma unroll
-    for (int j = 1; j < 12; j++) {
+    for (int j = 2; j < 12; j++) {
         yl = __fma_rn((double)poseidon_mds_entry(0, j), dl[j], yl);
         yh = __fma_rn((double)poseidon_mds_entry(0, j), dh[j], yh);
-    }
-    const double2* kk = c_poseidon_pair_k + pair * 12;
-    double al[12], ah[12];
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double2 k = kk[r];
-        al[r] = k.x;
-        ah[r] = k.y;
-#pragma unroll
-        for (int j = 1; j < 12; j++) {
-            al[r] = __fma_rn((double)poseidon_pair_entry(r, j), dl[j], al[r]);
-            ah[r] = __fma_rn((double)poseidon_pair_entry(r, j), dh[j], ah[r]);
-        }
     }
     const u64 x0 = poseidon_sbox(s[0]);
     dl[0] = u32_as_denormal((u32)x0);
     dh[0] = u32_as_denormal((u32)(x0 >> 32));
-    yl = __fma_rn((double)poseidon_mds_entry(0, 0), dl[0], yl);
+    yl = __fma_rn((double)poseidon_mds_entry(0, 0), dl[0], yl);      // Yraw
     yh = __fma_rn((double)poseidon_mds_entry(0, 0), dh[0], yh);
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        al[r] = __fma_rn((double)poseidon_pair_entry(r, 0), dl[0], al[r]);
-        ah[r] = __fma_rn((double)poseidon_pair_entry(r, 0), dh[0], ah[r]);
-    }
-    const u64 sigma = poseidon_sbox(poseidon_fold(yl, yh));
+    const double2 ky = c_poseidon_rc_split[(POSEIDON_FULL_HALF + 2 * pair + 1) * 12];
+    const u64 sigma = poseidon_sbox(poseidon_fold(yl + ky.x, yh + ky.y));
     const double gl = u32_as_denormal((u32)sigma), gh = u32_as_denormal((u32)(sigma >> 32));
+    double zl[12], zh[12];
+    poseidon_circ12<1>(dl, zl);
+    poseidon_circ12<1>(dh, zh);
+    const double wl = __fma_rn(8., dl[0], -yl), wh = __fma_rn(8., dh[0], -yh);
+    const double2* kk = c_poseidon_pair_k + pair * 12;
 #pragma unroll
     for (int r = 0; r < 12; r++) {
-        al[r] = __fma_rn((double)poseidon_mds_entry(r, 0), gl, al[r]);
-        ah[r] = __fma_rn((double)poseidon_mds_entry(r, 0), gh, ah[r]);
-        s[r] = poseidon_fold(al[r], ah[r]);
+        const double2 k = kk[r];
+        const double c0 = (double)(poseidon_mds_entry(r, 0) - (r == 0 ? 8 : 0));   // col0(CIRC)
+        double tl = __fma_rn((double)poseidon_mds_entry(r, 0), gl, k.x);
+        double th = __fma_rn((double)poseidon_mds_entry(r, 0), gh, k.y);
+        tl = __fma_rn(c0, wl, tl);
+        th = __fma_rn(c0, wh, th);
+        s[r] = poseidon_fold(zl[r] + tl, zh[r] + th);
     }
-}
-
-// One full round, accumulated COLUMN by column: as soon as lane j has gone through the S-box (integer pipes), its
-// 24 DFMAs (12 rows x 2 halves) can issue, so every warp feeds the FP64 pipe and the integer pipes at the same time
-// instead of alternating between an all-integer and an all-DFMA phase (which the warps of an SM do in lockstep:
-// ncu showed 20 % math-pipe-throttle + 18 % dispatch stalls with both pipes only ~45 % busy on average).
-GL_D void poseidon_full_round(u64 s[12], const double2* __restrict__ rc) {
-    double al[12], ah[12];
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double2 k = rc[r];
-        al[r] = k.x;
-        ah[r] = k.y;
-    }
-#pragma unroll
-    for (int j = 0; j < 12; j++) {
-        const u64 x = poseidon_sbox(s[j]);
-        const double dl = u32_as_denormal((u32)x), dh = u32_as_denormal((u32)(x >> 32));
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-            al[r] = __fma_rn((double)poseidon_mds_entry(r, j), dl, al[r]);
-            ah[r] = __fma_rn((double)poseidon_mds_entry(r, j), dh, ah[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) s[r] = poseidon_fold(al[r], ah[r]);
 }
 
 GL_D void poseidon_permute(u64 s[12]) {
