@@ -36,6 +36,32 @@ __global__ void k_kat(u64* io) {
     for (int i = 0; i < 12; i++) io[i] = gl_canon(s[i]);
 }
 
+// exactness of the FP64 linear layers at the extremes: every 32-bit half at 0xffffffff / 0 / random, compared with
+// 128-bit integer arithmetic on the device
+__global__ void k_circ_extremes(const u64* halves, int cases, int* bad) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cases) return;
+    const u64* h = halves + 12 * t;
+    double x[12], y1[12], y2[12];
+    for (int i = 0; i < 12; i++) x[i] = u32_as_denormal((u32)h[i]);
+    poseidon_circ12<0>(x, y1);
+    poseidon_circ12<1>(x, y2);
+    const int C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    u64 c1[12], c2[12];
+    for (int r = 0; r < 12; r++) {
+        u64 acc = 0;
+        for (int i = 0; i < 12; i++) acc += (u64)C[i] * h[(i + r) % 12];
+        c1[r] = acc;
+    }
+    for (int r = 0; r < 12; r++) {
+        u64 acc = 0;
+        for (int i = 0; i < 12; i++) acc += (u64)C[i] * c1[(i + r) % 12];
+        c2[r] = acc;
+    }
+    for (int r = 0; r < 12; r++)
+        if (double_bits(y1[r]) != c1[r] || double_bits(y2[r]) != c2[r]) atomicAdd(bad, 1);
+}
+
 int main() {
     u64 rc[360];
     if (!poseidon_constants::generate(rc)) { printf("constants fingerprint mismatch\n"); return 1; }
@@ -73,6 +99,34 @@ int main() {
     k_kat<<<1, 1>>>(d);
     cudaMemcpy(h, d, 96, cudaMemcpyDeviceToHost);
     for (int i = 0; i < 4; i++) ok &= h[i] == want_max[i];
+    {
+        const int cases = 1 << 16;
+        u64* hh = (u64*)malloc((size_t)cases * 12 * 8);
+        u64 st = 88172645463325252ULL;
+        for (int t = 0; t < cases; t++)
+            for (int i = 0; i < 12; i++) {
+                st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+                u64 v = st & 0xFFFFFFFFULL;
+                int mode = t & 7;   // 0: all max, 1: all zero, 2: alternating, 3: one hot max, 4..7: random with extremes
+                if (mode == 0) v = 0xFFFFFFFFULL;
+                else if (mode == 1) v = 0;
+                else if (mode == 2) v = ((i + (t >> 3)) & 1) ? 0xFFFFFFFFULL : 0;
+                else if (mode == 3) v = (i == (t >> 3) % 12) ? 0xFFFFFFFFULL : 0;
+                else if (mode == 4 && (st >> 40) % 3 == 0) v = 0xFFFFFFFFULL;
+                hh[(size_t)t * 12 + i] = v;
+            }
+        u64* dh;
+        int *dbad, hbad = 0;
+        cudaMalloc(&dh, (size_t)cases * 96);
+        cudaMalloc(&dbad, 4);
+        cudaMemcpy(dh, hh, (size_t)cases * 96, cudaMemcpyHostToDevice);
+        cudaMemset(dbad, 0, 4);
+        k_circ_extremes<<<cases / 128, 128>>>(dh, cases, dbad);
+        cudaMemcpy(&hbad, dbad, 4, cudaMemcpyDeviceToHost);
+        printf("{\"circ12_extreme_cases\": %d, \"mismatches\": %d}\n", cases, hbad);
+        ok &= hbad == 0;
+        free(hh);
+    }
     cudaDeviceProp p;
     cudaGetDeviceProperties(&p, 0);
     int blocks = p.multiProcessorCount * 16;
