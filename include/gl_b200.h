@@ -141,6 +141,18 @@ int gl_commit_from_values(gl_ctx *ctx, const uint64_t *values, uint32_t log_n, u
 int gl_commit_from_coeffs(gl_ctx *ctx, const uint64_t *coeffs, uint32_t log_n, uint32_t c,
                           uint32_t rate_bits, uint32_t cap_height, uint64_t *cap_out,
                           gl_commit **handle, int space);
+/* The same two commits with the polynomials where the reference keeps them: one host array per polynomial
+ * (`values: Vec<PolynomialValues<F>>`, each a Vec<F> of 2^log_n elements -- plonky2::fri::oracle from_values /
+ * from_coeffs; result `polynomials: Vec<PolynomialCoeffs<F>>`), so the binding passes `c` pointers and never
+ * flattens.  Host memory only; the arrays may be page-able: helper threads pack them into page-locked rings
+ * while the DMA engine and the transforms run (GL_B200_HOST_THREADS, default min(8, cores / 2)).
+ * coeffs_out: `c` pointers to arrays of 2^log_n (or NULL). */
+int gl_commit_from_values_cols(gl_ctx *ctx, const uint64_t *const *values, uint32_t log_n, uint32_t c,
+                               uint32_t rate_bits, uint32_t cap_height, uint64_t *const *coeffs_out,
+                               uint64_t *cap_out, gl_commit **handle);
+int gl_commit_from_coeffs_cols(gl_ctx *ctx, const uint64_t *const *coeffs, uint32_t log_n, uint32_t c,
+                               uint32_t rate_bits, uint32_t cap_height, uint64_t *cap_out,
+                               gl_commit **handle);
 /* The same commit fed column block by column block (from_coeffs as a stream): begin allocates the resident buffers,
  * add_coeffs copies the coefficients of polynomials [col0, col0 + ncols) ([ncols][2^log_n]) behind the handle and runs
  * their LDE, finish hashes the leaves and builds the tree once every column has arrived.  Lets a caller overlap the

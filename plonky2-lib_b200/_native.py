@@ -68,6 +68,8 @@ SIGNATURES = {
     "gl_coset_ifft_batch": (cint, [vp, vp, u32, u32, u64, cint]),
     "gl_commit_from_values": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(vp), cint]),
     "gl_commit_from_coeffs": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp), cint]),
+    "gl_commit_from_values_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(vp)]),
+    "gl_commit_from_coeffs_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
     "gl_commit_begin": (cint, [vp, u32, u32, u32, u32, C.POINTER(vp)]),
     "gl_commit_add_coeffs": (cint, [vp, u32, u32, vp, cint]),
     "gl_commit_finish": (cint, [vp, vp, cint]),

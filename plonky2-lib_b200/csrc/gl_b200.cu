@@ -27,6 +27,7 @@
 #include "gl_field.cuh"
 #include "fri_kernels.h"
 #include "hash_kernels.h"
+#include "host_staging.h"
 #include "ntt_kernels.h"
 #include "poseidon_constants.h"
 #include "smt_kernels.h"
@@ -62,6 +63,10 @@ struct gl_ctx {
     // phase boundaries of the last commit (CUDA events on `stream`)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // PCIe copies of the host-buffer commit pipeline
     std::vector<cudaEvent_t> pipe_ev;
+    staging::Ring h2d_ring;                 // page-able caller memory goes through these (host_staging.h)
+    staging::Downloader* downloader = nullptr;
+    cudaEvent_t dl_ev = nullptr;
+    bool downloads_pending = false;        // copy_out handed work to the downloader: finish() waits for it
     cudaEvent_t ev[GL_PHASES + 1] = {};
     bool ev_valid = false;
     float phase_ms[GL_PHASES] = {};
@@ -187,6 +192,56 @@ static void dev_release(gl_ctx* ctx, void* p, size_t bytes) {
     ctx->pool_bytes += bytes;
 }
 
+// Host <-> device copies of caller buffers.  Page-able memory of a megabyte or more is staged through
+// page-locked rings by helper threads (host_staging.h); small or page-locked buffers go straight to the DMA engine.
+static const size_t STAGED_MIN_BYTES = (size_t)1 << 20;
+static int h2d_copy(gl_ctx* ctx, void* ddst, const staging::HostSeg* segs, size_t count, cudaStream_t stream) {
+    CK(staging::h2d_gather(ctx->h2d_ring, ddst, segs, count, stream));
+    return GL_OK;
+}
+static int h2d_copy(gl_ctx* ctx, void* ddst, const void* src, size_t bytes, cudaStream_t stream) {
+    if (bytes < STAGED_MIN_BYTES) {
+        if (bytes) CK(cudaMemcpyAsync(ddst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return GL_OK;
+    }
+    staging::HostSeg seg{const_cast<void*>(src), bytes};
+    return h2d_copy(ctx, ddst, &seg, 1, stream);
+}
+// `ready`: an event already recorded after the producer of dsrc; the copy runs on d2h_stream (or its worker)
+// and is complete after downloads_wait().
+static int d2h_copy(gl_ctx* ctx, std::vector<staging::HostSeg> segs, const void* dsrc, cudaEvent_t ready) {
+    size_t total = 0;
+    bool pinned = true;
+    for (auto& sg : segs) {
+        total += sg.bytes;
+        if (pinned && sg.bytes) pinned = staging::is_pinned(sg.ptr);
+    }
+    if (!total) return GL_OK;
+    if (pinned || total < STAGED_MIN_BYTES) {
+        CK(cudaStreamWaitEvent(ctx->d2h_stream, ready, 0));
+        const char* from = (const char*)dsrc;
+        for (auto& sg : segs) {
+            if (sg.bytes) CK(cudaMemcpyAsync(sg.ptr, from, sg.bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            from += sg.bytes;
+        }
+        return GL_OK;
+    }
+    if (!ctx->downloader) {
+        ctx->downloader = new (std::nothrow) staging::Downloader(ctx->device, ctx->d2h_stream);
+        if (!ctx->downloader) return fail(ctx, GL_E_OOM, "host allocation failed");
+    }
+    ctx->downloader->submit(dsrc, std::move(segs), ready);
+    return GL_OK;
+}
+static int downloads_wait(gl_ctx* ctx) {
+    cudaError_t e = cudaSuccess;
+    if (ctx->downloader) e = ctx->downloader->wait();
+    cudaError_t e2 = cudaStreamSynchronize(ctx->d2h_stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "download to host memory");
+    if (e2 != cudaSuccess) return cuda_fail(ctx, e2, "download to host memory");
+    return GL_OK;
+}
+
 // caller buffer -> device pointer (no copy when the caller already is on the device)
 static int stage_in(gl_ctx* ctx, const void* src, size_t bytes, int space, int slot, const u64** out) {
     if (space == GL_DEVICE) {
@@ -195,12 +250,17 @@ static int stage_in(gl_ctx* ctx, const void* src, size_t bytes, int space, int s
     }
     void* d;
     TRY(scratch_get(ctx, slot, bytes ? bytes : 8, &d));
-    if (bytes) CK(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(h2d_copy(ctx, d, src, bytes, ctx->stream));
     *out = (const u64*)d;
     return GL_OK;
 }
 static int copy_out(gl_ctx* ctx, void* dst, const void* dsrc, size_t bytes, int space) {
     if (!dst || !bytes || dst == dsrc) return GL_OK;
+    if (space == GL_HOST && bytes >= STAGED_MIN_BYTES && !staging::is_pinned(dst)) {
+        CK(cudaEventRecord(ctx->dl_ev, ctx->stream));
+        ctx->downloads_pending = true;
+        return d2h_copy(ctx, {staging::HostSeg{dst, bytes}}, dsrc, ctx->dl_ev);
+    }
     CK(cudaMemcpyAsync(dst, dsrc, bytes, space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                        ctx->stream));
     return GL_OK;
@@ -208,6 +268,10 @@ static int copy_out(gl_ctx* ctx, void* dst, const void* dsrc, size_t bytes, int 
 static int finish(gl_ctx* ctx) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->downloads_pending) {
+        ctx->downloads_pending = false;
+        TRY(downloads_wait(ctx));
+    }
     return GL_OK;
 }
 
@@ -485,6 +549,7 @@ extern "C" int gl_ctx_create(int device, gl_ctx** out) {
         return rc;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    cudaEventCreateWithFlags(&ctx->dl_ev, cudaEventDisableTiming);
     uint64_t rc360[360];
     if (!poseidon_constants::generate(rc360)) {
         delete ctx;
@@ -506,6 +571,9 @@ extern "C" void gl_ctx_destroy(gl_ctx* ctx) {
     {
         Guard g(ctx);
         cudaStreamSynchronize(ctx->stream);
+        delete ctx->downloader;   // joins the worker
+        ctx->h2d_ring.destroy();
+        if (ctx->dl_ev) cudaEventDestroy(ctx->dl_ev);
         for (auto& kv : ctx->tables) cudaFree(kv.second);
         for (auto& b : ctx->scratch)
             if (b.p) cudaFree(b.p);
@@ -574,7 +642,9 @@ extern "C" int gl_copy(gl_ctx* ctx, void* dst, int dst_space, const void* src, i
     Guard g(ctx);
     cudaMemcpyKind kind = dst_space == GL_DEVICE ? (src_space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
                                                  : (src_space == GL_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
-    if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
+    if (kind == cudaMemcpyHostToDevice) TRY(h2d_copy(ctx, dst, src, bytes, ctx->stream));
+    else if (kind == cudaMemcpyDeviceToHost) TRY(copy_out(ctx, dst, src, bytes, GL_HOST));
+    else if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
     return finish(ctx);
 }
 
@@ -894,13 +964,34 @@ static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space) 
     return GL_OK;
 }
 
+// Where the polynomials of a host-side commit live: one [c][n] array, or one array per polynomial
+// (Vec<PolynomialValues<F>> / Vec<PolynomialCoeffs<F>> as the reference holds them).
+struct HostCols {
+    uint64_t* flat = nullptr;
+    uint64_t* const* cols = nullptr;
+    explicit operator bool() const { return flat || cols; }
+    void segs(uint32_t col0, uint32_t nc, u64 n, std::vector<staging::HostSeg>& out) const {
+        out.clear();
+        if (flat) {
+            out.push_back({flat + (size_t)col0 * n, (size_t)nc * n * 8});
+            return;
+        }
+        for (uint32_t j = 0; j < nc; j++) out.push_back({cols[col0 + j], (size_t)n * 8});
+    }
+};
+
 // Host buffers: the H2D copy of column block b+1, the IFFT + LDE of block b and the D2H copy of block b's
 // coefficients run on three streams, so PCIe traffic hides behind the transforms (PCIe is full duplex).
-static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const uint64_t* input, bool is_values,
-                                uint64_t* coeffs_out) {
+// Page-able arrays are packed into / unpacked from page-locked rings by helper threads (host_staging.h).
+static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input, bool is_values,
+                                const HostCols& coeffs_out) {
     const u64 n = (u64)1 << h->log_n;
     const size_t col_bytes = n * 8;
-    uint32_t cb = (uint32_t)(((size_t)96 << 20) / col_bytes);
+    // about six blocks per commit, between 2 MB (launch overhead) and 96 MB (memory for nothing)
+    size_t block_bytes = (size_t)h->c * col_bytes / 6;
+    if (block_bytes < ((size_t)2 << 20)) block_bytes = (size_t)2 << 20;
+    if (block_bytes > ((size_t)96 << 20)) block_bytes = (size_t)96 << 20;
+    uint32_t cb = (uint32_t)(block_bytes / col_bytes);
     if (cb < 1) cb = 1;
     if (cb > h->c) cb = h->c;
     const uint32_t nb = (h->c + cb - 1) / cb;
@@ -911,20 +1002,20 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const uint64_t* input
     }
     cudaEvent_t start = ctx->ev[1];   // recorded by the caller on the main stream
     CK(cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
-    CK(cudaStreamWaitEvent(ctx->d2h_stream, start, 0));
+    std::vector<staging::HostSeg> segs;
     for (uint32_t b = 0; b < nb; b++) {
         const uint32_t col0 = b * cb, nc = (col0 + cb <= h->c) ? cb : h->c - col0;
         u64* dcol = h->coeffs + (size_t)col0 * n;
-        CK(cudaMemcpyAsync(dcol, input + (size_t)col0 * n, nc * col_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+        input.segs(col0, nc, n, segs);
+        TRY(h2d_copy(ctx, dcol, segs.data(), segs.size(), ctx->h2d_stream));
         CK(cudaEventRecord(ctx->pipe_ev[2 * b], ctx->h2d_stream));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[2 * b], 0));
         if (is_values) {
             TRY(transform_natural(ctx, dcol, h->log_n, nc, true, nullptr, nullptr));  // "IFFT"
             if (coeffs_out) {
                 CK(cudaEventRecord(ctx->pipe_ev[2 * b + 1], ctx->stream));
-                CK(cudaStreamWaitEvent(ctx->d2h_stream, ctx->pipe_ev[2 * b + 1], 0));
-                CK(cudaMemcpyAsync(coeffs_out + (size_t)col0 * n, dcol, nc * col_bytes, cudaMemcpyDeviceToHost,
-                                   ctx->d2h_stream));
+                coeffs_out.segs(col0, nc, n, segs);
+                TRY(d2h_copy(ctx, segs, dcol, ctx->pipe_ev[2 * b + 1]));
             }
         }
         TRY(commit_lde_columns(ctx, h, col0, nc));
@@ -932,13 +1023,18 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const uint64_t* input
     return GL_OK;
 }
 
-static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uint32_t log_n, uint32_t c,
-                         uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_out, uint64_t* cap_out,
+static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uint32_t log_n, uint32_t c,
+                         uint32_t rate_bits, uint32_t cap_height, const HostCols& coeffs_out, uint64_t* cap_out,
                          gl_commit** handle, int space, const char* name) {
     if (!ctx) return GL_E_ARG;
     if (!handle || !input) return fail(ctx, GL_E_ARG, std::string(name) + ": NULL argument");
     *handle = nullptr;
     TRY(commit_check(ctx, log_n, c, rate_bits, cap_height, name));
+    if (input.cols || coeffs_out.cols) {
+        for (uint32_t j = 0; j < c; j++)
+            if ((input.cols && !input.cols[j]) || (coeffs_out.cols && !coeffs_out.cols[j]))
+                return fail(ctx, GL_E_ARG, std::string(name) + ": NULL polynomial pointer");
+    }
     Guard g(ctx);
     gl_commit* h = new (std::nothrow) gl_commit();
     if (!h) return fail(ctx, GL_E_OOM, "host allocation failed");
@@ -957,13 +1053,13 @@ static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uin
         mark(ctx, 3);
         rc = commit_pipeline_host(ctx, h, input, is_values, coeffs_out);
     } else if (rc == GL_OK) {
-        cudaError_t e = cudaMemcpyAsync(h->coeffs, input, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(h->coeffs, input.flat, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
         if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials");
         mark(ctx, 1);
         if (rc == GL_OK && is_values) {
             rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr);  // "IFFT"
             mark(ctx, 2);
-            if (rc == GL_OK) rc = copy_out(ctx, coeffs_out, h->coeffs, poly_bytes, space);
+            if (rc == GL_OK) rc = copy_out(ctx, coeffs_out.flat, h->coeffs, poly_bytes, space);
         } else {
             mark(ctx, 2);
         }
@@ -972,9 +1068,9 @@ static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uin
     }
     if (rc == GL_OK) rc = commit_tree(ctx, h, cap_out, space);
     if (rc == GL_OK) rc = finish(ctx);
-    if (rc == GL_OK && space == GL_HOST) {
-        cudaError_t e = cudaStreamSynchronize(ctx->d2h_stream);
-        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "coefficient download");
+    if (space == GL_HOST) {   // coefficient downloads (also after an error: they write into caller memory)
+        int rc2 = downloads_wait(ctx);
+        if (rc == GL_OK) rc = rc2;
     }
     if (rc == GL_OK) {
         for (int i = 0; i < GL_PHASES; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
@@ -996,13 +1092,36 @@ static int commit_common(gl_ctx* ctx, const uint64_t* input, bool is_values, uin
 extern "C" int gl_commit_from_values(gl_ctx* ctx, const uint64_t* values, uint32_t log_n, uint32_t c,
                                      uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_out, uint64_t* cap_out,
                                      gl_commit** handle, int space) {
-    return commit_common(ctx, values, true, log_n, c, rate_bits, cap_height, coeffs_out, cap_out, handle, space,
+    HostCols in, out;
+    in.flat = const_cast<uint64_t*>(values);
+    out.flat = coeffs_out;
+    return commit_common(ctx, in, true, log_n, c, rate_bits, cap_height, out, cap_out, handle, space,
                          "PolynomialBatch::from_values");
 }
 extern "C" int gl_commit_from_coeffs(gl_ctx* ctx, const uint64_t* coeffs, uint32_t log_n, uint32_t c,
                                      uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out, gl_commit** handle,
                                      int space) {
-    return commit_common(ctx, coeffs, false, log_n, c, rate_bits, cap_height, nullptr, cap_out, handle, space,
+    HostCols in;
+    in.flat = const_cast<uint64_t*>(coeffs);
+    return commit_common(ctx, in, false, log_n, c, rate_bits, cap_height, HostCols(), cap_out, handle, space,
+                         "PolynomialBatch::from_coeffs");
+}
+// One host array per polynomial, as the reference holds them (Vec<PolynomialValues<F>>, Vec<PolynomialCoeffs<F>>).
+extern "C" int gl_commit_from_values_cols(gl_ctx* ctx, const uint64_t* const* values, uint32_t log_n, uint32_t c,
+                                          uint32_t rate_bits, uint32_t cap_height, uint64_t* const* coeffs_out,
+                                          uint64_t* cap_out, gl_commit** handle) {
+    HostCols in, out;
+    in.cols = const_cast<uint64_t* const*>(values);
+    out.cols = coeffs_out;
+    return commit_common(ctx, in, true, log_n, c, rate_bits, cap_height, out, cap_out, handle, GL_HOST,
+                         "PolynomialBatch::from_values");
+}
+extern "C" int gl_commit_from_coeffs_cols(gl_ctx* ctx, const uint64_t* const* coeffs, uint32_t log_n, uint32_t c,
+                                          uint32_t rate_bits, uint32_t cap_height, uint64_t* cap_out,
+                                          gl_commit** handle) {
+    HostCols in;
+    in.cols = const_cast<uint64_t* const*>(coeffs);
+    return commit_common(ctx, in, false, log_n, c, rate_bits, cap_height, HostCols(), cap_out, handle, GL_HOST,
                          "PolynomialBatch::from_coeffs");
 }
 
@@ -1112,7 +1231,7 @@ extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* 
             for (u64 r0 = 0; r0 < h->n_local; r0 += chunk) {
                 launch_transpose_to_rows(h->lde, h->n_local, h->c, r0, chunk, (u64*)stage, ctx->stream);
                 TRY(copy_out(ctx, leaves_out + (size_t)r0 * h->c, stage, (size_t)chunk * h->c * 8, GL_HOST));
-                CK(cudaStreamSynchronize(ctx->stream));
+                TRY(finish(ctx));   // `stage` is reused by the next chunk
             }
         }
     }
@@ -1411,9 +1530,13 @@ extern "C" int gl_pow_grind(gl_ctx* ctx, const uint64_t state[12], uint32_t inpu
     unsigned long long none = ~0ULL;
     CK(cudaMemcpyAsync(dstate, state, 96, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dbest, &none, 8, cudaMemcpyHostToDevice, ctx->stream));
-    const u64 chunk = (u64)1 << 22;
+    // The first batch holds four times the expected number of tries (it finds a witness with probability
+    // 1 - e^-4); later batches double.  Batches are scanned in order and each keeps its minimum, so the
+    // result is the smallest witness whatever the batch sizes.
+    unsigned lg_chunk = min_leading_zeros + 2 < 14 ? 14 : (min_leading_zeros + 2 > 24 ? 24 : min_leading_zeros + 2);
+    u64 chunk = (u64)1 << lg_chunk;
     // witnesses are field elements: upstream searches 0 .. p-1
-    for (u64 start = 0; start < GL_P; start += chunk) {
+    for (u64 start = 0; start < GL_P; start += chunk, chunk = chunk < ((u64)1 << 26) ? chunk * 2 : chunk) {
         u64 count = GL_P - start < chunk ? GL_P - start : chunk;
         launch_pow_grind(dstate, input_pos, 7, min_leading_zeros, start, count, dbest, ctx->stream);
         unsigned long long best;

@@ -408,6 +408,8 @@ class PolynomialBatch:
         if blinding:
             raise GlPanic(N.GL_E_ARG, "blinding (zero_knowledge) is not supported: every reference config uses zero_knowledge = false")
         ctx = _ctx(ctx)
+        if isinstance(inputs, (list, tuple)) and inputs and all(isinstance(a, np.ndarray) and a.ndim == 1 for a in inputs):
+            return cls._make_cols(list(inputs), is_values, rate_bits, cap_height, ctx, want_coeffs)
         dev = _is_torch(inputs) and inputs.is_cuda
         if not dev:
             inputs = _h(inputs)
@@ -450,20 +452,57 @@ class PolynomialBatch:
         ctx.check(rc)
         if dev:
             cap = cap_dev.cpu().numpy().view(np.uint64)
+        self._finish_make(h, cap, n)
+        return self
+
+    @classmethod
+    def _make_cols(cls, cols, is_values: bool, rate_bits: int, cap_height: int, ctx, want_coeffs):
+        """One host array per polynomial, as the reference holds them (Vec<PolynomialValues<F>>): no flattening,
+        gl_commit_from_values_cols / gl_commit_from_coeffs_cols."""
+        cols = [_h(a) for a in cols]
+        c, n = len(cols), int(cols[0].shape[0])
+        if any(a.shape[0] != n for a in cols):
+            raise GlPanic(N.GL_E_ARG, "assert_eq!(p.len(), degree): polynomials of different lengths")
+        if n == 0 or n & (n - 1):
+            raise GlPanic(N.GL_E_ARG, "log2_strict: polynomial length is not a power of two")
+        lg = n.bit_length() - 1
+        self = object.__new__(cls)
+        self._ctx = ctx
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, False, cap_height
+        self.num_columns = c
+        cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        ptrs = (C.c_void_p * c)(*[a.ctypes.data for a in cols])
+        if is_values:
+            co, optrs = None, None
+            if want_coeffs:
+                co = [np.empty(n, dtype=np.uint64) for _ in range(c)]
+                optrs = (C.c_void_p * c)(*[a.ctypes.data for a in co])
+            rc = ctx._lib.gl_commit_from_values_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, optrs, cap.ctypes.data, C.byref(h))
+            self._polys = co
+        else:
+            rc = ctx._lib.gl_commit_from_coeffs_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, cap.ctypes.data, C.byref(h))
+            self._polys = cols
+        ctx.check(rc)
+        self._finish_make(h, cap, n)
+        return self
+
+    def _finish_make(self, h, cap, n):
+        ctx = self._ctx
         self._h = h
         lb, le = C.c_uint64(), C.c_uint64()
         ctx.check(ctx._lib.gl_commit_info(h, None, None, None, None, C.byref(lb), C.byref(le)))
         self.leaf_begin, self.leaf_end = lb.value, le.value
         self.num_local_leaves = le.value - lb.value
-        total = n << rate_bits
-        self.cap_local_bits = cap_height - ((total // self.num_local_leaves).bit_length() - 1)
+        total = n << self.rate_bits
+        self.cap_local_bits = self.cap_height - ((total // self.num_local_leaves).bit_length() - 1)
         self.merkle_tree = ResidentMerkleTree(self, cap)
-        return self
 
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None, fft_root_table=None,
                     ctx: Optional[Context] = None, want_coeffs: bool = True) -> "PolynomialBatch":
-        """values: [columns][n] evaluations on the subgroup (Vec<PolynomialValues<F>>).  `timing` and
+        """values: [columns][n] evaluations on the subgroup (Vec<PolynomialValues<F>>), or a list of 1-D arrays
+        (one per polynomial, never flattened: coefficients then come back the same way).  `timing` and
         `fft_root_table` are accepted for signature parity and ignored (the device keeps its own tables)."""
         return cls._make(values, True, rate_bits, blinding, cap_height, ctx, want_coeffs)
 
