@@ -270,11 +270,11 @@ class PolynomialBatch {
         if (n == 0 || (n & (n - 1))) throw Panic(GL_E_ARG, "log2_strict: polynomial length is not a power of two");
         uint32_t lg = 0;
         while ((1ull << lg) < n) lg++;
-        std::vector<F> flat;
-        flat.reserve(n * polys.size());
+        // one pointer per polynomial, exactly where the caller's Vecs lie (gl_commit_from_values_cols): no flattening
+        std::vector<const uint64_t*> cols;
         for (auto& p : polys) {
             if (p.size() != n) throw Panic(GL_E_ARG, "assert_eq!(p.len(), degree)");
-            flat.insert(flat.end(), p.begin(), p.end());
+            cols.push_back(p.data());
         }
         PolynomialBatch b;
         b.ctx_ = &c;
@@ -282,14 +282,19 @@ class PolynomialBatch {
         b.rate_bits = rate_bits;
         b.cap_height = cap_height;
         b.cap.resize(1ull << cap_height);
-        std::vector<F> coeffs(is_values ? flat.size() : 0);
-        int rc = is_values ? gl_commit_from_values(c.raw(), flat.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height,
-                                                   coeffs.data(), &b.cap[0].elements[0], &b.h_, GL_HOST)
-                           : gl_commit_from_coeffs(c.raw(), flat.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height,
-                                                   &b.cap[0].elements[0], &b.h_, GL_HOST);
+        int rc;
+        if (is_values) {
+            b.polynomials.assign(polys.size(), std::vector<F>(n));
+            std::vector<uint64_t*> outs;
+            for (auto& p : b.polynomials) outs.push_back(p.data());
+            rc = gl_commit_from_values_cols(c.raw(), cols.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height, outs.data(),
+                                            &b.cap[0].elements[0], &b.h_);
+        } else {
+            rc = gl_commit_from_coeffs_cols(c.raw(), cols.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height,
+                                            &b.cap[0].elements[0], &b.h_);
+            if (rc == GL_OK) b.polynomials = polys;
+        }
         c.check(rc);
-        const std::vector<F>& src = is_values ? coeffs : flat;
-        for (size_t j = 0; j < polys.size(); j++) b.polynomials.emplace_back(src.begin() + j * n, src.begin() + (j + 1) * n);
         return b;
     }
     gl_commit* h_ = nullptr;

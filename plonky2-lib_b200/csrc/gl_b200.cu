@@ -15,6 +15,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -66,7 +67,6 @@ struct gl_ctx {
     staging::Ring h2d_ring;                 // page-able caller memory goes through these (host_staging.h)
     staging::Downloader* downloader = nullptr;
     cudaEvent_t dl_ev = nullptr;
-    bool downloads_pending = false;        // copy_out handed work to the downloader: finish() waits for it
     cudaEvent_t ev[GL_PHASES + 1] = {};
     bool ev_valid = false;
     float phase_ms[GL_PHASES] = {};
@@ -194,8 +194,25 @@ static void dev_release(gl_ctx* ctx, void* p, size_t bytes) {
 
 // Host <-> device copies of caller buffers.  Page-able memory of a megabyte or more is staged through
 // page-locked rings by helper threads (host_staging.h); small or page-locked buffers go straight to the DMA engine.
-static const size_t STAGED_MIN_BYTES = (size_t)1 << 20;
+static size_t staged_min_bytes() {   // GL_B200_STAGING=0 hands page-able memory to the driver instead (A/B measurements)
+    static const size_t v = [] {
+        const char* e = getenv("GL_B200_STAGING");
+        return (e && e[0] == '0') ? ~(size_t)0 : (size_t)1 << 20;
+    }();
+    return v;
+}
+#define STAGED_MIN_BYTES staged_min_bytes()
 static int h2d_copy(gl_ctx* ctx, void* ddst, const staging::HostSeg* segs, size_t count, cudaStream_t stream) {
+    size_t total = 0;
+    for (size_t i = 0; i < count; i++) total += segs[i].bytes;
+    if (total < STAGED_MIN_BYTES) {
+        char* to = (char*)ddst;
+        for (size_t i = 0; i < count; i++) {
+            if (segs[i].bytes) CK(cudaMemcpyAsync(to, segs[i].ptr, segs[i].bytes, cudaMemcpyHostToDevice, stream));
+            to += segs[i].bytes;
+        }
+        return GL_OK;
+    }
     CK(staging::h2d_gather(ctx->h2d_ring, ddst, segs, count, stream));
     return GL_OK;
 }
@@ -257,9 +274,11 @@ static int stage_in(gl_ctx* ctx, const void* src, size_t bytes, int space, int s
 static int copy_out(gl_ctx* ctx, void* dst, const void* dsrc, size_t bytes, int space) {
     if (!dst || !bytes || dst == dsrc) return GL_OK;
     if (space == GL_HOST && bytes >= STAGED_MIN_BYTES && !staging::is_pinned(dst)) {
+        // Callers reuse or free `dsrc` right after this returns (stream order covered that when the copy was a
+        // cudaMemcpyAsync on ctx->stream), so the staged download completes before we go on.
         CK(cudaEventRecord(ctx->dl_ev, ctx->stream));
-        ctx->downloads_pending = true;
-        return d2h_copy(ctx, {staging::HostSeg{dst, bytes}}, dsrc, ctx->dl_ev);
+        TRY(d2h_copy(ctx, {staging::HostSeg{dst, bytes}}, dsrc, ctx->dl_ev));
+        return downloads_wait(ctx);
     }
     CK(cudaMemcpyAsync(dst, dsrc, bytes, space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                        ctx->stream));
@@ -268,10 +287,6 @@ static int copy_out(gl_ctx* ctx, void* dst, const void* dsrc, size_t bytes, int 
 static int finish(gl_ctx* ctx) {
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->downloads_pending) {
-        ctx->downloads_pending = false;
-        TRY(downloads_wait(ctx));
-    }
     return GL_OK;
 }
 
@@ -1231,7 +1246,7 @@ extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* 
             for (u64 r0 = 0; r0 < h->n_local; r0 += chunk) {
                 launch_transpose_to_rows(h->lde, h->n_local, h->c, r0, chunk, (u64*)stage, ctx->stream);
                 TRY(copy_out(ctx, leaves_out + (size_t)r0 * h->c, stage, (size_t)chunk * h->c * 8, GL_HOST));
-                TRY(finish(ctx));   // `stage` is reused by the next chunk
+                CK(cudaStreamSynchronize(ctx->stream));   // `stage` is reused by the next chunk
             }
         }
     }

@@ -132,3 +132,33 @@ def test_back_to_back_commits_reuse_the_rings(glb, ctx, oracle):
         assert np.array_equal(cap, bd.merkle_tree.cap)
         assert np.array_equal(coeffs, bd.polynomials.cpu().numpy().view(np.uint64))
         bd.free()
+
+
+def test_fri_final_poly_host_outputs_above_the_staging_threshold(glb, ctx, oracle, rng):
+    """gl_fri_final_poly writes the coefficients and then reuses the same device buffer for the values: with
+    page-able outputs of 2 MB each both go through the downloader and must not overtake each other."""
+    import importlib
+
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    degree_bits, cols = 14, (3, 2)
+    n = 1 << degree_bits
+    batches, polys = [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=900 + k)
+        batches.append(glb.PolynomialBatch.from_values(v, 3, False, 4))
+        polys.append(np.array(batches[-1].polynomials))
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)])]
+    alpha = tuple(int(x) for x in rand_field(rng, (2,)))
+    want_final = fo.final_poly_of_openings(polys, instance, alpha)
+    for _ in range(3):
+        got_coeffs, got_values = fri.fri_final_poly(batches, instance, alpha, 3)
+        assert np.array_equal(got_coeffs[:n], want_final) and not got_coeffs[n:].any()
+        assert np.array_equal(got_values, oracle.ext_coset_fft(got_coeffs, 7))
+    dc, dv = fri.fri_final_poly(batches, instance, alpha, 3, resident=True)
+    assert np.array_equal(dc.to_host(), got_coeffs) and np.array_equal(dv.to_host(), got_values)
+    dc.free(); dv.free()
+    for b in batches:
+        b.free()
