@@ -72,6 +72,11 @@ void gl_host_free(void *p);
 /* ---- P5/P6: PoseidonHash (plonky2::hash::poseidon) ------------------------------------------- */
 /* Poseidon::poseidon over m states [m][12], in place. */
 int gl_poseidon_permute_batch(gl_ctx *ctx, uint64_t *states, uint64_t m, int space);
+/* m consecutive Challenger::duplexing steps with a full input buffer (plonky2::iop::challenger, overwrite mode):
+ * for each chunk of 8 elements, state[0..8] = chunk, then permute.  One launch for the whole chain, so observing
+ * a Merkle cap (64 elements) costs 8 dependent permutations and ONE host round trip.  state: 12 elements, in and
+ * out; chunks: [m][8].  Host pointers. */
+int gl_poseidon_duplex_chain(gl_ctx *ctx, uint64_t *state, const uint64_t *chunks, uint64_t m);
 /* PoseidonHash::two_to_one (src/smt/goldilocks_poseidon/mod.rs:165, src/zkdsa/account.rs:165,
  * src/zkdsa/circuits/mod.rs:66-67): l, r, out are [m][4]. */
 int gl_poseidon_two_to_one_batch(gl_ctx *ctx, const uint64_t *l, const uint64_t *r, uint64_t *out,

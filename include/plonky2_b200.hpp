@@ -315,12 +315,26 @@ class Challenger {
         input_buffer.push_back(e % 0xFFFFFFFF00000001ULL);
         if (input_buffer.size() == PoseidonHash::SPONGE_RATE) duplexing();
     }
+    // same transcript as element-by-element observation; runs of full input buffers go to the device as one chain
     void observe_elements(const F* es, size_t n) {
-        for (size_t i = 0; i < n; i++) observe_element(es[i]);
+        const size_t R = PoseidonHash::SPONGE_RATE;
+        if ((input_buffer.size() + n) / R < 2) {
+            for (size_t i = 0; i < n; i++) observe_element(es[i]);
+            return;
+        }
+        std::vector<F> pending(input_buffer);
+        for (size_t i = 0; i < n; i++) pending.push_back(es[i] % 0xFFFFFFFF00000001ULL);
+        const size_t m = pending.size() / R;
+        ctx_->check(gl_poseidon_duplex_chain(ctx_->raw(), sponge_state, pending.data(), m));
+        input_buffer.assign(pending.begin() + m * R, pending.end());
+        output_buffer.clear();
+        if (input_buffer.empty()) output_buffer.assign(sponge_state, sponge_state + R);
     }
     void observe_hash(const HashOut& h) { observe_elements(h.elements, 4); }
     void observe_cap(const MerkleCap& cap) {
-        for (auto& h : cap) observe_hash(h);
+        std::vector<F> flat;
+        for (auto& h : cap) flat.insert(flat.end(), h.elements, h.elements + 4);
+        observe_elements(flat.data(), flat.size());
     }
     void observe_extension_element(const F e[2]) { observe_elements(e, 2); }
     F get_challenge() {

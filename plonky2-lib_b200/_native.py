@@ -56,6 +56,7 @@ SIGNATURES = {
     "gl_host_alloc": (cint, [C.c_size_t, C.POINTER(vp)]),
     "gl_host_free": (None, [vp]),
     "gl_poseidon_permute_batch": (cint, [vp, vp, u64, cint]),
+    "gl_poseidon_duplex_chain": (cint, [vp, vp, vp, u64]),
     "gl_poseidon_two_to_one_batch": (cint, [vp, vp, vp, vp, u64, cint]),
     "gl_poseidon_hash_no_pad_batch": (cint, [vp, vp, u32, u64, vp, cint]),
     "gl_smt_leaf_hash_batch": (cint, [vp, vp, vp, vp, u64, cint]),

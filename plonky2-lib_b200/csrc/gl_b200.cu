@@ -691,6 +691,22 @@ extern "C" int gl_poseidon_permute_batch(gl_ctx* ctx, uint64_t* states, uint64_t
     return finish(ctx);
 }
 
+extern "C" int gl_poseidon_duplex_chain(gl_ctx* ctx, uint64_t* state, const uint64_t* chunks, uint64_t m) {
+    if (!ctx) return GL_E_ARG;
+    if (!state || (m && !chunks)) return fail(ctx, GL_E_ARG, "gl_poseidon_duplex_chain: NULL argument");
+    if (m > ((uint64_t)1 << 24)) return fail(ctx, GL_E_ARG, "gl_poseidon_duplex_chain: chain too long");
+    if (m == 0) return GL_OK;
+    Guard g(ctx);
+    void* d;
+    TRY(scratch_get(ctx, 0, 96 + m * 64, &d));
+    u64* dstate = (u64*)d;
+    CK(cudaMemcpyAsync(dstate, state, 96, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dstate + 12, chunks, m * 64, cudaMemcpyHostToDevice, ctx->stream));
+    launch_duplex_chain(dstate, dstate + 12, m, ctx->stream);
+    CK(cudaMemcpyAsync(state, dstate, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    return finish(ctx);
+}
+
 extern "C" int gl_poseidon_two_to_one_batch(gl_ctx* ctx, const uint64_t* l, const uint64_t* r, uint64_t* out,
                                             uint64_t m, int space) {
     if (!ctx) return GL_E_ARG;

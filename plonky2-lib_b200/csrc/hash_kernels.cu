@@ -268,6 +268,24 @@ __device__ __noinline__ void poseidon_permute_call(u64* state) {
 #pragma unroll
     for (int i = 0; i < 12; i++) state[i] = s[i];
 }
+
+// Challenger::duplexing x m: a serial chain, one thread
+__global__ void __launch_bounds__(32) k_duplex_chain(u64* __restrict__ state, const u64* __restrict__ chunks, u64 m) {
+    if (threadIdx.x) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = state[k];
+    for (u64 i = 0; i < m; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) s[k] = chunks[8 * i + k];
+        poseidon_permute_call(s);
+#pragma unroll
+        for (int k = 0; k < 12; k++) s[k] = gl_canon(s[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 12; k++) state[k] = s[k];
+}
+
 GL_D void two_to_one_call(const u64 l[4], const u64 r[4], u64 out[4]) {
     u64 s[12];
 #pragma unroll
@@ -416,6 +434,10 @@ static inline unsigned nblk(u64 n, unsigned b) { return (unsigned)((n + b - 1) /
 
 void launch_permute_batch(u64* states, u64 m, cudaStream_t st) {
     if (m) { k_permute_batch<<<nblk(m, HASH_BLOCK), HASH_BLOCK, 0, st>>>(states, m); ++g_gl_launches; }
+}
+void launch_duplex_chain(u64* state, const u64* chunks, u64 m, cudaStream_t st) {
+    k_duplex_chain<<<1, 32, 0, st>>>(state, chunks, m);
+    ++g_gl_launches;
 }
 void launch_two_to_one_batch(const u64* l, const u64* r, u64* out, u64 m, cudaStream_t st) {
     if (m) { k_two_to_one_batch<<<nblk(m, HASH_BLOCK), HASH_BLOCK, 0, st>>>(l, r, out, m); ++g_gl_launches; }

@@ -12,6 +12,7 @@ extern std::atomic<unsigned long long> g_gl_launches;
 
 int gl_poseidon_upload_constants(const uint64_t* rc360);
 void launch_permute_batch(uint64_t* states, uint64_t m, cudaStream_t st);
+void launch_duplex_chain(uint64_t* state, const uint64_t* chunks, uint64_t m, cudaStream_t st);
 void launch_two_to_one_batch(const uint64_t* l, const uint64_t* r, uint64_t* out, uint64_t m, cudaStream_t st);
 void launch_hash_no_pad_rows(const uint64_t* in, uint32_t len, uint64_t m, uint64_t* out, cudaStream_t st);
 void launch_smt_leaf_hash_batch(const uint64_t* k, const uint64_t* v, uint64_t* out, uint64_t m, cudaStream_t st);

@@ -37,8 +37,24 @@ class Challenger:
             self._duplexing()
 
     def observe_elements(self, es):
-        for e in np.asarray(es, dtype=np.uint64).reshape(-1).tolist():
-            self.observe_element(e)
+        """Same transcript as element-by-element observation; runs of full input buffers become one
+        gl_poseidon_duplex_chain call (one launch and one host round trip instead of one per permutation)."""
+        es = np.asarray(es, dtype=np.uint64).reshape(-1) % np.uint64(P)
+        if es.size == 0:
+            return
+        pending = np.concatenate([np.array(self.input_buffer, dtype=np.uint64), es])
+        m = pending.size // SPONGE_RATE
+        if m < 2:
+            for e in es.tolist():
+                self.observe_element(e)
+            return
+        chunks = np.ascontiguousarray(pending[: m * SPONGE_RATE])
+        ctx = self._ctx
+        ctx.check(ctx._lib.gl_poseidon_duplex_chain(ctx._h, self.sponge_state.ctypes.data, chunks.ctypes.data, m))
+        rest = pending[m * SPONGE_RATE:]
+        self.input_buffer = [int(x) for x in rest]
+        # upstream: a duplexing refills output_buffer, the next observe_element clears it
+        self.output_buffer = [] if rest.size else [int(x) for x in self.sponge_state[:SPONGE_RATE]]
 
     def observe_hash(self, h):
         self.observe_elements(h)

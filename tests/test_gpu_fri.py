@@ -6,7 +6,7 @@ import importlib
 import numpy as np
 import pytest
 
-from conftest import rand_field
+from conftest import P, rand_field
 
 pytestmark = pytest.mark.gpu
 
@@ -84,6 +84,35 @@ def test_challenger_matches_oracle(glb, ctx, oracle, rng):
             a.observe_elements(xs)
             b.observe_elements(xs)
     assert a.get_extension_challenge() == b.get_extension_challenge()
+
+
+def test_challenger_chained_duplexing_matches_element_by_element(glb, ctx, oracle, rng):
+    """observe_elements sends runs of full input buffers to the device as ONE gl_poseidon_duplex_chain call; the
+    transcript (sponge state, pending inputs, buffered outputs) must be what upstream's element-by-element
+    observation leaves, whatever the alignment of the run with the buffer."""
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    for pre in range(0, 9):                       # elements already waiting in input_buffer
+        for length in (15, 16, 17, 64, 71, 256):  # a Merkle cap is 64
+            a, b = fri.Challenger(), fo.Challenger()
+            head = rand_field(rng, (pre,))
+            for e in head.tolist():
+                a.observe_element(e)
+                b.observe_element(e)
+            xs = rand_field(rng, (length,))
+            xs[0] = np.uint64(P)                  # non-canonical input: observed as 0
+            a.observe_elements(xs)
+            for e in xs.tolist():
+                b.observe_element(e)
+            assert [int(v) for v in a.sponge_state] == [int(v) for v in b.sponge_state]
+            assert list(a.input_buffer) == [int(v) for v in b.input_buffer]
+            assert list(a.output_buffer) == [int(v) for v in b.output_buffer]
+            assert [a.get_challenge() for _ in range(9)] == [b.get_challenge() for _ in range(9)]
+    # the raw entry point: a zero-length chain is a no-op, NULL arguments are rejected
+    st = np.arange(12, dtype=np.uint64)
+    assert ctx._lib.gl_poseidon_duplex_chain(ctx._h, st.ctypes.data, None, 0) == 0 and st[5] == 5
+    assert ctx._lib.gl_poseidon_duplex_chain(ctx._h, None, None, 1) == glb._native.GL_E_ARG
 
 
 @pytest.mark.parametrize("degree_bits,cols", [(5, (3, 2)), (8, (4, 9, 3)), (12, (84, 135, 20, 16))])
