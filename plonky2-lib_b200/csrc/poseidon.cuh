@@ -46,34 +46,6 @@ GL_D u64 poseidon_sbox(u64 x) {
 GL_D double u32_as_denormal(u32 x) { return __hiloint2double(0, (int)x); }
 GL_D u64 double_bits(double d) { return (u64)__double_as_longlong(d); }
 
-GL_D u64 poseidon_fold_fwd(double al, double ah);
-// out[r] = sum_i s[(i + r) % 12] * CIRC[i] + s[r] * DIAG[r] + rc[r]
-// CIRC = 17 15 41 16 2 28 13 13 39 18 34 20, DIAG = 8 0 ... 0
-GL_D void poseidon_mds_rc(u64 s[12], const double2* __restrict__ rc) {
-    constexpr double C[12] = {17., 15., 41., 16., 2., 28., 13., 13., 39., 18., 34., 20.};
-    double dl[12], dh[12];
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        dl[i] = u32_as_denormal((u32)s[i]);
-        dh[i] = u32_as_denormal((u32)(s[i] >> 32));
-    }
-#pragma unroll
-    for (int r = 0; r < 12; r++) {
-        double2 k = rc[r];
-        double al = k.x, ah = k.y;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            al = __fma_rn(C[i], dl[(i + r) % 12], al);
-            ah = __fma_rn(C[i], dh[(i + r) % 12], ah);
-        }
-        if (r == 0) {
-            al = __fma_rn(8., dl[0], al);
-            ah = __fma_rn(8., dh[0], ah);
-        }
-        s[r] = poseidon_fold_fwd(al, ah);
-    }
-}
-
 // MDS entries: M[r][j] = CIRC[(j - r) mod 12] + (r == j ? DIAG[r] : 0)
 __host__ __device__ constexpr int poseidon_mds_entry(int r, int j) {
     constexpr int C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -92,7 +64,6 @@ __host__ __device__ constexpr int poseidon_pair_entry(int r, int j) {
 __constant__ double2 c_poseidon_pair_k[(POSEIDON_PARTIAL / 2) * POSEIDON_WIDTH];
 
 GL_D u64 poseidon_fold(double al, double ah);
-GL_D u64 poseidon_fold_fwd(double al, double ah) { return poseidon_fold(al, ah); }
 GL_D u64 poseidon_fold(double al, double ah) {
     // value = A + 2^32 * B with A, B < 2^50 (integer bit patterns).  2^64 = 2^32 - 1 (mod p):
     //   t = A + (B >> 32) * (2^32 - 1)  (< 2^51, one IMAD.WIDE);  y = t + (B mod 2^32) * 2^32 wraps at most once

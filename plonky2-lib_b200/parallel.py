@@ -9,6 +9,9 @@ of n coefficients with N = n * 2^rate_bits leaves is split over `world` ranks:
     (`gl_ctx_set_shard`); no exchange;
   * the cap by ONE all-gather of 2^cap_height / world digests per rank;
   * query openings are answered by `owner_of_leaf`.
+
+Batches of independent items (SMT process proofs, P7; Poseidon batches) are cut evenly by `batch_range` with no
+exchange at all; `slice_proof_batch` rebases the sibling offsets of one rank's share.
 """
 from __future__ import annotations
 
@@ -65,3 +68,17 @@ def all_gather_cap(dist, local_cap, cap_all):
     """local_cap [2^cap_height / world][4] -> cap_all [2^cap_height][4] (MerkleCap) on every rank."""
     dist.all_gather_into_tensor(cap_all, local_cap)
     return cap_all
+
+
+def batch_range(rank: int, world: int, m: int) -> Tuple[int, int]:
+    """[lo, hi) of the items of `rank` when m independent items are split as evenly as possible."""
+    base, extra = divmod(m, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def slice_proof_batch(headers, sib_pool, sib_off, lo: int, hi: int):
+    """The share [lo, hi) of a batch of SparseMerkleProcessProofs laid out as gl_smt_verify_process_batch takes it
+    (headers [m], sib_pool [total][4], sib_off [m + 1]): the same three arrays for that share, offsets rebased."""
+    first, last = int(sib_off[lo]), int(sib_off[hi])
+    return headers[lo:hi], sib_pool[first:last], sib_off[lo:hi + 1] - sib_off[lo]

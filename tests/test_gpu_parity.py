@@ -307,6 +307,26 @@ def test_smt_process_proofs(glb, ctx, oracle, rng):
     assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_smt_process_proof_batch_shares_equal_the_whole_batch(glb, ctx, oracle, rng, world):
+    """a batch of process proofs is split evenly over the ranks with no exchange; every share, verified on
+    its own (sibling offsets rebased by parallel.slice_proof_batch), gives the statuses of its slice of the batch."""
+    import importlib
+
+    par = importlib.import_module("plonky2-lib_b200.parallel")
+    recs = _smt_proofs(oracle, rng)
+    recs["new_root"][7][0] ^= np.uint64(1)
+    recs["old_key"][20][3] ^= np.uint64(4)
+    hd, pool, off = _pack(glb, recs)
+    whole = glb.smt_check_process_proofs(hd, pool, off)
+    assert np.array_equal(whole, oracle.smt_verify_process_batch(recs)) and (whole != 0).sum() >= 2
+    got = []
+    for rank in range(world):
+        lo, hi = par.batch_range(rank, world, len(recs))
+        got.append(glb.smt_check_process_proofs(*par.slice_proof_batch(hd, pool, off, lo, hi)))
+    assert np.array_equal(np.concatenate(got), whole)
+
+
 def test_smt_fixture_root_three_inserts(glb, ctx, oracle):
     """(1->2), (12->1), (5->51) as in src/smt/gadgets/verify/mod.rs:24-34."""
     t = oracle.Smt()
