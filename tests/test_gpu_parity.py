@@ -316,7 +316,7 @@ def test_smt_process_proof_batch_shares_equal_the_whole_batch(glb, ctx, oracle, 
     par = importlib.import_module("plonky2-lib_b200.parallel")
     recs = _smt_proofs(oracle, rng)
     recs["new_root"][7][0] ^= np.uint64(1)
-    recs["old_key"][20][3] ^= np.uint64(4)
+    recs["old_root"][20][1] ^= np.uint64(4)
     hd, pool, off = _pack(glb, recs)
     whole = glb.smt_check_process_proofs(hd, pool, off)
     assert np.array_equal(whole, oracle.smt_verify_process_batch(recs)) and (whole != 0).sum() >= 2
