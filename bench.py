@@ -136,7 +136,7 @@ def run_reference(args):
     cores = int(o.lib().glo_num_threads())
     sample = (f"each step = one commit of 2^{lg} rows x {args.cols} cols (1/{1 << (args.log_n - lg)} of the workload rows); "
               f"oracle port of plonky2 v0.1.4 (the Rust reference cannot be built: no cargo, plonky2 fork not vendored)")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -144,7 +144,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 def synthetic_values_device(torch, cols, n, device, col0=0):
@@ -168,7 +168,31 @@ def synthetic_values_device(torch, cols, n, device, col0=0):
     return torch.where(ge, z + ((1 << 32) - 1), z).contiguous()
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Native libraries (NCCL's version banner, CUDA) write to
+    file descriptor 1 directly, so everything that is not the result goes to stderr: fd 1 is pointed at fd 2 for the
+    whole run and the result line is written to the saved descriptor at the end."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(result: dict):
+    line = (json.dumps(result) + "\n").encode()
+    sys.stdout.flush()
+    if _RESULT_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_RESULT_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -346,6 +370,98 @@ def main():
                                           "api": "gl_commit_from_values_cols, %d separate page-able arrays in and out" % cols}
         del hv, hc, pcols, ocols
 
+    if world > 1 and not args.no_e2e:
+        # ---- e2e at N GPUs: every rank keeps ITS columns of the input in page-locked host memory, uploads them round
+        # by round on a copy stream, and brings its columns of the coefficients back while the LDE and the tree run;
+        # rank 0 also reads the gathered cap.  Summed over the ranks every input cell crosses PCIe once each way.
+        hvals = torch.zeros((rounds, G, n), dtype=torch.int64).pin_memory()
+        hcoef = torch.zeros((rounds, G, n), dtype=torch.int64).pin_memory()
+        vh = values.cpu()
+        for j, (c0, c1) in enumerate(mine):
+            if c1 > c0:
+                hvals[j, : c1 - c0] = vh[c0:c1]
+        del vh
+        up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        ev_up = [torch.cuda.Event() for _ in range(rounds)]
+        ev_co = [torch.cuda.Event() for _ in range(rounds)]
+
+        trace = os.environ.get("BENCH_TRACE") and rank == 0
+        marks = []
+
+        def mark(name):
+            if trace:
+                marks.append((name, time.perf_counter()))
+
+        def estep():
+            marks.clear()
+            mark("start")
+            up.wait_stream(stream)
+            down.wait_stream(stream)
+            for j in range(rounds):
+                with torch.cuda.stream(up):
+                    slice_buf[j].copy_(hvals[j], non_blocking=True)
+                    ev_up[j].record(up)
+            works = []
+            h = C.c_void_p()
+            ctx.check(lib.gl_commit_begin(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT, C.byref(h)))
+
+            def lde(j):
+                works[j].wait()
+                c0 = j * world * G
+                ctx.check(lib.gl_commit_add_coeffs(h, c0, min(world * G, cols - c0), stage[j].data_ptr(), N.GL_DEVICE))
+                mark("lde%d" % j)
+
+            # round j arrives over PCIe while round j - 1 is extended (the C ABI calls block, the copy stream does not)
+            for j in range(rounds):
+                stream.wait_event(ev_up[j])
+                ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf[j].data_ptr(), log_n, G, N.GL_DEVICE))
+                ev_co[j].record(stream)
+                works.append(dist.all_gather_into_tensor(stage[j], slice_buf[j], async_op=True))
+                with torch.cuda.stream(down):
+                    down.wait_event(ev_co[j])
+                    hcoef[j].copy_(slice_buf[j], non_blocking=True)
+                mark("ifft%d" % j)
+                if j:
+                    lde(j - 1)
+            lde(rounds - 1)
+            ctx.check(lib.gl_commit_finish(h, cap_dev.data_ptr(), N.GL_DEVICE))
+            mark("tree")
+            lib.gl_commit_free(h)
+            par.all_gather_cap(dist, cap_dev[k0:k1].contiguous(), cap_all)
+            cap_h = cap_all.cpu() if rank == 0 else None     # the step's result on the host
+            mark("cap")
+            down.synchronize()
+            torch.cuda.current_stream().synchronize()
+            mark("end")
+            if trace:
+                sys.stderr.write("e2e trace ms: " + " ".join("%s=%.1f" % (k, (t - marks[0][1]) * 1e3) for k, t in marks[1:]) + "\n")
+            return cap_h
+
+        for _ in range(2):
+            estep()
+        barrier()
+        ksteps = max(2, min(args.steps, 5))
+        e0.record(stream)
+        for _ in range(ksteps):
+            cap_h = estep()
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / ksteps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        # the coefficients that came back are the ones the device-resident step gathers
+        j_last = max(j for j, (c0, c1) in enumerate(mine) if c1 > c0) if any(c1 > c0 for c0, c1 in mine) else None
+        if j_last is not None:
+            c0 = j_last * world * G + rank * G
+            assert torch.equal(hcoef[j_last, 0], stage[j_last, rank * G].cpu()), "e2e coefficients differ"
+        if rank == 0:
+            assert np.array_equal(cap_h.numpy().view(np.uint64), cap_host), "e2e cap differs from the device-resident run"
+            e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(cells * 8),
+                   "d2h_bytes_per_step": int(cells * 8 + cap_host.nbytes), "ms_per_step": ems,
+                   "api": "per rank: its IFFT columns H2D from pinned memory round by round, gl_ifft_batch, all-gather, "
+                          "gl_commit_begin/add_coeffs/finish, its coefficient columns D2H; rank 0 reads the cap"}
+        del hvals, hcoef
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -419,7 +535,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(min(args.cpu_log_n, log_n), cols)
         out["cpu_baseline"] = cb
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
