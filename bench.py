@@ -97,7 +97,7 @@ def cpu_baseline(log_n_sample: int, cols: int, repeat: int = 1):
     """The oracle port of the path on the host cores (bounded sample of the workload)."""
     from oracle import pyoracle as o
 
-    o.lib()
+    use_all_host_threads(o)
     v = o.synthetic_values(cols, 1 << log_n_sample)
     o.commit_from_values(o.synthetic_values(4, 256), RATE_BITS, CAP_HEIGHT, want_leaves=False)  # warm tables
     best = None
@@ -114,6 +114,15 @@ def cpu_baseline(log_n_sample: int, cols: int, repeat: int = 1):
     }, best
 
 
+def use_all_host_threads(o):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core it may run on."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    o.lib().glo_set_num_threads(max(1, n))
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation is un-buildable here (Rust, un-vendored
     plonky2 fork, no cargo) so the oracle port stands in, on all host cores, bounded sample per step."""
@@ -122,7 +131,7 @@ def run_reference(args):
         return
     from oracle import pyoracle as o
 
-    o.lib()
+    use_all_host_threads(o)
     lg = args.ref_log_n
     v = o.synthetic_values(args.cols, 1 << lg)
     for _ in range(max(args.warmup, 0)):
