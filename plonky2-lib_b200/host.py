@@ -737,8 +737,9 @@ def smt_build_tree(keys, values, want_nodes: bool = False, ctx=None):
     k, v = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4)
     if k.shape != v.shape:
         raise GlPanic(N.GL_E_ARG, "smt_build_tree: keys and values differ in shape")
-    keep = v.any(axis=1)
-    k, v = np.ascontiguousarray(k[keep]), np.ascontiguousarray(v[keep])
+    keep = (v[:, 0] | v[:, 1] | v[:, 2] | v[:, 3]) != 0
+    if not keep.all():                       # the usual batch has no removals: no copies then
+        k, v = np.ascontiguousarray(k[keep]), np.ascontiguousarray(v[keep])
     m = k.shape[0]
     root = np.zeros(4, dtype=np.uint64)
     count = C.c_uint64(0)
