@@ -364,6 +364,12 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
     int prev = enabled ? ST_TOP : ST_NA;
     bool ins_or_rem = fnc == 2;
     bool is_old0 = pf->is_old0 != 0;
+    // calc_old_new_root (src/smt/proof/process.rs:260-337) hashes twice at each of the 256 levels, but a level in
+    // state Na passes zeros on, old_hash is read only in state Top and new_hash only in Top / Bottom / NewOne: the
+    // discarded hashes are not computed here.  `last` = deepest level that is not Na (everything below it yields
+    // prev_old = prev_new = 0); the leaf hashes are computed only if some level reads them.
+    int last = -1;
+    bool need_old1 = false, need_new1 = false;
     for (int i = 0; i < LEVELS; i++) {
         int diff = key_bit(old_key, i) ^ key_bit(new_key, i);
         bool lev_ins = (i == ins_level);
@@ -380,33 +386,40 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
         }
         smw[i / 10] |= (u32)st << (3 * (i % 10));
         prev = st;
+        if (st != ST_NA) last = i;
+        need_old1 |= st == ST_BOT || st == ST_NEW1 || st == ST_UPD;
+        need_new1 |= st == ST_NEW1 || st == ST_OLD0 || st == ST_UPD;
     }
     if (prev == ST_TOP || prev == ST_BOT) { status[t] = 3; return; }
-    u64 old1_leaf[4], new1_leaf[4];
-    smt_leaf_hash_call(old_key, old_value, old1_leaf);
-    smt_leaf_hash_call(new_key, new_value, new1_leaf);
+    u64 old1_leaf[4] = {0, 0, 0, 0}, new1_leaf[4] = {0, 0, 0, 0};
+    if (need_old1) smt_leaf_hash_call(old_key, old_value, old1_leaf);
+    if (need_new1) smt_leaf_hash_call(new_key, new_value, new1_leaf);
     u64 prev_old[4] = {0, 0, 0, 0}, prev_new[4] = {0, 0, 0, 0};
     const u64 zero[4] = {0, 0, 0, 0};
 #pragma unroll 1
-    for (int i = LEVELS - 1; i >= 0; i--) {
+    for (int i = last; i >= 0; i--) {
         int st = (int)((smw[i / 10] >> (3 * (i % 10))) & 7u);
         bool pos = key_bit(new_key, i) != 0;
         u64 sb[4];
         if ((u32)i < ns) load_digest(sibs + 4 * i, sb);
         else { sb[0] = sb[1] = sb[2] = sb[3] = 0; }
-        u64 l[4], r[4], old_hash[4], new_hash[4];
-        sel4(l, sb, pos, prev_old);
-        sel4(r, prev_old, pos, sb);
-        two_to_one_call(l, r, old_hash);
+        u64 l[4], r[4], old_hash[4] = {0, 0, 0, 0}, new_hash[4] = {0, 0, 0, 0};
+        if (st == ST_TOP) {
+            sel4(l, sb, pos, prev_old);
+            sel4(r, prev_old, pos, sb);
+            two_to_one_call(l, r, old_hash);
+        }
         u64 n_left[4], n_right[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             n_left[j] = (st == ST_TOP || st == ST_BOT) ? prev_new[j] : (st == ST_NEW1 ? new1_leaf[j] : 0);
             n_right[j] = st == ST_TOP ? sb[j] : (st == ST_NEW1 ? old1_leaf[j] : 0);
         }
-        sel4(l, n_right, pos, n_left);
-        sel4(r, n_left, pos, n_right);
-        two_to_one_call(l, r, new_hash);
+        if (st == ST_TOP || st == ST_BOT || st == ST_NEW1) {
+            sel4(l, n_right, pos, n_left);
+            sel4(r, n_left, pos, n_right);
+            two_to_one_call(l, r, new_hash);
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             prev_old[j] = st == ST_TOP ? old_hash[j]

@@ -307,6 +307,48 @@ def test_smt_process_proofs(glb, ctx, oracle, rng):
     assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
 
 
+def test_smt_process_proofs_with_long_common_prefixes(glb, ctx, oracle, rng):
+    """Keys that agree on 3 .. 255 leading path bits: the inserts push the old leaf down a chain of Bottom levels
+    before NewOne.  The kernel computes only the hashes the verifier reads (state Top / Bottom / NewOne levels);
+    statuses must equal the oracle's full 2 x 256-level walk, for valid proofs and for corrupted ones."""
+    t = oracle.Smt()
+    recs = []
+    base = [rand_field(rng, (4,)) for _ in range(12)]
+    for k in base:
+        recs.append(t.set(k, rand_field(rng, (4,))))
+    for j, k in enumerate(base):
+        bit = (3, 17, 63, 64, 70, 127, 128, 200, 254, 255, 31, 191)[j]
+        k2 = k.copy()
+        k2[bit >> 6] ^= np.uint64(1) << np.uint64(bit & 63)
+        k2 %= np.uint64(P)
+        recs.append(t.set(k2, rand_field(rng, (4,))))          # insert next to its twin
+    for k in base[::2]:
+        recs.append(t.set(k, np.zeros(4, dtype=np.uint64)))    # delete: the twin climbs back up
+    for k in base[1::2]:
+        recs.append(t.set(k, rand_field(rng, (4,))))           # update deep in the tree
+    recs = np.array(recs, dtype=oracle.SMT_PROOF_DTYPE)
+    assert recs["num_siblings"].max() == 256       # the twin at bit 255: upstream's assert!(siblings.len() < 256) fires
+    want = oracle.smt_verify_process_batch(recs)
+    assert (want == 0).sum() == len(recs) - 1 and (want == 1).sum() == 1
+    assert np.array_equal(glb.smt_check_process_proofs(*_pack(glb, recs)), want)
+    bad = recs.copy()
+    for i in range(len(bad)):
+        which = i % 5
+        if which == 0:
+            bad["new_root"][i][i % 4] ^= np.uint64(1)
+        elif which == 1:
+            bad["old_value"][i][0] ^= np.uint64(2)
+        elif which == 2 and bad["num_siblings"][i]:
+            bad["siblings"][i][bad["num_siblings"][i] - 1][1] ^= np.uint64(4)
+        elif which == 3:
+            bad["new_key"][i][3] ^= np.uint64(1) << np.uint64(62)
+        else:
+            bad["is_old0"][i] ^= 1
+    want = oracle.smt_verify_process_batch(bad)
+    assert (want != 0).sum() > len(bad) // 2
+    assert np.array_equal(glb.smt_check_process_proofs(*_pack(glb, bad)), want)
+
+
 @pytest.mark.parametrize("world", [2, 3, 8])
 def test_smt_process_proof_batch_shares_equal_the_whole_batch(glb, ctx, oracle, rng, world):
     """a batch of process proofs is split evenly over the ranks with no exchange; every share, verified on

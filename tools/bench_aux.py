@@ -59,31 +59,54 @@ t = timeit(lambda: ctx.check(lib.gl_poseidon_hash_no_pad_batch(ctx._h, leaves.da
 out["hash_no_pad_rows"] = {"rows": nl, "len": ll, "ms": t * 1e3, "perms_per_s": nl * 17 / t}
 del leaves, dig
 
-# BASELINE config 4 (i): SparseMerkleProcessProof::check over a batch of 2^20 proofs.  The verifier always walks 256
-# levels (2 compressions each) + 2 leaf hashes = 516 permutations whatever the proof says, so the batch is made of
-# ProcessNoOp proofs (old == new, which is all a no-op proof has to satisfy) with 8..15 random siblings each: no tree
-# has to be built on the CPU to time the kernel.  Parity of real insert / update / delete proofs: tests/.
+# BASELINE config 4 (i): SparseMerkleProcessProof::check over a batch of 2^20 proofs.  The batch is made of VALID insert
+# proofs of the shape a tree of 2^20 entries produces: 20 non-zero siblings, the new leaf goes into an empty slot
+# (is_old0).  Their roots are computed here with the library's own batch hashes, level by level over the whole batch
+# (no tree and no CPU hashing needed).  The reference's verifier hashes 2 x 256 levels + leaf hashes = 516
+# permutations per proof; 474 of them are discarded (levels in state Na, old side below the insertion level) and
+# the kernel does not compute those: 42 permutations per proof here, same statuses.
 rng = np.random.default_rng(4)
-mm = 1 << 20
+mm, NS = 1 << 20, 20
+new_key, new_val = rand_dev((mm, 4)), rand_dev((mm, 4))
+sib = rand_dev((mm, NS, 4))
+prev_new = torch.empty((mm, 4), dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+ctx.check(lib.gl_smt_leaf_hash_batch(ctx._h, new_key.data_ptr(), new_val.data_ptr(), prev_new.data_ptr(), mm, N.GL_DEVICE))
+prev_old = torch.zeros((mm, 4), dtype=torch.int64, device=dev)
+nxt = torch.empty((mm, 4), dtype=torch.int64, device=dev)
+for i in range(NS - 1, -1, -1):
+    pos = ((new_key[:, i >> 6] >> (i & 63)) & 1).bool()[:, None]
+    s_i = sib[:, i, :].contiguous()
+    for prev in (prev_old, prev_new):
+        l, r = torch.where(pos, s_i, prev).contiguous(), torch.where(pos, prev, s_i).contiguous()
+        torch.cuda.synchronize()   # torch's stream and the library's are different streams
+        ctx.check(lib.gl_poseidon_two_to_one_batch(ctx._h, l.data_ptr(), r.data_ptr(), nxt.data_ptr(), mm, N.GL_DEVICE))
+        prev.copy_(nxt)
 hdr_all = np.zeros(mm, dtype=glb.host.SMT_HDR_DTYPE)
-roots, ks, vs = (rng.integers(0, P, (mm, 4), dtype=np.uint64) for _ in range(3))
-hdr_all["old_root"] = hdr_all["new_root"] = roots
-hdr_all["old_key"] = hdr_all["new_key"] = ks
-hdr_all["old_value"] = hdr_all["new_value"] = vs
-hdr_all["fnc"] = 0
-ns = rng.integers(8, 16, mm).astype(np.uint64)
-off_all = np.concatenate([[0], np.cumsum(ns)]).astype(np.uint64)
-pool_all = rng.integers(0, P, (int(off_all[-1]), 4), dtype=np.uint64)
+hdr_all["old_root"] = prev_old.cpu().numpy().view(np.uint64)
+hdr_all["new_root"] = prev_new.cpu().numpy().view(np.uint64)
+hdr_all["new_key"] = (new_key.cpu().numpy().view(np.uint64)) % np.uint64(P)
+hdr_all["new_value"] = (new_val.cpu().numpy().view(np.uint64)) % np.uint64(P)
+hdr_all["is_old0"] = 1
+hdr_all["fnc"] = 2
+off_all = (np.arange(mm + 1, dtype=np.uint64) * np.uint64(NS))
 d_hdr = torch.from_numpy(hdr_all.view(np.uint8)).to(dev)
-d_pool = torch.from_numpy(pool_all.view(np.int64)).to(dev)
+d_pool = sib.reshape(mm * NS, 4)
 d_off = torch.from_numpy(off_all.view(np.int64)).to(dev)
-d_status = torch.empty(hdr_all.shape[0], dtype=torch.int32, device=dev)
+d_status = torch.empty(mm, dtype=torch.int32, device=dev)
+torch.cuda.synchronize()
 t = timeit(lambda: ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr.data_ptr(), d_pool.data_ptr(), d_off.data_ptr(), mm,
                                                             d_status.data_ptr(), N.GL_DEVICE)), 3)
-assert int(d_status.abs().sum().item()) == 0
-out["smt_verify_process_batch"] = {"proofs": mm, "kind": "ProcessNoOp (fixed 516 permutations per proof)", "avg_siblings": float(ns.mean()), "ms": t * 1e3, "proofs_per_s": mm / t,
-                                   "perms_per_s": mm * 516 / t}
-del d_pool, d_hdr, hdr_all, pool_all, roots, ks, vs
+assert int(d_status.abs().sum().item()) == 0, "synthetic insert proofs must verify: %s" % torch.unique(d_status, return_counts=True).__repr__()
+# one flipped bit in a sibling must be caught
+d_pool[12345, 1] ^= 1
+torch.cuda.synchronize()
+ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr.data_ptr(), d_pool.data_ptr(), d_off.data_ptr(), mm, d_status.data_ptr(), N.GL_DEVICE))
+assert int((d_status != 0).sum().item()) == 1 and int(d_status[12345 // NS].item()) != 0
+out["smt_verify_process_batch"] = {"proofs": mm, "kind": "valid ProcessInsert proofs, %d siblings, is_old0" % NS, "ms": t * 1e3,
+                                   "proofs_per_s": mm / t, "permutations_computed_per_proof": 2 * NS + 2,
+                                   "perms_per_s": mm * (2 * NS + 2) / t, "reference_permutations_per_proof": 516}
+del d_pool, d_hdr, hdr_all, sib, new_key, new_val, prev_old, prev_new, nxt
 
 # N2: bulk build of the sparse Merkle tree over 2^20 entries (BASELINE config 4: "batch of 2^20 native leaf updates")
 mk = 1 << 20
