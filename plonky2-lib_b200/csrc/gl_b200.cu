@@ -13,6 +13,7 @@
 // There is no CPU fallback anywhere in this file: every entry point needs a live CUDA context.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -32,6 +33,7 @@
 #include "ntt_kernels.h"
 #include "poseidon_constants.h"
 #include "smt_kernels.h"
+#include "smt_proofs.h"
 
 std::atomic<unsigned long long> g_gl_launches{0};
 
@@ -858,6 +860,111 @@ extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* v
         if (nodes_out) TRY(copy_out(ctx, nodes_out, b.nodes, (count < nodes_cap ? count : nodes_cap) * 96, GL_HOST));
     }
     return finish(ctx);
+}
+
+// N2, second half: the process proofs of m successive inserts into an empty tree (smt_proofs.cu)
+extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m,
+                                    gl_smt_proof_hdr* proofs_out, uint64_t* sib_pool_out, uint64_t sib_cap,
+                                    uint64_t* sib_off_out, uint64_t* num_siblings_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!num_siblings_out || (m && (!keys || !values || !proofs_out || !sib_off_out)))
+        return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: NULL buffer");
+    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: at most 2^31 - 1 entries");
+    *num_siblings_out = 0;
+    if (m == 0) return GL_OK;
+    Guard g(ctx);
+    smt_build_buffers b;
+    memset(&b, 0, sizeof b);
+    b.m = m;
+    const u64 *dk, *dv;
+    TRY(stage_in(ctx, keys, m * 32, space, 0, &dk));
+    TRY(stage_in(ctx, values, m * 32, space, 1, &dv));
+    b.keys = dk;
+    b.values = dv;
+    b.sort_tmp_bytes = smt_sort_temp_bytes(m);
+    const size_t tmp_bytes = std::max(b.sort_tmp_bytes, smt_proof_temp_bytes(m));
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
+    const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
+                 o_lcp = take(m * 2), o_vf = take(m * 32), o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4 + 8),
+                 o_tmp = take(tmp_bytes), o_u32 = take(12 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
+                 o_off = take((m + 1) * 8), o_hdr = take(m * sizeof(gl_smt_proof_hdr));
+    void* base;
+    TRY(scratch_get(ctx, 2, off, &base));
+    char* p0 = (char*)base;
+    b.rk = (u64*)(p0 + o_rk); b.rk_alt = (u64*)(p0 + o_rka); b.perm = (uint32_t*)(p0 + o_perm); b.perm_alt = (uint32_t*)(p0 + o_perma);
+    b.leafh = (u64*)(p0 + o_leafh); b.lcp = (uint16_t*)(p0 + o_lcp); b.val_first = (u64*)(p0 + o_vf);
+    b.form_depth = (uint16_t*)(p0 + o_fd); b.last_valid = (uint8_t*)(p0 + o_lv); b.hist = (uint32_t*)(p0 + o_hist);
+    b.sort_tmp = p0 + o_tmp;
+    uint32_t* d_bad = b.hist + 257;
+    CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 8, ctx->stream));
+    smt_proofs_check_values(dv, m, d_bad, ctx->stream);
+    int rc = smt_build_prepare(b, ctx->stream);
+    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_insert_proofs: sort");
+    uint32_t hist[259];
+    CK(cudaMemcpyAsync(hist, b.hist, 258 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (hist[256]) return fail(ctx, GL_E_ARG, "SparseMerkleTree::insert: given key already exists (duplicate keys in the batch)");
+    if (hist[257]) return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: a value is zero (set with the default value is a removal, not an insert)");
+    int dmax = -1;
+    for (int d = 255; d >= 0; d--)
+        if (hist[d]) { dmax = d; break; }
+    smt_proof_buffers q;
+    memset(&q, 0, sizeof q);
+    q.m = m;
+    q.stride = (uint32_t)(dmax + 1 > 1 ? dmax + 1 : 1);
+    q.keys = dk; q.values = dv; q.rk = b.rk; q.perm = b.perm; q.lcp = b.lcp; q.leafh = b.leafh;
+    uint32_t* u = (uint32_t*)(p0 + o_u32);
+    q.a_cur = u; q.end_cur = u + m; q.ord_cur = u + 2 * m; q.inv_cur = u + 3 * m; q.tm_cur = u + 4 * m;
+    q.a_nxt = u + 5 * m; q.end_nxt = u + 6 * m; q.ord_nxt = u + 7 * m; q.inv_nxt = u + 8 * m; q.tm_nxt = u + 9 * m;
+    q.stop_depth = u + 10 * m; q.stop_old = u + 11 * m;
+    q.val_cur = (u64*)(p0 + o_val); q.val_nxt = q.val_cur + 4 * m;
+    q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
+    u64* sort_keys = (u64*)(p0 + o_keys);
+    u64* d_off = (u64*)(p0 + o_off);
+    // per-key sibling rows while sweeping: [m][stride][4]; counts (u32 [m + 1]) reuse the radix-sort double buffer
+    const size_t sib_bytes = (size_t)m * q.stride * 32;
+    u64* d_sib = nullptr;
+    TRY(dev_alloc(ctx, sib_bytes, &d_sib));
+    q.sib = d_sib;
+    uint32_t* counts = (uint32_t*)b.rk_alt;   // m * 8 bytes >= (m + 1) * 4
+    rc = smt_proofs_sweep(q, dmax, hist, sort_keys, sort_keys + m, b.perm_alt, counts, b.sort_tmp, tmp_bytes, ctx->stream);
+    if (rc == 0) rc = smt_proofs_offsets(counts, d_off, m, b.sort_tmp, tmp_bytes, ctx->stream);
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        dev_release(ctx, d_sib, sib_bytes);
+        return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_insert_proofs: sweep");
+    }
+    u64 total = 0;
+    cudaError_t e = cudaMemcpyAsync(&total, d_off + m, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        dev_release(ctx, d_sib, sib_bytes);
+        return cuda_fail(ctx, e, "gl_smt_insert_proofs");
+    }
+    *num_siblings_out = total;
+    int out_rc = GL_OK;
+    u64* d_pool = nullptr;
+    size_t pool_bytes = 0;
+    if (sib_pool_out && total <= sib_cap && total) {
+        if (space == GL_DEVICE) {
+            smt_proofs_gather(q, d_off, sib_cap, sib_pool_out, ctx->stream);
+        } else {
+            pool_bytes = (size_t)total * 32;
+            out_rc = dev_alloc(ctx, pool_bytes, &d_pool);
+            if (out_rc == GL_OK) {
+                smt_proofs_gather(q, d_off, total, d_pool, ctx->stream);
+                out_rc = copy_out(ctx, sib_pool_out, d_pool, pool_bytes, GL_HOST);
+            }
+        }
+    }
+    if (out_rc == GL_OK) out_rc = copy_out(ctx, proofs_out, q.hdr, m * sizeof(gl_smt_proof_hdr), space);
+    if (out_rc == GL_OK) out_rc = copy_out(ctx, sib_off_out, d_off, (m + 1) * 8, space);
+    int frc = finish(ctx);
+    dev_release(ctx, d_sib, sib_bytes);
+    if (d_pool) dev_release(ctx, d_pool, pool_bytes);
+    return out_rc != GL_OK ? out_rc : frc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -503,3 +503,4 @@ void launch_merkle_rows(const u64* leaves, u32 leaf_len, unsigned lg_leaves, uns
 
 // N2: SMT bulk build (shares this translation unit's Poseidon constants)
 #include "smt_kernels.cu"
+#include "smt_proofs.cu"

@@ -1,0 +1,237 @@
+// N2, second half: the m SparseMerkleProcessProofs that m successive `tree.set(key_t, value_t)` calls
+// (src/smt/tree.rs:143-155, insert :255-387, find :588-676) return when they start from an EMPTY tree and every
+// key is new -- all at once, although proof t is a statement about the tree that holds keys 0 .. t-1 only.
+//
+// With the keys sorted by path order, the keys below a trie position of depth d are a contiguous segment (maximal
+// run of adjacent pairs with LCP >= d).  A position holds: nothing (hash 0), one key (its leaf hash, hoisted), or
+// >= 2 keys (an internal node, possibly with one empty child).  Order the keys of every segment by insertion time:
+//   Val_d[i] = hash at that position once the i-th of them (by time) has been inserted
+//            = leaf hash                      for the first one,
+//              H(child slot 0, child slot 1)  afterwards, the child slots being Val_{d+1} of the two depth-(d+1)
+//                                             segments inside, taken at the same time.
+// The sweep runs from the deepest LCP up to depth 0; the child containing the key is read at the key's own
+// position in the depth-(d+1) order, the other child by a binary search over insertion times.  While key t has
+// >= 2 predecessors in its depth-d segment the position is an internal node on its `find` path and the other
+// child's slot value (strictly before t) is siblings[d] of proof t; the shallowest depth with <= 1 predecessors is
+// where `find` stops (empty slot: is_old0; one key: old_key / old_value).  Depth 0 yields old_root / new_root.
+// Work: one permutation per (key, depth above its stopping point) -- the hashes the sequential inserts compute,
+// ~ m log2 m in total -- plus one sort by (segment, time) for every depth at which segments merge.
+//
+// #included at the end of hash_kernels.cu after smt_kernels.cu (shares the Poseidon constants and helpers).
+#include <cub/device/device_scan.cuh>
+
+#include "smt_proofs.h"
+
+#define SP_NONE 0xFFFFFFFFu
+
+// path bit d of the key with input index `src` (rk holds bit-reversed limbs: bit d of limb d / 64 is bit 63 - d % 64)
+GL_D int smt_path_bit_perm(const u64* __restrict__ rk, u64 m, u32 src, unsigned d) {
+    return (int)((rk[(u64)(d >> 6) * m + src] >> (63 - (d & 63))) & 1);
+}
+
+__global__ void __launch_bounds__(256) k_sp_init(smt_proof_buffers p) {
+    u64 j = blockIdx.x * (u64)256 + threadIdx.x;
+    if (j >= p.m) return;
+    p.a_nxt[j] = (u32)j;
+    p.end_nxt[j] = (u32)j + 1;
+    p.ord_nxt[j] = (u32)j;
+    p.inv_nxt[j] = (u32)j;
+    p.tm_nxt[j] = p.perm[j];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = p.leafh[4 * j + k];
+    p.stop_depth[p.perm[j]] = 0;          // m == 1; otherwise the deepest level overwrites it for every key
+    p.stop_old[p.perm[j]] = SP_NONE;
+}
+
+// start flags of the depth-d segments, as scan input (index where a segment starts, else 0)
+__global__ void __launch_bounds__(256) k_sp_flags(smt_proof_buffers p, unsigned d, u32* __restrict__ flag_idx) {
+    u64 j = blockIdx.x * (u64)256 + threadIdx.x;
+    if (j >= p.m) return;
+    flag_idx[j] = (j == 0 || p.lcp[j - 1] < d) ? (u32)j : 0u;
+}
+// segment ends (indexed by segment start) and the (segment, time) sort keys
+__global__ void __launch_bounds__(256) k_sp_keys(smt_proof_buffers p, unsigned d, u64* __restrict__ keys, u32* __restrict__ vals) {
+    u64 j = blockIdx.x * (u64)256 + threadIdx.x;
+    if (j >= p.m) return;
+    const u32 a = p.a_cur[j];
+    if (j + 1 == p.m || p.lcp[j] < d) p.end_cur[a] = (u32)j + 1;
+    keys[j] = ((u64)a << 32) | p.perm[j];
+    vals[j] = (u32)j;
+}
+__global__ void __launch_bounds__(256) k_sp_unpack(smt_proof_buffers p, const u64* __restrict__ keys) {
+    u64 i = blockIdx.x * (u64)256 + threadIdx.x;
+    if (i >= p.m) return;
+    p.tm_cur[i] = (u32)keys[i];
+    p.inv_cur[p.ord_cur[i]] = (u32)i;
+}
+
+__global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, unsigned d) {
+    u64 i = blockIdx.x * (u64)SMT_BLOCK + threadIdx.x;
+    if (i >= p.m) return;
+    const u32 j = p.ord_cur[i];
+    const u32 a = p.a_cur[j], e = p.end_cur[a];
+    const u32 rank = (u32)i - a;
+    const u32 t = p.tm_cur[i];
+    if (rank == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) p.val_cur[4 * i + k] = p.leafh[4 * (u64)j + k];
+        p.stop_depth[t] = d;          // nothing under this position before t: an empty slot (unless a shallower
+        p.stop_old[t] = SP_NONE;      // depth overwrites this)
+        return;
+    }
+    const u32 a1 = p.a_nxt[j], e1 = p.end_nxt[a1];
+    u64 own[4], sib[4] = {0, 0, 0, 0}, out[4];
+    {
+        const u64 at = p.inv_nxt[j];
+#pragma unroll
+        for (int k = 0; k < 4; k++) own[k] = p.val_nxt[4 * at + k];
+    }
+    u32 lo = 0, hi = 0;
+    int bit;
+    if (a1 > a) { lo = a; hi = a1; bit = 1; }          // the key is in the right child
+    else if (e1 < e) { lo = e1; hi = e; bit = 0; }
+    else bit = smt_path_bit_perm(p.rk, p.m, p.perm[j], d);
+    if (hi > lo) {
+        // last entry of the other child's (time ordered) segment that was inserted before t
+        u32 l = lo, h = hi;
+        while (l < h) {
+            u32 mid = (l + h) >> 1;
+            if (p.tm_nxt[mid] < t) l = mid + 1;
+            else h = mid;
+        }
+        if (l > lo) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)(l - 1) + k];
+        }
+    }
+    if (bit) smt_two_to_one(sib, own, out);
+    else smt_two_to_one(own, sib, out);
+#pragma unroll
+    for (int k = 0; k < 4; k++) p.val_cur[4 * i + k] = out[k];
+    if (rank >= 2) {
+        u64* s = p.sib + ((u64)t * p.stride + d) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] = sib[k];
+    } else {
+        p.stop_depth[t] = d;
+        p.stop_old[t] = p.ord_cur[a];   // the one key that was there
+    }
+}
+
+// after depth 0 (one segment, time order): roots and trimmed sibling counts
+__global__ void __launch_bounds__(256) k_sp_roots(smt_proof_buffers p, u32* __restrict__ counts) {
+    u64 t = blockIdx.x * (u64)256 + threadIdx.x;
+    if (t >= p.m) return;
+    gl_smt_proof_hdr* h = p.hdr + t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        h->new_root[k] = p.val_cur[4 * t + k];
+        h->old_root[k] = t ? p.val_cur[4 * (t - 1) + k] : 0;
+        h->new_key[k] = gl_canon(p.keys[4 * t + k]);
+        h->new_value[k] = gl_canon(p.values[4 * t + k]);
+    }
+    const u32 so = p.stop_old[t];
+    if (so == SP_NONE) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) h->old_key[k] = h->old_value[k] = 0;
+        h->is_old0 = 1;
+    } else {
+        const u64 src = p.perm[so];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h->old_key[k] = gl_canon(p.keys[4 * src + k]);
+            h->old_value[k] = gl_canon(p.values[4 * src + k]);
+        }
+        h->is_old0 = 0;
+    }
+    h->fnc = 2;   // ProcessMerkleProofRole::ProcessInsert
+    u32 ns = p.stop_depth[t];
+    const u64* s = p.sib + (u64)t * p.stride * 4;
+    while (ns > 0 && (s[4 * (ns - 1)] | s[4 * (ns - 1) + 1] | s[4 * (ns - 1) + 2] | s[4 * (ns - 1) + 3]) == 0) ns--;
+    counts[t] = ns;
+}
+__global__ void __launch_bounds__(256) k_sp_gather(smt_proof_buffers p, const u64* __restrict__ off, u64 cap, u64* __restrict__ pool) {
+    u64 t = blockIdx.x * (u64)256 + threadIdx.x;
+    if (t >= p.m) return;
+    const u64 o = off[t], n = off[t + 1] - o;
+    if (o + n > cap) return;
+    const u64* s = p.sib + (u64)t * p.stride * 4;
+    for (u64 k = 0; k < 4 * n; k++) pool[4 * o + k] = s[k];
+}
+// any value that is all zero?  (`set` with the default value is a removal, not an insert)
+__global__ void __launch_bounds__(256) k_sp_check_values(const u64* __restrict__ values, u64 m, u32* __restrict__ bad) {
+    u64 t = blockIdx.x * (u64)256 + threadIdx.x;
+    if (t >= m) return;
+    if ((gl_canon(values[4 * t]) | gl_canon(values[4 * t + 1]) | gl_canon(values[4 * t + 2]) | gl_canon(values[4 * t + 3])) == 0) atomicAdd(bad, 1u);
+}
+
+size_t smt_proof_temp_bytes(uint64_t m) {
+    size_t a = 0, b = 0, c = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (const u64*)nullptr, (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr, (int)m);
+    cub::DeviceScan::InclusiveScan(nullptr, b, (const u32*)nullptr, (u32*)nullptr, cub::Max(), (int)m);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (const u32*)nullptr, (u64*)nullptr, (int)m + 1);
+    size_t r = a > b ? a : b;
+    return r > c ? r : c;
+}
+
+int smt_proofs_check_values(const u64* values, u64 m, u32* bad, cudaStream_t st) {
+    k_sp_check_values<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(values, m, bad);
+    ++g_gl_launches;
+    return 0;
+}
+
+// depths dmax .. 0; hist[d] = number of adjacent pairs with LCP == d (segments merge only at those depths).
+// The two sets of order arrays alternate: `nxt` is the live set (one level down), `cur` the one being written.
+int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, u64* sort_keys, u64* sort_keys_out, u32* sort_vals,
+                     u32* counts, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    const u64 m = p.m;
+    const unsigned b256 = (unsigned)((m + 255) / 256), bl = (unsigned)((m + SMT_BLOCK - 1) / SMT_BLOCK);
+    k_sp_init<<<b256, 256, 0, st>>>(p);
+    ++g_gl_launches;
+    int bits = 1;
+    while (((u64)1 << bits) < m) bits++;
+    u32* spare[5] = {p.a_cur, p.end_cur, p.ord_cur, p.inv_cur, p.tm_cur};
+    for (int d = dmax; d >= 0; d--) {
+        const bool merges = hist[d] != 0;
+        if (merges) {
+            p.a_cur = spare[0]; p.end_cur = spare[1]; p.ord_cur = spare[2]; p.inv_cur = spare[3]; p.tm_cur = spare[4];
+            // new segmentation: starts by a max-scan of the start flags, ends by scatter, order by (segment, time)
+            k_sp_flags<<<b256, 256, 0, st>>>(p, (unsigned)d, counts);
+            size_t tb = tmp_bytes;
+            cudaError_t e = cub::DeviceScan::InclusiveScan(tmp, tb, (const u32*)counts, p.a_cur, cub::Max(), (int)m, st);
+            if (e != cudaSuccess) return (int)e;
+            k_sp_keys<<<b256, 256, 0, st>>>(p, (unsigned)d, sort_keys, sort_vals);
+            tb = tmp_bytes;
+            e = cub::DeviceRadixSort::SortPairs(tmp, tb, (const u64*)sort_keys, sort_keys_out, (const u32*)sort_vals, p.ord_cur, (int)m, 0,
+                                                32 + bits, st);
+            if (e != cudaSuccess) return (int)e;
+            k_sp_unpack<<<b256, 256, 0, st>>>(p, sort_keys_out);
+            g_gl_launches += 8;
+        } else {
+            // no pair diverges at this depth: same segments and order as one level down (pure chain steps)
+            p.a_cur = p.a_nxt; p.end_cur = p.end_nxt; p.ord_cur = p.ord_nxt; p.inv_cur = p.inv_nxt; p.tm_cur = p.tm_nxt;
+        }
+        k_sp_level<<<bl, SMT_BLOCK, 0, st>>>(p, (unsigned)d);
+        ++g_gl_launches;
+        if (merges) {   // this depth becomes "one level down"; the old live set is the spare one now
+            spare[0] = p.a_nxt; spare[1] = p.end_nxt; spare[2] = p.ord_nxt; spare[3] = p.inv_nxt; spare[4] = p.tm_nxt;
+            p.a_nxt = p.a_cur; p.end_nxt = p.end_cur; p.ord_nxt = p.ord_cur; p.inv_nxt = p.inv_cur; p.tm_nxt = p.tm_cur;
+        }
+        u64* v = p.val_nxt; p.val_nxt = p.val_cur; p.val_cur = v;
+    }
+    p.val_cur = p.val_nxt;   // the depth-0 values (time order)
+    k_sp_roots<<<b256, 256, 0, st>>>(p, counts);
+    ++g_gl_launches;
+    return 0;
+}
+
+int smt_proofs_offsets(const u32* counts, u64* off, u64 m, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+    size_t tb = tmp_bytes;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(tmp, tb, counts, off, (int)m + 1, st);
+    g_gl_launches += 2;
+    return (int)e;
+}
+void smt_proofs_gather(const smt_proof_buffers& p, const u64* off, u64 cap, u64* pool, cudaStream_t st) {
+    k_sp_gather<<<(unsigned)((p.m + 255) / 256), 256, 0, st>>>(p, off, cap, pool);
+    ++g_gl_launches;
+}

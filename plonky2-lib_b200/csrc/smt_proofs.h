@@ -1,0 +1,35 @@
+// Internal interface of smt_proofs.cu: the process proofs of an insert-only batch (second half).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/gl_b200.h"
+
+struct smt_proof_buffers {
+    uint64_t m;
+    uint32_t stride;             // siblings kept per key while sweeping = deepest LCP + 1
+    // from smt_build_prepare (sorted by path order)
+    const uint64_t* keys;        // [m][4] input order
+    const uint64_t* values;      // [m][4] input order
+    const uint64_t* rk;          // [4][m] bit-reversed limbs, input order
+    const uint32_t* perm;        // sorted position -> input index = insertion time
+    const uint16_t* lcp;         // [m - 1]
+    const uint64_t* leafh;       // [m][4] sorted order
+    // segmentation and (segment, time) order of the depth being computed (cur) and of the one below it (nxt)
+    uint32_t *a_cur, *end_cur, *ord_cur, *inv_cur, *tm_cur;
+    uint32_t *a_nxt, *end_nxt, *ord_nxt, *inv_nxt, *tm_nxt;
+    uint64_t *val_cur, *val_nxt; // [m][4]
+    // per key, indexed by insertion time
+    uint64_t* sib;               // [m][stride][4]
+    uint32_t* stop_depth;        // where `find` stops
+    uint32_t* stop_old;          // sorted position of the key found there, SP_NONE for an empty slot
+    gl_smt_proof_hdr* hdr;       // [m]
+};
+
+size_t smt_proof_temp_bytes(uint64_t m);
+int smt_proofs_check_values(const uint64_t* values, uint64_t m, uint32_t* bad, cudaStream_t st);
+// spare: a second set of the five u32 arrays (the sweep alternates between the two sets)
+int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, uint64_t* sort_keys, uint64_t* sort_keys_out,
+                     uint32_t* sort_vals, uint32_t* counts /* [m + 1] */, void* tmp, size_t tmp_bytes, cudaStream_t st);
+int smt_proofs_offsets(const uint32_t* counts, uint64_t* off, uint64_t m, void* tmp, size_t tmp_bytes, cudaStream_t st);
+void smt_proofs_gather(const smt_proof_buffers& p, const uint64_t* off, uint64_t cap, uint64_t* pool, cudaStream_t st);

@@ -84,3 +84,86 @@ def test_bulk_build_scale(glb, ctx, oracle, rng):
     keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
     _, want = _oracle_root(oracle, keys, values)
     assert np.array_equal(glb.host.smt_build_tree(keys, values), want)
+
+
+# ---- process proofs of an insert-only batch (gl_smt_insert_proofs) ------------------------------------------------
+def _sequential_proofs(oracle, keys, values):
+    t = oracle.Smt()
+    return np.array([t.set(k, v) for k, v in zip(keys, values)], dtype=oracle.SMT_PROOF_DTYPE), t.root()
+
+
+def _check_proofs(glb, oracle, keys, values):
+    want, root = _sequential_proofs(oracle, keys, values)
+    hdr, pool, off = glb.host.smt_insert_proofs(keys, values)
+    m = len(keys)
+    assert off.shape == (m + 1,) and int(off[0]) == 0 and int(off[-1]) == pool.shape[0]
+    for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "is_old0", "fnc"):
+        assert np.array_equal(hdr[f], want[f]), f
+    assert np.array_equal(np.diff(off).astype(np.uint32), want["num_siblings"])
+    for t in range(m):
+        ns = int(want["num_siblings"][t])
+        assert np.array_equal(pool[int(off[t]):int(off[t + 1])], want["siblings"][t][:ns]), t
+    if m:
+        assert np.array_equal(hdr["new_root"][-1], root)
+        assert np.array_equal(glb.host.smt_build_tree(keys, values), root)
+    # and they are what the batch verifier accepts
+    assert not glb.smt_check_process_proofs(hdr, pool, off).any()
+    return hdr, pool, off
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 33, 700])
+def test_insert_proofs_match_sequential_sets(glb, ctx, oracle, rng, m):
+    keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
+    _check_proofs(glb, oracle, keys, values)
+
+
+def test_insert_proofs_reference_fixture(glb, ctx, oracle):
+    """(1 -> 2), (12 -> 1), (5 -> 51) in this order: src/smt/gadgets/verify/mod.rs:24-34."""
+    keys = np.stack([oracle.from_u128(k) for k in (1, 12, 5)])
+    values = np.stack([oracle.from_u128(v) for v in (2, 1, 51)])
+    hdr, pool, off = _check_proofs(glb, oracle, keys, values)
+    assert hdr["is_old0"].tolist() == [1, 0, 0]           # the first insert finds an empty tree, the others a leaf
+    assert hdr["new_root"][2].tolist() == [16994558480514381166, 8559105504417206749, 13458782878755336329, 17099432696459526118]
+
+
+def test_insert_proofs_long_common_prefixes_and_orders(glb, ctx, oracle, rng):
+    """Twins that agree on up to 255 leading path bits (deep one-child chains, zero siblings in the middle of a proof,
+    trailing zeros trimmed), small keys that share long runs of zero bits, and the same set in three insertion orders."""
+    base = rand_field(rng, (10, 4))
+    twins = []
+    for j, k in enumerate(base):
+        for bit in ((0, 1, 5, 63, 64, 65, 128, 191, 254, 255)[j], (7, 200, 33, 100, 250, 2, 70, 129, 9, 130)[j]):
+            k2 = k.copy()
+            k2[bit >> 6] ^= np.uint64(1) << np.uint64(bit & 63)
+            if int(k2[bit >> 6]) < P:
+                twins.append(k2)
+    small = np.stack([oracle.from_u128(x) for x in (0, 1, 2, 3, 4, 8, 12, 5, 1 << 40, (1 << 40) + 1, 1 << 100)])
+    keys = np.unique(np.concatenate([base, np.array(twins), small]), axis=0)
+    values = rand_field(rng, keys.shape) | np.uint64(1)
+    for order in (np.arange(len(keys)), np.arange(len(keys))[::-1], rng.permutation(len(keys))):
+        hdr, pool, off = _check_proofs(glb, oracle, keys[order].copy(), values[order].copy())
+    assert int(np.diff(off).max()) > 100        # proofs that walk more than a hundred levels down
+
+
+def test_insert_proofs_reject_duplicates_and_zero_values(glb, ctx, rng):
+    keys, values = rand_field(rng, (9, 4)), rand_field(rng, (9, 4)) | np.uint64(1)
+    bad = keys.copy()
+    bad[7] = bad[2]
+    with pytest.raises(glb.GlPanic, match="already exists"):
+        glb.host.smt_insert_proofs(bad, values)
+    z = values.copy()
+    z[4] = 0
+    with pytest.raises(glb.GlPanic, match="removal"):
+        glb.host.smt_insert_proofs(keys, z)
+
+
+def test_insert_proofs_at_scale_verify(glb, ctx, rng):
+    """2^17 inserts: every emitted proof passes the batch verifier and the chain of roots is consistent."""
+    m = 1 << 17
+    keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
+    hdr, pool, off = glb.host.smt_insert_proofs(keys, values)
+    assert not glb.smt_check_process_proofs(hdr, pool, off).any()
+    assert np.array_equal(hdr["old_root"][1:], hdr["new_root"][:-1]) and not hdr["old_root"][0].any()
+    assert np.array_equal(hdr["new_root"][-1], glb.host.smt_build_tree(keys, values))
+    ns = np.diff(off)
+    assert 14 < ns[m // 2:].mean() < 20          # ~ log2 of the tree size at insertion time
