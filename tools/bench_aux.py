@@ -114,7 +114,26 @@ kk = rng.integers(0, P, (mk, 4), dtype=np.uint64)
 vv = rng.integers(1, P, (mk, 4), dtype=np.uint64)
 t = timeit(lambda: glb.host.smt_build_tree(kk, vv), 2)
 out["smt_build_tree"] = {"entries": mk, "ms": t * 1e3, "entries_per_s": mk / t, "note": "host buffers: 64 MB H2D inside the call"}
-del kk, vv
+# N2, second half: the 2^20 process proofs of those inserts (in call order, from an empty tree), device-resident
+# outputs, then the batch verifier over what was emitted: BASELINE config 4 as a pipeline
+dk, dvv = torch.from_numpy(kk.view(np.int64)).to(dev), torch.from_numpy(vv.view(np.int64)).to(dev)
+d_hdr2 = torch.empty(mk * glb.host.SMT_HDR_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+cap2 = 24 * mk
+d_pool2 = torch.empty((cap2, 4), dtype=torch.int64, device=dev)
+d_off2 = torch.empty(mk + 1, dtype=torch.int64, device=dev)
+tot = C.c_uint64(0)
+torch.cuda.synchronize()
+t = timeit(lambda: ctx.check(lib.gl_smt_insert_proofs(ctx._h, dk.data_ptr(), dvv.data_ptr(), mk, d_hdr2.data_ptr(), d_pool2.data_ptr(), cap2,
+                                                     d_off2.data_ptr(), C.byref(tot), N.GL_DEVICE)), 2)
+assert tot.value <= cap2
+d_st2 = torch.empty(mk, dtype=torch.int32, device=dev)
+tv = timeit(lambda: ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr2.data_ptr(), d_pool2.data_ptr(), d_off2.data_ptr(), mk,
+                                                             d_st2.data_ptr(), N.GL_DEVICE)), 2)
+assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
+out["smt_insert_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
+                            "avg_siblings": tot.value / mk, "verify_emitted_ms": tv * 1e3,
+                            "note": "device-resident inputs and outputs; one permutation per sibling + sorts by (segment, time) per trie depth"}
+del kk, vv, dk, dvv, d_hdr2, d_pool2, d_off2
 
 # FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
 ln = 1 << 23
