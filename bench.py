@@ -7,7 +7,10 @@ A step = one commit.
 
   value   : inputs resident in HBM (GL_DEVICE), outputs left on the device, cap to the host.
   e2e     : the same call through the C ABI with HOST (pinned) buffers: values H2D, coefficients + cap D2H
-            inside the timed region.
+            inside the timed region; e2e.pageable_per_polynomial = the drop-in's own buffers (one ordinary array per
+            polynomial, gl_commit_from_values_cols).  At N > 1 every rank uploads its columns and downloads its
+            coefficient columns, pipelined with the LDE rounds.
+  proof_trace: informational, N = 1: the commits + prove_openings of one proof at config 1's row count.
   roofline: the dominant kernel (Poseidon leaf hashing) timed with the library's own CUDA events.
   cpu_baseline: the CPU oracle (a port of plonky2 v0.1.4 semantics, oracle/) on a bounded sample, rank 0, N=1.
 
@@ -114,6 +117,52 @@ def cpu_baseline(log_n_sample: int, cols: int, repeat: int = 1):
     }, best
 
 
+def proof_trace(glb, ctx, torch, lg=16):
+    """The other half of BASELINE.json's metric ("prove ms per circuit") as far as this path goes: the commit + opening
+    trace of one data.prove(pw) at the row count SURVEY 8d estimates for config 1 (single ECDSA, 2^16 rows): wires,
+    Z / partial products and quotient commits (135 + 20 + 16 polynomials, ordinary page-able host arrays in, coefficients
+    out) + prove_openings over those and the build-time constants/sigmas oracle (84 polynomials).  Witness generation and
+    compute_quotient_polys are host stages of the reference and are not part of this number.  Informational: never
+    fails the bench."""
+    try:
+        fri = importlib.import_module("plonky2-lib_b200.fri")
+        P = glb.host.P
+        n = 1 << lg
+        colsets = (84, 135, 20, 16)
+        rng = np.random.default_rng(lg)
+        vals = [rng.integers(0, P, size=(c, n), dtype=np.uint64) for c in colsets]
+        const_sigmas = glb.PolynomialBatch.from_values(vals[0], RATE_BITS, False, CAP_HEIGHT, want_coeffs=False, ctx=ctx)
+        zeta = (0x123456789ABCDEF % P, 0x0FEDCBA987654321 % P)
+        g = pow(pow(7, (P - 1) >> 32, P), 1 << (32 - lg), P)
+        inst = [(zeta, [(oi, pi) for oi, c in enumerate(colsets) for pi in range(c)]),
+                ((zeta[0] * g % P, zeta[1] * g % P), [(2, pi) for pi in range(20)])]
+        prm = fri.FriParams.for_degree(glb.FriConfig(), lg)
+
+        def once():
+            bs = [const_sigmas] + [glb.PolynomialBatch.from_values(v, RATE_BITS, False, CAP_HEIGHT, want_coeffs=True, ctx=ctx) for v in vals[1:]]
+            ch = fri.Challenger(ctx)
+            for b in bs:
+                ch.observe_cap(b.merkle_tree.cap)
+            proof = fri.prove_openings(bs, inst, ch, prm, ctx)
+            for b in bs[1:]:
+                b.free()
+            return proof
+
+        once()
+        best = None
+        for _ in range(3):
+            t = time.perf_counter()
+            proof = once()
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        const_sigmas.free()
+        return {"config1_ecdsa_2^%d_rows_ms" % lg: best * 1e3, "fri_layers": len(proof["commit_phase_merkle_caps"]),
+                "query_rounds": len(proof["query_round_proofs"]),
+                "what": "3 commits (135 + 20 + 16 polynomials, page-able host arrays, coefficients out) + prove_openings over 4 oracles; wall clock"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
+
+
 def use_all_host_threads(o):
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host core it may run on."""
     try:
@@ -213,6 +262,7 @@ def main():
     ap.add_argument("--cpu-log-n", type=int, default=17, help="rows (log2) of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-proof-trace", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -541,6 +591,8 @@ def main():
     }
     if e2e:
         out["e2e"] = e2e
+    if world == 1 and not args.no_proof_trace:
+        out["proof_trace"] = proof_trace(glb, ctx, torch)
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(min(args.cpu_log_n, log_n), cols)
         out["cpu_baseline"] = cb
