@@ -120,7 +120,8 @@ int gl_smt_build(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint
  * sib_pool_out[sib_off_out[t] .. sib_off_out[t+1]) exactly as `proof.siblings` (trailing zero siblings trimmed): the three
  * arrays are what gl_smt_verify_process_batch takes.  *num_siblings_out = total number of siblings; when it exceeds
  * sib_cap (or sib_pool_out is NULL) the pool is not written: call again with a larger pool.  proofs_out[m-1].new_root is
- * the root gl_smt_build returns.  Duplicate keys or an all-zero value return GL_E_ARG. */
+ * the root gl_smt_build returns.  A batch of new keys on a NON-empty tree: put the existing entries first (any order)
+ * and drop their proofs.  Duplicate keys or an all-zero value return GL_E_ARG. */
 int gl_smt_insert_proofs(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m,
                          gl_smt_proof_hdr *proofs_out, uint64_t *sib_pool_out, uint64_t sib_cap,
                          uint64_t *sib_off_out, uint64_t *num_siblings_out, int space);

@@ -146,6 +146,79 @@ struct PoseidonNodeHash {
     }
 };
 
+// ---- src/smt: batches over the sparse Merkle tree (P7, N2) ---------------------------------------------
+// SparseMerkleProcessProof (src/smt/proof/process.rs): what `tree.set(key, value)` returns
+struct SparseMerkleProcessProof {
+    HashOut old_root, old_key, old_value, new_root, new_key, new_value;
+    std::vector<HashOut> siblings;
+    bool is_old0 = false;
+    uint32_t fnc = 0;  // ProcessMerkleProofRole: 0 NoOp, 1 Update, 2 Insert, 3 Delete
+};
+struct SparseMerkleTreeBatch {
+    // SparseMerkleProcessProof::check for every proof (src/smt/proof/process.rs:47-51): 0 = holds, k = its k-th assert fails
+    static std::vector<int32_t> check_process_proofs(const Context& c, const std::vector<SparseMerkleProcessProof>& proofs) {
+        const size_t m = proofs.size();
+        std::vector<gl_smt_proof_hdr> hdr(m);
+        std::vector<uint64_t> off(m + 1, 0), pool;
+        for (size_t t = 0; t < m; t++) {
+            const SparseMerkleProcessProof& p = proofs[t];
+            for (int e = 0; e < 4; e++) {
+                hdr[t].old_root[e] = p.old_root.elements[e]; hdr[t].old_key[e] = p.old_key.elements[e];
+                hdr[t].old_value[e] = p.old_value.elements[e]; hdr[t].new_root[e] = p.new_root.elements[e];
+                hdr[t].new_key[e] = p.new_key.elements[e]; hdr[t].new_value[e] = p.new_value.elements[e];
+            }
+            hdr[t].is_old0 = p.is_old0;
+            hdr[t].fnc = p.fnc;
+            for (auto& sb : p.siblings) pool.insert(pool.end(), sb.elements, sb.elements + 4);
+            off[t + 1] = off[t] + p.siblings.size();
+        }
+        std::vector<int32_t> status(m);
+        if (pool.empty()) pool.resize(4);
+        c.check(gl_smt_verify_process_batch(c.raw(), hdr.data(), pool.data(), off.data(), m, status.data(), GL_HOST));
+        return status;
+    }
+    // root after `tree.set(keys[t], values[t])` for every t on an empty tree (new keys only; src/smt/tree.rs:143-155)
+    static HashOut root_of(const Context& c, const std::vector<HashOut>& keys, const std::vector<HashOut>& values) {
+        HashOut root{{0, 0, 0, 0}};
+        uint64_t count = 0;
+        c.check(gl_smt_build(c.raw(), keys.empty() ? nullptr : &keys[0].elements[0], values.empty() ? nullptr : &values[0].elements[0],
+                             keys.size(), root.elements, nullptr, 0, &count, nullptr, GL_HOST));
+        return root;
+    }
+    // the proofs those `set` calls return, in call order
+    static std::vector<SparseMerkleProcessProof> insert_proofs(const Context& c, const std::vector<HashOut>& keys,
+                                                               const std::vector<HashOut>& values) {
+        const size_t m = keys.size();
+        std::vector<SparseMerkleProcessProof> out(m);
+        if (!m) return out;
+        std::vector<gl_smt_proof_hdr> hdr(m);
+        std::vector<uint64_t> off(m + 1), pool((size_t)4 * 32 * m);
+        uint64_t total = 0;
+        for (;;) {
+            c.check(gl_smt_insert_proofs(c.raw(), &keys[0].elements[0], &values[0].elements[0], m, hdr.data(), pool.data(),
+                                         pool.size() / 4, off.data(), &total, GL_HOST));
+            if (total * 4 <= pool.size()) break;
+            pool.resize(total * 4);
+        }
+        for (size_t t = 0; t < m; t++) {
+            SparseMerkleProcessProof& p = out[t];
+            for (int e = 0; e < 4; e++) {
+                p.old_root.elements[e] = hdr[t].old_root[e]; p.old_key.elements[e] = hdr[t].old_key[e];
+                p.old_value.elements[e] = hdr[t].old_value[e]; p.new_root.elements[e] = hdr[t].new_root[e];
+                p.new_key.elements[e] = hdr[t].new_key[e]; p.new_value.elements[e] = hdr[t].new_value[e];
+            }
+            p.is_old0 = hdr[t].is_old0 != 0;
+            p.fnc = hdr[t].fnc;
+            for (uint64_t s = off[t]; s < off[t + 1]; s++) {
+                HashOut h;
+                for (int e = 0; e < 4; e++) h.elements[e] = pool[4 * s + e];
+                p.siblings.push_back(h);
+            }
+        }
+        return out;
+    }
+};
+
 // ---- MerkleTree ---------------------------------------------------------------------------------------
 struct MerkleTree {
     std::vector<std::vector<F>> leaves;

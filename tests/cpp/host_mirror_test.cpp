@@ -40,6 +40,27 @@ int main() {
     CHECK(leaf == a && a == b);
     CHECK(leaf.elements[0] == 9613647271972624781ULL);
 
+    // src/smt: (1 -> 2), (12 -> 1), (5 -> 51) as in src/smt/gadgets/verify/mod.rs:24-34 -- bulk root, the process proofs
+    // of the three inserts, and the batch verifier over them
+    {
+        std::vector<HashOut> keys = {{{1, 0, 0, 0}}, {{12, 0, 0, 0}}, {{5, 0, 0, 0}}};
+        std::vector<HashOut> vals = {{{2, 0, 0, 0}}, {{1, 0, 0, 0}}, {{51, 0, 0, 0}}};
+        HashOut root = SparseMerkleTreeBatch::root_of(ctx, keys, vals);
+        HashOut want_root{{16994558480514381166ULL, 8559105504417206749ULL, 13458782878755336329ULL, 17099432696459526118ULL}};
+        CHECK(root == want_root);
+        std::vector<SparseMerkleProcessProof> proofs = SparseMerkleTreeBatch::insert_proofs(ctx, keys, vals);
+        CHECK(proofs.size() == 3 && proofs[2].new_root == want_root && proofs[0].is_old0 && !proofs[1].is_old0);
+        CHECK(proofs[0].old_root == zero && proofs[1].old_root == proofs[0].new_root && proofs[2].old_root == proofs[1].new_root);
+        CHECK(proofs[0].new_root == PoseidonNodeHash::calc_leaf_hash_batch(ctx, &keys[0], &vals[0], 1)[0]);
+        CHECK(proofs[1].old_key == keys[0] && proofs[1].old_value == vals[0] && proofs[1].fnc == 2);
+        std::vector<int32_t> st = SparseMerkleTreeBatch::check_process_proofs(ctx, proofs);
+        CHECK(st[0] == 0 && st[1] == 0 && st[2] == 0);
+        proofs[2].new_root.elements[1] ^= 1;      // a wrong new root is assert 5 of verify_smt_process_proof
+        proofs[1].old_value.elements[0] ^= 1;     // a wrong old leaf changes the old root: assert 4
+        st = SparseMerkleTreeBatch::check_process_proofs(ctx, proofs);
+        CHECK(st[0] == 0 && st[1] == 4 && st[2] == 5);
+    }
+
     // commit + open: every opened row hashes up to the cap through MerkleTree semantics
     const CircuitConfig cfg = CircuitConfig::standard_recursion_config();
     const uint32_t lg = 8, cols = 20;
