@@ -921,7 +921,8 @@ extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uin
     q.stop_depth = u + 10 * m; q.stop_old = u + 11 * m;
     q.val_cur = (u64*)(p0 + o_val); q.val_nxt = q.val_cur + 4 * m;
     q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
-    u64* sort_keys = (u64*)(p0 + o_keys);
+    q.other = (uint32_t*)(p0 + o_keys);       // m * 4 bytes
+    q.bit = (uint8_t*)(p0 + o_keys) + 4 * m;   // m bytes
     u64* d_off = (u64*)(p0 + o_off);
     // per-key sibling rows while sweeping: [m][stride][4]; counts (u32 [m + 1]) reuse the radix-sort double buffer
     const size_t sib_bytes = (size_t)m * q.stride * 32;
@@ -929,7 +930,7 @@ extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uin
     TRY(dev_alloc(ctx, sib_bytes, &d_sib));
     q.sib = d_sib;
     uint32_t* counts = (uint32_t*)b.rk_alt;   // m * 8 bytes >= (m + 1) * 4
-    rc = smt_proofs_sweep(q, dmax, hist, sort_keys, sort_keys + m, b.perm_alt, counts, b.sort_tmp, tmp_bytes, ctx->stream);
+    rc = smt_proofs_sweep(q, dmax, hist, counts, b.sort_tmp, tmp_bytes, ctx->stream);
     if (rc == 0) rc = smt_proofs_offsets(counts, d_off, m, b.sort_tmp, tmp_bytes, ctx->stream);
     if (rc) {
         cudaStreamSynchronize(ctx->stream);

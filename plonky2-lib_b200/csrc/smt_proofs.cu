@@ -15,7 +15,7 @@
 // child's slot value (strictly before t) is siblings[d] of proof t; the shallowest depth with <= 1 predecessors is
 // where `find` stops (empty slot: is_old0; one key: old_key / old_value).  Depth 0 yields old_root / new_root.
 // Work: one permutation per (key, depth above its stopping point) -- the hashes the sequential inserts compute,
-// ~ m log2 m in total -- plus one sort by (segment, time) for every depth at which segments merge.
+// ~ m log2 m in total.  No sorting in the sweep: merging two time-ordered children is the same binary search.
 //
 // #included at the end of hash_kernels.cu after smt_kernels.cu (shares the Poseidon constants and helpers).
 #include <cub/device/device_scan.cuh>
@@ -49,27 +49,45 @@ __global__ void __launch_bounds__(256) k_sp_flags(smt_proof_buffers p, unsigned 
     if (j >= p.m) return;
     flag_idx[j] = (j == 0 || p.lcp[j - 1] < d) ? (u32)j : 0u;
 }
-// segment ends (indexed by segment start) and the (segment, time) sort keys
-__global__ void __launch_bounds__(256) k_sp_keys(smt_proof_buffers p, unsigned d, u64* __restrict__ keys, u32* __restrict__ vals) {
+// segment ends, indexed by segment start
+__global__ void __launch_bounds__(256) k_sp_ends(smt_proof_buffers p, unsigned d) {
     u64 j = blockIdx.x * (u64)256 + threadIdx.x;
     if (j >= p.m) return;
-    const u32 a = p.a_cur[j];
-    if (j + 1 == p.m || p.lcp[j] < d) p.end_cur[a] = (u32)j + 1;
-    keys[j] = ((u64)a << 32) | p.perm[j];
-    vals[j] = (u32)j;
+    if (j + 1 == p.m || p.lcp[j] < d) p.end_cur[p.a_cur[j]] = (u32)j + 1;
 }
-__global__ void __launch_bounds__(256) k_sp_unpack(smt_proof_buffers p, const u64* __restrict__ keys) {
-    u64 i = blockIdx.x * (u64)256 + threadIdx.x;
-    if (i >= p.m) return;
-    p.tm_cur[i] = (u32)keys[i];
-    p.inv_cur[p.ord_cur[i]] = (u32)i;
+// The (segment, time) order of depth d without sorting: a depth-d segment is the concatenation of (at most) two
+// depth-(d+1) segments that are already in time order, so the new position of a key is
+//   segment start + its rank in its own child + the number of keys of the other child inserted before it,
+// and that count is the binary search the hash needs anyway (kept in `other` for k_sp_level).
+__global__ void __launch_bounds__(256) k_sp_place(smt_proof_buffers p, unsigned d) {
+    u64 j = blockIdx.x * (u64)256 + threadIdx.x;
+    if (j >= p.m) return;
+    const u32 a = p.a_cur[j], e = p.end_cur[a];
+    const u32 a1 = p.a_nxt[j], e1 = p.end_nxt[a1];
+    const u32 t = p.perm[j];
+    u32 lo = 0, hi = 0, bit;
+    if (a1 > a) { lo = a; hi = a1; bit = 1; }          // the key is in the right child
+    else if (e1 < e) { lo = e1; hi = e; bit = 0; }
+    else bit = (u32)smt_path_bit_perm(p.rk, p.m, t, d);
+    u32 l = lo, h = hi;
+    while (l < h) {                                     // keys of the other child inserted before t
+        u32 mid = (l + h) >> 1;
+        if (p.tm_nxt[mid] < t) l = mid + 1;
+        else h = mid;
+    }
+    const u32 i = a + (p.inv_nxt[j] - a1) + (l - lo);
+    p.ord_cur[i] = (u32)j;
+    p.inv_cur[j] = i;
+    p.tm_cur[i] = t;
+    p.other[i] = (l > lo ? (l - 1) : SP_NONE) | 0u;     // where the other child's slot value at that time lives
+    p.bit[i] = (uint8_t)bit;
 }
 
-__global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, unsigned d) {
+__global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, unsigned d, int merged) {
     u64 i = blockIdx.x * (u64)SMT_BLOCK + threadIdx.x;
     if (i >= p.m) return;
     const u32 j = p.ord_cur[i];
-    const u32 a = p.a_cur[j], e = p.end_cur[a];
+    const u32 a = p.a_cur[j];
     const u32 rank = (u32)i - a;
     const u32 t = p.tm_cur[i];
     if (rank == 0) {
@@ -79,30 +97,22 @@ __global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, uns
         p.stop_old[t] = SP_NONE;      // depth overwrites this)
         return;
     }
-    const u32 a1 = p.a_nxt[j], e1 = p.end_nxt[a1];
     u64 own[4], sib[4] = {0, 0, 0, 0}, out[4];
     {
         const u64 at = p.inv_nxt[j];
 #pragma unroll
         for (int k = 0; k < 4; k++) own[k] = p.val_nxt[4 * at + k];
     }
-    u32 lo = 0, hi = 0;
     int bit;
-    if (a1 > a) { lo = a; hi = a1; bit = 1; }          // the key is in the right child
-    else if (e1 < e) { lo = e1; hi = e; bit = 0; }
-    else bit = smt_path_bit_perm(p.rk, p.m, p.perm[j], d);
-    if (hi > lo) {
-        // last entry of the other child's (time ordered) segment that was inserted before t
-        u32 l = lo, h = hi;
-        while (l < h) {
-            u32 mid = (l + h) >> 1;
-            if (p.tm_nxt[mid] < t) l = mid + 1;
-            else h = mid;
-        }
-        if (l > lo) {
+    if (merged) {
+        bit = p.bit[i];
+        const u32 o = p.other[i];
+        if (o != SP_NONE) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)(l - 1) + k];
+            for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)o + k];
         }
+    } else {
+        bit = smt_path_bit_perm(p.rk, p.m, t, d);      // no pair diverges here: every position is a one-child node
     }
     if (bit) smt_two_to_one(sib, own, out);
     else smt_two_to_one(own, sib, out);
@@ -167,7 +177,6 @@ __global__ void __launch_bounds__(256) k_sp_check_values(const u64* __restrict__
 
 size_t smt_proof_temp_bytes(uint64_t m) {
     size_t a = 0, b = 0, c = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, a, (const u64*)nullptr, (u64*)nullptr, (const u32*)nullptr, (u32*)nullptr, (int)m);
     cub::DeviceScan::InclusiveScan(nullptr, b, (const u32*)nullptr, (u32*)nullptr, cub::Max(), (int)m);
     cub::DeviceScan::ExclusiveSum(nullptr, c, (const u32*)nullptr, (u64*)nullptr, (int)m + 1);
     size_t r = a > b ? a : b;
@@ -182,36 +191,29 @@ int smt_proofs_check_values(const u64* values, u64 m, u32* bad, cudaStream_t st)
 
 // depths dmax .. 0; hist[d] = number of adjacent pairs with LCP == d (segments merge only at those depths).
 // The two sets of order arrays alternate: `nxt` is the live set (one level down), `cur` the one being written.
-int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, u64* sort_keys, u64* sort_keys_out, u32* sort_vals,
-                     u32* counts, void* tmp, size_t tmp_bytes, cudaStream_t st) {
+int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, u32* counts, void* tmp, size_t tmp_bytes, cudaStream_t st) {
     const u64 m = p.m;
     const unsigned b256 = (unsigned)((m + 255) / 256), bl = (unsigned)((m + SMT_BLOCK - 1) / SMT_BLOCK);
     k_sp_init<<<b256, 256, 0, st>>>(p);
     ++g_gl_launches;
-    int bits = 1;
-    while (((u64)1 << bits) < m) bits++;
     u32* spare[5] = {p.a_cur, p.end_cur, p.ord_cur, p.inv_cur, p.tm_cur};
     for (int d = dmax; d >= 0; d--) {
         const bool merges = hist[d] != 0;
         if (merges) {
             p.a_cur = spare[0]; p.end_cur = spare[1]; p.ord_cur = spare[2]; p.inv_cur = spare[3]; p.tm_cur = spare[4];
-            // new segmentation: starts by a max-scan of the start flags, ends by scatter, order by (segment, time)
+            // new segmentation: starts by a max-scan of the start flags, ends by scatter, then the merged time order
             k_sp_flags<<<b256, 256, 0, st>>>(p, (unsigned)d, counts);
             size_t tb = tmp_bytes;
             cudaError_t e = cub::DeviceScan::InclusiveScan(tmp, tb, (const u32*)counts, p.a_cur, cub::Max(), (int)m, st);
             if (e != cudaSuccess) return (int)e;
-            k_sp_keys<<<b256, 256, 0, st>>>(p, (unsigned)d, sort_keys, sort_vals);
-            tb = tmp_bytes;
-            e = cub::DeviceRadixSort::SortPairs(tmp, tb, (const u64*)sort_keys, sort_keys_out, (const u32*)sort_vals, p.ord_cur, (int)m, 0,
-                                                32 + bits, st);
-            if (e != cudaSuccess) return (int)e;
-            k_sp_unpack<<<b256, 256, 0, st>>>(p, sort_keys_out);
-            g_gl_launches += 8;
+            k_sp_ends<<<b256, 256, 0, st>>>(p, (unsigned)d);
+            k_sp_place<<<b256, 256, 0, st>>>(p, (unsigned)d);
+            g_gl_launches += 5;
         } else {
             // no pair diverges at this depth: same segments and order as one level down (pure chain steps)
             p.a_cur = p.a_nxt; p.end_cur = p.end_nxt; p.ord_cur = p.ord_nxt; p.inv_cur = p.inv_nxt; p.tm_cur = p.tm_nxt;
         }
-        k_sp_level<<<bl, SMT_BLOCK, 0, st>>>(p, (unsigned)d);
+        k_sp_level<<<bl, SMT_BLOCK, 0, st>>>(p, (unsigned)d, merges ? 1 : 0);
         ++g_gl_launches;
         if (merges) {   // this depth becomes "one level down"; the old live set is the spare one now
             spare[0] = p.a_nxt; spare[1] = p.end_nxt; spare[2] = p.ord_nxt; spare[3] = p.inv_nxt; spare[4] = p.tm_nxt;

@@ -19,6 +19,8 @@ struct smt_proof_buffers {
     uint32_t *a_cur, *end_cur, *ord_cur, *inv_cur, *tm_cur;
     uint32_t *a_nxt, *end_nxt, *ord_nxt, *inv_nxt, *tm_nxt;
     uint64_t *val_cur, *val_nxt; // [m][4]
+    uint32_t* other;             // [m] per position of the current order: index in val_nxt of the other child's value
+    uint8_t* bit;                // [m] path bit of the key at this depth (1: the key is in the right child)
     // per key, indexed by insertion time
     uint64_t* sib;               // [m][stride][4]
     uint32_t* stop_depth;        // where `find` stops
@@ -28,8 +30,7 @@ struct smt_proof_buffers {
 
 size_t smt_proof_temp_bytes(uint64_t m);
 int smt_proofs_check_values(const uint64_t* values, uint64_t m, uint32_t* bad, cudaStream_t st);
-// spare: a second set of the five u32 arrays (the sweep alternates between the two sets)
-int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, uint64_t* sort_keys, uint64_t* sort_keys_out,
-                     uint32_t* sort_vals, uint32_t* counts /* [m + 1] */, void* tmp, size_t tmp_bytes, cudaStream_t st);
+int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, uint32_t* counts /* [m + 1] */, void* tmp,
+                     size_t tmp_bytes, cudaStream_t st);
 int smt_proofs_offsets(const uint32_t* counts, uint64_t* off, uint64_t m, void* tmp, size_t tmp_bytes, cudaStream_t st);
 void smt_proofs_gather(const smt_proof_buffers& p, const uint64_t* off, uint64_t cap, uint64_t* pool, cudaStream_t st);

@@ -132,7 +132,7 @@ tv = timeit(lambda: ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr2.dat
 assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
 out["smt_insert_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
                             "avg_siblings": tot.value / mk, "verify_emitted_ms": tv * 1e3,
-                            "note": "device-resident inputs and outputs; one permutation per sibling + sorts by (segment, time) per trie depth"}
+                            "note": "device-resident inputs and outputs; one permutation per (key, depth above its stopping point); the time order of a depth is merged from its children by the same binary search the hash needs"}
 del kk, vv, dk, dvv, d_hdr2, d_pool2, d_off2
 
 # FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
