@@ -462,7 +462,11 @@ def main():
                     ev_up[j].record(up)
             works = []
             h = C.c_void_p()
-            ctx.check(lib.gl_commit_begin(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT, C.byref(h)))
+            # GL_COMMIT_STREAM_HASH: the leaves absorb each block as soon as it is extended, so the hashing runs while the
+            # next blocks are still on PCIe (the upload, not the arithmetic, is what the e2e step waits for at N = 8)
+            # (at 2 GPUs the step is bound by the arithmetic and the upload is already hidden: plain begin there)
+            ctx.check(lib.gl_commit_begin_ex(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT,
+                                             N.GL_COMMIT_STREAM_HASH if world >= 4 else 0, C.byref(h)))
 
             def lde(j):
                 works[j].wait()
@@ -518,7 +522,7 @@ def main():
             e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(cells * 8),
                    "d2h_bytes_per_step": int(cells * 8 + cap_host.nbytes), "ms_per_step": ems,
                    "api": "per rank: its IFFT columns H2D from pinned memory round by round, gl_ifft_batch, all-gather, "
-                          "gl_commit_begin/add_coeffs/finish, its coefficient columns D2H; rank 0 reads the cap"}
+                          "gl_commit_begin_ex(%s)/add_coeffs/finish, its coefficient columns D2H; rank 0 reads the cap" % ("GL_COMMIT_STREAM_HASH" if world >= 4 else "0")}
         del hvals, hcoef
 
     if rank != 0:

@@ -175,6 +175,13 @@ int gl_commit_from_coeffs_cols(gl_ctx *ctx, const uint64_t *const *coeffs, uint3
  * their LDE, finish hashes the leaves and builds the tree once every column has arrived.  Lets a caller overlap the
  * arrival of coefficients (PCIe, or an NCCL all-gather in the multi-GPU plan) with the transforms of earlier blocks. */
 int gl_commit_begin(gl_ctx *ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height, gl_commit **handle);
+/* flags: GL_COMMIT_STREAM_HASH -- when the blocks are added in polynomial order, every complete group of 8 polynomials
+ * (the sponge rate) is absorbed into the per-leaf Poseidon state as soon as its LDE exists, so the leaf hashing of the
+ * blocks that have arrived overlaps the arrival (PCIe, NCCL) of the next ones instead of starting after the last;
+ * costs 96 B of state per leaf until finish.  Same digests either way. */
+#define GL_COMMIT_STREAM_HASH 1u
+int gl_commit_begin_ex(gl_ctx *ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height, uint32_t flags,
+                       gl_commit **handle);
 int gl_commit_add_coeffs(gl_commit *h, uint32_t col0, uint32_t ncols, const uint64_t *coeffs, int space);
 int gl_commit_finish(gl_commit *h, uint64_t *cap_out, int space);
 /* PolynomialBatch.polynomials: the coefficients [c][2^log_n] kept on the device behind the handle. */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libgl_b200.so")
 
 GL_OK, GL_E_ARG, GL_E_CUDA, GL_E_OOM, GL_E_STATE = 0, 1, 2, 3, 4
 GL_HOST, GL_DEVICE = 0, 1
+GL_COMMIT_STREAM_HASH = 1
 
 u64p = C.POINTER(C.c_uint64)
 vp = C.c_void_p
@@ -73,6 +74,7 @@ SIGNATURES = {
     "gl_commit_from_values_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(vp)]),
     "gl_commit_from_coeffs_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
     "gl_commit_begin": (cint, [vp, u32, u32, u32, u32, C.POINTER(vp)]),
+    "gl_commit_begin_ex": (cint, [vp, u32, u32, u32, u32, u32, C.POINTER(vp)]),
     "gl_commit_add_coeffs": (cint, [vp, u32, u32, vp, cint]),
     "gl_commit_finish": (cint, [vp, vp, cint]),
     "gl_commit_coeffs": (cint, [vp, vp, cint]),

@@ -89,6 +89,11 @@ struct gl_commit {
     size_t coeffs_bytes = 0, lde_bytes = 0, digests_bytes = 0, cap_bytes = 0;
     uint32_t cols_added = 0;   // gl_commit_begin / add_coeffs / finish
     bool finished = true;
+    // GL_COMMIT_STREAM_HASH: leaves are absorbed 8 polynomials at a time as the blocks arrive
+    bool stream_hash = false;
+    uint32_t next_col = 0, hashed_cols = 0;
+    u64* hstate = nullptr;     // [12][n_local] sponge states between blocks
+    size_t hstate_bytes = 0;
 };
 
 static int fail(gl_ctx* ctx, int code, const std::string& msg) {
@@ -1038,6 +1043,7 @@ static void commit_release(gl_commit* h) {
     dev_release(h->ctx, h->lde, h->lde_bytes);
     dev_release(h->ctx, h->digests, h->digests_bytes);
     dev_release(h->ctx, h->cap, h->cap_bytes);
+    if (h->hstate) dev_release(h->ctx, h->hstate, h->hstate_bytes);
     delete h;
 }
 static void mark(gl_ctx* ctx, int i) { cudaEventRecord(ctx->ev[i], ctx->stream); }
@@ -1089,10 +1095,11 @@ static int commit_lde_columns(gl_ctx* ctx, gl_commit* h, uint32_t col0, uint32_t
 }
 
 // "build Merkle tree"
-static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space) {
+static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space, bool leaves_hashed = false) {
     const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
     mark(ctx, 4);
-    launch_leaf_hash_cols(h->lde, h->n_local, h->c, lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
+    if (!leaves_hashed)
+        launch_leaf_hash_cols(h->lde, h->n_local, h->c, lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 5);
     launch_merkle_levels(lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 6);
@@ -1266,8 +1273,13 @@ extern "C" int gl_commit_from_coeffs_cols(gl_ctx* ctx, const uint64_t* const* co
 
 extern "C" int gl_commit_begin(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height,
                                gl_commit** handle) {
+    return gl_commit_begin_ex(ctx, log_n, c, rate_bits, cap_height, 0, handle);
+}
+extern "C" int gl_commit_begin_ex(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height,
+                                  uint32_t flags, gl_commit** handle) {
     if (!ctx) return GL_E_ARG;
     if (!handle) return fail(ctx, GL_E_ARG, "gl_commit_begin: NULL handle");
+    if (flags & ~(uint32_t)GL_COMMIT_STREAM_HASH) return fail(ctx, GL_E_ARG, "gl_commit_begin_ex: unknown flag");
     *handle = nullptr;
     TRY(commit_check(ctx, log_n, c, rate_bits, cap_height, "PolynomialBatch::from_coeffs"));
     Guard g(ctx);
@@ -1277,6 +1289,7 @@ extern "C" int gl_commit_begin(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t
     h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
     h->coeffs_bytes = ((size_t)c << log_n) * 8;
     h->finished = false;
+    h->stream_hash = (flags & GL_COMMIT_STREAM_HASH) && c > 4;   // <= 4 polynomials: hash_or_noop copies, nothing to absorb
     int rc = dev_alloc(ctx, h->coeffs_bytes, &h->coeffs);
     if (rc == GL_OK) rc = commit_prepare(ctx, h);
     if (rc != GL_OK) {
@@ -1299,6 +1312,25 @@ extern "C" int gl_commit_add_coeffs(gl_commit* h, uint32_t col0, uint32_t ncols,
                        space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     TRY(commit_lde_columns(ctx, h, col0, ncols));
     h->cols_added += ncols;
+    if (h->stream_hash) {
+        if (col0 != h->next_col) {
+            h->stream_hash = false;   // blocks out of order: the sponge needs them in polynomial order; hash at finish
+        } else {
+            h->next_col += ncols;
+            const uint32_t complete = h->next_col == h->c ? h->c : (h->next_col & ~7u);
+            if (complete > h->hashed_cols) {
+                const bool first = h->hashed_cols == 0, last = complete == h->c;
+                if (!h->hstate && !(first && last)) {
+                    h->hstate_bytes = (size_t)h->n_local * 12 * 8;
+                    TRY(dev_alloc(ctx, h->hstate_bytes, &h->hstate));
+                }
+                const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
+                launch_leaf_absorb_cols(h->lde, h->n_local, h->hashed_cols, complete, lg_local, h->cap_local_bits, h->hstate, first,
+                                        last, h->digests, h->cap, ctx->stream);
+                h->hashed_cols = complete;
+            }
+        }
+    }
     return finish(ctx);
 }
 extern "C" int gl_commit_finish(gl_commit* h, uint64_t* cap_out, int space) {
@@ -1307,9 +1339,13 @@ extern "C" int gl_commit_finish(gl_commit* h, uint64_t* cap_out, int space) {
     if (h->finished) return fail(ctx, GL_E_STATE, "gl_commit_finish: the commit is already finished");
     if (h->cols_added != h->c) return fail(ctx, GL_E_STATE, "gl_commit_finish: not every polynomial has been added");
     Guard g(ctx);
-    TRY(commit_tree(ctx, h, cap_out, space));
+    TRY(commit_tree(ctx, h, cap_out, space, h->stream_hash && h->hashed_cols == h->c));
     TRY(finish(ctx));
     h->finished = true;
+    if (h->hstate) {
+        dev_release(ctx, h->hstate, h->hstate_bytes);
+        h->hstate = nullptr;
+    }
     for (int i = 0; i < GL_PHASES; i++) cudaEventElapsedTime(&ctx->phase_ms[i], ctx->ev[i], ctx->ev[i + 1]);
     ctx->ev_valid = true;
     return GL_OK;

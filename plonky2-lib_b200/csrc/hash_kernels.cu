@@ -189,6 +189,38 @@ k_leaf_hash_cols(const u64* __restrict__ lde, u64 ld, u32 c, u64 num_leaves, uns
     store_digest(node_slot(digests, cap, sub_bits, 0, i), d);
 }
 
+// The same sponge fed in column blocks as they arrive (gl_commit_add_coeffs with GL_COMMIT_STREAM_HASH): absorbs the
+// 8-column groups of [col_begin, col_end) into the per-leaf sponge state (state[k * num_leaves + i], k < 12), so the
+// hashing of the polynomials that are already extended overlaps the arrival of the next ones.  col_begin is a multiple
+// of 8; col_end is a multiple of 8 or c; `first` starts from the zero state, `last` (col_end == c) writes the digests.
+__global__ void __launch_bounds__(HASH_BLOCK, 4)
+k_leaf_absorb_cols(const u64* __restrict__ lde, u64 ld, u32 col_begin, u32 col_end, u64 num_leaves, unsigned sub_bits,
+                   u64* __restrict__ state, int first, int last, u64* __restrict__ digests, u64* __restrict__ cap) {
+    u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
+    if (i >= num_leaves) return;
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = first ? 0 : state[(u64)k * num_leaves + i];
+    const u64* col = lde + i + (u64)col_begin * ld;
+#pragma unroll 1
+    for (u32 off = col_begin; off < col_end; off += 8, col += 8 * ld) {
+        const u32 k = col_end - off < 8 ? col_end - off : 8;
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (j < k) s[j] = col[(u64)j * ld];
+        poseidon_permute(s);
+    }
+    if (last) {
+        u64 d[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[j] = gl_canon(s[j]);
+        store_digest(node_slot(digests, cap, sub_bits, 0, i), d);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 12; k++) state[(u64)k * num_leaves + i] = s[k];
+    }
+}
+
 // leaves row-major ([num_leaves][leaf_len]) -- MerkleTree::new(leaves: Vec<Vec<F>>, cap_height)
 __global__ void __launch_bounds__(HASH_BLOCK, 4)
 k_leaf_hash_rows(const u64* __restrict__ leaves, u32 leaf_len, u64 num_leaves, unsigned sub_bits,
@@ -476,6 +508,14 @@ void launch_leaf_hash_cols(const u64* lde, u64 ld, u32 c, unsigned lg_leaves, un
     u64 n = (u64)1 << lg_leaves;
     unsigned sub_bits = lg_leaves - cap_height;
     { k_leaf_hash_cols<<<nblk(n, HASH_BLOCK), HASH_BLOCK, 0, st>>>(lde, ld, c, n, sub_bits, digests, cap); ++g_gl_launches; }
+}
+void launch_leaf_absorb_cols(const u64* lde, u64 ld, u32 col_begin, u32 col_end, unsigned lg_leaves, unsigned cap_height,
+                             u64* state, bool first, bool last, u64* digests, u64* cap, cudaStream_t st) {
+    u64 n = (u64)1 << lg_leaves;
+    unsigned sub_bits = lg_leaves - cap_height;
+    k_leaf_absorb_cols<<<nblk(n, HASH_BLOCK), HASH_BLOCK, 0, st>>>(lde, ld, col_begin, col_end, n, sub_bits, state, first ? 1 : 0,
+                                                                    last ? 1 : 0, digests, cap);
+    ++g_gl_launches;
 }
 void launch_merkle_levels(unsigned lg_leaves, unsigned cap_height, u64* digests, u64* cap, cudaStream_t st) {
     u64 n = (u64)1 << lg_leaves;

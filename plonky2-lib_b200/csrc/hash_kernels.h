@@ -22,6 +22,9 @@ void launch_pow_grind(const uint64_t* state12, unsigned pos, unsigned out_pos, u
                       uint64_t count, unsigned long long* best, cudaStream_t st);
 void launch_leaf_hash_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned lg_leaves, unsigned cap_height,
                            uint64_t* digests, uint64_t* cap, cudaStream_t st);
+void launch_leaf_absorb_cols(const uint64_t* lde, uint64_t ld, uint32_t col_begin, uint32_t col_end, unsigned lg_leaves,
+                             unsigned cap_height, uint64_t* state, bool first, bool last, uint64_t* digests, uint64_t* cap,
+                             cudaStream_t st);
 void launch_merkle_levels(unsigned lg_leaves, unsigned cap_height, uint64_t* digests, uint64_t* cap, cudaStream_t st);
 void launch_merkle_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned lg_leaves, unsigned cap_height,
                         uint64_t* digests, uint64_t* cap, cudaStream_t st);

@@ -457,3 +457,68 @@ def test_streaming_commit_equals_from_coeffs(glb, ctx, oracle, rng):
     ctx.check(lib.gl_commit_download(h, leaves.ctypes.data, None, N.GL_HOST))
     assert np.array_equal(leaves, want["leaves"])
     lib.gl_commit_free(h)
+
+
+STREAM_HASH_CASES = [
+    # c, lg, block sizes fed in order (None = out of order: falls back to hashing at finish)
+    (21, 9, [8, 8, 5]), (21, 9, [5, 5, 5, 6]), (21, 9, [21]), (21, 9, [1] * 21), (135, 8, [28, 28, 28, 28, 23]),
+    (135, 8, [32, 32, 32, 32, 7]), (16, 7, [3, 13]), (9, 6, [8, 1]), (8, 6, [4, 4]), (5, 6, [2, 3]), (4, 6, [2, 2]), (1, 5, [1]),
+    (21, 9, None),
+]
+
+
+@pytest.mark.parametrize("c,lg,blocks", STREAM_HASH_CASES)
+def test_streamed_leaf_hashing_gives_the_same_commit(glb, ctx, oracle, rng, c, lg, blocks):
+    """GL_COMMIT_STREAM_HASH: the sponge absorbs every complete group of 8 polynomials as soon as its block has been
+    extended (partial groups wait for the next block; the last block closes the ragged group).  Digests, cap and
+    openings must equal the one-shot commit for every way of cutting the batch into blocks."""
+    import ctypes as C
+
+    lib, N = ctx._lib, glb._native
+    coeffs = rand_field(rng, (c, 1 << lg))
+    want = oracle.commit_from_coeffs(coeffs, 3, 4)
+    h = C.c_void_p()
+    ctx.check(lib.gl_commit_begin_ex(ctx._h, lg, c, 3, 4, N.GL_COMMIT_STREAM_HASH, C.byref(h)))
+    if blocks is None:
+        order = [(16, 5), (0, 8), (8, 8)]
+    else:
+        order, at = [], 0
+        for nc in blocks:
+            order.append((at, nc))
+            at += nc
+        assert at == c
+    for col0, nc in order:
+        blk = np.ascontiguousarray(coeffs[col0:col0 + nc])
+        ctx.check(lib.gl_commit_add_coeffs(h, col0, nc, blk.ctypes.data, N.GL_HOST))
+    cap = np.zeros((16, 4), dtype=np.uint64)
+    ctx.check(lib.gl_commit_finish(h, cap.ctypes.data, N.GL_HOST))
+    assert np.array_equal(cap, want["cap"])
+    NL = (1 << lg) << 3
+    digests = np.zeros((2 * (NL - 16), 4), dtype=np.uint64)
+    ctx.check(lib.gl_commit_download(h, None, digests.ctypes.data, N.GL_HOST))
+    assert np.array_equal(digests, want["digests"])
+    lib.gl_commit_free(h)
+    assert lib.gl_commit_begin_ex(ctx._h, lg, c, 3, 4, 2, C.byref(h)) == N.GL_E_ARG      # unknown flag
+
+
+def test_streamed_leaf_hashing_sharded(glb, oracle, rng):
+    """The same on a shard (one coset block = top-level subtrees of one rank)."""
+    import ctypes as C
+
+    N = glb._native
+    c, lg = 19, 8
+    coeffs = rand_field(rng, (c, 1 << lg))
+    want = oracle.commit_from_coeffs(coeffs, 3, 4)
+    cap = np.zeros((16, 4), dtype=np.uint64)
+    for rank in range(4):
+        cx = glb.Context(0)
+        cx.set_shard(rank, 4)
+        h = C.c_void_p()
+        cx.check(cx._lib.gl_commit_begin_ex(cx._h, lg, c, 3, 4, N.GL_COMMIT_STREAM_HASH, C.byref(h)))
+        for col0, nc in [(0, 7), (7, 7), (14, 5)]:
+            blk = np.ascontiguousarray(coeffs[col0:col0 + nc])
+            cx.check(cx._lib.gl_commit_add_coeffs(h, col0, nc, blk.ctypes.data, N.GL_HOST))
+        cx.check(cx._lib.gl_commit_finish(h, cap.ctypes.data, N.GL_HOST))    # writes its 4 entries at their global index
+        cx._lib.gl_commit_free(h)
+        cx.close()
+    assert np.array_equal(cap, want["cap"])

@@ -73,4 +73,4 @@ def trace(lg, reps=4):
     return {k: round(v, 3) for k, v in best.items()}
 
 
-print(json.dumps({"2^%d" % lg: trace(lg) for lg in (13, 15, 16)}))
+print(json.dumps({"2^%d" % lg: trace(lg) for lg in [int(x) for x in (sys.argv[1:] or ["13", "15", "16"])]}))
