@@ -1110,6 +1110,31 @@ static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space, 
     return GL_OK;
 }
 
+// Streamed leaf hashing: polynomials [col0, col0 + ncols) have just been extended.  While the blocks come in polynomial
+// order, every complete group of 8 polynomials (the sponge rate) is absorbed into the per-leaf Poseidon state right
+// away, so the hashing overlaps the arrival of the next block; the last block closes the ragged group and writes the
+// digests.  Out-of-order blocks switch the commit back to one hashing pass at the end.
+static int commit_absorb_block(gl_ctx* ctx, gl_commit* h, uint32_t col0, uint32_t ncols) {
+    if (!h->stream_hash) return GL_OK;
+    if (col0 != h->next_col) {
+        h->stream_hash = false;
+        return GL_OK;
+    }
+    h->next_col += ncols;
+    const uint32_t complete = h->next_col == h->c ? h->c : (h->next_col & ~7u);
+    if (complete <= h->hashed_cols) return GL_OK;
+    const bool first = h->hashed_cols == 0, last = complete == h->c;
+    if (!h->hstate && !(first && last)) {
+        h->hstate_bytes = (size_t)h->n_local * 12 * 8;
+        TRY(dev_alloc(ctx, h->hstate_bytes, &h->hstate));
+    }
+    const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
+    launch_leaf_absorb_cols(h->lde, h->n_local, h->hashed_cols, complete, lg_local, h->cap_local_bits, h->hstate, first, last,
+                            h->digests, h->cap, ctx->stream);
+    h->hashed_cols = complete;
+    return GL_OK;
+}
+
 // Where the polynomials of a host-side commit live: one [c][n] array, or one array per polynomial
 // (Vec<PolynomialValues<F>> / Vec<PolynomialCoeffs<F>> as the reference holds them).
 struct HostCols {
@@ -1129,17 +1154,27 @@ struct HostCols {
 // Host buffers: the H2D copy of column block b+1, the IFFT + LDE of block b and the D2H copy of block b's
 // coefficients run on three streams, so PCIe traffic hides behind the transforms (PCIe is full duplex).
 // Page-able arrays are packed into / unpacked from page-locked rings by helper threads (host_staging.h).
-static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input, bool is_values,
-                                const HostCols& coeffs_out) {
-    const u64 n = (u64)1 << h->log_n;
-    const size_t col_bytes = n * 8;
-    // about six blocks per commit, between 2 MB (launch overhead) and 96 MB (memory for nothing)
+// polynomials per block of the host pipeline: about six blocks per commit, between 2 MB (launch overhead) and 96 MB
+static uint32_t host_block_cols(const gl_commit* h) {
+    const size_t col_bytes = ((size_t)1 << h->log_n) * 8;
     size_t block_bytes = (size_t)h->c * col_bytes / 6;
     if (block_bytes < ((size_t)2 << 20)) block_bytes = (size_t)2 << 20;
     if (block_bytes > ((size_t)96 << 20)) block_bytes = (size_t)96 << 20;
     uint32_t cb = (uint32_t)(block_bytes / col_bytes);
     if (cb < 1) cb = 1;
     if (cb > h->c) cb = h->c;
+    return cb;
+}
+static uint32_t nblocks_host(const gl_commit* h) {
+    const uint32_t cb = host_block_cols(h);
+    return (h->c + cb - 1) / cb;
+}
+
+static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input, bool is_values,
+                                const HostCols& coeffs_out) {
+    const u64 n = (u64)1 << h->log_n;
+    const size_t col_bytes = n * 8;
+    const uint32_t cb = host_block_cols(h);
     const uint32_t nb = (h->c + cb - 1) / cb;
     while (ctx->pipe_ev.size() < 2 * (size_t)nb) {
         cudaEvent_t e;
@@ -1165,6 +1200,7 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input
             }
         }
         TRY(commit_lde_columns(ctx, h, col0, nc));
+        TRY(commit_absorb_block(ctx, h, col0, nc));   // hashing of what has arrived runs under the next block's PCIe time
     }
     return GL_OK;
 }
@@ -1197,6 +1233,7 @@ static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uin
         mark(ctx, 1);
         mark(ctx, 2);
         mark(ctx, 3);
+        h->stream_hash = c > 4 && nblocks_host(h) > 1;
         rc = commit_pipeline_host(ctx, h, input, is_values, coeffs_out);
     } else if (rc == GL_OK) {
         cudaError_t e = cudaMemcpyAsync(h->coeffs, input.flat, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1212,8 +1249,12 @@ static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uin
         mark(ctx, 3);
         if (rc == GL_OK) rc = commit_lde_columns(ctx, h, 0, c);
     }
-    if (rc == GL_OK) rc = commit_tree(ctx, h, cap_out, space);
+    if (rc == GL_OK) rc = commit_tree(ctx, h, cap_out, space, h->stream_hash && h->hashed_cols == h->c);
     if (rc == GL_OK) rc = finish(ctx);
+    if (h->hstate) {
+        dev_release(ctx, h->hstate, h->hstate_bytes);
+        h->hstate = nullptr;
+    }
     if (space == GL_HOST) {   // coefficient downloads (also after an error: they write into caller memory)
         int rc2 = downloads_wait(ctx);
         if (rc == GL_OK) rc = rc2;
@@ -1312,25 +1353,7 @@ extern "C" int gl_commit_add_coeffs(gl_commit* h, uint32_t col0, uint32_t ncols,
                        space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     TRY(commit_lde_columns(ctx, h, col0, ncols));
     h->cols_added += ncols;
-    if (h->stream_hash) {
-        if (col0 != h->next_col) {
-            h->stream_hash = false;   // blocks out of order: the sponge needs them in polynomial order; hash at finish
-        } else {
-            h->next_col += ncols;
-            const uint32_t complete = h->next_col == h->c ? h->c : (h->next_col & ~7u);
-            if (complete > h->hashed_cols) {
-                const bool first = h->hashed_cols == 0, last = complete == h->c;
-                if (!h->hstate && !(first && last)) {
-                    h->hstate_bytes = (size_t)h->n_local * 12 * 8;
-                    TRY(dev_alloc(ctx, h->hstate_bytes, &h->hstate));
-                }
-                const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
-                launch_leaf_absorb_cols(h->lde, h->n_local, h->hashed_cols, complete, lg_local, h->cap_local_bits, h->hstate, first,
-                                        last, h->digests, h->cap, ctx->stream);
-                h->hashed_cols = complete;
-            }
-        }
-    }
+    TRY(commit_absorb_block(ctx, h, col0, ncols));
     return finish(ctx);
 }
 extern "C" int gl_commit_finish(gl_commit* h, uint64_t* cap_out, int space) {
