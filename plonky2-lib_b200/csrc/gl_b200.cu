@@ -1175,7 +1175,9 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input
     const u64 n = (u64)1 << h->log_n;
     const size_t col_bytes = n * 8;
     const uint32_t cb = host_block_cols(h);
-    const uint32_t nb = (h->c + cb - 1) / cb;
+    // the first block is an eighth of the others: nothing runs under its upload, so it should be short
+    const uint32_t cb0 = (cb >= 8 && h->c > cb) ? cb / 8 : cb;
+    const uint32_t nb = 1 + (h->c - cb0 + cb - 1) / cb;
     while (ctx->pipe_ev.size() < 2 * (size_t)nb) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1184,8 +1186,10 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input
     cudaEvent_t start = ctx->ev[1];   // recorded by the caller on the main stream
     CK(cudaStreamWaitEvent(ctx->h2d_stream, start, 0));
     std::vector<staging::HostSeg> segs;
-    for (uint32_t b = 0; b < nb; b++) {
-        const uint32_t col0 = b * cb, nc = (col0 + cb <= h->c) ? cb : h->c - col0;
+    uint32_t col0 = 0;
+    for (uint32_t b = 0; col0 < h->c; b++) {
+        const uint32_t want = b == 0 ? cb0 : cb;
+        const uint32_t nc = (col0 + want <= h->c) ? want : h->c - col0;
         u64* dcol = h->coeffs + (size_t)col0 * n;
         input.segs(col0, nc, n, segs);
         TRY(h2d_copy(ctx, dcol, segs.data(), segs.size(), ctx->h2d_stream));
@@ -1201,6 +1205,7 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input
         }
         TRY(commit_lde_columns(ctx, h, col0, nc));
         TRY(commit_absorb_block(ctx, h, col0, nc));   // hashing of what has arrived runs under the next block's PCIe time
+        col0 += nc;
     }
     return GL_OK;
 }
