@@ -162,3 +162,35 @@ def test_fri_final_poly_host_outputs_above_the_staging_threshold(glb, ctx, oracl
     dc.free(); dv.free()
     for b in batches:
         b.free()
+
+
+def test_mixed_page_locked_and_pageable_polynomials(glb, ctx, oracle):
+    """Per-polynomial arrays where some are page-locked (gl_host_alloc) and some are ordinary memory, inputs and outputs:
+    large page-locked ones go straight to the DMA engine in the middle of a staged run, the rest through the rings."""
+    lg_n, c = 19, 6                       # 4 MB per polynomial = one ring slot
+    n = 1 << lg_n
+    values = oracle.synthetic_values(c, n)
+    cols, outs = [], []
+    for j in range(c):
+        if j % 2:
+            a = glb.pinned_empty((n,))
+            a[:] = values[j]
+            cols.append(a)
+            outs.append(np.zeros(n, dtype=np.uint64))
+        else:
+            cols.append(values[j].copy())
+            outs.append(glb.pinned_empty((n,)))
+    ip = (C.c_void_p * c)(*[a.ctypes.data for a in cols])
+    op = (C.c_void_p * c)(*[a.ctypes.data for a in outs])
+    cap = np.zeros((16, 4), dtype=np.uint64)
+    h = C.c_void_p()
+    ctx.check(ctx._lib.gl_commit_from_values_cols(ctx._h, ip, lg_n, c, 3, 4, op, cap.ctypes.data, C.byref(h)))
+    ctx._lib.gl_commit_free(h)
+    import torch
+
+    bd = glb.PolynomialBatch.from_values(torch.from_numpy(values.view(np.int64)).cuda(), 3, False, 4)
+    assert np.array_equal(cap, bd.merkle_tree.cap)
+    want = bd.polynomials.cpu().numpy().view(np.uint64)
+    for j in range(c):
+        assert np.array_equal(outs[j], want[j]), j
+    bd.free()
