@@ -36,6 +36,15 @@ struct HashOut {
         return elements[0] == o.elements[0] && elements[1] == o.elements[1] && elements[2] == o.elements[2] &&
                elements[3] == o.elements[3];
     }
+    // WrappedHashOut's text form (src/smt/goldilocks_poseidon/hash/mod.rs:84-119): "0x" + the 32 bytes of to_bytes()
+    // (4 x u64 little endian) in reverse order, i.e. elements[3] first, each as 16 hex digits
+    std::string to_hex() const {
+        static const char* d = "0123456789abcdef";
+        std::string s = "0x";
+        for (int e = 3; e >= 0; e--)
+            for (int sh = 60; sh >= 0; sh -= 4) s.push_back(d[(elements[e] >> sh) & 15]);
+        return s;
+    }
 };
 using MerkleCap = std::vector<HashOut>;
 struct MerkleProof {

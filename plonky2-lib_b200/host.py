@@ -212,6 +212,30 @@ class _PinnedArray(np.ndarray):
 
 
 # ------------------------------------------------------------------------------------------------
+# WrappedHashOut text form (src/smt/goldilocks_poseidon/hash/mod.rs:84-119; the JSON the zkdsa tests pin,
+# src/zkdsa/circuits/mod.rs:136-153): "0x" + hex of HashOut::to_bytes() (4 x u64 little endian) byte-reversed
+# ------------------------------------------------------------------------------------------------
+def hash_out_to_hex(h) -> str:
+    b = np.ascontiguousarray(h, dtype="<u8").reshape(4).tobytes()
+    return "0x" + b[::-1].hex()
+
+
+def hash_out_from_hex(s: str) -> np.ndarray:
+    """Accepts what the reference's Deserialize accepts: a 0x prefix, an even number of hex digits, at most 32 bytes
+    (shorter strings are the low-order bytes)."""
+    if not s.startswith("0x"):
+        raise ValueError(f"fail to strip 0x-prefix: given value {s} does not start with 0x")
+    try:
+        b = bytes.fromhex(s[2:])
+    except ValueError as e:
+        raise ValueError(f"fail to parse a hex string: {e}") from None
+    if len(b) > 32:
+        raise ValueError("too long hexadecimal sequence")
+    le = b[::-1] + bytes(32 - len(b))
+    return np.frombuffer(le, dtype="<u8").astype(np.uint64)
+
+
+# ------------------------------------------------------------------------------------------------
 # plonky2::hash::poseidon::PoseidonHash (Hasher<F>)
 # ------------------------------------------------------------------------------------------------
 class PoseidonHash:

@@ -32,6 +32,8 @@ int main() {
     HashOut h = PoseidonHash::two_to_one(ctx, zero, zero);
     HashOut want{{4330397376401421145ULL, 14124799381142128323ULL, 8742572140681234676ULL, 14345658006221440202ULL}};
     CHECK(h == want);
+    // src/zkdsa/circuits/mod.rs:136-153: the same digest as the JSON of the public inputs spells it
+    CHECK(h.to_hex() == "0xc71603f33a1144ca7953db0ab48808f4c4055e3364a246c33c18a9786cb0b359");
     // src/smt/gadgets/common.rs:67-101 vs src/smt/goldilocks_poseidon/mod.rs:167-181
     HashOut k{{1, 0, 0, 0}}, v{{2, 0, 0, 0}};
     HashOut leaf = PoseidonNodeHash::calc_leaf_hash_batch(ctx, &k, &v, 1)[0];

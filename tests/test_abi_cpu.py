@@ -60,3 +60,29 @@ def test_fri_config_matches_standard_recursion_config(glb):
     assert f.reduction_strategy.reduction_arity_bits(20, 3, 4) == [4, 4, 4, 4]
     assert glb.CircuitConfig.standard_ecc_config().num_wires == 136
     assert glb.CircuitConfig.wide_ecc_config().num_wires == 234
+
+
+def test_hash_out_text_form_matches_the_reference():
+    """WrappedHashOut Display / Serialize / Deserialize (src/smt/goldilocks_poseidon/hash/mod.rs:62-78, 84-137) and the
+    zkdsa public-input JSON (src/zkdsa/circuits/mod.rs:136-153): host-side formatting, no device needed."""
+    import importlib
+
+    import numpy as np
+
+    host = importlib.import_module("plonky2-lib_b200.host")
+    one = np.array([1, 0, 0, 0], dtype=np.uint64)
+    assert host.hash_out_to_hex(one) == "0x0000000000000000000000000000000000000000000000000000000000000001"
+    assert host.hash_out_from_hex("0x01").tolist() == one.tolist()
+    kat = np.array([4330397376401421145, 14124799381142128323, 8742572140681234676, 14345658006221440202], dtype=np.uint64)
+    text = "0xc71603f33a1144ca7953db0ab48808f4c4055e3364a246c33c18a9786cb0b359"
+    assert host.hash_out_to_hex(kat) == text and host.hash_out_from_hex(text).tolist() == kat.tolist()
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        h = rng.integers(0, 2**64, 4, dtype=np.uint64)
+        s = host.hash_out_to_hex(h)
+        assert len(s) == 66 and host.hash_out_from_hex(s).tolist() == h.tolist()
+    import pytest
+
+    for bad in ("01", "0x1", "0xzz", "0x" + "00" * 33):
+        with pytest.raises(ValueError):
+            host.hash_out_from_hex(bad)
