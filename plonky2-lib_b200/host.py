@@ -805,3 +805,28 @@ def smt_insert_proofs(keys, values, ctx=None):
         if total.value <= cap:
             return hdr, pool[: total.value].copy() if total.value < cap // 2 else pool[: total.value], off
         cap = int(total.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# src/zkdsa: the native (non-circuit) side of the Poseidon signature scheme, over batches
+# ------------------------------------------------------------------------------------------------
+def zkdsa_public_keys(private_keys, ctx=None) -> np.ndarray:
+    """private_key_to_public_key for every key: PoseidonHash::two_to_one(sk, sk) (src/zkdsa/account.rs:164-166)."""
+    sk = _h(private_keys).reshape(-1, 4)
+    return PoseidonHash.two_to_one_batch(sk, sk, ctx=ctx)
+
+
+def zkdsa_addresses(public_keys) -> np.ndarray:
+    """public_key_to_address: the first element of the public key (src/zkdsa/account.rs:168-170)."""
+    return _h(public_keys).reshape(-1, 4)[:, 0].copy()
+
+
+def zkdsa_sign(private_keys, messages, ctx=None) -> np.ndarray:
+    """SimpleSignature: PoseidonHash::two_to_one(private_key, message) (src/zkdsa/circuits/mod.rs:62-75)."""
+    return PoseidonHash.two_to_one_batch(_h(private_keys).reshape(-1, 4), _h(messages).reshape(-1, 4), ctx=ctx)
+
+
+def zkdsa_public_inputs_json(message, public_key, signature) -> str:
+    """SerializableSimpleSignaturePublicInputs as serde_json writes it (src/zkdsa/circuits/mod.rs:108-153)."""
+    return ('{"message":"%s","public_key":"%s","signature":"%s"}'
+            % (hash_out_to_hex(message), hash_out_to_hex(public_key), hash_out_to_hex(signature)))

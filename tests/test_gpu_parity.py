@@ -522,3 +522,22 @@ def test_streamed_leaf_hashing_sharded(glb, oracle, rng):
         cx._lib.gl_commit_free(h)
         cx.close()
     assert np.array_equal(cap, want["cap"])
+
+
+def test_zkdsa_native_batch_and_public_input_json(glb, ctx, oracle, rng):
+    """src/zkdsa: public keys, addresses and signatures over a batch, and the JSON the reference pins for the default
+    (all-zero) signature (src/zkdsa/circuits/mod.rs:77-106, 136-153)."""
+    host = glb.host
+    z = np.zeros((1, 4), dtype=np.uint64)
+    pk, sig = host.zkdsa_public_keys(z), host.zkdsa_sign(z, z)
+    assert pk[0].tolist() == KAT_TWO_TO_ONE_ZERO and sig[0].tolist() == KAT_TWO_TO_ONE_ZERO
+    want = ('{"message":"0x0000000000000000000000000000000000000000000000000000000000000000",'
+            '"public_key":"0xc71603f33a1144ca7953db0ab48808f4c4055e3364a246c33c18a9786cb0b359",'
+            '"signature":"0xc71603f33a1144ca7953db0ab48808f4c4055e3364a246c33c18a9786cb0b359"}')
+    assert host.zkdsa_public_inputs_json(z[0], pk[0], sig[0]) == want
+    sk, msg = rand_field(rng, (300, 4)), rand_field(rng, (300, 4))
+    pks, sigs = host.zkdsa_public_keys(sk), host.zkdsa_sign(sk, msg)
+    for i in (0, 7, 299):
+        assert pks[i].tolist() == oracle.two_to_one(sk[i], sk[i]).tolist()
+        assert sigs[i].tolist() == oracle.two_to_one(sk[i], msg[i]).tolist()
+    assert host.zkdsa_addresses(pks).tolist() == pks[:, 0].tolist()
