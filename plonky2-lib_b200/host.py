@@ -813,7 +813,7 @@ def smt_insert_proofs(keys, values, ctx=None):
 def zkdsa_public_keys(private_keys, ctx=None) -> np.ndarray:
     """private_key_to_public_key for every key: PoseidonHash::two_to_one(sk, sk) (src/zkdsa/account.rs:164-166)."""
     sk = _h(private_keys).reshape(-1, 4)
-    return PoseidonHash.two_to_one_batch(sk, sk, ctx=ctx)
+    return PoseidonHash.two_to_one(sk, sk, ctx=ctx)
 
 
 def zkdsa_addresses(public_keys) -> np.ndarray:
@@ -823,7 +823,7 @@ def zkdsa_addresses(public_keys) -> np.ndarray:
 
 def zkdsa_sign(private_keys, messages, ctx=None) -> np.ndarray:
     """SimpleSignature: PoseidonHash::two_to_one(private_key, message) (src/zkdsa/circuits/mod.rs:62-75)."""
-    return PoseidonHash.two_to_one_batch(_h(private_keys).reshape(-1, 4), _h(messages).reshape(-1, 4), ctx=ctx)
+    return PoseidonHash.two_to_one(_h(private_keys).reshape(-1, 4), _h(messages).reshape(-1, 4), ctx=ctx)
 
 
 def zkdsa_public_inputs_json(message, public_key, signature) -> str:
