@@ -139,6 +139,7 @@ struct Guard {  // binds the ctx's device for the duration of a call and seriali
 };
 
 static int scratch_get(gl_ctx* ctx, int slot, size_t bytes, void** out) {
+    *out = nullptr;
     DevBuf& b = ctx->scratch[slot];
     if (b.cap < bytes) {
         if (b.p) {
@@ -1173,7 +1174,6 @@ static uint32_t nblocks_host(const gl_commit* h) {
 static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input, bool is_values,
                                 const HostCols& coeffs_out) {
     const u64 n = (u64)1 << h->log_n;
-    const size_t col_bytes = n * 8;
     const uint32_t cb = host_block_cols(h);
     // the first block is an eighth of the others: nothing runs under its upload, so it should be short
     const uint32_t cb0 = (cb >= 8 && h->c > cb) ? cb / 8 : cb;
