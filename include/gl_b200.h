@@ -115,14 +115,15 @@ int gl_smt_build(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint
                  int space);
 
 /* The m SparseMerkleProcessProofs that m successive `tree.set(keys[t], values[t])` calls return, in call order, when they
- * start from an EMPTY tree and every key is new (ProcessInsert; src/smt/tree.rs:143-155, insert :255-387, find :588-676) --
- * proof t is against the tree holding keys 0 .. t-1.  proofs_out [m]; the siblings of proof t are
- * sib_pool_out[sib_off_out[t] .. sib_off_out[t+1]) exactly as `proof.siblings` (trailing zero siblings trimmed): the three
- * arrays are what gl_smt_verify_process_batch takes.  *num_siblings_out = total number of siblings; when it exceeds
- * sib_cap (or sib_pool_out is NULL) the pool is not written: call again with a larger pool.  proofs_out[m-1].new_root is
- * the root gl_smt_build returns.  A batch of new keys on a NON-empty tree: put the existing entries first (any order)
- * and drop their proofs.  Duplicate keys or an all-zero value return GL_E_ARG. */
-int gl_smt_insert_proofs(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m,
+ * start from an EMPTY tree and no value is zero (src/smt/tree.rs:143-155; find :588-676, update :174-253, insert :255-387):
+ * the first occurrence of a key is a ProcessInsert, later occurrences are ProcessUpdates; proof t is against the tree the
+ * first t calls left.  proofs_out [m]; the siblings of proof t are sib_pool_out[sib_off_out[t] .. sib_off_out[t+1]) exactly
+ * as `proof.siblings` (an insert trims its trailing zero siblings): the three arrays are what gl_smt_verify_process_batch
+ * takes.  *num_siblings_out = total number of siblings; when it exceeds sib_cap (or sib_pool_out is NULL) the pool is not
+ * written: call again with a larger pool.  proofs_out[m-1].new_root is the root of the final tree.  A batch on a
+ * NON-empty tree: put the existing entries first (any order) and drop their proofs.  An all-zero value (a removal)
+ * returns GL_E_ARG. */
+int gl_smt_set_proofs(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m,
                          gl_smt_proof_hdr *proofs_out, uint64_t *sib_pool_out, uint64_t sib_cap,
                          uint64_t *sib_off_out, uint64_t *num_siblings_out, int space);
 

@@ -195,7 +195,7 @@ struct SparseMerkleTreeBatch {
         return root;
     }
     // the proofs those `set` calls return, in call order
-    static std::vector<SparseMerkleProcessProof> insert_proofs(const Context& c, const std::vector<HashOut>& keys,
+    static std::vector<SparseMerkleProcessProof> set_proofs(const Context& c, const std::vector<HashOut>& keys,
                                                                const std::vector<HashOut>& values) {
         const size_t m = keys.size();
         std::vector<SparseMerkleProcessProof> out(m);
@@ -204,7 +204,7 @@ struct SparseMerkleTreeBatch {
         std::vector<uint64_t> off(m + 1), pool((size_t)4 * 32 * m);
         uint64_t total = 0;
         for (;;) {
-            c.check(gl_smt_insert_proofs(c.raw(), &keys[0].elements[0], &values[0].elements[0], m, hdr.data(), pool.data(),
+            c.check(gl_smt_set_proofs(c.raw(), &keys[0].elements[0], &values[0].elements[0], m, hdr.data(), pool.data(),
                                          pool.size() / 4, off.data(), &total, GL_HOST));
             if (total * 4 <= pool.size()) break;
             pool.resize(total * 4);

@@ -869,13 +869,13 @@ extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* v
 }
 
 // N2, second half: the process proofs of m successive inserts into an empty tree (smt_proofs.cu)
-extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m,
+extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m,
                                     gl_smt_proof_hdr* proofs_out, uint64_t* sib_pool_out, uint64_t sib_cap,
                                     uint64_t* sib_off_out, uint64_t* num_siblings_out, int space) {
     if (!ctx) return GL_E_ARG;
     if (!num_siblings_out || (m && (!keys || !values || !proofs_out || !sib_off_out)))
-        return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: NULL buffer");
-    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: at most 2^31 - 1 entries");
+        return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: NULL buffer");
+    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: at most 2^31 - 1 entries");
     *num_siblings_out = 0;
     if (m == 0) return GL_OK;
     Guard g(ctx);
@@ -894,7 +894,7 @@ extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uin
     auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
     const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
                  o_lcp = take(m * 2), o_vf = take(m * 32), o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4 + 8),
-                 o_tmp = take(tmp_bytes), o_u32 = take(12 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
+                 o_tmp = take(tmp_bytes), o_u32 = take(17 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
                  o_off = take((m + 1) * 8), o_hdr = take(m * sizeof(gl_smt_proof_hdr));
     void* base;
     TRY(scratch_get(ctx, 2, off, &base));
@@ -907,24 +907,26 @@ extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uin
     CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 8, ctx->stream));
     smt_proofs_check_values(dv, m, d_bad, ctx->stream);
     int rc = smt_build_prepare(b, ctx->stream);
-    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_insert_proofs: sort");
+    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_set_proofs: sort");
     uint32_t hist[259];
     CK(cudaMemcpyAsync(hist, b.hist, 258 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (hist[256]) return fail(ctx, GL_E_ARG, "SparseMerkleTree::insert: given key already exists (duplicate keys in the batch)");
-    if (hist[257]) return fail(ctx, GL_E_ARG, "gl_smt_insert_proofs: a value is zero (set with the default value is a removal, not an insert)");
+    // hist[256] = adjacent events with the same key: later occurrences are updates
+    if (hist[257]) return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: a value is zero (set with the default value is a removal, not an insert or update)");
     int dmax = -1;
     for (int d = 255; d >= 0; d--)
         if (hist[d]) { dmax = d; break; }
     smt_proof_buffers q;
     memset(&q, 0, sizeof q);
     q.m = m;
-    q.stride = (uint32_t)(dmax + 1 > 1 ? dmax + 1 : 1);
+    q.bottom = (uint32_t)(dmax + 1);
+    q.stride = q.bottom > 1 ? q.bottom : 1;
     q.keys = dk; q.values = dv; q.rk = b.rk; q.perm = b.perm; q.lcp = b.lcp; q.leafh = b.leafh;
     uint32_t* u = (uint32_t*)(p0 + o_u32);
     q.a_cur = u; q.end_cur = u + m; q.ord_cur = u + 2 * m; q.inv_cur = u + 3 * m; q.tm_cur = u + 4 * m;
     q.a_nxt = u + 5 * m; q.end_nxt = u + 6 * m; q.ord_nxt = u + 7 * m; q.inv_nxt = u + 8 * m; q.tm_nxt = u + 9 * m;
     q.stop_depth = u + 10 * m; q.stop_old = u + 11 * m;
+    q.dc_cur = u + 12 * m; q.dc_nxt = u + 13 * m; q.rep_cur = u + 14 * m; q.rep_nxt = u + 15 * m; q.pos_of_time = u + 16 * m;
     q.val_cur = (u64*)(p0 + o_val); q.val_nxt = q.val_cur + 4 * m;
     q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
     q.other = (uint32_t*)(p0 + o_keys);       // m * 4 bytes
@@ -941,14 +943,14 @@ extern "C" int gl_smt_insert_proofs(gl_ctx* ctx, const uint64_t* keys, const uin
     if (rc) {
         cudaStreamSynchronize(ctx->stream);
         dev_release(ctx, d_sib, sib_bytes);
-        return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_insert_proofs: sweep");
+        return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_set_proofs: sweep");
     }
     u64 total = 0;
     cudaError_t e = cudaMemcpyAsync(&total, d_off + m, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         dev_release(ctx, d_sib, sib_bytes);
-        return cuda_fail(ctx, e, "gl_smt_insert_proofs");
+        return cuda_fail(ctx, e, "gl_smt_set_proofs");
     }
     *num_siblings_out = total;
     int out_rc = GL_OK;

@@ -1,21 +1,25 @@
 // N2, second half: the m SparseMerkleProcessProofs that m successive `tree.set(key_t, value_t)` calls
-// (src/smt/tree.rs:143-155, insert :255-387, find :588-676) return when they start from an EMPTY tree and every
-// key is new -- all at once, although proof t is a statement about the tree that holds keys 0 .. t-1 only.
+// (src/smt/tree.rs:143-155, find :588-676, update :174-253, insert :255-387) return when they start from an EMPTY
+// tree and no value is zero -- all at once, although proof t is a statement about the tree the first t calls left.
+// A key may occur several times: its first occurrence is an insert, the later ones are updates.
 //
-// With the keys sorted by path order, the keys below a trie position of depth d are a contiguous segment (maximal
-// run of adjacent pairs with LCP >= d).  A position holds: nothing (hash 0), one key (its leaf hash, hoisted), or
-// >= 2 keys (an internal node, possibly with one empty child).  Order the keys of every segment by insertion time:
-//   Val_d[i] = hash at that position once the i-th of them (by time) has been inserted
-//            = leaf hash                      for the first one,
-//              H(child slot 0, child slot 1)  afterwards, the child slots being Val_{d+1} of the two depth-(d+1)
-//                                             segments inside, taken at the same time.
-// The sweep runs from the deepest LCP up to depth 0; the child containing the key is read at the key's own
-// position in the depth-(d+1) order, the other child by a binary search over insertion times.  While key t has
-// >= 2 predecessors in its depth-d segment the position is an internal node on its `find` path and the other
-// child's slot value (strictly before t) is siblings[d] of proof t; the shallowest depth with <= 1 predecessors is
-// where `find` stops (empty slot: is_old0; one key: old_key / old_value).  Depth 0 yields old_root / new_root.
-// Work: one permutation per (key, depth above its stopping point) -- the hashes the sequential inserts compute,
-// ~ m log2 m in total.  No sorting in the sweep: merging two time-ordered children is the same binary search.
+// Sort the events (key, value, time) by path order, ties (the same key) in time order.  The events below a trie
+// position of depth d are a contiguous segment (maximal run of adjacent pairs with LCP >= d).  A position holds:
+// nothing (hash 0), one key (its leaf hash, hoisted), or >= 2 keys (an internal node, possibly with one empty
+// child).  Order the events of every segment by time:
+//   Val_d[i] = hash at that position right after the i-th event,  dc_d[i] = distinct keys below it at that time
+//            = the value of the child holding the event's key                 when dc == 1 (hoisted leaf),
+//              H(child slot 0, child slot 1)                                   when dc >= 2,
+// the child slots being Val_{d+1} of the two depth-(d+1) segments inside, taken at the same time: the child with
+// the event's key at the event's own position in the depth-(d+1) order, the other one by a binary search over
+// times.  The same search gives the time order of depth d without sorting (segment start + rank in the own child +
+// events of the other child before it).  The sweep starts from the same-key groups ("depth 256") and runs from the
+// deepest LCP between different keys up to depth 0.  With n = distinct keys below the position just before event t:
+// n >= 2 means an internal node on t's `find` path and the other child's value just before t is siblings[d]; the
+// shallowest depth with n <= 1 is where `find` stops -- an empty slot (is_old0), another key's leaf (old_key /
+// old_value), or the key's own leaf (an update: old_value = its previous value).  Depth 0 yields old_root / new_root.
+// Work: one permutation per (event, depth above its stopping point) -- the hashes the sequential calls compute,
+// ~ m log2 m in total.
 //
 // #included at the end of hash_kernels.cu after smt_kernels.cu (shares the Poseidon constants and helpers).
 #include <cub/device/device_scan.cuh>
@@ -29,18 +33,25 @@ GL_D int smt_path_bit_perm(const u64* __restrict__ rk, u64 m, u32 src, unsigned 
     return (int)((rk[(u64)(d >> 6) * m + src] >> (63 - (d & 63))) & 1);
 }
 
+// "depth 256": segments = the events of one key (already in time order: the radix sort is stable)
 __global__ void __launch_bounds__(256) k_sp_init(smt_proof_buffers p) {
     u64 j = blockIdx.x * (u64)256 + threadIdx.x;
     if (j >= p.m) return;
-    p.a_nxt[j] = (u32)j;
-    p.end_nxt[j] = (u32)j + 1;
+    // a_nxt comes from the scan of the depth-256 flags; ends by scatter
+    if (j + 1 == p.m || p.lcp[j] < 256) p.end_nxt[p.a_nxt[j]] = (u32)j + 1;
     p.ord_nxt[j] = (u32)j;
     p.inv_nxt[j] = (u32)j;
     p.tm_nxt[j] = p.perm[j];
 #pragma unroll
     for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = p.leafh[4 * j + k];
-    p.stop_depth[p.perm[j]] = 0;          // m == 1; otherwise the deepest level overwrites it for every key
-    p.stop_old[p.perm[j]] = SP_NONE;
+    p.dc_nxt[j] = 1;
+    p.rep_nxt[j] = (u32)j;
+    const u32 t = p.perm[j];
+    p.pos_of_time[t] = (u32)j;
+    // below every LCP between different keys the position holds this key alone (or nothing, before its insert)
+    const bool insert = j == 0 || p.lcp[j - 1] < 256;
+    p.stop_depth[t] = p.bottom;
+    p.stop_old[t] = insert ? SP_NONE : (u32)j - 1;
 }
 
 // start flags of the depth-d segments, as scan input (index where a segment starts, else 0)
@@ -87,44 +98,44 @@ __global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, uns
     u64 i = blockIdx.x * (u64)SMT_BLOCK + threadIdx.x;
     if (i >= p.m) return;
     const u32 j = p.ord_cur[i];
-    const u32 a = p.a_cur[j];
-    const u32 rank = (u32)i - a;
     const u32 t = p.tm_cur[i];
-    if (rank == 0) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) p.val_cur[4 * i + k] = p.leafh[4 * (u64)j + k];
-        p.stop_depth[t] = d;          // nothing under this position before t: an empty slot (unless a shallower
-        p.stop_old[t] = SP_NONE;      // depth overwrites this)
-        return;
-    }
+    const u32 at = p.inv_nxt[j];                       // the event's position in the order one level down
+    const u32 o = merged ? p.other[i] : SP_NONE;       // latest earlier event of the other child, if any
+    const u32 dc_own = p.dc_nxt[at], dc_sib = o != SP_NONE ? p.dc_nxt[o] : 0;
+    const u32 dc = dc_own + dc_sib;
     u64 own[4], sib[4] = {0, 0, 0, 0}, out[4];
-    {
-        const u64 at = p.inv_nxt[j];
 #pragma unroll
-        for (int k = 0; k < 4; k++) own[k] = p.val_nxt[4 * at + k];
+    for (int k = 0; k < 4; k++) own[k] = p.val_nxt[4 * (u64)at + k];
+    if (o != SP_NONE) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)o + k];
     }
-    int bit;
-    if (merged) {
-        bit = p.bit[i];
-        const u32 o = p.other[i];
-        if (o != SP_NONE) {
+    p.dc_cur[i] = dc;
+    if (dc == 1) {
+        // one key below this position: its leaf hash stands for the subtree
 #pragma unroll
-            for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)o + k];
-        }
+        for (int k = 0; k < 4; k++) out[k] = own[k];
+        p.rep_cur[i] = p.rep_nxt[at];
     } else {
-        bit = smt_path_bit_perm(p.rk, p.m, t, d);      // no pair diverges here: every position is a one-child node
+        const int bit = merged ? (int)p.bit[i] : smt_path_bit_perm(p.rk, p.m, t, d);
+        if (bit) smt_two_to_one(sib, own, out);
+        else smt_two_to_one(own, sib, out);
+        p.rep_cur[i] = SP_NONE;
     }
-    if (bit) smt_two_to_one(sib, own, out);
-    else smt_two_to_one(own, sib, out);
 #pragma unroll
     for (int k = 0; k < 4; k++) p.val_cur[4 * i + k] = out[k];
-    if (rank >= 2) {
+    // the proof of event t at this depth
+    const bool insert = j == 0 || p.lcp[j - 1] < 256;
+    const u32 before = dc - (insert ? 1u : 0u);        // distinct keys below the position just before t
+    if (before >= 2) {
         u64* s = p.sib + ((u64)t * p.stride + d) * 4;
 #pragma unroll
         for (int k = 0; k < 4; k++) s[k] = sib[k];
     } else {
         p.stop_depth[t] = d;
-        p.stop_old[t] = p.ord_cur[a];   // the one key that was there
+        if (!insert) p.stop_old[t] = j - 1;            // its own leaf: the previous event of the same key
+        else if (before == 0) p.stop_old[t] = SP_NONE;
+        else p.stop_old[t] = dc_sib ? p.rep_nxt[o] : p.rep_nxt[at - 1];   // the one other key, in either child
     }
 }
 
@@ -140,6 +151,8 @@ __global__ void __launch_bounds__(256) k_sp_roots(smt_proof_buffers p, u32* __re
         h->new_key[k] = gl_canon(p.keys[4 * t + k]);
         h->new_value[k] = gl_canon(p.values[4 * t + k]);
     }
+    const u32 j = p.pos_of_time[t];
+    const bool insert = j == 0 || p.lcp[j - 1] < 256;
     const u32 so = p.stop_old[t];
     if (so == SP_NONE) {
 #pragma unroll
@@ -154,10 +167,12 @@ __global__ void __launch_bounds__(256) k_sp_roots(smt_proof_buffers p, u32* __re
         }
         h->is_old0 = 0;
     }
-    h->fnc = 2;   // ProcessMerkleProofRole::ProcessInsert
+    h->fnc = insert ? 2 : 1;   // ProcessMerkleProofRole::ProcessInsert / ProcessUpdate
     u32 ns = p.stop_depth[t];
-    const u64* s = p.sib + (u64)t * p.stride * 4;
-    while (ns > 0 && (s[4 * (ns - 1)] | s[4 * (ns - 1) + 1] | s[4 * (ns - 1) + 2] | s[4 * (ns - 1) + 3]) == 0) ns--;
+    if (insert) {              // insert trims the trailing zero siblings, update keeps what find returned
+        const u64* s = p.sib + (u64)t * p.stride * 4;
+        while (ns > 0 && (s[4 * (ns - 1)] | s[4 * (ns - 1) + 1] | s[4 * (ns - 1) + 2] | s[4 * (ns - 1) + 3]) == 0) ns--;
+    }
     counts[t] = ns;
 }
 __global__ void __launch_bounds__(256) k_sp_gather(smt_proof_buffers p, const u64* __restrict__ off, u64 cap, u64* __restrict__ pool) {
@@ -194,8 +209,14 @@ int smt_proofs_check_values(const u64* values, u64 m, u32* bad, cudaStream_t st)
 int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, u32* counts, void* tmp, size_t tmp_bytes, cudaStream_t st) {
     const u64 m = p.m;
     const unsigned b256 = (unsigned)((m + 255) / 256), bl = (unsigned)((m + SMT_BLOCK - 1) / SMT_BLOCK);
-    k_sp_init<<<b256, 256, 0, st>>>(p);
-    ++g_gl_launches;
+    {   // same-key groups: starts by the scan of the depth-256 flags
+        k_sp_flags<<<b256, 256, 0, st>>>(p, 256u, counts);
+        size_t tb = tmp_bytes;
+        cudaError_t e = cub::DeviceScan::InclusiveScan(tmp, tb, (const u32*)counts, p.a_nxt, cub::Max(), (int)m, st);
+        if (e != cudaSuccess) return (int)e;
+        k_sp_init<<<b256, 256, 0, st>>>(p);
+        g_gl_launches += 4;
+    }
     u32* spare[5] = {p.a_cur, p.end_cur, p.ord_cur, p.inv_cur, p.tm_cur};
     for (int d = dmax; d >= 0; d--) {
         const bool merges = hist[d] != 0;
@@ -220,6 +241,8 @@ int smt_proofs_sweep(smt_proof_buffers p, int dmax, const uint32_t* hist, u32* c
             p.a_nxt = p.a_cur; p.end_nxt = p.end_cur; p.ord_nxt = p.ord_cur; p.inv_nxt = p.inv_cur; p.tm_nxt = p.tm_cur;
         }
         u64* v = p.val_nxt; p.val_nxt = p.val_cur; p.val_cur = v;
+        u32* x = p.dc_nxt; p.dc_nxt = p.dc_cur; p.dc_cur = x;
+        x = p.rep_nxt; p.rep_nxt = p.rep_cur; p.rep_cur = x;
     }
     p.val_cur = p.val_nxt;   // the depth-0 values (time order)
     k_sp_roots<<<b256, 256, 0, st>>>(p, counts);

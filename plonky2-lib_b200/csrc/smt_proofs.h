@@ -1,4 +1,4 @@
-// Internal interface of smt_proofs.cu: the process proofs of an insert-only batch (second half).
+// Internal interface of smt_proofs.cu: the process proofs of a batch of inserts and updates (second half).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,7 +7,8 @@
 
 struct smt_proof_buffers {
     uint64_t m;
-    uint32_t stride;             // siblings kept per key while sweeping = deepest LCP + 1
+    uint32_t stride;             // siblings kept per event while sweeping = max(1, bottom)
+    uint32_t bottom;             // deepest LCP between different keys + 1: below it every position holds one key
     // from smt_build_prepare (sorted by path order)
     const uint64_t* keys;        // [m][4] input order
     const uint64_t* values;      // [m][4] input order
@@ -19,6 +20,9 @@ struct smt_proof_buffers {
     uint32_t *a_cur, *end_cur, *ord_cur, *inv_cur, *tm_cur;
     uint32_t *a_nxt, *end_nxt, *ord_nxt, *inv_nxt, *tm_nxt;
     uint64_t *val_cur, *val_nxt; // [m][4]
+    uint32_t *dc_cur, *dc_nxt;   // [m] distinct keys below the position after the event
+    uint32_t *rep_cur, *rep_nxt; // [m] while dc == 1: sorted position of the latest event of that one key
+    uint32_t* pos_of_time;       // [m] insertion time -> sorted position
     uint32_t* other;             // [m] per position of the current order: index in val_nxt of the other child's value
     uint8_t* bit;                // [m] path bit of the key at this depth (1: the key is in the right child)
     // per key, indexed by insertion time

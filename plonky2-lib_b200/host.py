@@ -784,7 +784,7 @@ def smt_build_tree(keys, values, want_nodes: bool = False, ctx=None):
     return root
 
 
-def smt_insert_proofs(keys, values, ctx=None):
+def smt_set_proofs(keys, values, ctx=None):
     """N2: the SparseMerkleProcessProofs of m successive `tree.set(keys[t], values[t])` calls on an EMPTY tree with every
     key new (src/smt/tree.rs:143-155, 255-387), all computed in one pass on the device.  Returns (headers [m] of
     SMT_HDR_DTYPE, sib_pool [total][4], sib_off [m + 1]) -- the layout smt_check_process_proofs takes; the siblings of
@@ -792,7 +792,7 @@ def smt_insert_proofs(keys, values, ctx=None):
     ctx = _ctx(ctx)
     k, v = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4)
     if k.shape != v.shape:
-        raise GlPanic(N.GL_E_ARG, "smt_insert_proofs: keys and values differ in shape")
+        raise GlPanic(N.GL_E_ARG, "smt_set_proofs: keys and values differ in shape")
     m = k.shape[0]
     hdr = np.zeros(m, dtype=SMT_HDR_DTYPE)
     off = np.zeros(m + 1, dtype=np.uint64)
@@ -800,7 +800,7 @@ def smt_insert_proofs(keys, values, ctx=None):
     cap = max(32 * m, 1024)       # a random batch needs ~ log2(m) siblings per proof
     while True:
         pool = np.empty((cap, 4), dtype=np.uint64)
-        ctx.check(ctx._lib.gl_smt_insert_proofs(ctx._h, k.ctypes.data, v.ctypes.data, m, hdr.ctypes.data, pool.ctypes.data, cap,
+        ctx.check(ctx._lib.gl_smt_set_proofs(ctx._h, k.ctypes.data, v.ctypes.data, m, hdr.ctypes.data, pool.ctypes.data, cap,
                                                 off.ctypes.data, C.byref(total), N.GL_HOST))
         if total.value <= cap:
             return hdr, pool[: total.value].copy() if total.value < cap // 2 else pool[: total.value], off

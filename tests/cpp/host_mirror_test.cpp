@@ -50,7 +50,7 @@ int main() {
         HashOut root = SparseMerkleTreeBatch::root_of(ctx, keys, vals);
         HashOut want_root{{16994558480514381166ULL, 8559105504417206749ULL, 13458782878755336329ULL, 17099432696459526118ULL}};
         CHECK(root == want_root);
-        std::vector<SparseMerkleProcessProof> proofs = SparseMerkleTreeBatch::insert_proofs(ctx, keys, vals);
+        std::vector<SparseMerkleProcessProof> proofs = SparseMerkleTreeBatch::set_proofs(ctx, keys, vals);
         CHECK(proofs.size() == 3 && proofs[2].new_root == want_root && proofs[0].is_old0 && !proofs[1].is_old0);
         CHECK(proofs[0].old_root == zero && proofs[1].old_root == proofs[0].new_root && proofs[2].old_root == proofs[1].new_root);
         CHECK(proofs[0].new_root == PoseidonNodeHash::calc_leaf_hash_batch(ctx, &keys[0], &vals[0], 1)[0]);

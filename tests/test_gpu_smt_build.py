@@ -86,7 +86,7 @@ def test_bulk_build_scale(glb, ctx, oracle, rng):
     assert np.array_equal(glb.host.smt_build_tree(keys, values), want)
 
 
-# ---- process proofs of an insert-only batch (gl_smt_insert_proofs) ------------------------------------------------
+# ---- process proofs of a batch of inserts and updates (gl_smt_set_proofs) ------------------------------------------------
 def _sequential_proofs(oracle, keys, values):
     t = oracle.Smt()
     return np.array([t.set(k, v) for k, v in zip(keys, values)], dtype=oracle.SMT_PROOF_DTYPE), t.root()
@@ -94,7 +94,7 @@ def _sequential_proofs(oracle, keys, values):
 
 def _check_proofs(glb, oracle, keys, values):
     want, root = _sequential_proofs(oracle, keys, values)
-    hdr, pool, off = glb.host.smt_insert_proofs(keys, values)
+    hdr, pool, off = glb.host.smt_set_proofs(keys, values)
     m = len(keys)
     assert off.shape == (m + 1,) and int(off[0]) == 0 and int(off[-1]) == pool.shape[0]
     for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "is_old0", "fnc"):
@@ -112,12 +112,12 @@ def _check_proofs(glb, oracle, keys, values):
 
 
 @pytest.mark.parametrize("m", [1, 2, 3, 4, 33, 700])
-def test_insert_proofs_match_sequential_sets(glb, ctx, oracle, rng, m):
+def test_set_proofs_match_sequential_sets(glb, ctx, oracle, rng, m):
     keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
     _check_proofs(glb, oracle, keys, values)
 
 
-def test_insert_proofs_reference_fixture(glb, ctx, oracle):
+def test_set_proofs_reference_fixture(glb, ctx, oracle):
     """(1 -> 2), (12 -> 1), (5 -> 51) in this order: src/smt/gadgets/verify/mod.rs:24-34."""
     keys = np.stack([oracle.from_u128(k) for k in (1, 12, 5)])
     values = np.stack([oracle.from_u128(v) for v in (2, 1, 51)])
@@ -126,7 +126,7 @@ def test_insert_proofs_reference_fixture(glb, ctx, oracle):
     assert hdr["new_root"][2].tolist() == [16994558480514381166, 8559105504417206749, 13458782878755336329, 17099432696459526118]
 
 
-def test_insert_proofs_long_common_prefixes_and_orders(glb, ctx, oracle, rng):
+def test_set_proofs_long_common_prefixes_and_orders(glb, ctx, oracle, rng):
     """Twins that agree on up to 255 leading path bits (deep one-child chains, zero siblings in the middle of a proof,
     trailing zeros trimmed), small keys that share long runs of zero bits, and the same set in three insertion orders."""
     base = rand_field(rng, (10, 4))
@@ -145,25 +145,89 @@ def test_insert_proofs_long_common_prefixes_and_orders(glb, ctx, oracle, rng):
     assert int(np.diff(off).max()) > 100        # proofs that walk more than a hundred levels down
 
 
-def test_insert_proofs_reject_duplicates_and_zero_values(glb, ctx, rng):
+def test_set_proofs_reject_zero_values(glb, ctx, rng):
     keys, values = rand_field(rng, (9, 4)), rand_field(rng, (9, 4)) | np.uint64(1)
-    bad = keys.copy()
-    bad[7] = bad[2]
-    with pytest.raises(glb.GlPanic, match="already exists"):
-        glb.host.smt_insert_proofs(bad, values)
     z = values.copy()
     z[4] = 0
     with pytest.raises(glb.GlPanic, match="removal"):
-        glb.host.smt_insert_proofs(keys, z)
+        glb.host.smt_set_proofs(keys, z)
 
 
-def test_insert_proofs_at_scale_verify(glb, ctx, rng):
+def _check_set_proofs(glb, oracle, keys, values):
+    """like _check_proofs, for batches in which keys repeat (later occurrences are updates)"""
+    want, root = _sequential_proofs(oracle, keys, values)
+    hdr, pool, off = glb.host.smt_set_proofs(keys, values)
+    for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "is_old0", "fnc"):
+        assert np.array_equal(hdr[f], want[f]), f
+    assert np.array_equal(np.diff(off).astype(np.uint32), want["num_siblings"])
+    for t in range(len(keys)):
+        ns = int(want["num_siblings"][t])
+        assert np.array_equal(pool[int(off[t]):int(off[t + 1])], want["siblings"][t][:ns]), t
+    assert np.array_equal(hdr["new_root"][-1], root)
+    # the batch verifier says what the reference's says (a proof with 256 siblings -- twins that differ in their last
+    # path bit only -- trips its assert!(siblings.len() < 256): status 1)
+    assert np.array_equal(glb.smt_check_process_proofs(hdr, pool, off), oracle.smt_verify_process_batch(want))
+    return hdr
+
+
+@pytest.mark.parametrize("m,distinct", [(2, 1), (5, 1), (40, 7), (600, 150), (900, 900)])
+def test_set_proofs_with_updates_match_sequential_sets(glb, ctx, oracle, rng, m, distinct):
+    """A key may occur several times in the batch: its first occurrence is a ProcessInsert, the later ones are
+    ProcessUpdates of the value the previous occurrence left (src/smt/tree.rs:174-253)."""
+    pool_keys = rand_field(rng, (distinct, 4))
+    keys = pool_keys[rng.integers(0, distinct, m)]
+    values = rand_field(rng, (m, 4)) | np.uint64(1)
+    hdr = _check_set_proofs(glb, oracle, keys, values)
+    n_ins = len({tuple(k) for k in keys.tolist()})
+    assert int((hdr["fnc"] == 2).sum()) == n_ins and int((hdr["fnc"] == 1).sum()) == m - n_ins
+
+
+def test_set_proofs_updates_deep_in_the_tree(glb, ctx, oracle, rng):
+    """Twins sharing up to 255 path bits, inserted, then updated several times in interleaved order: update proofs walk
+    the whole chain down to the leaf (siblings are not trimmed for updates)."""
+    base = rand_field(rng, (6, 4))
+    keys = []
+    for j, k in enumerate(base):
+        k2 = k.copy()
+        bit = (3, 64, 130, 200, 254, 255)[j]
+        k2[bit >> 6] ^= np.uint64(1) << np.uint64(bit & 63)
+        if int(k2[bit >> 6]) < P:
+            keys += [k, k2]
+        else:
+            keys += [k]
+    keys = np.array(keys)
+    order = np.concatenate([np.arange(len(keys)), rng.permutation(len(keys)), rng.permutation(len(keys))[:7], np.arange(len(keys))[::-1]])
+    ks = keys[order].copy()
+    vs = rand_field(rng, ks.shape) | np.uint64(1)
+    hdr = _check_set_proofs(glb, oracle, ks, vs)
+    assert (hdr["fnc"][len(keys):] == 1).all()
+
+
+def test_set_proofs_at_scale_verify(glb, ctx, rng):
     """2^17 inserts: every emitted proof passes the batch verifier and the chain of roots is consistent."""
     m = 1 << 17
     keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
-    hdr, pool, off = glb.host.smt_insert_proofs(keys, values)
+    hdr, pool, off = glb.host.smt_set_proofs(keys, values)
     assert not glb.smt_check_process_proofs(hdr, pool, off).any()
     assert np.array_equal(hdr["old_root"][1:], hdr["new_root"][:-1]) and not hdr["old_root"][0].any()
     assert np.array_equal(hdr["new_root"][-1], glb.host.smt_build_tree(keys, values))
     ns = np.diff(off)
     assert 14 < ns[m // 2:].mean() < 20          # ~ log2 of the tree size at insertion time
+
+
+def test_set_proofs_mixed_at_scale_verify(glb, ctx, rng):
+    """2^16 inserts followed by 2^16 updates of random existing keys: the verifier accepts every proof, the roots chain,
+    and the final root is the bulk-built tree over the last value of every key."""
+    m = 1 << 16
+    keys0, values0 = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
+    pick = rng.integers(0, m, m)
+    keys = np.concatenate([keys0, keys0[pick]])
+    values = np.concatenate([values0, rand_field(rng, (m, 4)) | np.uint64(1)])
+    hdr, pool, off = glb.host.smt_set_proofs(keys, values)
+    assert not glb.smt_check_process_proofs(hdr, pool, off).any()
+    assert np.array_equal(hdr["old_root"][1:], hdr["new_root"][:-1])
+    assert (hdr["fnc"][:m] == 2).all() and (hdr["fnc"][m:] == 1).all()
+    final = values0.copy()
+    for i, p_ in enumerate(pick):
+        final[p_] = values[m + i]
+    assert np.array_equal(hdr["new_root"][-1], glb.host.smt_build_tree(keys0, final))

@@ -123,14 +123,14 @@ d_pool2 = torch.empty((cap2, 4), dtype=torch.int64, device=dev)
 d_off2 = torch.empty(mk + 1, dtype=torch.int64, device=dev)
 tot = C.c_uint64(0)
 torch.cuda.synchronize()
-t = timeit(lambda: ctx.check(lib.gl_smt_insert_proofs(ctx._h, dk.data_ptr(), dvv.data_ptr(), mk, d_hdr2.data_ptr(), d_pool2.data_ptr(), cap2,
+t = timeit(lambda: ctx.check(lib.gl_smt_set_proofs(ctx._h, dk.data_ptr(), dvv.data_ptr(), mk, d_hdr2.data_ptr(), d_pool2.data_ptr(), cap2,
                                                      d_off2.data_ptr(), C.byref(tot), N.GL_DEVICE)), 2)
 assert tot.value <= cap2
 d_st2 = torch.empty(mk, dtype=torch.int32, device=dev)
 tv = timeit(lambda: ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr2.data_ptr(), d_pool2.data_ptr(), d_off2.data_ptr(), mk,
                                                              d_st2.data_ptr(), N.GL_DEVICE)), 2)
 assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
-out["smt_insert_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
+out["smt_set_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
                             "avg_siblings": tot.value / mk, "verify_emitted_ms": tv * 1e3,
                             "note": "device-resident inputs and outputs; one permutation per (key, depth above its stopping point); the time order of a depth is merged from its children by the same binary search the hash needs"}
 del kk, vv, dk, dvv, d_hdr2, d_pool2, d_off2
