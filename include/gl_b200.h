@@ -115,14 +115,14 @@ int gl_smt_build(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint
                  int space);
 
 /* The m SparseMerkleProcessProofs that m successive `tree.set(keys[t], values[t])` calls return, in call order, when they
- * start from an EMPTY tree and no value is zero (src/smt/tree.rs:143-155; find :588-676, update :174-253, insert :255-387):
- * the first occurrence of a key is a ProcessInsert, later occurrences are ProcessUpdates; proof t is against the tree the
- * first t calls left.  proofs_out [m]; the siblings of proof t are sib_pool_out[sib_off_out[t] .. sib_off_out[t+1]) exactly
- * as `proof.siblings` (an insert trims its trailing zero siblings): the three arrays are what gl_smt_verify_process_batch
- * takes.  *num_siblings_out = total number of siblings; when it exceeds sib_cap (or sib_pool_out is NULL) the pool is not
- * written: call again with a larger pool.  proofs_out[m-1].new_root is the root of the final tree.  A batch on a
- * NON-empty tree: put the existing entries first (any order) and drop their proofs.  An all-zero value (a removal)
- * returns GL_E_ARG. */
+ * start from an EMPTY tree (src/smt/tree.rs:143-155; find :588-676, update :174-253, insert :255-387, remove :389-586).
+ * Keys may repeat and values may be zero, exactly as with `set`: a non-zero value inserts the key or updates it, a zero
+ * value removes it (ProcessDelete) or does nothing when it is not there (ProcessNoOp); proof t is against the tree the
+ * first t calls left.  proofs_out [m]; the siblings of proof t are sib_pool_out[sib_off_out[t] .. sib_off_out[t+1])
+ * exactly as `proof.siblings`: the three arrays are what gl_smt_verify_process_batch takes.  *num_siblings_out = total
+ * number of siblings; when it exceeds sib_cap (or sib_pool_out is NULL) the pool is not written: call again with a
+ * larger pool.  proofs_out[m-1].new_root is the root of the final tree.  A batch on a NON-empty tree: put the existing
+ * entries first (any order) and drop their proofs. */
 int gl_smt_set_proofs(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m,
                          gl_smt_proof_hdr *proofs_out, uint64_t *sib_pool_out, uint64_t sib_cap,
                          uint64_t *sib_off_out, uint64_t *num_siblings_out, int space);

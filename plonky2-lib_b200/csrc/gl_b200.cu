@@ -894,7 +894,7 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
     const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
                  o_lcp = take(m * 2), o_vf = take(m * 32), o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4 + 8),
-                 o_tmp = take(tmp_bytes), o_u32 = take(17 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
+                 o_tmp = take(tmp_bytes), o_u32 = take(19 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
                  o_off = take((m + 1) * 8), o_hdr = take(m * sizeof(gl_smt_proof_hdr));
     void* base;
     TRY(scratch_get(ctx, 2, off, &base));
@@ -905,14 +905,13 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     b.sort_tmp = p0 + o_tmp;
     uint32_t* d_bad = b.hist + 257;
     CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 8, ctx->stream));
-    smt_proofs_check_values(dv, m, d_bad, ctx->stream);
+    (void)d_bad;
     int rc = smt_build_prepare(b, ctx->stream);
     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_set_proofs: sort");
     uint32_t hist[259];
     CK(cudaMemcpyAsync(hist, b.hist, 258 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    // hist[256] = adjacent events with the same key: later occurrences are updates
-    if (hist[257]) return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: a value is zero (set with the default value is a removal, not an insert or update)");
+    // hist[256] = adjacent events with the same key (updates, removals, re-inserts); zero values are removals
     int dmax = -1;
     for (int d = 255; d >= 0; d--)
         if (hist[d]) { dmax = d; break; }
@@ -927,6 +926,7 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     q.a_nxt = u + 5 * m; q.end_nxt = u + 6 * m; q.ord_nxt = u + 7 * m; q.inv_nxt = u + 8 * m; q.tm_nxt = u + 9 * m;
     q.stop_depth = u + 10 * m; q.stop_old = u + 11 * m;
     q.dc_cur = u + 12 * m; q.dc_nxt = u + 13 * m; q.rep_cur = u + 14 * m; q.rep_nxt = u + 15 * m; q.pos_of_time = u + 16 * m;
+    q.deep_dc = u + 17 * m; q.deep_rep = u + 18 * m;
     q.val_cur = (u64*)(p0 + o_val); q.val_nxt = q.val_cur + 4 * m;
     q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
     q.other = (uint32_t*)(p0 + o_keys);       // m * 4 bytes

@@ -34,6 +34,19 @@ GL_D int smt_path_bit_perm(const u64* __restrict__ rk, u64 m, u32 src, unsigned 
 }
 
 // "depth 256": segments = the events of one key (already in time order: the radix sort is stable)
+// `set(key, value)`: a zero value removes.  What an event does depends on whether its key is in the tree just before it,
+// i.e. on the value of the previous event of the same key (sorted position j - 1 when it is in the same group).
+enum { SP_NOOP = 0, SP_UPDATE = 1, SP_INSERT = 2, SP_REMOVE = 3 };   // = ProcessMerkleProofRole
+GL_D bool sp_present(const smt_proof_buffers& p, u32 j) {            // is the key in the tree right after event j?
+    const u64* v = p.values + 4 * (u64)p.perm[j];
+    return (gl_canon(v[0]) | gl_canon(v[1]) | gl_canon(v[2]) | gl_canon(v[3])) != 0;
+}
+GL_D int sp_kind(const smt_proof_buffers& p, u32 j) {
+    const bool same_key_before = j > 0 && p.lcp[j - 1] >= 256;
+    const bool was = same_key_before && sp_present(p, j - 1), is = sp_present(p, j);
+    return is ? (was ? SP_UPDATE : SP_INSERT) : (was ? SP_REMOVE : SP_NOOP);
+}
+
 __global__ void __launch_bounds__(256) k_sp_init(smt_proof_buffers p) {
     u64 j = blockIdx.x * (u64)256 + threadIdx.x;
     if (j >= p.m) return;
@@ -42,16 +55,19 @@ __global__ void __launch_bounds__(256) k_sp_init(smt_proof_buffers p) {
     p.ord_nxt[j] = (u32)j;
     p.inv_nxt[j] = (u32)j;
     p.tm_nxt[j] = p.perm[j];
+    const bool present = sp_present(p, (u32)j);
 #pragma unroll
-    for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = p.leafh[4 * j + k];
-    p.dc_nxt[j] = 1;
+    for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = present ? p.leafh[4 * j + k] : 0;
+    p.dc_nxt[j] = present ? 1 : 0;
     p.rep_nxt[j] = (u32)j;
     const u32 t = p.perm[j];
     p.pos_of_time[t] = (u32)j;
-    // below every LCP between different keys the position holds this key alone (or nothing, before its insert)
-    const bool insert = j == 0 || p.lcp[j - 1] < 256;
+    // below every LCP between different keys the position holds this key alone, or nothing
+    const int kind = sp_kind(p, (u32)j);
     p.stop_depth[t] = p.bottom;
-    p.stop_old[t] = insert ? SP_NONE : (u32)j - 1;
+    p.stop_old[t] = (kind == SP_UPDATE || kind == SP_REMOVE) ? (u32)j - 1 : SP_NONE;
+    p.deep_dc[t] = 0;
+    p.deep_rep[t] = SP_NONE;
 }
 
 // start flags of the depth-d segments, as scan input (index where a segment starts, else 0)
@@ -111,11 +127,12 @@ __global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, uns
         for (int k = 0; k < 4; k++) sib[k] = p.val_nxt[4 * (u64)o + k];
     }
     p.dc_cur[i] = dc;
-    if (dc == 1) {
-        // one key below this position: its leaf hash stands for the subtree
+    if (dc <= 1) {
+        // nothing, or one key below this position: its leaf hash stands for the subtree, whichever child holds it
+        const bool in_own = dc_own == 1;
 #pragma unroll
-        for (int k = 0; k < 4; k++) out[k] = own[k];
-        p.rep_cur[i] = p.rep_nxt[at];
+        for (int k = 0; k < 4; k++) out[k] = dc == 0 ? 0 : (in_own ? own[k] : sib[k]);
+        p.rep_cur[i] = dc == 0 ? SP_NONE : (in_own ? p.rep_nxt[at] : p.rep_nxt[o]);
     } else {
         const int bit = merged ? (int)p.bit[i] : smt_path_bit_perm(p.rk, p.m, t, d);
         if (bit) smt_two_to_one(sib, own, out);
@@ -125,54 +142,81 @@ __global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, uns
 #pragma unroll
     for (int k = 0; k < 4; k++) p.val_cur[4 * i + k] = out[k];
     // the proof of event t at this depth
-    const bool insert = j == 0 || p.lcp[j - 1] < 256;
-    const u32 before = dc - (insert ? 1u : 0u);        // distinct keys below the position just before t
+    const int kind = sp_kind(p, j);
+    const u32 before = dc - (kind == SP_INSERT ? 1u : 0u) + (kind == SP_REMOVE ? 1u : 0u);   // distinct keys just before t
     if (before >= 2) {
         u64* s = p.sib + ((u64)t * p.stride + d) * 4;
 #pragma unroll
         for (int k = 0; k < 4; k++) s[k] = sib[k];
+        if (d + 1 == p.stop_depth[t]) {                // the deepest internal node on the path: what hangs next to the leaf
+            p.deep_dc[t] = dc_sib;
+            p.deep_rep[t] = dc_sib == 1 ? p.rep_nxt[o] : SP_NONE;
+        }
     } else {
         p.stop_depth[t] = d;
-        if (!insert) p.stop_old[t] = j - 1;            // its own leaf: the previous event of the same key
+        if (kind == SP_UPDATE || kind == SP_REMOVE) p.stop_old[t] = j - 1;   // its own leaf: the previous event of the key
         else if (before == 0) p.stop_old[t] = SP_NONE;
-        else p.stop_old[t] = dc_sib ? p.rep_nxt[o] : p.rep_nxt[at - 1];   // the one other key, in either child
+        else p.stop_old[t] = dc_sib == 1 ? p.rep_nxt[o] : (at ? p.rep_nxt[at - 1] : SP_NONE);   // the one other key, in either child
     }
 }
 
 // after depth 0 (one segment, time order): roots and trimmed sibling counts
+GL_D void sp_copy_kv(const smt_proof_buffers& p, u32 sorted_pos, u64* key_out, u64* value_out) {
+    const u64 src = p.perm[sorted_pos];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        key_out[k] = gl_canon(p.keys[4 * src + k]);
+        value_out[k] = gl_canon(p.values[4 * src + k]);
+    }
+}
 __global__ void __launch_bounds__(256) k_sp_roots(smt_proof_buffers p, u32* __restrict__ counts) {
     u64 t = blockIdx.x * (u64)256 + threadIdx.x;
     if (t >= p.m) return;
     gl_smt_proof_hdr* h = p.hdr + t;
+    const u32 j = p.pos_of_time[t];
+    const int kind = sp_kind(p, j);
+    u64 key[4], value[4], zero4[4] = {0, 0, 0, 0};
+    sp_copy_kv(p, j, key, value);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         h->new_root[k] = p.val_cur[4 * t + k];
         h->old_root[k] = t ? p.val_cur[4 * (t - 1) + k] : 0;
-        h->new_key[k] = gl_canon(p.keys[4 * t + k]);
-        h->new_value[k] = gl_canon(p.values[4 * t + k]);
+        h->old_key[k] = h->old_value[k] = h->new_key[k] = h->new_value[k] = 0;
     }
-    const u32 j = p.pos_of_time[t];
-    const bool insert = j == 0 || p.lcp[j - 1] < 256;
-    const u32 so = p.stop_old[t];
-    if (so == SP_NONE) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) h->old_key[k] = h->old_value[k] = 0;
-        h->is_old0 = 1;
-    } else {
-        const u64 src = p.perm[so];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            h->old_key[k] = gl_canon(p.keys[4 * src + k]);
-            h->old_value[k] = gl_canon(p.values[4 * src + k]);
-        }
-        h->is_old0 = 0;
-    }
-    h->fnc = insert ? 2 : 1;   // ProcessMerkleProofRole::ProcessInsert / ProcessUpdate
+    h->fnc = (uint32_t)kind;
+    h->is_old0 = 0;
+    const u64* s = p.sib + (u64)t * p.stride * 4;
+    auto is_zero = [&](u32 lvl) { return (s[4 * lvl] | s[4 * lvl + 1] | s[4 * lvl + 2] | s[4 * lvl + 3]) == 0; };
     u32 ns = p.stop_depth[t];
-    if (insert) {              // insert trims the trailing zero siblings, update keeps what find returned
-        const u64* s = p.sib + (u64)t * p.stride * 4;
-        while (ns > 0 && (s[4 * (ns - 1)] | s[4 * (ns - 1) + 1] | s[4 * (ns - 1) + 2] | s[4 * (ns - 1) + 3]) == 0) ns--;
+    const u32 so = p.stop_old[t];
+    if (kind == SP_NOOP) {                 // removing a key that is not there: nothing happens, nothing to show
+#pragma unroll
+        for (int k = 0; k < 4; k++) h->old_key[k] = h->new_key[k] = key[k];
+        h->is_old0 = 1;
+        ns = 0;
+    } else if (kind == SP_INSERT) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { h->new_key[k] = key[k]; h->new_value[k] = value[k]; }
+        if (so == SP_NONE) h->is_old0 = 1;
+        else sp_copy_kv(p, so, h->old_key, h->old_value);
+        while (ns > 0 && is_zero(ns - 1)) ns--;          // insert trims the trailing zero siblings
+    } else if (kind == SP_UPDATE) {
+        sp_copy_kv(p, so, h->old_key, h->old_value);      // the key itself with its previous value
+#pragma unroll
+        for (int k = 0; k < 4; k++) { h->new_key[k] = key[k]; h->new_value[k] = value[k]; }
+    } else {                               // remove = the insert of this key into the tree it leaves, old and new swapped
+        sp_copy_kv(p, so, h->old_key, h->old_value);
+        if (ns > 0 && p.deep_dc[t] == 1) {                // a lone leaf hung next to it: that leaf moves up
+            sp_copy_kv(p, p.deep_rep[t], h->new_key, h->new_value);
+            ns--;                                         // its own level goes away with the node
+            while (ns > 0 && is_zero(ns - 1)) ns--;
+        } else {                                          // an internal node next to it (or the tree is empty now)
+#pragma unroll
+            for (int k = 0; k < 4; k++) h->new_key[k] = key[k];
+            h->is_old0 = 1;
+        }
     }
+    (void)zero4;
     counts[t] = ns;
 }
 __global__ void __launch_bounds__(256) k_sp_gather(smt_proof_buffers p, const u64* __restrict__ off, u64 cap, u64* __restrict__ pool) {

@@ -23,6 +23,7 @@ struct smt_proof_buffers {
     uint32_t *dc_cur, *dc_nxt;   // [m] distinct keys below the position after the event
     uint32_t *rep_cur, *rep_nxt; // [m] while dc == 1: sorted position of the latest event of that one key
     uint32_t* pos_of_time;       // [m] insertion time -> sorted position
+    uint32_t *deep_dc, *deep_rep;// [m] per event: keys below (and, if one, which) the sibling of the deepest internal node on its path
     uint32_t* other;             // [m] per position of the current order: index in val_nxt of the other child's value
     uint8_t* bit;                // [m] path bit of the key at this depth (1: the key is in the right child)
     // per key, indexed by insertion time

@@ -785,10 +785,10 @@ def smt_build_tree(keys, values, want_nodes: bool = False, ctx=None):
 
 
 def smt_set_proofs(keys, values, ctx=None):
-    """N2: the SparseMerkleProcessProofs of m successive `tree.set(keys[t], values[t])` calls on an EMPTY tree with every
-    key new (src/smt/tree.rs:143-155, 255-387), all computed in one pass on the device.  Returns (headers [m] of
-    SMT_HDR_DTYPE, sib_pool [total][4], sib_off [m + 1]) -- the layout smt_check_process_proofs takes; the siblings of
-    proof t are sib_pool[sib_off[t]:sib_off[t + 1]]."""
+    """N2: the SparseMerkleProcessProofs of m successive `tree.set(keys[t], values[t])` calls on an EMPTY tree
+    (src/smt/tree.rs:143-155), all computed in one pass on the device.  Keys may repeat and values may be zero, as with
+    `set`: insert / update / delete / no-op.  Returns (headers [m] of SMT_HDR_DTYPE, sib_pool [total][4], sib_off [m + 1])
+    -- the layout smt_check_process_proofs takes; the siblings of proof t are sib_pool[sib_off[t]:sib_off[t + 1]]."""
     ctx = _ctx(ctx)
     k, v = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4)
     if k.shape != v.shape:

@@ -145,14 +145,6 @@ def test_set_proofs_long_common_prefixes_and_orders(glb, ctx, oracle, rng):
     assert int(np.diff(off).max()) > 100        # proofs that walk more than a hundred levels down
 
 
-def test_set_proofs_reject_zero_values(glb, ctx, rng):
-    keys, values = rand_field(rng, (9, 4)), rand_field(rng, (9, 4)) | np.uint64(1)
-    z = values.copy()
-    z[4] = 0
-    with pytest.raises(glb.GlPanic, match="removal"):
-        glb.host.smt_set_proofs(keys, z)
-
-
 def _check_set_proofs(glb, oracle, keys, values):
     """like _check_proofs, for batches in which keys repeat (later occurrences are updates)"""
     want, root = _sequential_proofs(oracle, keys, values)
@@ -231,3 +223,42 @@ def test_set_proofs_mixed_at_scale_verify(glb, ctx, rng):
     for i, p_ in enumerate(pick):
         final[p_] = values[m + i]
     assert np.array_equal(hdr["new_root"][-1], glb.host.smt_build_tree(keys0, final))
+
+
+@pytest.mark.parametrize("m,distinct,p_zero,seed", [(6, 2, 0.5, 1), (60, 5, 0.4, 2), (400, 40, 0.3, 3), (1500, 300, 0.25, 4),
+                                                      (300, 300, 0.5, 5), (50, 1, 0.5, 6)])
+def test_set_proofs_with_removals_match_sequential_sets(glb, ctx, oracle, m, distinct, p_zero, seed):
+    """Arbitrary `set` sequences: a zero value removes (ProcessDelete when the key is there, ProcessNoOp when it is not),
+    keys come back after having been removed, subtrees collapse to a hoisted leaf and grow again
+    (src/smt/tree.rs:143-155, remove :389-586)."""
+    rng = np.random.default_rng(seed)
+    pool_keys = rand_field(rng, (distinct, 4))
+    keys = pool_keys[rng.integers(0, distinct, m)]
+    values = rand_field(rng, (m, 4)) | np.uint64(1)
+    values[rng.random(m) < p_zero] = 0
+    hdr = _check_set_proofs(glb, oracle, keys, values)
+    assert set(hdr["fnc"].tolist()) >= ({0, 1, 2, 3} if m >= 60 and distinct > 1 else set())
+
+
+def test_set_proofs_removals_between_twins(glb, ctx, oracle, rng):
+    """Twins sharing long prefixes: removing one hoists the other up the whole chain; removing a key whose neighbour is
+    an internal node leaves a one-child node behind."""
+    base = rand_field(rng, (5, 4))
+    ks = []
+    for j, k in enumerate(base):
+        for bit in ((2, 70, 128, 250, 33)[j], (9, 71, 190, 254, 40)[j]):
+            k2 = k.copy()
+            k2[bit >> 6] ^= np.uint64(1) << np.uint64(bit & 63)
+            if int(k2[bit >> 6]) < P:
+                ks.append(k2)
+        ks.append(k)
+    ks = np.array(ks)
+    n = len(ks)
+    v = rand_field(rng, (n, 4)) | np.uint64(1)
+    z = np.zeros((n, 4), dtype=np.uint64)
+    perm = rng.permutation(n)
+    keys = np.concatenate([ks, ks[perm], ks[perm][::-1], ks[::2], ks[::2]])
+    values = np.concatenate([v, z, v, z[::2], z[::2]])           # insert all, remove all, insert again, remove half, no-ops
+    hdr = _check_set_proofs(glb, oracle, keys, values)
+    assert (hdr["fnc"][n:2 * n] == 3).all() and (hdr["fnc"][-len(ks[::2]):] == 0).all()
+    assert not hdr["new_root"][2 * n - 1].any()                  # the tree was empty in between
