@@ -133,7 +133,21 @@ assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
 out["smt_set_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
                             "avg_siblings": tot.value / mk, "verify_emitted_ms": tv * 1e3,
                             "note": "device-resident inputs and outputs; one permutation per (key, depth above its stopping point); the time order of a depth is merged from its children by the same binary search the hash needs"}
-del kk, vv, dk, dvv, d_hdr2, d_pool2, d_off2
+# the same number of `set` calls as account updates: 2^19 inserts, then 2^19 updates / removals of random existing keys
+half = mk // 2
+pick = torch.randint(0, half, (half,), device=dev)
+dk2 = torch.cat([dk[:half], dk[:half][pick]]).contiguous()
+dv2 = torch.cat([dvv[:half], dvv[half:]]).contiguous()
+dv2[half + (half * 3) // 4:] = 0                           # the last eighth of the calls remove their key (or do nothing)
+torch.cuda.synchronize()
+t2 = timeit(lambda: ctx.check(lib.gl_smt_set_proofs(ctx._h, dk2.data_ptr(), dv2.data_ptr(), mk, d_hdr2.data_ptr(), d_pool2.data_ptr(), cap2,
+                                                    d_off2.data_ptr(), C.byref(tot), N.GL_DEVICE)), 2)
+assert tot.value <= cap2
+ctx.check(lib.gl_smt_verify_process_batch(ctx._h, d_hdr2.data_ptr(), d_pool2.data_ptr(), d_off2.data_ptr(), mk, d_st2.data_ptr(), N.GL_DEVICE))
+assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
+out["smt_set_proofs_mixed"] = {"calls": mk, "what": "2^19 inserts, then 2^19 calls on random existing keys: 3/4 updates, 1/4 removals or no-ops",
+                               "ms": t2 * 1e3, "proofs_per_s": mk / t2, "siblings_total": int(tot.value)}
+del kk, vv, dk, dvv, dk2, dv2, d_hdr2, d_pool2, d_off2
 
 # FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
 ln = 1 << 23
