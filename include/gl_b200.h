@@ -127,6 +127,20 @@ int gl_smt_set_proofs(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values,
                          gl_smt_proof_hdr *proofs_out, uint64_t *sib_pool_out, uint64_t sib_cap,
                          uint64_t *sib_off_out, uint64_t *num_siblings_out, int space);
 
+/* SparseMerkleInclusionProof (src/smt/proof/inclusion.rs:5-33) without its siblings */
+typedef struct gl_smt_inclusion_hdr {
+    uint64_t root[4], key[4], value[4], not_found_key[4], not_found_value[4];
+    uint32_t found;   /* the key is in the tree: `value` is its value */
+    uint32_t is_old0; /* not found and the search ended in an empty slot (else, when not found: not_found_key / _value) */
+} gl_smt_inclusion_hdr;
+/* `tree.find(queries[i])` (src/smt/tree.rs:588-676) for nq keys against the tree that the m `set` calls of
+ * (keys, values) leave when they start from an empty tree (same rules as gl_smt_set_proofs: keys may repeat, a zero
+ * value removes).  proofs_out [nq]; siblings of proof i = sib_pool_out[sib_off_out[i] .. sib_off_out[i+1]), top level
+ * first, every level down to where the search stops.  Pool sizing as in gl_smt_set_proofs. */
+int gl_smt_find_batch(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values, uint64_t m, const uint64_t *queries,
+                      uint64_t nq, gl_smt_inclusion_hdr *proofs_out, uint64_t *sib_pool_out, uint64_t sib_cap,
+                      uint64_t *sib_off_out, uint64_t *num_siblings_out, int space);
+
 /* ---- P4: MerkleTree::new(leaves: Vec<Vec<F>>, cap_height) (plonky2::hash::merkle_tree) --------- */
 /* leaves [num_leaves][leaf_len] row-major; digests_out [2*(num_leaves - 2^cap_height)][4] in
  * plonky2's recursive in-order layout (what MerkleTree::prove indexes); cap_out [2^cap_height][4].

@@ -868,34 +868,28 @@ extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* v
     return finish(ctx);
 }
 
-// N2, second half: the process proofs of m successive inserts into an empty tree (smt_proofs.cu)
-extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m,
-                                    gl_smt_proof_hdr* proofs_out, uint64_t* sib_pool_out, uint64_t sib_cap,
-                                    uint64_t* sib_off_out, uint64_t* num_siblings_out, int space) {
-    if (!ctx) return GL_E_ARG;
-    if (!num_siblings_out || (m && (!keys || !values || !proofs_out || !sib_off_out)))
-        return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: NULL buffer");
-    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: at most 2^31 - 1 entries");
-    *num_siblings_out = 0;
-    if (m == 0) return GL_OK;
-    Guard g(ctx);
+// The sweep of smt_proofs.cu over m events already on the device: the first m_sets are `set` calls, the rest `find`
+// queries.  Set mode (m_sets == m) writes m process proofs, find mode m - m_sets inclusion proofs.
+static int smt_events_run(gl_ctx* ctx, const u64* dk, const u64* dv, uint64_t m, uint64_t m_sets, void* hdr_out,
+                          uint64_t* sib_pool_out, uint64_t sib_cap, uint64_t* sib_off_out, uint64_t* num_siblings_out,
+                          int space, const char* name) {
+    const bool find_mode = m_sets < m;
+    const uint64_t n_out = find_mode ? m - m_sets : m;
     smt_build_buffers b;
     memset(&b, 0, sizeof b);
     b.m = m;
-    const u64 *dk, *dv;
-    TRY(stage_in(ctx, keys, m * 32, space, 0, &dk));
-    TRY(stage_in(ctx, values, m * 32, space, 1, &dv));
     b.keys = dk;
     b.values = dv;
     b.sort_tmp_bytes = smt_sort_temp_bytes(m);
     const size_t tmp_bytes = std::max(b.sort_tmp_bytes, smt_proof_temp_bytes(m));
+    const size_t hdr_bytes = find_mode ? n_out * sizeof(gl_smt_inclusion_hdr) : n_out * sizeof(gl_smt_proof_hdr);
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
     const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
                  o_lcp = take(m * 2), o_vf = take(m * 32), o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4 + 8),
                  o_tmp = take(tmp_bytes), o_u32 = take(19 * m * 4 + 64), o_val = take(2 * m * 32), o_keys = take(2 * m * 8),
-                 o_off = take((m + 1) * 8), o_hdr = take(m * sizeof(gl_smt_proof_hdr));
+                 o_off = take((m + 1) * 8), o_hdr = take(hdr_bytes);
     void* base;
     TRY(scratch_get(ctx, 2, off, &base));
     char* p0 = (char*)base;
@@ -903,21 +897,20 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     b.leafh = (u64*)(p0 + o_leafh); b.lcp = (uint16_t*)(p0 + o_lcp); b.val_first = (u64*)(p0 + o_vf);
     b.form_depth = (uint16_t*)(p0 + o_fd); b.last_valid = (uint8_t*)(p0 + o_lv); b.hist = (uint32_t*)(p0 + o_hist);
     b.sort_tmp = p0 + o_tmp;
-    uint32_t* d_bad = b.hist + 257;
     CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 8, ctx->stream));
-    (void)d_bad;
     int rc = smt_build_prepare(b, ctx->stream);
-    if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_set_proofs: sort");
-    uint32_t hist[259];
-    CK(cudaMemcpyAsync(hist, b.hist, 258 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rc) return cuda_fail(ctx, (cudaError_t)rc, name);
+    uint32_t hist[257];
+    CK(cudaMemcpyAsync(hist, b.hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    // hist[256] = adjacent events with the same key (updates, removals, re-inserts); zero values are removals
+    // hist[256] = adjacent events with the same key (updates, removals, re-inserts, queries)
     int dmax = -1;
     for (int d = 255; d >= 0; d--)
         if (hist[d]) { dmax = d; break; }
     smt_proof_buffers q;
     memset(&q, 0, sizeof q);
     q.m = m;
+    q.m_sets = m_sets;
     q.bottom = (uint32_t)(dmax + 1);
     q.stride = q.bottom > 1 ? q.bottom : 1;
     q.keys = dk; q.values = dv; q.rk = b.rk; q.perm = b.perm; q.lcp = b.lcp; q.leafh = b.leafh;
@@ -928,11 +921,12 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     q.dc_cur = u + 12 * m; q.dc_nxt = u + 13 * m; q.rep_cur = u + 14 * m; q.rep_nxt = u + 15 * m; q.pos_of_time = u + 16 * m;
     q.deep_dc = u + 17 * m; q.deep_rep = u + 18 * m;
     q.val_cur = (u64*)(p0 + o_val); q.val_nxt = q.val_cur + 4 * m;
-    q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
+    if (find_mode) q.inc = (gl_smt_inclusion_hdr*)(p0 + o_hdr);
+    else q.hdr = (gl_smt_proof_hdr*)(p0 + o_hdr);
     q.other = (uint32_t*)(p0 + o_keys);       // m * 4 bytes
     q.bit = (uint8_t*)(p0 + o_keys) + 4 * m;   // m bytes
     u64* d_off = (u64*)(p0 + o_off);
-    // per-key sibling rows while sweeping: [m][stride][4]; counts (u32 [m + 1]) reuse the radix-sort double buffer
+    // per-event sibling rows while sweeping: [m][stride][4]; counts (u32 [m + 1]) reuse the radix-sort double buffer
     const size_t sib_bytes = (size_t)m * q.stride * 32;
     u64* d_sib = nullptr;
     TRY(dev_alloc(ctx, sib_bytes, &d_sib));
@@ -943,14 +937,14 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
     if (rc) {
         cudaStreamSynchronize(ctx->stream);
         dev_release(ctx, d_sib, sib_bytes);
-        return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_set_proofs: sweep");
+        return cuda_fail(ctx, (cudaError_t)rc, name);
     }
     u64 total = 0;
     cudaError_t e = cudaMemcpyAsync(&total, d_off + m, 8, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         dev_release(ctx, d_sib, sib_bytes);
-        return cuda_fail(ctx, e, "gl_smt_set_proofs");
+        return cuda_fail(ctx, e, name);
     }
     *num_siblings_out = total;
     int out_rc = GL_OK;
@@ -968,12 +962,59 @@ extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64
             }
         }
     }
-    if (out_rc == GL_OK) out_rc = copy_out(ctx, proofs_out, q.hdr, m * sizeof(gl_smt_proof_hdr), space);
-    if (out_rc == GL_OK) out_rc = copy_out(ctx, sib_off_out, d_off, (m + 1) * 8, space);
+    if (out_rc == GL_OK) out_rc = copy_out(ctx, hdr_out, p0 + o_hdr, hdr_bytes, space);
+    // in find mode the sets have no siblings, so the offsets of the queries start at 0
+    if (out_rc == GL_OK) out_rc = copy_out(ctx, sib_off_out, d_off + (m - n_out), (n_out + 1) * 8, space);
     int frc = finish(ctx);
     dev_release(ctx, d_sib, sib_bytes);
     if (d_pool) dev_release(ctx, d_pool, pool_bytes);
     return out_rc != GL_OK ? out_rc : frc;
+}
+
+// N2, second half: the process proofs of m successive `set` calls on an empty tree (smt_proofs.cu)
+extern "C" int gl_smt_set_proofs(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m,
+                                 gl_smt_proof_hdr* proofs_out, uint64_t* sib_pool_out, uint64_t sib_cap,
+                                 uint64_t* sib_off_out, uint64_t* num_siblings_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!num_siblings_out || (m && (!keys || !values || !proofs_out || !sib_off_out)))
+        return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: NULL buffer");
+    if (m >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_set_proofs: at most 2^31 - 1 entries");
+    *num_siblings_out = 0;
+    if (m == 0) return GL_OK;
+    Guard g(ctx);
+    const u64 *dk, *dv;
+    TRY(stage_in(ctx, keys, m * 32, space, 0, &dk));
+    TRY(stage_in(ctx, values, m * 32, space, 1, &dv));
+    return smt_events_run(ctx, dk, dv, m, m, proofs_out, sib_pool_out, sib_cap, sib_off_out, num_siblings_out, space,
+                          "gl_smt_set_proofs");
+}
+
+// tree.find for a batch of keys against the tree those sets leave
+extern "C" int gl_smt_find_batch(gl_ctx* ctx, const uint64_t* keys, const uint64_t* values, uint64_t m, const uint64_t* queries,
+                                 uint64_t nq, gl_smt_inclusion_hdr* proofs_out, uint64_t* sib_pool_out, uint64_t sib_cap,
+                                 uint64_t* sib_off_out, uint64_t* num_siblings_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!num_siblings_out || (m && (!keys || !values)) || (nq && (!queries || !proofs_out || !sib_off_out)))
+        return fail(ctx, GL_E_ARG, "gl_smt_find_batch: NULL buffer");
+    if (m + nq >= ((uint64_t)1 << 31)) return fail(ctx, GL_E_ARG, "gl_smt_find_batch: at most 2^31 - 1 entries and queries");
+    *num_siblings_out = 0;
+    if (nq == 0) return GL_OK;
+    Guard g(ctx);
+    // one event list on the device: the sets, then the queries (their values are not looked at)
+    const uint64_t all = m + nq;
+    void *k_all, *v_all;
+    TRY(scratch_get(ctx, 0, all * 32, &k_all));
+    TRY(scratch_get(ctx, 1, all * 32, &v_all));
+    const cudaMemcpyKind kind = space == GL_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (m) {
+        CK(cudaMemcpyAsync(k_all, keys, m * 32, kind, ctx->stream));
+        CK(cudaMemcpyAsync(v_all, values, m * 32, kind, ctx->stream));
+    }
+    CK(cudaMemcpyAsync((char*)k_all + m * 32, queries, nq * 32, kind, ctx->stream));
+    CK(cudaMemsetAsync((char*)v_all + m * 32, 0, nq * 32, ctx->stream));
+    if (space == GL_HOST) CK(cudaStreamSynchronize(ctx->stream));   // the caller's arrays are free again
+    return smt_events_run(ctx, (const u64*)k_all, (const u64*)v_all, all, m, proofs_out, sib_pool_out, sib_cap, sib_off_out,
+                          num_siblings_out, space, "gl_smt_find_batch");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -36,14 +36,30 @@ GL_D int smt_path_bit_perm(const u64* __restrict__ rk, u64 m, u32 src, unsigned 
 // "depth 256": segments = the events of one key (already in time order: the radix sort is stable)
 // `set(key, value)`: a zero value removes.  What an event does depends on whether its key is in the tree just before it,
 // i.e. on the value of the previous event of the same key (sorted position j - 1 when it is in the same group).
-enum { SP_NOOP = 0, SP_UPDATE = 1, SP_INSERT = 2, SP_REMOVE = 3 };   // = ProcessMerkleProofRole
-GL_D bool sp_present(const smt_proof_buffers& p, u32 j) {            // is the key in the tree right after event j?
+enum { SP_NOOP = 0, SP_UPDATE = 1, SP_INSERT = 2, SP_REMOVE = 3, SP_FIND = 4 };   // 0..3 = ProcessMerkleProofRole
+// Events with time >= m_sets are `tree.find(key)` queries against the tree the sets left (gl_smt_find_batch): they
+// come after every set of their key in the sorted order and change nothing.
+GL_D bool sp_is_find(const smt_proof_buffers& p, u32 j) { return p.perm[j] >= p.m_sets; }
+// the last `set` of event j's key at or before j (sorted position), or SP_NONE
+GL_D u32 sp_last_set(const smt_proof_buffers& p, u32 j) {
+    while (sp_is_find(p, j)) {
+        if (j == 0 || p.lcp[j - 1] < 256) return SP_NONE;
+        j--;
+    }
+    return j;
+}
+GL_D bool sp_value_nonzero(const smt_proof_buffers& p, u32 j) {
     const u64* v = p.values + 4 * (u64)p.perm[j];
     return (gl_canon(v[0]) | gl_canon(v[1]) | gl_canon(v[2]) | gl_canon(v[3])) != 0;
 }
+GL_D bool sp_present(const smt_proof_buffers& p, u32 j) {            // is the key in the tree right after event j?
+    const u32 s = sp_last_set(p, j);
+    return s != SP_NONE && sp_value_nonzero(p, s);
+}
 GL_D int sp_kind(const smt_proof_buffers& p, u32 j) {
+    if (sp_is_find(p, j)) return SP_FIND;
     const bool same_key_before = j > 0 && p.lcp[j - 1] >= 256;
-    const bool was = same_key_before && sp_present(p, j - 1), is = sp_present(p, j);
+    const bool was = same_key_before && sp_present(p, j - 1), is = sp_value_nonzero(p, j);
     return is ? (was ? SP_UPDATE : SP_INSERT) : (was ? SP_REMOVE : SP_NOOP);
 }
 
@@ -55,11 +71,12 @@ __global__ void __launch_bounds__(256) k_sp_init(smt_proof_buffers p) {
     p.ord_nxt[j] = (u32)j;
     p.inv_nxt[j] = (u32)j;
     p.tm_nxt[j] = p.perm[j];
-    const bool present = sp_present(p, (u32)j);
+    const u32 ls = sp_last_set(p, (u32)j);              // j itself unless j is a query
+    const bool present = ls != SP_NONE && sp_value_nonzero(p, ls);
 #pragma unroll
-    for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = present ? p.leafh[4 * j + k] : 0;
+    for (int k = 0; k < 4; k++) p.val_nxt[4 * j + k] = present ? p.leafh[4 * (u64)ls + k] : 0;
     p.dc_nxt[j] = present ? 1 : 0;
-    p.rep_nxt[j] = (u32)j;
+    p.rep_nxt[j] = present ? ls : (u32)j;
     const u32 t = p.perm[j];
     p.pos_of_time[t] = (u32)j;
     // below every LCP between different keys the position holds this key alone, or nothing
@@ -156,6 +173,7 @@ __global__ void __launch_bounds__(SMT_BLOCK) k_sp_level(smt_proof_buffers p, uns
         p.stop_depth[t] = d;
         if (kind == SP_UPDATE || kind == SP_REMOVE) p.stop_old[t] = j - 1;   // its own leaf: the previous event of the key
         else if (before == 0) p.stop_old[t] = SP_NONE;
+        else if (kind == SP_FIND) p.stop_old[t] = dc_own == 1 ? p.rep_nxt[at] : p.rep_nxt[o];   // a query adds nothing to its child
         else p.stop_old[t] = dc_sib == 1 ? p.rep_nxt[o] : (at ? p.rep_nxt[at - 1] : SP_NONE);   // the one other key, in either child
     }
 }
@@ -169,11 +187,40 @@ GL_D void sp_copy_kv(const smt_proof_buffers& p, u32 sorted_pos, u64* key_out, u
         value_out[k] = gl_canon(p.values[4 * src + k]);
     }
 }
+// tree.find(key) against the final tree (src/smt/tree.rs:588-676): SparseMerkleInclusionProof
+GL_D void sp_inclusion(const smt_proof_buffers& p, u64 t, u32 j, u32* __restrict__ counts) {
+    gl_smt_inclusion_hdr* h = p.inc + (t - p.m_sets);
+    u64 key[4], unused[4];
+    sp_copy_kv(p, j, key, unused);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        h->root[k] = p.val_cur[4 * t + k];
+        h->key[k] = key[k];
+        h->value[k] = h->not_found_key[k] = h->not_found_value[k] = 0;
+    }
+    h->found = 0;
+    h->is_old0 = 0;
+    const u32 ls = sp_last_set(p, j);
+    if (ls != SP_NONE && sp_value_nonzero(p, ls)) {
+        h->found = 1;
+        sp_copy_kv(p, ls, unused, h->value);
+    } else if (p.stop_old[t] == SP_NONE) {
+        h->is_old0 = 1;
+    } else {
+        sp_copy_kv(p, p.stop_old[t], h->not_found_key, h->not_found_value);
+    }
+    counts[t] = p.stop_depth[t];   // find returns every sibling down to where it stops
+}
 __global__ void __launch_bounds__(256) k_sp_roots(smt_proof_buffers p, u32* __restrict__ counts) {
     u64 t = blockIdx.x * (u64)256 + threadIdx.x;
     if (t >= p.m) return;
-    gl_smt_proof_hdr* h = p.hdr + t;
     const u32 j = p.pos_of_time[t];
+    if (p.m_sets < p.m) {          // gl_smt_find_batch: only the queries produce output
+        if (t >= p.m_sets) sp_inclusion(p, t, j, counts);
+        else counts[t] = 0;
+        return;
+    }
+    gl_smt_proof_hdr* h = p.hdr + t;
     const int kind = sp_kind(p, j);
     u64 key[4], value[4], zero4[4] = {0, 0, 0, 0};
     sp_copy_kv(p, j, key, value);

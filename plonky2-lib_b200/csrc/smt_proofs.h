@@ -6,7 +6,8 @@
 #include "../../include/gl_b200.h"
 
 struct smt_proof_buffers {
-    uint64_t m;
+    uint64_t m;                  // events: the sets, then (gl_smt_find_batch) the queries
+    uint64_t m_sets;             // events with time >= m_sets are queries
     uint32_t stride;             // siblings kept per event while sweeping = max(1, bottom)
     uint32_t bottom;             // deepest LCP between different keys + 1: below it every position holds one key
     // from smt_build_prepare (sorted by path order)
@@ -30,7 +31,8 @@ struct smt_proof_buffers {
     uint64_t* sib;               // [m][stride][4]
     uint32_t* stop_depth;        // where `find` stops
     uint32_t* stop_old;          // sorted position of the key found there, SP_NONE for an empty slot
-    gl_smt_proof_hdr* hdr;       // [m]
+    gl_smt_proof_hdr* hdr;       // [m] process proofs (set mode)
+    gl_smt_inclusion_hdr* inc;   // [m - m_sets] inclusion proofs (find mode)
 };
 
 size_t smt_proof_temp_bytes(uint64_t m);

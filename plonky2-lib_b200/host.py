@@ -830,3 +830,31 @@ def zkdsa_public_inputs_json(message, public_key, signature) -> str:
     """SerializableSimpleSignaturePublicInputs as serde_json writes it (src/zkdsa/circuits/mod.rs:108-153)."""
     return ('{"message":"%s","public_key":"%s","signature":"%s"}'
             % (hash_out_to_hex(message), hash_out_to_hex(public_key), hash_out_to_hex(signature)))
+
+
+SMT_INCLUSION_DTYPE = np.dtype(
+    [("root", "<u8", 4), ("key", "<u8", 4), ("value", "<u8", 4), ("not_found_key", "<u8", 4), ("not_found_value", "<u8", 4),
+     ("found", "<u4"), ("is_old0", "<u4")]
+)
+
+
+def smt_find_batch(keys, values, queries, ctx=None):
+    """`tree.find(q)` (src/smt/tree.rs:588-676) for every query against the tree that `tree.set(keys[t], values[t])`,
+    t = 0 .. m-1, leave when they start from an empty tree.  Returns (SparseMerkleInclusionProof headers [nq] of
+    SMT_INCLUSION_DTYPE, sib_pool [total][4], sib_off [nq + 1]); siblings of proof i = sib_pool[sib_off[i]:sib_off[i + 1]]."""
+    ctx = _ctx(ctx)
+    k, v, q = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4), _h(queries).reshape(-1, 4)
+    if k.shape != v.shape:
+        raise GlPanic(N.GL_E_ARG, "smt_find_batch: keys and values differ in shape")
+    m, nq = k.shape[0], q.shape[0]
+    hdr = np.zeros(nq, dtype=SMT_INCLUSION_DTYPE)
+    off = np.zeros(nq + 1, dtype=np.uint64)
+    total = C.c_uint64(0)
+    cap = max(48 * nq, 1024)
+    while True:
+        pool = np.empty((cap, 4), dtype=np.uint64)
+        ctx.check(ctx._lib.gl_smt_find_batch(ctx._h, k.ctypes.data, v.ctypes.data, m, q.ctypes.data, nq, hdr.ctypes.data,
+                                             pool.ctypes.data, cap, off.ctypes.data, C.byref(total), N.GL_HOST))
+        if total.value <= cap:
+            return hdr, pool[: total.value].copy(), off
+        cap = int(total.value)

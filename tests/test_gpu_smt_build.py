@@ -262,3 +262,56 @@ def test_set_proofs_removals_between_twins(glb, ctx, oracle, rng):
     hdr = _check_set_proofs(glb, oracle, keys, values)
     assert (hdr["fnc"][n:2 * n] == 3).all() and (hdr["fnc"][-len(ks[::2]):] == 0).all()
     assert not hdr["new_root"][2 * n - 1].any()                  # the tree was empty in between
+
+
+# ---- tree.find over a batch of queries (gl_smt_find_batch) -----------------------------------------------------------
+def _check_find(glb, oracle, keys, values, queries):
+    t = oracle.Smt()
+    for k, v in zip(keys, values):
+        t.set(k, v)
+    hdr, pool, off = glb.host.smt_find_batch(keys, values, queries)
+    assert hdr.itemsize == 168 and off.shape == (len(queries) + 1,) and int(off[0]) == 0 and int(off[-1]) == pool.shape[0]
+    root = t.root()
+    for i, q in enumerate(queries):
+        want = t.find(q)
+        h = hdr[i]
+        assert np.array_equal(h["root"], root) and np.array_equal(h["key"], q % np.uint64(P))
+        assert bool(h["found"]) == want["found"] and bool(h["is_old0"]) == want["is_old0"], i
+        assert np.array_equal(pool[int(off[i]):int(off[i + 1])], want["siblings"]), i
+        if want["found"]:
+            assert np.array_equal(h["value"], want["value"]) and not h["not_found_key"].any() and not h["not_found_value"].any()
+        else:
+            assert not h["value"].any()
+            assert np.array_equal(h["not_found_key"], want["not_found_key"]) and np.array_equal(h["not_found_value"], want["value"])
+    return hdr
+
+
+@pytest.mark.parametrize("m,nq", [(0, 3), (1, 4), (2, 5), (40, 60), (700, 500)])
+def test_find_batch_matches_sequential_find(glb, ctx, oracle, rng, m, nq):
+    keys, values = rand_field(rng, (m, 4)), rand_field(rng, (m, 4)) | np.uint64(1)
+    present = keys[rng.integers(0, m, nq // 2)] if m else np.zeros((0, 4), dtype=np.uint64)
+    queries = np.concatenate([present, rand_field(rng, (nq - len(present), 4))])
+    hdr = _check_find(glb, oracle, keys, values, queries)
+    assert int(hdr["found"].sum()) == len(present)
+
+
+def test_find_batch_near_misses_removed_keys_and_repeats(glb, ctx, oracle, rng):
+    """Queries that share long prefixes with stored keys (they end at that key's leaf or in an empty slot deep down),
+    keys that were removed again or overwritten by the sets, the same query several times, and the empty tree."""
+    base = rand_field(rng, (8, 4))
+    near = []
+    for j, k in enumerate(base):
+        for bit in ((0, 5, 64, 100, 191, 254, 255, 30)[j], (1, 63, 65, 128, 200, 250, 17, 90)[j]):
+            k2 = k.copy()
+            k2[bit >> 6] ^= np.uint64(1) << np.uint64(bit & 63)
+            if int(k2[bit >> 6]) < P:
+                near.append(k2)
+    near = np.array(near)
+    keys = np.concatenate([base, near[::2], base[:3], base[3:5]])
+    values = np.concatenate([rand_field(rng, (8 + len(near[::2]) + 3, 4)) | np.uint64(1), np.zeros((2, 4), dtype=np.uint64)])
+    queries = np.concatenate([base, near, base[:2], rand_field(rng, (9, 4))])
+    hdr = _check_find(glb, oracle, keys, values, queries)
+    assert not hdr["found"][3] and not hdr["found"][4] and hdr["found"][0]      # keys 3, 4 were removed by the last two sets
+    z = np.zeros((0, 4), dtype=np.uint64)
+    h0 = _check_find(glb, oracle, z, z, base[:2])
+    assert h0["is_old0"].all() and not h0["root"].any()
