@@ -32,6 +32,15 @@ class SmtProofHdr(C.Structure):
     ]
 
 
+class SmtInclusionHdr(C.Structure):
+    """gl_smt_inclusion_hdr == SparseMerkleInclusionProof minus siblings (src/smt/proof/inclusion.rs:5-33)."""
+
+    _fields_ = [
+        ("root", u64 * 4), ("key", u64 * 4), ("value", u64 * 4), ("not_found_key", u64 * 4), ("not_found_value", u64 * 4),
+        ("found", u32), ("is_old0", u32),
+    ]
+
+
 class FriBatch(C.Structure):
     _fields_ = [("point", u64 * 2), ("first_poly", u32), ("num_polys", u32)]
 

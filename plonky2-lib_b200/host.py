@@ -838,6 +838,9 @@ SMT_INCLUSION_DTYPE = np.dtype(
 )
 
 
+assert SMT_INCLUSION_DTYPE.itemsize == C.sizeof(N.SmtInclusionHdr)
+
+
 def smt_find_batch(keys, values, queries, ctx=None):
     """`tree.find(q)` (src/smt/tree.rs:588-676) for every query against the tree that `tree.set(keys[t], values[t])`,
     t = 0 .. m-1, leave when they start from an empty tree.  Returns (SparseMerkleInclusionProof headers [nq] of
