@@ -148,6 +148,14 @@ int gl_smt_find_batch(gl_ctx *ctx, const uint64_t *keys, const uint64_t *values,
 int gl_merkle_build(gl_ctx *ctx, const uint64_t *leaves, uint64_t num_leaves, uint32_t leaf_len,
                     uint32_t cap_height, uint64_t *digests_out, uint64_t *cap_out, int space);
 
+/* verify_merkle_proof_to_cap (plonky2::hash::merkle_proofs, the verifier's side of MerkleTree::prove) for k proofs against
+ * one cap: leaves [k][leaf_len] (hash_or_noop applies), leaf_indices [k], paths [k][path_len][4] (siblings, leaf level
+ * first), cap [2^cap_height][4]; ok[i] = 1 when the path leads to cap[leaf_index >> path_len], else 0.  rows / paths are
+ * laid out as gl_commit_open writes them. */
+int gl_merkle_verify_batch(gl_ctx *ctx, const uint64_t *leaves, uint32_t leaf_len, const uint64_t *leaf_indices,
+                           const uint64_t *paths, uint32_t path_len, const uint64_t *cap, uint32_t cap_height,
+                           uint64_t k, int32_t *ok, int space);
+
 /* ---- P1/P2/P9: plonky2_field::fft on batches of columns ----------------------------------------- */
 /* In place on [c][2^log_n] (column after column), natural order in and out.
  * gl_fft_batch      = PolynomialCoeffs::fft            (coeffs -> values on <w_n>)

@@ -74,6 +74,7 @@ SIGNATURES = {
     "gl_smt_build": (cint, [vp, vp, vp, u64, vp, vp, u64, u64p, vp, cint]),
     "gl_smt_find_batch": (cint, [vp, vp, vp, u64, vp, u64, vp, vp, u64, vp, C.POINTER(u64), cint]),
     "gl_smt_set_proofs": (cint, [vp, vp, vp, u64, vp, vp, u64, vp, C.POINTER(u64), cint]),
+    "gl_merkle_verify_batch": (cint, [vp, vp, u32, vp, vp, u32, vp, u32, u64, vp, cint]),
     "gl_merkle_build": (cint, [vp, vp, u64, u32, u32, vp, vp, cint]),
     "gl_fft_batch": (cint, [vp, vp, u32, u32, cint]),
     "gl_ifft_batch": (cint, [vp, vp, u32, u32, cint]),

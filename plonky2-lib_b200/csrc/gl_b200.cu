@@ -1017,6 +1017,32 @@ extern "C" int gl_smt_find_batch(gl_ctx* ctx, const uint64_t* keys, const uint64
                           num_siblings_out, space, "gl_smt_find_batch");
 }
 
+// verify_merkle_proof_to_cap for k (leaf, index, path) triples against one cap
+extern "C" int gl_merkle_verify_batch(gl_ctx* ctx, const uint64_t* leaves, uint32_t leaf_len, const uint64_t* leaf_indices,
+                                      const uint64_t* paths, uint32_t path_len, const uint64_t* cap, uint32_t cap_height,
+                                      uint64_t k, int32_t* ok, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (k && (!leaves || !leaf_indices || !cap || !ok || (path_len && !paths)))
+        return fail(ctx, GL_E_ARG, "gl_merkle_verify_batch: NULL buffer");
+    if (leaf_len == 0 || cap_height > 30 || path_len > 64) return fail(ctx, GL_E_ARG, "gl_merkle_verify_batch: bad shape");
+    if (k == 0) return GL_OK;
+    Guard g(ctx);
+    const u64 *dl, *di, *dp, *dc;
+    TRY(stage_in(ctx, leaves, k * leaf_len * 8, space, 0, &dl));
+    TRY(stage_in(ctx, leaf_indices, k * 8, space, 1, &di));
+    TRY(stage_in(ctx, paths, k * (size_t)path_len * 32, space, 2, &dp));
+    TRY(stage_in(ctx, cap, ((size_t)32) << cap_height, space, 3, &dc));
+    int* d_ok = (int*)ok;
+    if (space == GL_HOST) {
+        void* d;
+        TRY(scratch_get(ctx, 4, k * 4, &d));
+        d_ok = (int*)d;
+    }
+    launch_merkle_verify_batch(dl, leaf_len, di, dp, path_len, dc, cap_height, k, d_ok, ctx->stream);
+    TRY(copy_out(ctx, ok, d_ok, k * 4, space));
+    return finish(ctx);
+}
+
 // ------------------------------------------------------------------------------------------------
 // MerkleTree::new on caller-provided row-major leaves
 // ------------------------------------------------------------------------------------------------

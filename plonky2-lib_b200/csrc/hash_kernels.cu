@@ -337,6 +337,52 @@ GL_D void smt_leaf_hash_call(const u64 k[4], const u64 v[4], u64 out[4]) {
     for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
 }
 
+// verify_merkle_proof_to_cap over a batch (plonky2::hash::merkle_proofs; the verifier's side of P11): one proof per
+// thread -- hash_or_noop of the leaf row, then the sibling path up to the cap entry the index ends in.
+__global__ void __launch_bounds__(128)
+k_merkle_verify_batch(const u64* __restrict__ leaves, u32 leaf_len, const u64* __restrict__ leaf_indices,
+                      const u64* __restrict__ paths, u32 path_len, const u64* __restrict__ cap, u32 cap_height, u64 k,
+                      int* __restrict__ ok) {
+    u64 t = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (t >= k) return;
+    const u64* row = leaves + (u64)leaf_len * t;
+    u64 d[4];
+    if (leaf_len <= 4) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[j] = j < leaf_len ? gl_canon(row[j]) : 0;
+    } else {
+        u64 s[12];
+#pragma unroll
+        for (int j = 0; j < 12; j++) s[j] = 0;
+        for (u32 off = 0; off < leaf_len; off += 8) {
+            const u32 n = leaf_len - off < 8 ? leaf_len - off : 8;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                if (j < n) s[j] = row[off + j];
+            poseidon_permute_call(s);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[j] = gl_canon(s[j]);
+    }
+    u64 idx = leaf_indices[t];
+    const u64* sib = paths + (u64)t * path_len * 4;
+    for (u32 l = 0; l < path_len; l++, sib += 4, idx >>= 1) {
+        u64 sb[4], nd[4];
+        load_digest(sib, sb);
+        if (idx & 1) two_to_one_call(sb, d, nd);
+        else two_to_one_call(d, sb, nd);
+#pragma unroll
+        for (int j = 0; j < 4; j++) d[j] = nd[j];
+    }
+    int good = idx < ((u64)1 << cap_height);
+    if (good) {
+        const u64* c = cap + 4 * idx;
+#pragma unroll
+        for (int j = 0; j < 4; j++) good &= d[j] == gl_canon(c[j]);
+    }
+    ok[t] = good;
+}
+
 enum { ST_TOP = 0, ST_BOT = 1, ST_OLD0 = 2, ST_NEW1 = 3, ST_UPD = 4, ST_NA = 5 };
 
 GL_D bool is_zero4(const u64 h[4]) { return (h[0] | h[1] | h[2] | h[3]) == 0; }
@@ -496,6 +542,10 @@ void launch_smt_leaf_hash_batch(const u64* k, const u64* v, u64* out, u64 m, cud
 void launch_smt_verify_process(const gl_smt_proof_hdr* p, const u64* sib_pool, const u64* sib_off, u64 m,
                                int* status, cudaStream_t st) {
     if (m) { k_smt_verify_process<<<nblk(m, 128), 128, 0, st>>>(p, sib_pool, sib_off, m, status); ++g_gl_launches; }
+}
+void launch_merkle_verify_batch(const u64* leaves, u32 leaf_len, const u64* idx, const u64* paths, u32 path_len, const u64* cap,
+                                u32 cap_height, u64 k, int* ok, cudaStream_t st) {
+    if (k) { k_merkle_verify_batch<<<nblk(k, 128), 128, 0, st>>>(leaves, leaf_len, idx, paths, path_len, cap, cap_height, k, ok); ++g_gl_launches; }
 }
 void launch_pow_grind(const u64* state12, unsigned pos, unsigned out_pos, unsigned min_lz, u64 start, u64 count,
                       unsigned long long* best, cudaStream_t st) {

@@ -18,6 +18,8 @@ void launch_hash_no_pad_rows(const uint64_t* in, uint32_t len, uint64_t m, uint6
 void launch_smt_leaf_hash_batch(const uint64_t* k, const uint64_t* v, uint64_t* out, uint64_t m, cudaStream_t st);
 void launch_smt_verify_process(const gl_smt_proof_hdr* p, const uint64_t* sib_pool, const uint64_t* sib_off,
                                uint64_t m, int* status, cudaStream_t st);
+void launch_merkle_verify_batch(const uint64_t* leaves, uint32_t leaf_len, const uint64_t* idx, const uint64_t* paths,
+                                uint32_t path_len, const uint64_t* cap, uint32_t cap_height, uint64_t k, int* ok, cudaStream_t st);
 void launch_pow_grind(const uint64_t* state12, unsigned pos, unsigned out_pos, unsigned min_lz, uint64_t start,
                       uint64_t count, unsigned long long* best, cudaStream_t st);
 void launch_leaf_hash_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned lg_leaves, unsigned cap_height,

@@ -418,6 +418,24 @@ class ResidentMerkleTree:
         return self._b.open([leaf_index])[1][0]
 
 
+def merkle_verify_batch(leaves, leaf_indices, paths, cap, ctx: Optional[Context] = None) -> np.ndarray:
+    """verify_merkle_proof_to_cap (plonky2::hash::merkle_proofs) for k proofs against one cap: leaves [k][leaf_len],
+    leaf_indices [k], paths [k][L][4] (what PolynomialBatch.open / MerkleTree.prove return), cap [2^h][4].
+    Returns a bool array: does proof i lead to its cap entry."""
+    ctx = _ctx(ctx)
+    lv, ix, pt, cp = _h(leaves), _h(leaf_indices).reshape(-1), _h(paths), _h(cap).reshape(-1, 4)
+    k = ix.shape[0]
+    if lv.ndim != 2 or lv.shape[0] != k or pt.ndim != 3 or pt.shape[0] != k or pt.shape[2] != 4:
+        raise GlPanic(N.GL_E_ARG, "merkle_verify_batch: leaves [k][len], leaf_indices [k], paths [k][L][4] expected")
+    h = cp.shape[0]
+    if h == 0 or h & (h - 1):
+        raise GlPanic(N.GL_E_ARG, "merkle_verify_batch: the cap must hold a power of two of digests")
+    ok = np.zeros(k, dtype=np.int32)
+    ctx.check(ctx._lib.gl_merkle_verify_batch(ctx._h, lv.ctypes.data, lv.shape[1], ix.ctypes.data, pt.ctypes.data, pt.shape[1],
+                                              cp.ctypes.data, h.bit_length() - 1, k, ok.ctypes.data, N.GL_HOST))
+    return ok.astype(bool)
+
+
 # ------------------------------------------------------------------------------------------------
 # plonky2::fri::oracle::PolynomialBatch
 # ------------------------------------------------------------------------------------------------

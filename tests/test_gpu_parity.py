@@ -541,3 +541,32 @@ def test_zkdsa_native_batch_and_public_input_json(glb, ctx, oracle, rng):
         assert pks[i].tolist() == oracle.two_to_one(sk[i], sk[i]).tolist()
         assert sigs[i].tolist() == oracle.two_to_one(sk[i], msg[i]).tolist()
     assert host.zkdsa_addresses(pks).tolist() == pks[:, 0].tolist()
+
+
+@pytest.mark.parametrize("lg_n,c,rate_bits,cap_height", [(6, 20, 3, 4), (9, 135, 3, 4), (5, 3, 1, 0), (4, 9, 2, 6), (7, 4, 3, 2)])
+def test_merkle_verify_batch_accepts_openings_and_rejects_tampering(glb, ctx, oracle, rng, lg_n, c, rate_bits, cap_height):
+    """verify_merkle_proof_to_cap over a batch: everything gl_commit_open returns verifies against the cap; a flipped bit in
+    a leaf, a sibling, the index or the cap entry is caught -- proof by proof as the oracle's verifier decides."""
+    n = 1 << lg_n
+    N = n << rate_bits
+    values = oracle.synthetic_values(c, n)
+    b = glb.PolynomialBatch.from_values(values, rate_bits, False, cap_height)
+    cap = b.merkle_tree.cap.copy()
+    idx = np.unique(rng.integers(0, N, 64)).astype(np.uint64)
+    rows, paths = b.open(idx)
+    b.free()
+    assert glb.host.merkle_verify_batch(rows, idx, paths, cap).all()
+    bad_rows, bad_idx, bad_paths = rows.copy(), idx.copy(), paths.copy()
+    k = len(idx)
+    bad_rows[0, c - 1] ^= np.uint64(1)
+    if paths.shape[1]:
+        bad_paths[1, paths.shape[1] - 1, 2] ^= np.uint64(1 << 40)
+        bad_paths[2, 0, 0] ^= np.uint64(1)
+    bad_idx[3] ^= np.uint64(1)
+    got = glb.host.merkle_verify_batch(bad_rows, bad_idx, bad_paths, cap)
+    want = np.array([oracle.merkle_verify(bad_rows[i], int(bad_idx[i]), bad_paths[i], cap, cap_height) for i in range(k)])
+    assert np.array_equal(got, want) and not got[0] and got[4:].all()
+    cap2 = cap.copy()
+    cap2[int(idx[5]) >> paths.shape[1], 3] ^= np.uint64(1)
+    got = glb.host.merkle_verify_batch(rows, idx, paths, cap2)
+    assert not got[5] and np.array_equal(got, np.array([oracle.merkle_verify(rows[i], int(idx[i]), paths[i], cap2, cap_height) for i in range(k)]))
