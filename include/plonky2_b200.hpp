@@ -256,6 +256,28 @@ struct MerkleTree {
         return t;
     }
     const std::vector<F>& get(size_t i) const { return leaves[i]; }
+    // verify_merkle_proof_to_cap (plonky2::hash::merkle_proofs) for a batch of openings against one cap; every proof
+    // must have the same length (they do when they come from one tree)
+    static std::vector<bool> verify_batch(const Context& c, const std::vector<std::vector<F>>& rows, const std::vector<uint64_t>& idx,
+                                          const std::vector<MerkleProof>& proofs, const MerkleCap& cap) {
+        const size_t k = rows.size();
+        std::vector<bool> out(k);
+        if (!k) return out;
+        const uint32_t len = (uint32_t)rows[0].size(), L = (uint32_t)proofs[0].siblings.size();
+        std::vector<F> flat, paths;
+        for (size_t i = 0; i < k; i++) {
+            if (rows[i].size() != len || proofs[i].siblings.size() != L) throw Panic(GL_E_ARG, "verify_batch: ragged openings");
+            flat.insert(flat.end(), rows[i].begin(), rows[i].end());
+            for (auto& s : proofs[i].siblings) paths.insert(paths.end(), s.elements, s.elements + 4);
+        }
+        uint32_t h = 0;
+        while ((1ull << h) < cap.size()) h++;
+        std::vector<int32_t> ok(k);
+        if (paths.empty()) paths.resize(4);
+        c.check(gl_merkle_verify_batch(c.raw(), flat.data(), len, idx.data(), paths.data(), L, &cap[0].elements[0], h, k, ok.data(), GL_HOST));
+        for (size_t i = 0; i < k; i++) out[i] = ok[i] != 0;
+        return out;
+    }
     MerkleProof prove(size_t leaf_index) const {
         MerkleProof p;
         size_t n = leaves.size();

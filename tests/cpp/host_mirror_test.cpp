@@ -96,6 +96,15 @@ int main() {
         }
         CHECK(d == pb.cap[i]);
     }
+    {   // the same check for the whole batch on the device, and a tampered row is caught
+        std::vector<uint64_t> idx = {0, 77, N - 1};
+        std::vector<bool> ok = MerkleTree::verify_batch(ctx, opened.first, idx, opened.second, pb.cap);
+        CHECK(ok[0] && ok[1] && ok[2]);
+        auto tampered = opened.first;
+        tampered[1][3] ^= 1;
+        ok = MerkleTree::verify_batch(ctx, tampered, idx, opened.second, pb.cap);
+        CHECK(ok[0] && !ok[1] && ok[2]);
+    }
     CHECK(pb.get_lde_values(3, 8) == rows[192]);  // leaves[reverse_bits(3 * 8, 11)] = leaves[192]
     // panics like upstream
     bool threw = false;
