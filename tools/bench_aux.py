@@ -149,6 +149,36 @@ out["smt_set_proofs_mixed"] = {"calls": mk, "what": "2^19 inserts, then 2^19 cal
                                "ms": t2 * 1e3, "proofs_per_s": mk / t2, "siblings_total": int(tot.value)}
 del kk, vv, dk, dvv, dk2, dv2, d_hdr2, d_pool2, d_off2
 
+# verifier's side: 2^18 openings of a 2^20-leaf tree over 135-element rows checked against the cap in one call
+lgv, kv = 20, 1 << 18
+vrows = rand_dev((1 << lgv, 135))
+vdig = torch.empty((2 * ((1 << lgv) - 16), 4), dtype=torch.int64, device=dev)
+vcap = torch.empty((16, 4), dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+ctx.check(lib.gl_merkle_build(ctx._h, vrows.data_ptr(), 1 << lgv, 135, 4, vdig.data_ptr(), vcap.data_ptr(), N.GL_DEVICE))
+vidx = torch.randint(0, 1 << lgv, (kv,), dtype=torch.int64, device=dev)
+# sibling paths gathered from the digest buffer with torch (plonky2's in-order layout: MerkleTree::prove)
+L = lgv - 4
+sub = vidx >> L
+pair = vidx & ((1 << L) - 1)
+per_sub = 2 * ((1 << L) - 1)
+vpaths = torch.empty((kv, L, 4), dtype=torch.int64, device=dev)
+pp = pair.clone()
+for i in range(L):
+    parity = pp & 1
+    pp = pp >> 1
+    sib = 2 * ((pp << (i + 1)) + (1 << i) - 1) + (1 - parity)
+    vpaths[:, i, :] = vdig[sub * per_sub + sib]
+vleaf = vrows[vidx].contiguous()
+vok = torch.empty(kv, dtype=torch.int32, device=dev)
+torch.cuda.synchronize()
+t = timeit(lambda: ctx.check(lib.gl_merkle_verify_batch(ctx._h, vleaf.data_ptr(), 135, vidx.data_ptr(), vpaths.data_ptr(), L, vcap.data_ptr(), 4,
+                                                      kv, vok.data_ptr(), N.GL_DEVICE)), 3)
+assert int(vok.sum().item()) == kv, "every opening must verify"
+out["merkle_verify_batch"] = {"openings": kv, "leaf_len": 135, "path_len": L, "ms": t * 1e3, "openings_per_s": kv / t,
+                              "perms_per_s": kv * (17 + L) / t}
+del vrows, vdig, vpaths, vleaf
+
 # FRI: first reduction layer of a 2^20-row proof (N = 2^23 extension values, arity 16)
 ln = 1 << 23
 vals = rand_dev((ln, 2))
