@@ -159,3 +159,97 @@ def test_prove_openings_matches_oracle_and_verifies(glb, ctx, oracle, rng, degre
                               pow_bits, rounds)
     for b in batches_dev:
         b.free()
+
+
+@pytest.mark.parametrize("degree_bits,cols", [(5, (3, 2)), (9, (4, 9, 3)), (12, (84, 135, 20, 16))])
+def test_device_verifier_accepts_proofs_and_rejects_tampering(glb, ctx, oracle, rng, degree_bits, cols):
+    """plonky2::fri::verifier on the product side (fri_verifier.py: Merkle openings batched on the device, transcript on
+    the product Challenger, interpolation in exact integers on the host): accepts the device prover's proof AND the
+    oracle prover's proof, and rejects each kind of tampering where the oracle's restatement of the verifier rejects it."""
+    import copy
+
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    fv = importlib.import_module("plonky2-lib_b200.fri_verifier")
+    rate_bits, cap_height, pow_bits, rounds = 3, 4, 8, 28
+    n = 1 << degree_bits
+    batches_dev, polys, trees = [], [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=300 + k)
+        batches_dev.append(glb.PolynomialBatch.from_values(v, rate_bits, False, cap_height))
+        res = oracle.commit_from_values(v, rate_bits, cap_height)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], cap_height))
+    caps = [t.cap for t in trees]
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    g = oracle.lib().glo_primitive_root_of_unity(degree_bits)
+    zs = min(len(cols) - 1, 2)
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+                (fo.ext_scalar(zeta, g), [(zs, pi) for pi in range(min(2, cols[zs]))])]
+    openings = fo.opening_set(polys, instance)
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+
+    def transcript():
+        ch = fri.Challenger()
+        for cap in caps:
+            ch.observe_cap(cap)
+        return ch
+
+    proof = fri.prove_openings(batches_dev, instance, transcript(), params)
+    assert fv.verify_openings(instance, openings, caps, proof, transcript(), params) is True
+    # a proof made by the oracle's prover
+    och = fo.Challenger()
+    for cap in caps:
+        och.observe_cap(cap)
+    oproof = fo.prove_openings(polys, trees, instance, och, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    assert fv.verify_openings(instance, openings, caps, oproof, transcript(), params) is True
+
+    def oracle_accepts(p, ops):
+        vch = fo.Challenger()
+        for cap in caps:
+            vch.observe_cap(cap)
+        try:
+            return bool(fo.verify_openings(p, ops, caps, instance, vch, degree_bits, rate_bits, cap_height, pow_bits, rounds))
+        except AssertionError:
+            return False
+
+    def tampered(kind):
+        p, ops = copy.deepcopy(proof), copy.deepcopy(openings)
+        r = p["query_round_proofs"][3]
+        if kind == "pow":
+            p["pow_witness"] = int(p["pow_witness"]) + 1
+        elif kind == "final":
+            p["final_poly"] = np.array(p["final_poly"], copy=True)
+            p["final_poly"][0, 0] ^= np.uint64(1)
+        elif kind == "eval" and r["steps"]:
+            r["steps"][0]["evals"] = np.array(r["steps"][0]["evals"], copy=True)
+            r["steps"][0]["evals"][1, 1] ^= np.uint64(2)
+        elif kind == "sibling" and r["steps"] and len(r["steps"][0]["merkle_proof"]):
+            r["steps"][0]["merkle_proof"] = np.array(r["steps"][0]["merkle_proof"], copy=True)
+            r["steps"][0]["merkle_proof"][0, 3] ^= np.uint64(1)
+        elif kind == "row":
+            row, path = r["initial_trees_proof"][0]
+            row = np.array(row, copy=True)
+            row[0] ^= np.uint64(1)
+            r["initial_trees_proof"][0] = (row, path)
+        elif kind == "opening":
+            ops[0][0] = ((int(ops[0][0][0]) + 1) % P, int(ops[0][0][1]))
+        elif kind == "cap" and p["commit_phase_merkle_caps"]:
+            p["commit_phase_merkle_caps"][0] = np.array(p["commit_phase_merkle_caps"][0], copy=True)
+            p["commit_phase_merkle_caps"][0][0, 0] ^= np.uint64(1)
+        else:
+            return None
+        return p, ops
+
+    for kind in ("pow", "final", "eval", "sibling", "row", "opening", "cap"):
+        t = tampered(kind)
+        if t is None:
+            continue
+        p, ops = t
+        assert not oracle_accepts(p, ops), kind
+        with pytest.raises(fv.FriVerifyError):
+            fv.verify_openings(instance, ops, caps, p, transcript(), params)
+    for b in batches_dev:
+        b.free()
