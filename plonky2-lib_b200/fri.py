@@ -3,8 +3,8 @@ phase, with the data-parallel work on the device and the serial Fiat-Shamir tran
 plonky2::iop::challenger) on the host.
 
 Every layer tree stays resident (`gl_fri_layer_commit`); the 28 query rounds of a proof are answered with one
-`gl_commit_open` per tree.  The Challenger's permutations are single-state `gl_poseidon_permute_batch` calls
-(there is no CPU Poseidon in the product).  Upstream's `fri_proof_of_work` takes any satisfying witness found
+`gl_commit_open` per tree.  The Challenger's permutations run on the device (single states, or one
+`gl_poseidon_duplex_chain` launch for a run of full input buffers; there is no CPU Poseidon in the product).  Upstream's `fri_proof_of_work` takes any satisfying witness found
 by rayon `find_any`; here it is the smallest one (`gl_pow_grind`), which makes proofs deterministic.
 """
 from __future__ import annotations
