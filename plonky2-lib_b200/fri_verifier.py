@@ -208,21 +208,3 @@ def verify_openings(instance, openings, initial_merkle_caps, proof: dict, challe
     the caps and the openings as the prover's caller did), then verify_fri_proof."""
     ch = fri_challenges(challenger, proof, params.degree_bits, params)
     return verify_fri_proof(instance, openings, ch, initial_merkle_caps, proof, params, ctx)
-
-
-def opening_values(oracles, instance, ctx: Context = None):
-    """FriOpenings for tests and examples: every polynomial of every batch evaluated at the batch's point, from the
-    coefficients the resident commits hold (exact integer Horner on the host: one proof's worth of points)."""
-    out = []
-    for point, polys in instance:
-        z = _e(point)
-        vals = []
-        for oi, pi in polys:
-            polys_of = oracles[oi].polynomials
-            coeffs = np.asarray(polys_of[pi])
-            acc: Ext = (0, 0)
-            for c in coeffs[::-1].tolist():
-                acc = _eadd(_emul(acc, z), (int(c) % P, 0))
-            vals.append(acc)
-        out.append(vals)
-    return out
