@@ -209,6 +209,10 @@ int gl_commit_add_coeffs(gl_commit *h, uint32_t col0, uint32_t ncols, const uint
 int gl_commit_finish(gl_commit *h, uint64_t *cap_out, int space);
 /* PolynomialBatch.polynomials: the coefficients [c][2^log_n] kept on the device behind the handle. */
 int gl_commit_coeffs(gl_commit *h, uint64_t *coeffs_out, int space);
+/* OpeningSet::new (plonky2::plonk::proof; PolynomialCoeffs::eval at an extension-field point) for every polynomial of
+ * the commit: values_out [c][2] = polynomial j evaluated at point = (a0, a1) of F[X]/(X^2 - 7), from the resident
+ * coefficients (nothing but c x 16 bytes crosses PCIe). */
+int gl_commit_eval(gl_commit *h, const uint64_t point[2], uint64_t *values_out, int space);
 /* "mirror mode": fill the upstream structs.  leaves_out [N_local][c] row-major in leaf order
  * (= MerkleTree.leaves after transpose + reverse_index_bits), digests_out [2*(N_local - caps_local)][4]
  * (= MerkleTree.digests).  Either may be NULL. */

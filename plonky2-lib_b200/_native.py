@@ -88,6 +88,7 @@ SIGNATURES = {
     "gl_commit_begin_ex": (cint, [vp, u32, u32, u32, u32, u32, C.POINTER(vp)]),
     "gl_commit_add_coeffs": (cint, [vp, u32, u32, vp, cint]),
     "gl_commit_finish": (cint, [vp, vp, cint]),
+    "gl_commit_eval": (cint, [vp, vp, vp, cint]),
     "gl_commit_coeffs": (cint, [vp, vp, cint]),
     "gl_commit_download": (cint, [vp, vp, vp, cint]),
     "gl_commit_open": (cint, [vp, vp, u32, vp, vp, cint]),

@@ -113,6 +113,79 @@ k_ext_to_padded_cols(const u64* __restrict__ ext, u64 n, u64 N, u64* __restrict_
     padded[2 * i + 1] = b;
 }
 
+// OpeningSet::new / PolynomialCoeffs::eval at an extension point for every polynomial of a resident commit:
+// out[j] = sum_i coeffs[j][i] * z^i.  A block takes EVAL_CHUNK consecutive coefficients of one polynomial: thread t sums
+// c[base + t + 256 k] * (z^256)^k by Horner in k, scales by z^t (binary powering, 8 steps) and by z^base (one thread,
+// powering of z^EVAL_CHUNK), and the block adds up; a second pass adds the chunks of each polynomial.
+#define EVAL_CHUNK 4096
+GL_D gl_ext gl_ext_pow_dev(gl_ext x, u64 e) {
+    gl_ext acc = {1, 0};
+    while (e) {
+        if (e & 1) acc = gl_ext_mul(acc, x);
+        x = gl_ext_mul(x, x);
+        e >>= 1;
+    }
+    return acc;
+}
+__global__ void __launch_bounds__(256)
+k_eval_chunks(const u64* __restrict__ coeffs, u64 n, u64 za, u64 zb, u64 z256a, u64 z256b, u64 zca, u64 zcb, u64* __restrict__ partial) {
+    __shared__ u64 red[2][256];
+    __shared__ u64 zbase[2];
+    const u64 chunk = blockIdx.x, poly = blockIdx.y, chunks = gridDim.x;
+    const u64 base = chunk * EVAL_CHUNK;
+    const unsigned t = threadIdx.x;
+    const u64* c = coeffs + poly * n + base;
+    if (t == 0) {
+        gl_ext zb_ = gl_ext_pow_dev({zca, zcb}, chunk);
+        zbase[0] = zb_.a;
+        zbase[1] = zb_.b;
+    }
+    const gl_ext z256 = {z256a, z256b};
+    gl_ext acc = {0, 0};
+#pragma unroll 1
+    for (int k = EVAL_CHUNK / 256 - 1; k >= 0; k--) {
+        const u64 i = base + t + 256ull * k;
+        acc = gl_ext_mul(acc, z256);
+        if (i < n) acc.a = gl_add(acc.a, c[t + 256ull * k]);
+    }
+    acc = gl_ext_mul(acc, gl_ext_pow_dev({za, zb}, t));
+    __syncthreads();
+    acc = gl_ext_mul(acc, {zbase[0], zbase[1]});
+    red[0][t] = gl_canon(acc.a);
+    red[1][t] = gl_canon(acc.b);
+    __syncthreads();
+    for (unsigned s_ = 128; s_ > 0; s_ >>= 1) {
+        if (t < s_) {
+            red[0][t] = gl_canon(gl_add(red[0][t], red[0][t + s_]));
+            red[1][t] = gl_canon(gl_add(red[1][t], red[1][t + s_]));
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        partial[2 * (poly * chunks + chunk)] = red[0][0];
+        partial[2 * (poly * chunks + chunk) + 1] = red[1][0];
+    }
+}
+__global__ void __launch_bounds__(128) k_eval_sum(const u64* __restrict__ partial, u64 chunks, u32 c, u64* __restrict__ out) {
+    const u32 poly = blockIdx.x * 128 + threadIdx.x;
+    if (poly >= c) return;
+    u64 a = 0, b = 0;
+    for (u64 k = 0; k < chunks; k++) {
+        a = gl_add(a, partial[2 * (poly * chunks + k)]);
+        b = gl_add(b, partial[2 * (poly * chunks + k) + 1]);
+    }
+    out[2 * poly] = gl_canon(a);
+    out[2 * poly + 1] = gl_canon(b);
+}
+// partial: scratch [c][ceil(n / EVAL_CHUNK)][2]; z256 = z^256, zc = z^EVAL_CHUNK (host, exact)
+void launch_eval_at(const u64* coeffs, u64 n, u32 c, const u64 z[2], const u64 z256[2], const u64 zc[2], u64* partial, u64* out,
+                    cudaStream_t st) {
+    const u64 chunks = (n + EVAL_CHUNK - 1) / EVAL_CHUNK;
+    k_eval_chunks<<<dim3((unsigned)chunks, c), 256, 0, st>>>(coeffs, n, z[0], z[1], z256[0], z256[1], zc[0], zc[1], partial);
+    k_eval_sum<<<(c + 127) / 128, 128, 0, st>>>(partial, chunks, c, out);
+    g_gl_launches += 2;
+}
+
 void launch_fri_reduce_polys(const u64* const* polys, u32 k, u64 n, const u64* alpha_pows, u64* comp_ext, cudaStream_t st) {
     k_fri_reduce_polys<<<(unsigned)((n + 255) / 256), 256, 2 * k * sizeof(u64), st>>>(polys, k, n, alpha_pows, comp_ext);
     ++g_gl_launches;

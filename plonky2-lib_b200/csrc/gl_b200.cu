@@ -1487,6 +1487,27 @@ extern "C" int gl_commit_coeffs(gl_commit* h, uint64_t* coeffs_out, int space) {
     return finish(ctx);
 }
 
+// OpeningSet::new: every polynomial of the commit at one extension point, without bringing the coefficients back
+extern "C" int gl_commit_eval(gl_commit* h, const uint64_t point[2], uint64_t* values_out, int space) {
+    if (!h || !point || !values_out) return GL_E_ARG;
+    gl_ctx* ctx = h->ctx;
+    if (!h->coeffs) return fail(ctx, GL_E_STATE, "gl_commit_eval: this handle has no polynomials (FRI layer tree)");
+    if (!h->finished && h->cols_added != h->c) return fail(ctx, GL_E_STATE, "gl_commit_eval: not every polynomial has been added");
+    Guard g(ctx);
+    const u64 n = (u64)1 << h->log_n;
+    const u64 chunks = (n + FRI_EVAL_CHUNK - 1) / FRI_EVAL_CHUNK;
+    const glh::ext z = {glh::canon(point[0]), glh::canon(point[1])};
+    const glh::ext z256 = glh::ext_pow(z, 256), zc = glh::ext_pow(z, FRI_EVAL_CHUNK);
+    const u64 zz[2] = {z.a, z.b}, z2[2] = {z256.a, z256.b}, z3[2] = {zc.a, zc.b};
+    void* d;
+    TRY(scratch_get(ctx, 0, ((size_t)h->c * chunks + h->c) * 16, &d));
+    u64* partial = (u64*)d;
+    u64* d_out = space == GL_DEVICE ? values_out : partial + 2 * (size_t)h->c * chunks;
+    launch_eval_at(h->coeffs, n, h->c, zz, z2, z3, partial, d_out, ctx->stream);
+    if (space == GL_HOST) TRY(copy_out(ctx, values_out, d_out, (size_t)h->c * 16, GL_HOST));
+    return finish(ctx);
+}
+
 extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* digests_out, int space) {
     if (!h) return GL_E_ARG;
     gl_ctx* ctx = h->ctx;

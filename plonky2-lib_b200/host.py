@@ -561,6 +561,14 @@ class PolynomialBatch:
             self._ctx.check(self._ctx._lib.gl_commit_coeffs(self._h, self._polys.ctypes.data, N.GL_HOST))
         return self._polys
 
+    def eval_at(self, point) -> np.ndarray:
+        """OpeningSet::new for this batch: every polynomial at the extension point (a0, a1) -> [columns][2], computed from
+        the resident coefficients."""
+        pt = (C.c_uint64 * 2)(int(point[0]) % P, int(point[1]) % P)
+        out = np.empty((self.num_columns, 2), dtype=np.uint64)
+        self._ctx.check(self._ctx._lib.gl_commit_eval(self._h, pt, out.ctypes.data, N.GL_HOST))
+        return out
+
     def get_lde_values(self, index, step: int) -> np.ndarray:
         """PolynomialBatch::get_lde_values(index, step) for one index or a list: [k][columns]."""
         idx = _h(np.atleast_1d(index))

@@ -253,3 +253,18 @@ def test_device_verifier_accepts_proofs_and_rejects_tampering(glb, ctx, oracle, 
             fv.verify_openings(instance, ops, caps, p, transcript(), params)
     for b in batches_dev:
         b.free()
+
+
+@pytest.mark.parametrize("lg_n,c", [(0, 3), (3, 5), (8, 20), (12, 135), (13, 7), (14, 2)])
+def test_commit_eval_matches_oracle(glb, ctx, oracle, rng, lg_n, c):
+    """gl_commit_eval = OpeningSet::new: every polynomial of a resident commit at an extension-field point (one chunk,
+    exactly one chunk, several chunks of 4096 coefficients)."""
+    n = 1 << lg_n
+    values = oracle.synthetic_values(c, n, seed=40 + lg_n)
+    b = glb.PolynomialBatch.from_values(values, 3 if lg_n else 0, False, 0)
+    coeffs = np.asarray(b.polynomials)
+    for point in (tuple(int(x) for x in rand_field(rng, (2,))), (0, 0), (1, 0), (P - 1, P - 1), (5, 0)):
+        got = b.eval_at(point)
+        for j in (0, c // 2, c - 1):
+            assert tuple(int(x) for x in got[j]) == oracle.eval_base_poly_at_ext(coeffs[j], np.array(point, dtype=np.uint64)), (point, j)
+    b.free()
