@@ -210,6 +210,9 @@ cols = (84, 135, 20, 16)
 instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
             ((zeta[0] * g % P, zeta[1] * g % P), [(2, pi) for pi in range(20)])]
 params = fri.FriParams.for_degree(glb.FriConfig(), lg)
+t = timeit(lambda: [b.eval_at(zeta) for b in batches], 3)
+out["opening_set_2^20"] = {"polynomials": sum(cols), "ms": t * 1e3,
+                           "note": "OpeningSet::new at zeta for the 4 oracles (gl_commit_eval): 255 polynomials of 2^20 coefficients, results to the host"}
 
 
 def run_open():
