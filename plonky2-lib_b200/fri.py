@@ -283,6 +283,22 @@ def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Contex
     return coeffs, values
 
 
+def opening_set(oracles, batches) -> list:
+    """OpeningSet::new / FriOpenings: for every batch (point, [(oracle_index, polynomial_index), ...]) the values of its
+    polynomials at its point, evaluated on the device from the resident coefficients (gl_commit_eval: one call per oracle
+    and point)."""
+    out = []
+    for point, polys in batches:
+        cache = {}
+        vals = []
+        for oi, pi in polys:
+            if oi not in cache:
+                cache[oi] = oracles[oi].eval_at(point)
+            vals.append((int(cache[oi][pi][0]), int(cache[oi][pi][1])))
+        out.append(vals)
+    return out
+
+
 def prove_openings(oracles, batches, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None) -> dict:
     """plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params)."""
     ctx = _ctx(ctx)

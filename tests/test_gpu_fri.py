@@ -188,6 +188,7 @@ def test_device_verifier_accepts_proofs_and_rejects_tampering(glb, ctx, oracle, 
     instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
                 (fo.ext_scalar(zeta, g), [(zs, pi) for pi in range(min(2, cols[zs]))])]
     openings = fo.opening_set(polys, instance)
+    assert fri.opening_set(batches_dev, instance) == [[tuple(int(x) for x in v) for v in b] for b in openings]   # OpeningSet::new on the device
     cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
     params = fri.FriParams.for_degree(cfg, degree_bits)
 
