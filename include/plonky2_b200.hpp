@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <memory>
 #include <stdexcept>
+#include <array>
 #include <string>
 #include <utility>
 #include <vector>
@@ -331,6 +332,12 @@ class PolynomialBatch {
             }
             out.second.push_back(std::move(p));
         }
+        return out;
+    }
+    // OpeningSet::new for this batch: every polynomial at the extension point (a0, a1) -> [columns] x (c0, c1)
+    std::vector<std::array<F, 2>> eval_at(const F point[2]) const {
+        std::vector<std::array<F, 2>> out(polynomials.size());
+        ctx_->check(gl_commit_eval(h_, point, &out[0][0], GL_HOST));
         return out;
     }
     std::vector<F> get_lde_values(uint64_t index, uint64_t step) const {

@@ -105,6 +105,15 @@ int main() {
         ok = MerkleTree::verify_batch(ctx, tampered, idx, opened.second, pb.cap);
         CHECK(ok[0] && !ok[1] && ok[2]);
     }
+    {   // OpeningSet::new at the base-field point 1: the sum of the coefficients (2^64 = 2^32 - 1 mod p)
+        const F one[2] = {1, 0};
+        auto at1 = pb.eval_at(one);
+        CHECK(at1.size() == cols);
+        const unsigned __int128 p = 0xFFFFFFFF00000001ULL;
+        unsigned __int128 sum = 0;
+        for (F cf : pb.polynomials[7]) sum = (sum + cf) % p;
+        CHECK(at1[7][0] == (F)sum && at1[7][1] == 0);
+    }
     CHECK(pb.get_lde_values(3, 8) == rows[192]);  // leaves[reverse_bits(3 * 8, 11)] = leaves[192]
     // panics like upstream
     bool threw = false;
