@@ -133,6 +133,23 @@ assert int(d_st2.abs().sum().item()) == 0, "emitted proofs must verify"
 out["smt_set_proofs"] = {"entries": mk, "ms": t * 1e3, "proofs_per_s": mk / t, "siblings_total": int(tot.value),
                             "avg_siblings": tot.value / mk, "verify_emitted_ms": tv * 1e3,
                             "note": "device-resident inputs and outputs; one permutation per (key, depth above its stopping point); the time order of a depth is merged from its children by the same binary search the hash needs"}
+# config 4's "256-proof membership circuit": tree.find for 256 stored keys against the 2^20-entry tree (the witnesses of
+# the inclusion circuits), tree build included
+nq = 256
+dq = dk[:: mk // nq].contiguous()
+d_inc = torch.empty(nq * glb.host.SMT_INCLUSION_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+d_poolq = torch.empty((64 * nq, 4), dtype=torch.int64, device=dev)
+d_offq = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+totq = C.c_uint64(0)
+torch.cuda.synchronize()
+tq = timeit(lambda: ctx.check(lib.gl_smt_find_batch(ctx._h, dk.data_ptr(), dvv.data_ptr(), mk, dq.data_ptr(), nq, d_inc.data_ptr(), d_poolq.data_ptr(),
+                                                    64 * nq, d_offq.data_ptr(), C.byref(totq), N.GL_DEVICE)), 2)
+inc = np.frombuffer(d_inc.cpu().numpy().tobytes(), dtype=glb.host.SMT_INCLUSION_DTYPE)
+assert inc["found"].all() and totq.value <= 64 * nq
+out["smt_find_batch"] = {"entries": mk, "queries": nq, "ms": tq * 1e3, "avg_siblings": totq.value / nq,
+                         "note": "sort + versioned sweep over 2^20 sets and 256 queries; every query found"}
+del dq, d_inc, d_poolq, d_offq
+
 # the same number of `set` calls as account updates: 2^19 inserts, then 2^19 updates / removals of random existing keys
 half = mk // 2
 pick = torch.randint(0, half, (half,), device=dev)
