@@ -72,3 +72,17 @@ def test_final_polynomial_evaluation(fv):
     coeffs = rng.integers(0, P, (32, 2), dtype=np.uint64)
     x = _r(rng)
     assert fv._eval_final_poly(coeffs, x) == tuple(fo.eval_ext_poly(coeffs, (x, 0)))
+
+
+def test_reduction_strategy_matches_the_oracle():
+    """FriReductionStrategy::ConstantArityBits(4, 5) -> reduction_arity_bits for every degree the configs can see."""
+    from oracle import fri_oracle as fo
+
+    glb = importlib.import_module("plonky2-lib_b200")
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    for rate_bits, cap_height in ((3, 4), (1, 0), (2, 3), (4, 4)):
+        cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height)
+        for degree_bits in range(0, 25):
+            got = list(fri.FriParams.for_degree(cfg, degree_bits).reduction_arity_bits)
+            assert got == fo.reduction_arity_bits(degree_bits, rate_bits, cap_height), (degree_bits, rate_bits, cap_height)
+            assert sum(got) <= degree_bits or not got
