@@ -5,6 +5,10 @@ poseidon_kat.json : the permutation vectors of SURVEY.md 8c.  The all-zero vecto
                     the constants recipe and match upstream plonky2's poseidon_goldilocks test_vectors.
 commit_caps.json  : Merkle caps of PolynomialBatch::from_values on the synthetic input of SURVEY 8d,
                     produced by the oracle itself ("parity unpinned" rows: regression fixtures only).
+smt_sets.json     : a fixed sequence of 40 `tree.set` calls on 10 keys (inserts, updates, removals, no-ops, keys that come
+                    back; (1,2), (12,1), (5,51) of src/smt/gadgets/verify/mod.rs:24-34 first) with the process proof of
+                    every call and `find` results against the final tree, produced by the oracle's restatement of
+                    src/smt/tree.rs ("parity unpinned": regression fixture).
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import json
@@ -42,4 +46,35 @@ for lg_n, c, r, h in [(3, 5, 3, 4), (6, 20, 3, 4), (8, 135, 3, 4), (10, 16, 3, 4
                   "cap": [f"{int(x):016x}" for x in res["cap"].reshape(-1)]})
 json.dump({"source": "oracle/gl_oracle.c glo_commit_from_values on pyoracle.synthetic_values (seed 0x706C6F6E6B7932)",
            "cases": cases}, open(os.path.join(HERE, "commit_caps.json"), "w"), indent=1)
+
+
+def hx(a):
+    return [f"{int(x):016x}" for x in np.asarray(a).reshape(-1)]
+
+
+rng = np.random.default_rng(0x736D74)
+pool = [o.from_u128(k) for k in (1, 12, 5)] + [rng.integers(0, P, 4, dtype=np.uint64) for _ in range(7)]
+twin = pool[3].copy()
+twin[2] ^= np.uint64(1) << np.uint64(9)            # shares 137 path bits with pool[3]
+pool[9] = twin
+seq_k = [pool[0], pool[1], pool[2]] + [pool[int(i)] for i in rng.integers(0, 10, 37)]
+seq_v = [o.from_u128(2), o.from_u128(1), o.from_u128(51)]
+for i in range(37):
+    seq_v.append(np.zeros(4, dtype=np.uint64) if rng.random() < 0.3 else rng.integers(1, P, 4, dtype=np.uint64))
+tree = o.Smt()
+calls = []
+for k, v in zip(seq_k, seq_v):
+    r = tree.set(k, v)
+    ns = int(r["num_siblings"])
+    calls.append({"key": hx(k), "value": hx(v), "fnc": int(r["fnc"]), "is_old0": int(r["is_old0"]), "old_root": hx(r["old_root"]),
+                  "new_root": hx(r["new_root"]), "old_key": hx(r["old_key"]), "old_value": hx(r["old_value"]), "new_key": hx(r["new_key"]),
+                  "new_value": hx(r["new_value"]), "siblings": hx(r["siblings"][:ns])})
+finds = []
+for q in pool + [rng.integers(0, P, 4, dtype=np.uint64) for _ in range(4)]:
+    f = tree.find(q)
+    finds.append({"key": hx(q), "found": bool(f["found"]), "is_old0": bool(f["is_old0"]), "value": hx(f["value"]),
+                  "not_found_key": hx(f["not_found_key"]), "siblings": hx(f["siblings"])})
+assert {c["fnc"] for c in calls} == {0, 1, 2, 3}
+json.dump({"source": "oracle/gl_oracle.c glo_smt_set / glo_smt_find (restatement of src/smt/tree.rs); calls[0:3] = src/smt/gadgets/verify/mod.rs:24-34",
+           "root": hx(tree.root()), "calls": calls, "finds": finds}, open(os.path.join(HERE, "smt_sets.json"), "w"), indent=1)
 print("wrote", HERE)

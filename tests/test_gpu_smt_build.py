@@ -315,3 +315,32 @@ def test_find_batch_near_misses_removed_keys_and_repeats(glb, ctx, oracle, rng):
     z = np.zeros((0, 4), dtype=np.uint64)
     h0 = _check_find(glb, oracle, z, z, base[:2])
     assert h0["is_old0"].all() and not h0["root"].any()
+
+
+def test_golden_smt_sets(glb, ctx):
+    """The committed fixture tests/golden/smt_sets.json (40 `set` calls on 10 keys: inserts, updates, removals, no-ops, a
+    twin sharing 137 path bits; then 14 `find`s) against the device, without the oracle in the loop."""
+    import json
+    import os
+
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smt_sets.json")))
+    un = lambda xs: np.array([int(x, 16) for x in xs], dtype=np.uint64)  # noqa: E731
+    keys = np.stack([un(c["key"]) for c in g["calls"]])
+    values = np.stack([un(c["value"]) for c in g["calls"]])
+    hdr, pool, off = glb.host.smt_set_proofs(keys, values)
+    for t, c in enumerate(g["calls"]):
+        assert int(hdr["fnc"][t]) == c["fnc"] and int(hdr["is_old0"][t]) == c["is_old0"], t
+        for f in ("old_root", "new_root", "old_key", "old_value", "new_key", "new_value"):
+            assert np.array_equal(hdr[f][t], un(c[f])), (t, f)
+        assert np.array_equal(pool[int(off[t]):int(off[t + 1])].reshape(-1), un(c["siblings"])), t
+    assert np.array_equal(hdr["new_root"][-1], un(g["root"]))
+    queries = np.stack([un(q["key"]) for q in g["finds"]])
+    inc, qpool, qoff = glb.host.smt_find_batch(keys, values, queries)
+    for i, q in enumerate(g["finds"]):
+        assert bool(inc["found"][i]) == q["found"] and bool(inc["is_old0"][i]) == q["is_old0"], i
+        assert np.array_equal(inc["root"][i], un(g["root"]))
+        assert np.array_equal(qpool[int(qoff[i]):int(qoff[i + 1])].reshape(-1), un(q["siblings"])), i
+        if q["found"]:
+            assert np.array_equal(inc["value"][i], un(q["value"]))
+        else:
+            assert np.array_equal(inc["not_found_key"][i], un(q["not_found_key"])) and np.array_equal(inc["not_found_value"][i], un(q["value"]))

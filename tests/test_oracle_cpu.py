@@ -137,3 +137,25 @@ def test_golden_commit_caps(oracle):
         v = oracle.synthetic_values(case["c"], 1 << case["lg_n"])
         res = oracle.commit_from_values(v, case["rate_bits"], case["cap_height"], want_leaves=False)
         assert [f"{int(x):016x}" for x in res["cap"].reshape(-1)] == case["cap"]
+
+
+def test_golden_smt_sets(oracle):
+    """tests/golden/smt_sets.json (make_golden.py): the oracle's tree.set / tree.find replayed call by call."""
+    import json
+
+    g = json.load(open(os.path.join(GOLDEN, "smt_sets.json")))
+    un = lambda xs: np.array([int(x, 16) for x in xs], dtype=np.uint64)  # noqa: E731
+    t = oracle.Smt()
+    for c in g["calls"]:
+        r = t.set(un(c["key"]), un(c["value"]))
+        assert int(r["fnc"]) == c["fnc"] and int(r["is_old0"]) == c["is_old0"]
+        for f in ("old_root", "new_root", "old_key", "old_value", "new_key", "new_value"):
+            assert np.array_equal(r[f], un(c[f])), f
+        ns = int(r["num_siblings"])
+        assert np.array_equal(r["siblings"][:ns].reshape(-1), un(c["siblings"]))
+    assert np.array_equal(t.root(), un(g["root"]))
+    assert g["calls"][2]["new_root"][0] == f"{16994558480514381166:016x}"      # the three-insert fixture of SURVEY Appendix B
+    for q in g["finds"]:
+        f = t.find(un(q["key"]))
+        assert bool(f["found"]) == q["found"] and bool(f["is_old0"]) == q["is_old0"]
+        assert np.array_equal(f["siblings"].reshape(-1), un(q["siblings"]))
