@@ -9,6 +9,8 @@ smt_sets.json     : a fixed sequence of 40 `tree.set` calls on 10 keys (inserts,
                     back; (1,2), (12,1), (5,51) of src/smt/gadgets/verify/mod.rs:24-34 first) with the process proof of
                     every call and `find` results against the final tree, produced by the oracle's restatement of
                     src/smt/tree.rs ("parity unpinned": regression fixture).
+fri_proof.json    : prove_openings of two small oracles (2^5 rows; 3 + 2 polynomials; 8-bit PoW; 28 queries) by the oracle's
+                    restatement of plonky2::fri::prover, flattened field by field ("parity unpinned": regression fixture).
 Run from the repo root:  python tests/golden/make_golden.py
 """
 import json
@@ -77,4 +79,45 @@ for q in pool + [rng.integers(0, P, 4, dtype=np.uint64) for _ in range(4)]:
 assert {c["fnc"] for c in calls} == {0, 1, 2, 3}
 json.dump({"source": "oracle/gl_oracle.c glo_smt_set / glo_smt_find (restatement of src/smt/tree.rs); calls[0:3] = src/smt/gadgets/verify/mod.rs:24-34",
            "root": hx(tree.root()), "calls": calls, "finds": finds}, open(os.path.join(HERE, "smt_sets.json"), "w"), indent=1)
+from oracle import fri_oracle as fo  # noqa: E402
+
+
+def flatten_proof(proof):
+    out = []
+    for cap in proof["commit_phase_merkle_caps"]:
+        out += [int(x) for x in np.asarray(cap).reshape(-1)]
+    out += [int(x) for x in np.asarray(proof["final_poly"]).reshape(-1)]
+    out.append(int(proof["pow_witness"]))
+    for r in proof["query_round_proofs"]:
+        out.append(int(r["x_index"]))
+        for row, path in r["initial_trees_proof"]:
+            out += [int(x) for x in np.asarray(row).reshape(-1)] + [int(x) for x in np.asarray(path).reshape(-1)]
+        for st in r["steps"]:
+            out += [int(x) for x in np.asarray(st["evals"]).reshape(-1)] + [int(x) for x in np.asarray(st["merkle_proof"]).reshape(-1)]
+    return out
+
+
+DEG, RATE, CAPH, POW, ROUNDS = 5, 3, 4, 8, 28
+cols = (3, 2)
+vals, polys, trees = [], [], []
+for k, c in enumerate(cols):
+    v = o.synthetic_values(c, 1 << DEG, seed=4242 + k)
+    res = o.commit_from_values(v, RATE, CAPH)
+    vals.append(v)
+    polys.append(res["coeffs"])
+    trees.append(fo.MerkleTree(res["leaves"], CAPH))
+zeta = (0x1234567, 0x89ABCDE)
+gen = o.lib().glo_primitive_root_of_unity(DEG)
+instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]), (fo.ext_scalar(zeta, gen), [(1, 0), (1, 1)])]
+ch = fo.Challenger()
+for t_ in trees:
+    ch.observe_cap(t_.cap)
+proof = fo.prove_openings(polys, trees, instance, ch, DEG, RATE, CAPH, POW, ROUNDS)
+json.dump({"source": "oracle/fri_oracle.py prove_openings (restatement of plonky2::fri::prover / oracle)",
+           "degree_bits": DEG, "rate_bits": RATE, "cap_height": CAPH, "proof_of_work_bits": POW, "num_query_rounds": ROUNDS,
+           "values": [[hx(col) for col in v] for v in vals],
+           "instance": [[list(int(x) for x in pt), [list(p_) for p_ in ps]] for pt, ps in instance],
+           "caps": [hx(t_.cap) for t_ in trees],
+           "openings": [[[int(x) for x in ov] for ov in b] for b in fo.opening_set(polys, instance)],
+           "proof_flat": [f"{x:x}" for x in flatten_proof(proof)]}, open(os.path.join(HERE, "fri_proof.json"), "w"), indent=0)
 print("wrote", HERE)

@@ -269,3 +269,48 @@ def test_commit_eval_matches_oracle(glb, ctx, oracle, rng, lg_n, c):
         for j in (0, c // 2, c - 1):
             assert tuple(int(x) for x in got[j]) == oracle.eval_base_poly_at_ext(coeffs[j], np.array(point, dtype=np.uint64)), (point, j)
     b.free()
+
+
+def test_golden_fri_proof(glb, ctx):
+    """The committed fixture tests/golden/fri_proof.json against the device prover and the product verifier, without the
+    oracle in the loop: commits, OpeningSet, every field of the opening proof."""
+    import json
+    import os
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    fv = importlib.import_module("plonky2-lib_b200.fri_verifier")
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fri_proof.json")))
+    un = lambda xs: np.array([int(x, 16) for x in xs], dtype=np.uint64)  # noqa: E731
+    batches = [glb.PolynomialBatch.from_values(np.stack([un(col) for col in v]), g["rate_bits"], False, g["cap_height"]) for v in g["values"]]
+    caps = [b.merkle_tree.cap for b in batches]
+    for cap, want in zip(caps, g["caps"]):
+        assert np.array_equal(cap.reshape(-1), un(want))
+    instance = [(tuple(pt), [tuple(p) for p in ps]) for pt, ps in g["instance"]]
+    openings = fri.opening_set(batches, instance)
+    assert [[list(ov) for ov in b] for b in openings] == g["openings"]
+    cfg = glb.FriConfig(rate_bits=g["rate_bits"], cap_height=g["cap_height"], proof_of_work_bits=g["proof_of_work_bits"],
+                        num_query_rounds=g["num_query_rounds"])
+    params = fri.FriParams.for_degree(cfg, g["degree_bits"])
+
+    def transcript():
+        ch = fri.Challenger()
+        for cap in caps:
+            ch.observe_cap(cap)
+        return ch
+
+    proof = fri.prove_openings(batches, instance, transcript(), params)
+    flat = []
+    for cap in proof["commit_phase_merkle_caps"]:
+        flat += [int(x) for x in np.asarray(cap).reshape(-1)]
+    flat += [int(x) for x in np.asarray(proof["final_poly"]).reshape(-1)]
+    flat.append(int(proof["pow_witness"]))
+    for r in proof["query_round_proofs"]:
+        flat.append(int(r["x_index"]))
+        for row, path in r["initial_trees_proof"]:
+            flat += [int(x) for x in np.asarray(row).reshape(-1)] + [int(x) for x in np.asarray(path).reshape(-1)]
+        for st in r["steps"]:
+            flat += [int(x) for x in np.asarray(st["evals"]).reshape(-1)] + [int(x) for x in np.asarray(st["merkle_proof"]).reshape(-1)]
+    assert [f"{x:x}" for x in flat] == g["proof_flat"]
+    assert fv.verify_openings(instance, openings, caps, proof, transcript(), params) is True
+    for b in batches:
+        b.free()
