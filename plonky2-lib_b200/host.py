@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -887,3 +887,83 @@ def smt_find_batch(keys, values, queries, ctx=None):
         if total.value <= cap:
             return hdr, pool[: total.value].copy(), off
         cap = int(total.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# serde_json forms of the SMT proofs (src/smt/proof/process.rs:12-23,53-59; src/smt/proof/inclusion.rs:5-33):
+# fields in declaration order, hashes as WrappedHashOut hex strings, the role as its variant name
+# ------------------------------------------------------------------------------------------------
+PROCESS_ROLES = ("ProcessNoOp", "ProcessUpdate", "ProcessInsert", "ProcessDelete")
+
+
+def smt_process_proofs_to_json(headers: np.ndarray, sib_pool: np.ndarray, sib_off: np.ndarray) -> List[str]:
+    """One serde_json string per SparseMerkleProcessProof<GoldilocksHashOut, ..> of the batch layout."""
+    import json
+
+    hd = np.ascontiguousarray(headers, dtype=SMT_HDR_DTYPE)
+    pool, off = _h(sib_pool).reshape(-1, 4), _h(sib_off)
+    out = []
+    for t in range(hd.shape[0]):
+        h = hd[t]
+        obj = {f: hash_out_to_hex(h[f]) for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value")}
+        obj["siblings"] = [hash_out_to_hex(x) for x in pool[int(off[t]):int(off[t + 1])]]
+        obj["is_old0"] = bool(h["is_old0"])
+        obj["fnc"] = PROCESS_ROLES[int(h["fnc"])]
+        out.append(json.dumps(obj, separators=(",", ":")))
+    return out
+
+
+def smt_process_proofs_from_json(texts: Sequence[str]):
+    """The inverse: (headers, sib_pool, sib_off) in the layout gl_smt_verify_process_batch takes."""
+    import json
+
+    hd = np.zeros(len(texts), dtype=SMT_HDR_DTYPE)
+    off = np.zeros(len(texts) + 1, dtype=np.uint64)
+    sibs = []
+    for t, text in enumerate(texts):
+        obj = json.loads(text)
+        for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value"):
+            hd[f][t] = hash_out_from_hex(obj[f])
+        hd["is_old0"][t] = 1 if obj["is_old0"] else 0
+        if obj["fnc"] not in PROCESS_ROLES:
+            raise ValueError(f"unknown variant `{obj['fnc']}`, expected one of {', '.join('`%s`' % r for r in PROCESS_ROLES)}")
+        hd["fnc"][t] = PROCESS_ROLES.index(obj["fnc"])
+        sibs += [hash_out_from_hex(x) for x in obj["siblings"]]
+        off[t + 1] = len(sibs)
+    pool = np.array(sibs, dtype=np.uint64).reshape(-1, 4) if sibs else np.zeros((0, 4), dtype=np.uint64)
+    return hd, pool, off
+
+
+def smt_inclusion_proofs_to_json(headers: np.ndarray, sib_pool: np.ndarray, sib_off: np.ndarray) -> List[str]:
+    """One serde_json string per SparseMerkleInclusionProof<GoldilocksHashOut, ..> (what smt_find_batch returns)."""
+    import json
+
+    hd = np.ascontiguousarray(headers, dtype=SMT_INCLUSION_DTYPE)
+    pool, off = _h(sib_pool).reshape(-1, 4), _h(sib_off)
+    out = []
+    for i in range(hd.shape[0]):
+        h = hd[i]
+        obj = {"root": hash_out_to_hex(h["root"]), "found": bool(h["found"]), "key": hash_out_to_hex(h["key"]),
+               "value": hash_out_to_hex(h["value"]), "not_found_key": hash_out_to_hex(h["not_found_key"]),
+               "not_found_value": hash_out_to_hex(h["not_found_value"]),
+               "siblings": [hash_out_to_hex(x) for x in pool[int(off[i]):int(off[i + 1])]], "is_old0": bool(h["is_old0"])}
+        out.append(json.dumps(obj, separators=(",", ":")))
+    return out
+
+
+def smt_inclusion_proofs_from_json(texts: Sequence[str]):
+    import json
+
+    hd = np.zeros(len(texts), dtype=SMT_INCLUSION_DTYPE)
+    off = np.zeros(len(texts) + 1, dtype=np.uint64)
+    sibs = []
+    for i, text in enumerate(texts):
+        obj = json.loads(text)
+        for f in ("root", "key", "value", "not_found_key", "not_found_value"):
+            hd[f][i] = hash_out_from_hex(obj[f])
+        hd["found"][i] = 1 if obj["found"] else 0
+        hd["is_old0"][i] = 1 if obj["is_old0"] else 0
+        sibs += [hash_out_from_hex(x) for x in obj["siblings"]]
+        off[i + 1] = len(sibs)
+    pool = np.array(sibs, dtype=np.uint64).reshape(-1, 4) if sibs else np.zeros((0, 4), dtype=np.uint64)
+    return hd, pool, off

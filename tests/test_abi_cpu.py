@@ -86,3 +86,52 @@ def test_hash_out_text_form_matches_the_reference():
     for bad in ("01", "0x1", "0xzz", "0x" + "00" * 33):
         with pytest.raises(ValueError):
             host.hash_out_from_hex(bad)
+
+
+def test_smt_proof_json_forms_match_the_reference_layout():
+    """serde_json of SparseMerkleProcessProof / SparseMerkleInclusionProof over GoldilocksHashOut
+    (src/smt/proof/process.rs:12-23,53-59, src/smt/proof/inclusion.rs:5-33,62-80): fields in declaration order, hashes as
+    0x-hex strings, the role as its variant name.  Host-side formatting only; uses the golden fixture for real proofs."""
+    import importlib
+    import json
+    import os
+
+    import numpy as np
+    import pytest
+
+    host = importlib.import_module("plonky2-lib_b200.host")
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smt_sets.json")))
+    un = lambda xs: np.array([int(x, 16) for x in xs], dtype=np.uint64)  # noqa: E731
+    m = len(g["calls"])
+    hd = np.zeros(m, dtype=host.SMT_HDR_DTYPE)
+    off = np.zeros(m + 1, dtype=np.uint64)
+    sibs = []
+    for t, c in enumerate(g["calls"]):
+        for f in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value"):
+            hd[f][t] = un(c[f])
+        hd["is_old0"][t], hd["fnc"][t] = c["is_old0"], c["fnc"]
+        sibs.append(un(c["siblings"]).reshape(-1, 4))
+        off[t + 1] = off[t] + np.uint64(sibs[-1].shape[0])
+    pool = np.concatenate(sibs)
+    texts = host.smt_process_proofs_to_json(hd, pool, off)
+    first = json.loads(texts[0])
+    assert list(first) == ["old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "siblings", "is_old0", "fnc"]
+    assert first["fnc"] == "ProcessInsert" and first["is_old0"] is True and first["siblings"] == []
+    assert first["new_key"] == "0x0000000000000000000000000000000000000000000000000000000000000001"   # key 1
+    assert first["old_root"] == "0x" + "00" * 32 and " " not in texts[0]
+    assert {json.loads(x)["fnc"] for x in texts} == set(host.PROCESS_ROLES)
+    hd2, pool2, off2 = host.smt_process_proofs_from_json(texts)
+    assert np.array_equal(hd2, hd) and np.array_equal(pool2, pool) and np.array_equal(off2, off)
+    with pytest.raises(ValueError):
+        host.smt_process_proofs_from_json([texts[0].replace("ProcessInsert", "ProcessUpsert")])
+    # inclusion proofs: the shape of the reference's test_serialize_merkle_proof
+    inc = np.zeros(1, dtype=host.SMT_INCLUSION_DTYPE)
+    inc["root"][0][0], inc["key"][0][0], inc["value"][0][0] = 1, 2, 3
+    inc["not_found_key"][0][0], inc["not_found_value"][0][0], inc["found"][0] = 5, 6, 1
+    sib = np.array([[4, 0, 0, 0]], dtype=np.uint64)
+    text = host.smt_inclusion_proofs_to_json(inc, sib, np.array([0, 1], dtype=np.uint64))[0]
+    obj = json.loads(text)
+    assert list(obj) == ["root", "found", "key", "value", "not_found_key", "not_found_value", "siblings", "is_old0"]
+    assert obj["found"] is True and obj["is_old0"] is False and obj["siblings"] == ["0x" + "00" * 31 + "04"]
+    back = host.smt_inclusion_proofs_from_json([text])
+    assert np.array_equal(back[0], inc) and np.array_equal(back[1], sib) and back[2].tolist() == [0, 1]
