@@ -135,3 +135,18 @@ def test_smt_proof_json_forms_match_the_reference_layout():
     assert obj["found"] is True and obj["is_old0"] is False and obj["siblings"] == ["0x" + "00" * 31 + "04"]
     back = host.smt_inclusion_proofs_from_json([text])
     assert np.array_equal(back[0], inc) and np.array_equal(back[1], sib) and back[2].tolist() == [0, 1]
+
+
+def test_every_entry_point_has_its_reference_side_binding_documented():
+    """INTEGRATION.md shows the Rust `extern "C"` declaration a maintainer of the fork would add for every function of
+    include/gl_b200.h (instrumentation-only entry points may be named in a comment instead)."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "gl_b200.h")).read()
+    integ = open(os.path.join(root, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(gl_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (gl_[a-z0-9_]+)", integ))
+    missing = {n for n in declared - bound if n not in integ}
+    assert not missing, sorted(missing)
