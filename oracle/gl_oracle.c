@@ -211,8 +211,8 @@ static void permute_with(u64 s[12], void (*mds)(u64 *)) {
  * src/zkdsa/circuits/mod.rs:66-67) and PoseidonHash::hash_pad (src/smt/goldilocks_poseidon/mod.rs:170). */
 void glo_poseidon_permute_naive(u64 s[12]) { permute_with(s, mds_layer_naive); }
 
-/* The permutation every other oracle routine uses; identical results, faster MDS (CPU baseline). */
-void glo_poseidon_permute(u64 s[12]) {
+/* The pre-round-2 schedule (literal rounds, mds_row_shf-style MDS): kept as a second cross-check. */
+void glo_poseidon_permute_slow(u64 s[12]) {
     ensure_rc();
     const u64 *rc = RC;
     for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
@@ -229,6 +229,217 @@ void glo_poseidon_permute(u64 s[12]) {
         }
         mds_layer(s);
     }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Upstream's CPU schedule of the SAME permutation (plonky2::hash::poseidon::Poseidon::poseidon:
+ * full_rounds, then partial_rounds = partial_first_constant_layer + mds_partial_layer_init + 22 x
+ * (sbox_monomial on lane 0, one lane-0 constant, mds_partial_layer_fast), then full_rounds).
+ * Upstream ships the "fast partial round" tables as literals; that source is not on this disk, so the
+ * tables are DERIVED here from the MDS matrix and the round constants (exact arithmetic mod p) and
+ * the result is cross-checked against the literal schedule on random states (tests/test_oracle_cpu.py)
+ * and against the reference's KAT.  Only outputs are comparable with upstream, not the tables.
+ *
+ * Derivation (column vectors; M = [[m00, v], [w, Mh]], S = x^7 on lane 0 only, R = 22):
+ *   y_{r+1} = M S(y_r) + c_{r+1}.  With A_r = diag(1, Mh^-(R-r)) and u_r = A_r^-1 y_r, A_r commutes
+ *   with S and u_{r+1} = Sp_r S(u_r) + A_{r+1}^-1 c_{r+1},  Sp_r = [[m00, v Mh^-(R-r)], [Mh^(R-r-1) w, I]]
+ *   (A_R = I, so u_R is the true state).  A constant K = (K0, Kh) pending after Sp_r equals
+ *   Sp_r (0, Kh) + (K0 - v_r . Kh) e0, and (0, Kh) passes backwards through S: every round keeps ONE
+ *   lane-0 constant, the rest accumulates into the constants added before the initial dense matrix.
+ * Cost per partial round: 1 S-box, a 12-term dot product (one 160-bit accumulation, one reduction)
+ * and 11 multiply-accumulates -- upstream's mds_partial_layer_fast has exactly this shape.
+ * ---------------------------------------------------------------------------------------------- */
+#define NP 22
+static u64 FP_FIRST[12];      /* added to the state that enters the partial rounds */
+static u64 FP_INIT[11][11];   /* Mh^R: mds_partial_layer_init on lanes 1..11 */
+static u64 FP_POST[11];       /* constants on lanes 1..11 after the initial matrix */
+static u64 FP_ALPHA[NP];      /* lane-0 constant after the sparse matrix of round r */
+static u64 FP_V[NP][11], FP_W[NP][11];
+static int fp_ready = 0;
+
+static void mat11_mul(const u64 a[11][11], const u64 b[11][11], u64 o[11][11]) {
+    u64 t[11][11];
+    for (int i = 0; i < 11; i++)
+        for (int j = 0; j < 11; j++) {
+            u64 acc = 0;
+            for (int k = 0; k < 11; k++) acc = f_add(acc, f_mul(a[i][k], b[k][j]));
+            t[i][j] = acc;
+        }
+    memcpy(o, t, sizeof t);
+}
+static void mat11_inv(const u64 a[11][11], u64 inv[11][11]) {
+    u64 m[11][22];
+    for (int i = 0; i < 11; i++)
+        for (int j = 0; j < 11; j++) { m[i][j] = canon(a[i][j]); m[i][11 + j] = (i == j); }
+    for (int c = 0; c < 11; c++) {
+        int piv = c;
+        while (piv < 11 && m[piv][c] == 0) piv++;
+        if (piv == 11) abort(); /* the MDS minor is invertible */
+        if (piv != c) for (int j = 0; j < 22; j++) { u64 t = m[c][j]; m[c][j] = m[piv][j]; m[piv][j] = t; }
+        u64 iv = glo_inv(m[c][c]);
+        for (int j = 0; j < 22; j++) m[c][j] = f_mul(m[c][j], iv);
+        for (int i = 0; i < 11; i++) {
+            if (i == c || m[i][c] == 0) continue;
+            u64 f = m[i][c];
+            for (int j = 0; j < 22; j++) m[i][j] = f_sub(m[i][j], f_mul(f, m[c][j]));
+        }
+    }
+    for (int i = 0; i < 11; i++) for (int j = 0; j < 11; j++) inv[i][j] = m[i][11 + j];
+}
+
+static void derive_fast_partial(void) {
+    u64 Mh[11][11], Mhi[11][11], v[11], w[11];
+    for (int i = 0; i < 11; i++) {
+        v[i] = MDS_CIRC[(i + 1) % 12];            /* M[0][j], j = i + 1 */
+        w[i] = MDS_CIRC[(12 - (i + 1)) % 12];     /* M[i + 1][0] */
+        for (int j = 0; j < 11; j++) Mh[i][j] = MDS_CIRC[((j - i) % 12 + 12) % 12]; /* M[i+1][j+1]; the diagonal term is only at [0][0] */
+    }
+    mat11_inv(Mh, Mhi);
+    /* Ainv[r] = Mh^(R-r) (r = 0..R), A[r] = Mh^-(R-r) */
+    static u64 Apow[NP + 1][11][11], Aneg[NP + 1][11][11];
+    for (int i = 0; i < 11; i++) for (int j = 0; j < 11; j++) Apow[NP][i][j] = Aneg[NP][i][j] = (i == j);
+    for (int r = NP - 1; r >= 0; r--) {
+        mat11_mul(Apow[r + 1], Mh, Apow[r]);
+        mat11_mul(Aneg[r + 1], Mhi, Aneg[r]);
+    }
+    for (int r = 0; r < NP; r++) {
+        for (int j = 0; j < 11; j++) {
+            u64 a = 0, b = 0;
+            for (int k = 0; k < 11; k++) {
+                a = f_add(a, f_mul(v[k], Aneg[r][k][j]));        /* v_r = v Mh^-(R-r) */
+                b = f_add(b, f_mul(Apow[r + 1][j][k], w[k]));    /* w_r = Mh^(R-r-1) w */
+            }
+            FP_V[r][j] = a;
+            FP_W[r][j] = b;
+        }
+    }
+    /* constants, from the last partial round backwards */
+    u64 pend[11] = {0};
+    FP_ALPHA[NP - 1] = 0;
+    for (int j = NP - 1; j >= 1; j--) {
+        const u64 *c = RC + 12 * (4 + j);
+        u64 K0 = c[0], Kh[11];
+        for (int i = 0; i < 11; i++) {
+            u64 acc = pend[i];
+            for (int k = 0; k < 11; k++) acc = f_add(acc, f_mul(Apow[j][i][k], c[1 + k]));
+            Kh[i] = acc;
+        }
+        u64 dot = 0;
+        for (int i = 0; i < 11; i++) dot = f_add(dot, f_mul(FP_V[j - 1][i], Kh[i]));
+        FP_ALPHA[j - 1] = f_sub(K0, dot);
+        memcpy(pend, Kh, sizeof pend);
+    }
+    memcpy(FP_POST, pend, sizeof pend);
+    memcpy(FP_FIRST, RC + 12 * 4, sizeof FP_FIRST);
+    memcpy(FP_INIT, Apow[0], sizeof FP_INIT);
+}
+
+static void ensure_fp(void) {
+    ensure_rc();
+    if (!fp_ready) {
+#pragma omp critical(glo_fp)
+        {
+            if (!fp_ready) {
+                derive_fast_partial();
+                fp_ready = 1;
+            }
+        }
+    }
+}
+void glo_poseidon_fast_tables(u64 *first12, u64 *init121, u64 *post11, u64 *alpha22, u64 *v242, u64 *w242) {
+    ensure_fp();
+    memcpy(first12, FP_FIRST, sizeof FP_FIRST);
+    memcpy(init121, FP_INIT, sizeof FP_INIT);
+    memcpy(post11, FP_POST, sizeof FP_POST);
+    memcpy(alpha22, FP_ALPHA, sizeof FP_ALPHA);
+    memcpy(v242, FP_V, sizeof FP_V);
+    memcpy(w242, FP_W, sizeof FP_W);
+}
+
+/* x in [0, 2^64) -> x mod-p representative in [0, 2^64) (not canonical), from a 128-bit value */
+static inline u64 red128_nc(u128 x) {
+    u64 lo = (u64)x, hi = (u64)(x >> 64);
+    u64 hi_hi = hi >> 32, hi_lo = hi & EPS;
+    u64 t0 = lo - hi_hi;
+    t0 -= EPS & (0 - (u64)(lo < hi_hi));
+    u64 t1 = hi_lo * EPS;
+    u64 r = t0 + t1;
+    r += EPS & (0 - (u64)(r < t1));
+    return r;
+}
+static inline u64 mul_nc(u64 a, u64 b) { return red128_nc((u128)a * b); }
+static inline u64 sbox7_nc(u64 x) {
+    u64 x2 = mul_nc(x, x), x4 = mul_nc(x2, x2), x3 = mul_nc(x, x2);
+    return mul_nc(x3, x4);
+}
+static inline u64 add_nc(u64 a, u64 b_canonical) { /* a any u64, b < p: at most one wrap */
+    u64 t = a + b_canonical;
+    return t + (EPS & (0 - (u64)(t < b_canonical)));
+}
+static inline void full_round_nc(u64 s[12], const u64 *rc) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7_nc(add_nc(s[i], rc[i]));
+    u64 lo[24], hi[24];
+    for (int i = 0; i < 12; i++) {
+        lo[i] = lo[i + 12] = s[i] & EPS;
+        hi[i] = hi[i + 12] = s[i] >> 32;
+    }
+    for (int r = 0; r < 12; r++) {
+        u64 al = 0, ah = 0;
+        for (int i = 0; i < 12; i++) {
+            al += lo[r + i] * MDS_CIRC[i];
+            ah += hi[r + i] * MDS_CIRC[i];
+        }
+        if (r == 0) { al += lo[0] * MDS_DIAG0; ah += hi[0] * MDS_DIAG0; }
+        s[r] = red128_nc((u128)al + ((u128)ah << 32));
+    }
+}
+
+/* The permutation every other oracle routine uses: upstream's schedule, canonical output. */
+void glo_poseidon_permute(u64 s[12]) {
+    ensure_fp();
+    const u64 *rc = RC;
+    for (int r = 0; r < 4; r++, rc += 12) full_round_nc(s, rc);
+    /* partial_first_constant_layer + mds_partial_layer_init */
+    u64 t[12];
+    for (int i = 0; i < 12; i++) t[i] = add_nc(s[i], FP_FIRST[i]);
+    s[0] = t[0];
+    for (int i = 0; i < 11; i++) {
+        u128 acc = 0;
+        u32 top = 0;
+        for (int k = 0; k < 11; k++) {
+            u128 pr = (u128)t[1 + k] * FP_INIT[i][k];
+            acc += pr;
+            top += acc < pr;
+        }
+        /* acc + top * 2^128, 2^128 = -2^32 (mod p) */
+        u64 r0 = red128_nc(acc);
+        u64 corr = (u64)top << 32; /* < 2^36 */
+        u64 d = r0 - corr;
+        d -= EPS & (0 - (u64)(r0 < corr));
+        s[1 + i] = add_nc(d, FP_POST[i]);
+    }
+    for (int r = 0; r < NP; r++) {
+        const u64 s0 = sbox7_nc(s[0]);
+        u128 acc = (u128)s0 * (MDS_CIRC[0] + MDS_DIAG0);
+        u32 top = 0;
+        for (int k = 0; k < 11; k++) {
+            u128 pr = (u128)s[1 + k] * FP_V[r][k];
+            acc += pr;
+            top += acc < pr;
+        }
+        u64 r0 = red128_nc(acc);
+        u64 corr = (u64)top << 32;
+        u64 d = r0 - corr;
+        d -= EPS & (0 - (u64)(r0 < corr));
+        for (int k = 0; k < 11; k++) {
+            /* multiply_accumulate: s[k] + s0 * w, one 128-bit sum (s0 * w <= (2^64-1)^2, + s[k] cannot overflow) */
+            s[1 + k] = red128_nc((u128)s0 * FP_W[r][k] + s[1 + k]);
+        }
+        s[0] = add_nc(d, FP_ALPHA[r]);
+    }
+    rc = RC + 12 * 26;
+    for (int r = 0; r < 4; r++, rc += 12) full_round_nc(s, rc);
+    for (int i = 0; i < 12; i++) s[i] = canon(s[i]);
 }
 
 /* hashing::hash_n_to_m_no_pad with overwrite-mode absorption, RATE = 8, 4 outputs */

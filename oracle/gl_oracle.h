@@ -43,6 +43,10 @@ void glo_ext_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
 void glo_poseidon_round_constants(uint64_t out[360]);
 void glo_poseidon_permute(uint64_t state[12]);
 void glo_poseidon_permute_naive(uint64_t state[12]); /* literal mds_layer; cross-check only */
+void glo_poseidon_permute_slow(uint64_t state[12]);  /* literal rounds, MDS on 32-bit halves; cross-check only */
+/* the derived fast-partial-round tables of glo_poseidon_permute (upstream's schedule), for inspection */
+void glo_poseidon_fast_tables(uint64_t *first12, uint64_t *init121, uint64_t *post11, uint64_t *alpha22,
+                              uint64_t *v242, uint64_t *w242);
 void glo_hash_no_pad(const uint64_t *in, size_t len, uint64_t out[4]);
 void glo_hash_pad(const uint64_t *in, size_t len, uint64_t out[4]);
 void glo_hash_or_noop(const uint64_t *in, size_t len, uint64_t out[4]);

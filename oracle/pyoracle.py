@@ -85,6 +85,8 @@ def lib():
         "glo_ext_mul": (None, [u64p, u64p, u64p]),
         "glo_poseidon_round_constants": (None, [u64p]),
         "glo_poseidon_permute": (None, [u64p]),
+        "glo_poseidon_permute_naive": (None, [u64p]),
+        "glo_poseidon_permute_slow": (None, [u64p]),
         "glo_hash_no_pad": (None, [u64p, sz, u64p]),
         "glo_hash_pad": (None, [u64p, sz, u64p]),
         "glo_hash_or_noop": (None, [u64p, sz, u64p]),
