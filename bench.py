@@ -172,37 +172,100 @@ def use_all_host_threads(o):
     o.lib().glo_set_num_threads(max(1, n))
 
 
+def config_for(log_n, cols, world):
+    """The workload both arms run (the reference arm prints the same dict: same shape, same cells per step)."""
+    return {
+        "workload": workload_name(log_n, cols), "cells_per_step": cols << log_n,
+        "l2": "inputs (1.13 GB) and LDE (9.06 GB) are larger than the 126 MB L2 (and than any host cache); no flush needed",
+        "parallelism": ("N=1: one GPU runs the whole commit" if world == 1 else
+                        f"N={world}: one commit sharded over {world} GPUs behind the C ABI (gl_group_*): IFFT by column blocks, NCCL "
+                        "all-gather of the coefficients in rounds overlapped with the LDE, LDE/Merkle by coset block = top-level "
+                        "subtree, NCCL all-gather of the cap") + "; the reference arm runs the same commit on the host cores",
+    }
+
+
+def golden_case(log_n, cols):
+    """The full-size fixture the CPU oracle produced once for the benchmarked shapes (tests/golden/commit_fullsize.json)."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "commit_fullsize.json")))
+    except Exception:
+        return None
+    for case in g["cases"]:
+        if (case["lg_n"], case["c"], case["rate_bits"], case["cap_height"]) == (log_n, cols, RATE_BITS, CAP_HEIGHT):
+            return case
+    return None
+
+
+def check_parity(cap_host, log_n, cols):
+    """Every N: the cap this run produced must be the oracle's, bit for bit.  A mismatch fails the run."""
+    case = golden_case(log_n, cols)
+    if case is None:
+        return {"parity_checked": False, "parity_note": "no full-size golden fixture for this shape (tests/golden/commit_fullsize.json holds 2^18 and 2^20 x 135)"}
+    got = [f"{int(x):016x}" for x in np.asarray(cap_host).reshape(-1)]
+    if got != case["cap"]:
+        raise SystemExit("bench.py: PARITY FAILURE: the Merkle cap differs from tests/golden/commit_fullsize.json (oracle) at 2^%d x %d" % (log_n, cols))
+    return {"parity_checked": True, "parity_note": "cap (16 x 4 field elements) equals the CPU oracle's at this exact shape: tests/golden/commit_fullsize.json"}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation is un-buildable here (Rust, un-vendored
-    plonky2 fork, no cargo) so the oracle port stands in, on all host cores, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation is un-buildable here (Rust, un-vendored plonky2 fork, no
+    cargo) so the oracle port stands in: upstream's CPU schedule (fast partial rounds, MDS on 32-bit halves, per-column
+    FFTs, transpose, recursive subtree Merkle), OpenMP where upstream uses rayon, on every host core.
+
+    SAME CONFIG as the GPU arm: every timed step is one commit of the full workload (2^20 rows x 135 columns).  A 2^16-row
+    calibration commit projects the cost first; only if K full-size steps would not fit --ref-budget-s (slow or few
+    cores) is the per-step sample cut to the largest 2^k rows that fits, and the line says so (config.sample).  Warm-up
+    steps are small commits: they spin up the thread pool and build the twiddle / Poseidon tables, there is no JIT."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pyoracle as o
 
     use_all_host_threads(o)
-    lg = args.ref_log_n
-    v = o.synthetic_values(args.cols, 1 << lg)
+    cores = int(o.lib().glo_num_threads())
     for _ in range(max(args.warmup, 0)):
         o.commit_from_values(o.synthetic_values(args.cols, 1 << 10), RATE_BITS, CAP_HEIGHT, want_leaves=False)
+    lg = args.ref_log_n
+    if lg <= 0:
+        cal = min(16, args.log_n)
+        vc = o.synthetic_values(args.cols, 1 << cal)
+        t = time.perf_counter()
+        o.commit_from_values(vc, RATE_BITS, CAP_HEIGHT, want_leaves=True)
+        t_cal = time.perf_counter() - t
+        lg = args.log_n
+        # measured here: a 2^20-row commit costs ~1.3x what 16 commits of 2^16 rows do (caches, page faults)
+        while lg > cal and args.steps * t_cal * (1 << (lg - cal)) * 1.3 > args.ref_budget_s:
+            lg -= 1
+        del vc
+    v = o.synthetic_values(args.cols, 1 << lg)
+    cap = None
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        o.commit_from_values(v, RATE_BITS, CAP_HEIGHT, want_leaves=True)
+        cap = o.commit_from_values(v, RATE_BITS, CAP_HEIGHT, want_leaves=True)["cap"]
     dt = time.perf_counter() - t0
     cells = args.cols << lg
     val = cells * args.steps / dt
-    cores = int(o.lib().glo_num_threads())
-    sample = (f"each step = one commit of 2^{lg} rows x {args.cols} cols (1/{1 << (args.log_n - lg)} of the workload rows); "
-              f"oracle port of plonky2 v0.1.4 (the Rust reference cannot be built: no cargo, plonky2 fork not vendored)")
-    emit({
+    full = lg == args.log_n
+    sample = (("each step = one commit of the FULL workload, 2^%d rows x %d cols" % (lg, args.cols)) if full else
+              ("each step = one commit of 2^%d rows x %d cols (1/%d of the workload rows: %d full-size steps would not fit "
+               "--ref-budget-s %d on this host)" % (lg, args.cols, 1 << (args.log_n - lg), args.steps, args.ref_budget_s)))
+    sample += ("; oracle port of plonky2 v0.1.4's CPU schedule (fast partial rounds), %d OpenMP threads; the Rust reference "
+               "cannot be built: no cargo, plonky2 fork not vendored" % cores)
+    config = config_for(args.log_n, args.cols, args.gpus)
+    if not full:
+        config["sample"] = sample
+    out = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_n, args.cols), "sample": sample},
+        "config": config,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    })
+        "gpu_launches": 0, "same_config": full,
+    }
+    if full:
+        out.update(check_parity(cap, args.log_n, args.cols))
+    emit(out)
 
 
 def synthetic_values_device(torch, cols, n, device, col0=0):
@@ -258,8 +321,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N)
     ap.add_argument("--cols", type=int, default=COLS)
-    ap.add_argument("--ref-log-n", type=int, default=16, help="rows (log2) of the reference arm's per-step sample")
-    ap.add_argument("--cpu-log-n", type=int, default=17, help="rows (log2) of the cpu_baseline sample")
+    ap.add_argument("--ref-log-n", type=int, default=0, help="rows (log2) of the reference arm's per-step commit; 0 = the full workload if K steps fit --ref-budget-s")
+    ap.add_argument("--ref-budget-s", type=int, default=600, help="time budget of the reference arm's K timed steps")
+    ap.add_argument("--cpu-log-n", type=int, default=18, help="rows (log2) of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-proof-trace", action="store_true")
@@ -307,37 +371,28 @@ def main():
             lib.gl_commit_free(h)
             return cap_dev
     else:
-        # Pipelined plan (plonky2-lib_b200/parallel.py round_blocks): the columns are cut into ~5 rounds of W * G
-        # consecutive columns; rank r inverse-transforms G of them per round; round j is all-gathered on NCCL's
-        # stream while the LDE of round j - 1 runs on the library's stream (gl_commit_begin / add_coeffs / finish).
+        # One commit sharded over the ranks, entirely behind the C ABI (gl_group_*, csrc/gl_group.inc.cu): rank r
+        # inverse-transforms its polynomials of every round, the rounds are all-gathered in place by the library's own
+        # NCCL communicator while the previous round is extended, every rank builds its leaf blocks + subtrees, and the cap
+        # is all-gathered.  torch.distributed is the launcher's control plane only (token broadcast, barrier, max of times).
         par = importlib.import_module("plonky2-lib_b200.parallel")
         par.check_shardable(world, RATE_BITS, CAP_HEIGHT)
-        G, rounds, mine = par.round_blocks(rank, world, cols)
-        ctx.set_shard(rank, world)
-        slice_buf = torch.zeros((rounds, G, n), dtype=torch.int64, device=dev)
-        stage = torch.empty((rounds, world * G, n), dtype=torch.int64, device=dev)
-        cap_all = torch.zeros((1 << CAP_HEIGHT, 4), dtype=torch.int64, device=dev)
-        k0, k1 = par.cap_range(rank, world, CAP_HEIGHT)
+        ctx.check(lib.gl_ctx_bind_host_numa(ctx._h)) if os.environ.get("BENCH_NUMA_BIND", "1") == "1" else None
+        tok = torch.zeros(N.GL_GROUP_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            tok.copy_(torch.frombuffer(bytearray(glb.Group.unique_id()), dtype=torch.uint8))
+        dist.broadcast(tok, 0)
+        group = glb.Group.from_token(ctx, rank, world, bytes(tok.cpu().numpy().tobytes()))
+        vptr = (C.c_void_p * 1)(values.data_ptr())
+        capptr = (C.c_void_p * 1)(cap_dev.data_ptr())
+        hs = (C.c_void_p * 1)()
 
         def step():
-            for j, (c0, c1) in enumerate(mine):
-                if c1 > c0:
-                    slice_buf[j, : c1 - c0].copy_(values[c0:c1])
-            # one IFFT launch over all of this rank's columns (padding rows are zeros and stay zeros)
-            ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf.data_ptr(), log_n, rounds * G, N.GL_DEVICE))
-            works = [dist.all_gather_into_tensor(stage[j], slice_buf[j], async_op=True) for j in range(rounds)]
-            h = C.c_void_p()
-            ctx.check(lib.gl_commit_begin(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT, C.byref(h)))
-            for j in range(rounds):
-                works[j].wait()                       # the library's stream waits for round j; the host does not
-                c0 = j * world * G
-                ctx.check(lib.gl_commit_add_coeffs(h, c0, min(world * G, cols - c0), stage[j].data_ptr(), N.GL_DEVICE))
-            ctx.check(lib.gl_commit_finish(h, cap_dev.data_ptr(), N.GL_DEVICE))
-            phases.append(ctx.commit_phase_ms())
-            lib.gl_commit_free(h)
-            par.all_gather_cap(dist, cap_dev[k0:k1].contiguous(), cap_all)  # MerkleCap: 2^cap_height digests
-            torch.cuda.current_stream().synchronize()
-            return cap_all
+            group.check(lib.gl_group_commit_from_values(group._h, vptr, log_n, cols, RATE_BITS, CAP_HEIGHT, None, capptr, hs,
+                                                        N.GL_DEVICE, 0))
+            phases.append(group.commit_phase_ms())
+            lib.gl_commit_free(hs[0])
+            return cap_dev
 
     def barrier():
         if world > 1:
@@ -430,75 +485,24 @@ def main():
         del hv, hc, pcols, ocols
 
     if world > 1 and not args.no_e2e:
-        # ---- e2e at N GPUs: every rank keeps ITS columns of the input in page-locked host memory, uploads them round
-        # by round on a copy stream, and brings its columns of the coefficients back while the LDE and the tree run;
-        # rank 0 also reads the gathered cap.  Summed over the ranks every input cell crosses PCIe once each way.
-        hvals = torch.zeros((rounds, G, n), dtype=torch.int64).pin_memory()
-        hcoef = torch.zeros((rounds, G, n), dtype=torch.int64).pin_memory()
-        vh = values.cpu()
-        for j, (c0, c1) in enumerate(mine):
-            if c1 > c0:
-                hvals[j, : c1 - c0] = vh[c0:c1]
-        del vh
-        up, down = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        ev_up = [torch.cuda.Event() for _ in range(rounds)]
-        ev_co = [torch.cuda.Event() for _ in range(rounds)]
-
-        trace = os.environ.get("BENCH_TRACE") and rank == 0
-        marks = []
-
-        def mark(name):
-            if trace:
-                marks.append((name, time.perf_counter()))
+        # ---- e2e at N GPUs: the same collective C-ABI call with HOST buffers.  Every rank holds the batch in page-locked
+        # host memory (allocated after gl_ctx_bind_host_numa, i.e. on the GPU's NUMA node), uploads only the polynomials it
+        # inverse-transforms, and brings exactly those coefficient vectors back while the LDE and the tree run; every rank
+        # receives the whole cap on the host.  Summed over the ranks each input cell crosses PCIe once each way.
+        hv = glb.pinned_empty((cols, n))
+        hc = glb.pinned_empty((cols, n))
+        hc[:] = 0
+        hcap = np.zeros((1 << CAP_HEIGHT, 4), dtype=np.uint64)
+        hv[:] = values.cpu().numpy().view(np.uint64)
+        hvp, hcp, hcapp = (C.c_void_p * 1)(hv.ctypes.data), (C.c_void_p * 1)(hc.ctypes.data), (C.c_void_p * 1)(hcap.ctypes.data)
+        # GL_COMMIT_STREAM_HASH: the leaves absorb each round as soon as it is extended, so hashing runs while the next
+        # rounds are still on PCIe / NVLink (at 2 GPUs the step is bound by the arithmetic: plain hashing there)
+        eflags = N.GL_COMMIT_STREAM_HASH if world >= 4 else 0
 
         def estep():
-            marks.clear()
-            mark("start")
-            up.wait_stream(stream)
-            down.wait_stream(stream)
-            for j in range(rounds):
-                with torch.cuda.stream(up):
-                    slice_buf[j].copy_(hvals[j], non_blocking=True)
-                    ev_up[j].record(up)
-            works = []
-            h = C.c_void_p()
-            # GL_COMMIT_STREAM_HASH: the leaves absorb each block as soon as it is extended, so the hashing runs while the
-            # next blocks are still on PCIe (the upload, not the arithmetic, is what the e2e step waits for at N = 8)
-            # (at 2 GPUs the step is bound by the arithmetic and the upload is already hidden: plain begin there)
-            ctx.check(lib.gl_commit_begin_ex(ctx._h, log_n, cols, RATE_BITS, CAP_HEIGHT,
-                                             N.GL_COMMIT_STREAM_HASH if world >= 4 else 0, C.byref(h)))
-
-            def lde(j):
-                works[j].wait()
-                c0 = j * world * G
-                ctx.check(lib.gl_commit_add_coeffs(h, c0, min(world * G, cols - c0), stage[j].data_ptr(), N.GL_DEVICE))
-                mark("lde%d" % j)
-
-            # round j arrives over PCIe while round j - 1 is extended (the C ABI calls block, the copy stream does not)
-            for j in range(rounds):
-                stream.wait_event(ev_up[j])
-                ctx.check(lib.gl_ifft_batch(ctx._h, slice_buf[j].data_ptr(), log_n, G, N.GL_DEVICE))
-                ev_co[j].record(stream)
-                works.append(dist.all_gather_into_tensor(stage[j], slice_buf[j], async_op=True))
-                with torch.cuda.stream(down):
-                    down.wait_event(ev_co[j])
-                    hcoef[j].copy_(slice_buf[j], non_blocking=True)
-                mark("ifft%d" % j)
-                if j:
-                    lde(j - 1)
-            lde(rounds - 1)
-            ctx.check(lib.gl_commit_finish(h, cap_dev.data_ptr(), N.GL_DEVICE))
-            mark("tree")
-            lib.gl_commit_free(h)
-            par.all_gather_cap(dist, cap_dev[k0:k1].contiguous(), cap_all)
-            cap_h = cap_all.cpu() if rank == 0 else None     # the step's result on the host
-            mark("cap")
-            down.synchronize()
-            torch.cuda.current_stream().synchronize()
-            mark("end")
-            if trace:
-                sys.stderr.write("e2e trace ms: " + " ".join("%s=%.1f" % (k, (t - marks[0][1]) * 1e3) for k, t in marks[1:]) + "\n")
-            return cap_h
+            group.check(lib.gl_group_commit_from_values(group._h, hvp, log_n, cols, RATE_BITS, CAP_HEIGHT, hcp, hcapp, hs,
+                                                        N.GL_HOST, eflags))
+            lib.gl_commit_free(hs[0])
 
         for _ in range(2):
             estep()
@@ -506,27 +510,34 @@ def main():
         ksteps = max(2, min(args.steps, 5))
         e0.record(stream)
         for _ in range(ksteps):
-            cap_h = estep()
+            estep()
         e1.record(stream)
         barrier()
         t = torch.tensor([e0.elapsed_time(e1) / ksteps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = float(t.item())
-        # the coefficients that came back are the ones the device-resident step gathers
-        j_last = max(j for j, (c0, c1) in enumerate(mine) if c1 > c0) if any(c1 > c0 for c0, c1 in mine) else None
-        if j_last is not None:
-            c0 = j_last * world * G + rank * G
-            assert torch.equal(hcoef[j_last, 0], stage[j_last, rank * G].cpu()), "e2e coefficients differ"
+        assert np.array_equal(hcap, cap_host), "e2e cap differs from the device-resident run"
+        # the coefficient vectors that came back: every polynomial on exactly one rank, and the fixture's sample columns
+        mine = np.array([bool(hc[j].any()) for j in range(cols)])
+        cnt = torch.tensor(mine.astype(np.int64), device=dev)
+        dist.all_reduce(cnt)
+        assert bool((cnt == 1).all()), "e2e: every coefficient vector must come back on exactly one rank"
+        case = golden_case(log_n, cols)
+        if case is not None:
+            import hashlib
+            for j, want in case["coeff_cols"].items():
+                if mine[int(j)]:
+                    assert hashlib.sha256(np.ascontiguousarray(hc[int(j)]).tobytes()).hexdigest() == want, "e2e coefficients differ from the oracle's"
         if rank == 0:
-            assert np.array_equal(cap_h.numpy().view(np.uint64), cap_host), "e2e cap differs from the device-resident run"
             e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(cells * 8),
-                   "d2h_bytes_per_step": int(cells * 8 + cap_host.nbytes), "ms_per_step": ems,
-                   "api": "per rank: its IFFT columns H2D from pinned memory round by round, gl_ifft_batch, all-gather, "
-                          "gl_commit_begin_ex(%s)/add_coeffs/finish, its coefficient columns D2H; rank 0 reads the cap" % ("GL_COMMIT_STREAM_HASH" if world >= 4 else "0")}
-        del hvals, hcoef
+                   "d2h_bytes_per_step": int(cells * 8 + world * cap_host.nbytes), "ms_per_step": ems,
+                   "api": "gl_group_commit_from_values(space=GL_HOST%s): per rank its polynomials H2D from pinned memory, its "
+                          "coefficient vectors D2H, the whole cap D2H" % (", GL_COMMIT_STREAM_HASH" if eflags else "")}
+        del hv, hc
 
     if rank != 0:
         if world > 1:
+            group.close()
             dist.destroy_process_group()
         return
 
@@ -584,15 +595,12 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic",
-        "config": {
-            "workload": workload_name(log_n, cols), "cells_per_step": cells,
-            "l2": "inputs (1.13 GB) and LDE (9.06 GB) are larger than the 126 MB L2; no flush needed",
-            "parallelism": "single GPU" if world == 1 else f"{world} GPUs: IFFT by column blocks, NCCL all-gather of the coefficients in ~5 rounds overlapped with the LDE of the previous round, LDE/Merkle by coset block, NCCL all-gather of the cap",
-        },
+        "config": config_for(log_n, cols, world),
         "phases_ms": phase_mean, "wall_ms_per_step": wall / args.steps * 1e3,
         "roofline": roofline, "roofline_int": roofline_int, "clocks": clocks, "gpu_launches": int(launches),
         "cap0": [f"{int(x):016x}" for x in cap_host[0]],
     }
+    out.update(check_parity(cap_host, log_n, cols))
     if e2e:
         out["e2e"] = e2e
     if world == 1 and not args.no_proof_trace:
@@ -602,6 +610,7 @@ def main():
         out["cpu_baseline"] = cb
     emit(out)
     if world > 1:
+        group.close()
         dist.destroy_process_group()
 
 

@@ -36,6 +36,7 @@ extern "C" {
 #define GL_E_CUDA 2  /* CUDA runtime error (no device, launch failure, ...) */
 #define GL_E_OOM 3   /* device or pinned host allocation failed */
 #define GL_E_STATE 4 /* handle used on the wrong ctx / after free */
+#define GL_E_NCCL 5  /* NCCL missing or a collective failed (gl_group_* only) */
 
 #define GL_HOST 0
 #define GL_DEVICE 1
@@ -231,6 +232,46 @@ int gl_commit_info(const gl_commit *h, uint32_t *log_n, uint32_t *c, uint32_t *r
 int gl_commit_device_ptrs(const gl_commit *h, const uint64_t **lde_cols, uint64_t *ld,
                           const uint64_t **digests);
 void gl_commit_free(gl_commit *h);
+
+/* ---- (e) multi-GPU: one commit sharded over the GPUs of a box, NCCL behind this ABI -----------------------
+ * One rank = one gl_ctx = one GPU.  Rank r owns leaf block r of nranks (LDE cosets = whole top-level Merkle subtrees and
+ * their cap entries); the IFFT is sharded by polynomial and the coefficients are all-gathered round by round while the
+ * previous round is extended; the cap is all-gathered; query openings are exchanged by gl_group_commit_open.  A process
+ * may hold all ranks (the Rust prover: one process, 8 GPUs, id = NULL) or some of them (one rank per process under a
+ * torchrun-style launcher: rank 0 calls gl_group_unique_id and hands the 128 bytes to the others out of band).
+ * NCCL is bound at run time (dlopen): nothing else in this header needs it.  Replaces the rayon data parallelism of
+ * plonky2_maybe_rayon 0.1.1 (Cargo.lock:993-998) inside from_values / from_coeffs, reached from data.prove(pw)
+ * (e.g. src/zkdsa/circuits/mod.rs:326, src/ecdsa/gadgets/ecdsa.rs:349). */
+typedef struct gl_group gl_group;
+#define GL_GROUP_ID_BYTES 128
+int gl_group_unique_id(uint8_t *id_out /* [GL_GROUP_ID_BYTES] */);
+/* ctxs [nlocal]: this process's ranks rank0 .. rank0 + nlocal - 1 of nranks (a power of two dividing 2^rate_bits and
+ * 2^cap_height of every commit made with the group).  Sets each ctx's shard to (rank, nranks).  Collective. */
+int gl_group_create(gl_ctx *const *ctxs, uint32_t nlocal, uint32_t rank0, uint32_t nranks, const uint8_t *id, gl_group **out);
+void gl_group_destroy(gl_group *g);
+const char *gl_group_last_error(const gl_group *g);
+int gl_group_info(const gl_group *g, uint32_t *nlocal, uint32_t *rank0, uint32_t *nranks, int *nccl_version);
+int gl_group_commit_phase_ms(const gl_group *g, float *out6); /* first local rank, as gl_ctx_commit_phase_ms */
+/* PolynomialBatch::from_values / from_coeffs, sharded.  Collective: every rank calls it with the same geometry.
+ * values [nlocal]: per local rank the WHOLE batch [c][2^log_n] in `space` memory of that rank (GL_DEVICE: on its GPU;
+ * GL_HOST: host memory, the pointers may be equal); a rank reads only the polynomials it inverse-transforms.
+ * coeffs_out [nlocal] or NULL: GL_DEVICE: every rank receives all c coefficient vectors; GL_HOST: a rank writes only ITS
+ * polynomials into coeffs_out[i] (one shared array is complete when the process holds every rank).
+ * cap_out [nlocal] or NULL: the WHOLE cap [2^cap_height][4] on every rank.  handles [nlocal]: this rank's shard
+ * (gl_commit_open serves its own leaves, gl_group_commit_open any leaf).  flags: GL_COMMIT_STREAM_HASH. */
+int gl_group_commit_from_values(gl_group *g, const uint64_t *const *values, uint32_t log_n, uint32_t c, uint32_t rate_bits,
+                                uint32_t cap_height, uint64_t *const *coeffs_out, uint64_t *const *cap_out,
+                                gl_commit **handles, int space, uint32_t flags);
+int gl_group_commit_from_coeffs(gl_group *g, const uint64_t *const *coeffs, uint32_t log_n, uint32_t c, uint32_t rate_bits,
+                                uint32_t cap_height, uint64_t *const *cap_out, gl_commit **handles, int space, uint32_t flags);
+/* MerkleTree::get(i) + MerkleTree::prove(i) for k GLOBAL leaf indices of a sharded commit (fri_prover_query_round's
+ * initial-tree openings): each index is served by the rank that owns the leaf and the rows / paths are exchanged over
+ * NCCL; every rank ends with rows_out[i] [k][c] and paths_out[i] [k][log2(N) - cap_height][4].  Collective; host buffers. */
+int gl_group_commit_open(gl_group *g, gl_commit *const *handles, const uint64_t *leaf_indices, uint32_t k,
+                         uint64_t *const *rows_out, uint64_t *const *paths_out, int space);
+/* Pins the calling thread to the CPUs next to the ctx's GPU (sysfs local_cpulist), so that page-locked buffers it
+ * allocates afterwards and the staging threads' copies stay on the GPU's NUMA node. */
+int gl_ctx_bind_host_numa(gl_ctx *ctx);
 
 /* ---- P8: one reduction layer of fri_committed_trees (plonky2::fri::prover) ---------------------- */
 /* values_ext: len extension elements [len][2] in natural order of their coset.  Builds the layer

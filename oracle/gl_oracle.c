@@ -784,19 +784,25 @@ int glo_smt_verify_process_proof(const glo_smt_process_proof *pf) {
     enum { LEVELS = 256 };
     int enabled = pf->fnc != 0;
     u32 fnc = pf->fnc;
-    const u64 *old_key = pf->old_key, *old_value = pf->old_value, *old_root = pf->old_root;
-    const u64 *new_key = pf->new_key, *new_value = pf->new_value, *new_root = pf->new_root;
+    /* Every word is a field element: the reference takes key bits from HashOut::to_bytes (canonical u64s,
+     * src/smt/proof/process.rs:193-203) and compares hashes as field elements -> reduce mod p on entry. */
+    u64 hk[6][4];
+    for (int j = 0; j < 4; j++) {
+        hk[0][j] = canon(pf->old_key[j]); hk[1][j] = canon(pf->old_value[j]); hk[2][j] = canon(pf->old_root[j]);
+        hk[3][j] = canon(pf->new_key[j]); hk[4][j] = canon(pf->new_value[j]); hk[5][j] = canon(pf->new_root[j]);
+    }
+    const u64 *old_key = hk[0], *old_value = hk[1], *old_root = hk[2];
+    const u64 *new_key = hk[3], *new_value = hk[4], *new_root = hk[5];
     if (fnc == 3) { /* a remove proof is an insert proof with old and new flipped */
         fnc = 2;
-        old_key = pf->new_key; old_value = pf->new_value; old_root = pf->new_root;
-        new_key = pf->old_key; new_value = pf->old_value; new_root = pf->old_root;
+        old_key = hk[3]; old_value = hk[4]; old_root = hk[5];
+        new_key = hk[0]; new_value = hk[1]; new_root = hk[2];
     }
     if (pf->num_siblings >= LEVELS) return 1; /* assert!(siblings.len() < n2b_new.len()) */
     /* siblings.resize(256, default) : the struct is already zero padded */
     u64 sib[LEVELS][4];
     for (unsigned i = 0; i < LEVELS; i++) {
-        if (i < pf->num_siblings) memcpy(sib[i], pf->siblings[i], 32);
-        else memset(sib[i], 0, 32);
+        for (int j = 0; j < 4; j++) sib[i][j] = i < pf->num_siblings ? canon(pf->siblings[i][j]) : 0;
     }
     /* smt_lev_ins */
     if (enabled && !is_zero4(sib[LEVELS - 1])) return 2; /* assert!(is_zeros.last()) */

@@ -9,7 +9,7 @@ The directory name contains a hyphen, so import it with
 from . import _native  # noqa: F401
 from .host import *  # noqa: F401,F403
 from .host import (  # noqa: F401
-    CircuitConfig, Context, FriConfig, FriReductionStrategy, GlPanic, MerkleTree, PolynomialBatch, PoseidonHash,
+    CircuitConfig, Context, FriConfig, Group, ShardedPolynomialBatch, FriReductionStrategy, GlPanic, MerkleTree, PolynomialBatch, PoseidonHash,
     PoseidonNodeHash, coset_fft, coset_ifft, fft, fri_fold, fri_layer_tree, fri_proof_of_work, ifft, pinned_empty,
     smt_check_process_proofs,
 )

@@ -11,7 +11,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgl_b200.so")
 
-GL_OK, GL_E_ARG, GL_E_CUDA, GL_E_OOM, GL_E_STATE = 0, 1, 2, 3, 4
+GL_OK, GL_E_ARG, GL_E_CUDA, GL_E_OOM, GL_E_STATE, GL_E_NCCL = 0, 1, 2, 3, 4, 5
+GL_GROUP_ID_BYTES = 128
 GL_HOST, GL_DEVICE = 0, 1
 GL_COMMIT_STREAM_HASH = 1
 
@@ -101,6 +102,16 @@ SIGNATURES = {
     "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
     "gl_fri_final_poly": (cint, [vp, vp, u32, vp, u32, vp, u64p, u32, vp, vp, cint]),
     "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
+    "gl_group_unique_id": (cint, [vp]),
+    "gl_group_create": (cint, [vp, u32, u32, u32, vp, C.POINTER(vp)]),
+    "gl_group_destroy": (None, [vp]),
+    "gl_group_last_error": (C.c_char_p, [vp]),
+    "gl_group_info": (cint, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(cint)]),
+    "gl_group_commit_phase_ms": (cint, [vp, C.POINTER(C.c_float)]),
+    "gl_group_commit_from_values": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, vp, cint, u32]),
+    "gl_group_commit_from_coeffs": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, cint, u32]),
+    "gl_group_commit_open": (cint, [vp, vp, vp, u32, vp, vp, cint]),
+    "gl_ctx_bind_host_numa": (cint, [vp]),
 }
 
 _lib = None

@@ -584,6 +584,14 @@ extern "C" int gl_ctx_create(int device, gl_ctx** out) {
         delete ctx;
         return rc;
     }
+    int st = gl_field_selftest(ctx->stream);
+    if (st != 0) {
+        int rc = st < 0 ? cuda_fail(nullptr, (cudaError_t)(-st), "field self-test")
+                        : fail(nullptr, GL_E_STATE, "gl_ctx_create: Goldilocks add/sub/mul self-test failed on this device/toolchain (pair " +
+                                                        std::to_string(st - 1) + ")");
+        gl_ctx_destroy(ctx);
+        return rc;
+    }
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     *out = ctx;
     return GL_OK;
@@ -827,7 +835,7 @@ extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* v
     auto take = [&](size_t bytes) { size_t at = off; off += al(bytes); return at; };
     const size_t o_rk = take(m * 32), o_rka = take(m * 8), o_perm = take(m * 4), o_perma = take(m * 4), o_leafh = take(m * 32),
                  o_lcp = take(m * 2), o_vf = take(m * 32), o_vl = take(m * 32), o_end = take(m * 4), o_start = take(m * 4),
-                 o_fd = take(m * 2), o_lv = take(m), o_hist = take(257 * 4), o_cnt = take(8), o_root = take(32),
+                 o_fd = take(m * 2), o_lv = take(m), o_hist = take(258 * 4), o_cnt = take(8), o_root = take(32),
                  o_tmp = take(b.sort_tmp_bytes), o_lh = take(leaf_hashes_out && space == GL_HOST ? m * 32 : 0),
                  o_nodes = take(nodes_out && space == GL_HOST ? nodes_cap * 96 : 0);
     void* base;
@@ -842,13 +850,15 @@ extern "C" int gl_smt_build(gl_ctx* ctx, const uint64_t* keys, const uint64_t* v
     b.nodes = nodes_out ? (space == GL_HOST ? (u64*)(p + o_nodes) : nodes_out) : nullptr;
     b.nodes_cap = nodes_out ? nodes_cap : 0;
     u64* d_root = (u64*)(p + o_root);
-    CK(cudaMemsetAsync(b.hist, 0, 257 * 4 + 0, ctx->stream));
+    b.zero_values = b.hist + 257;
+    CK(cudaMemsetAsync(b.hist, 0, 258 * 4, ctx->stream));
     CK(cudaMemsetAsync(b.node_count, 0, 8, ctx->stream));
     int rc = smt_build_prepare(b, ctx->stream);
     if (rc) return cuda_fail(ctx, (cudaError_t)rc, "gl_smt_build: sort");
-    uint32_t hist[257];
+    uint32_t hist[258];
     CK(cudaMemcpyAsync(hist, b.hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (hist[257]) return fail(ctx, GL_E_ARG, "SparseMerkleTree::insert: value must be non-zero (src/smt/tree.rs: a zero value is a removal; use gl_smt_set_proofs for sequences with removals)");
     if (hist[256]) return fail(ctx, GL_E_ARG, "SparseMerkleTree::insert: given key already exists (duplicate keys in the batch)");
     int dmax = -1;
     for (int d = 255; d >= 0; d--)
@@ -1843,3 +1853,6 @@ extern "C" int gl_pow_grind(gl_ctx* ctx, const uint64_t state[12], uint32_t inpu
     }
     return fail(ctx, GL_E_STATE, "gl_pow_grind: no witness found");
 }
+
+// multi-GPU plane (NCCL behind the C ABI)
+#include "gl_group.inc.cu"

@@ -124,12 +124,12 @@ GL_D u64 gl_add(u64 a, u64 b) {
         ".reg .u32 m;\n\t"
         "add.cc.u32 %0, %2, %4;\n\t"
         "addc.cc.u32 %1, %3, %5;\n\t"
-        "subc.u32 m, 0, 0;\n\t"          // 0 + ~0 + CF = carry - 1  (ptxas: CF is always "carry", never "borrow")
-        "not.b32 m, m;\n\t"              // carry ? 0xffffffff : 0  = carry * (2^32 - 1)
-        "add.cc.u32 %0, %0, m;\n\t"
+        "addc.u32 m, 0, 0;\n\t"          // the carry, through add-family instructions only (PTX defines CC.CF for
+        "neg.s32 m, m;\n\t"              // addc after add.cc; nothing here reads it as a borrow): carry ? 0xffffffff : 0
+        "add.cc.u32 %0, %0, m;\n\t"     //   = carry * (2^32 - 1)
         "addc.cc.u32 %1, %1, 0;\n\t"
-        "subc.u32 m, 0, 0;\n\t"
-        "not.b32 m, m;\n\t"
+        "addc.u32 m, 0, 0;\n\t"
+        "neg.s32 m, m;\n\t"
         "add.cc.u32 %0, %0, m;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
         "}"
@@ -144,7 +144,7 @@ GL_D u64 gl_sub(u64 a, u64 b) {
         ".reg .u32 m;\n\t"
         "sub.cc.u32 %0, %2, %4;\n\t"
         "subc.cc.u32 %1, %3, %5;\n\t"
-        "subc.u32 m, 0, 0;\n\t"          // 0 + ~0 + CF = (no borrow) - 1 = borrow ? 0xffffffff : 0
+        "subc.u32 m, 0, 0;\n\t"          // 0 - 0 - borrow (sub family after sub.cc, as PTX defines it): borrow ? 0xffffffff : 0
         "sub.cc.u32 %0, %0, m;\n\t"
         "subc.cc.u32 %1, %1, 0;\n\t"
         "subc.u32 m, 0, 0;\n\t"

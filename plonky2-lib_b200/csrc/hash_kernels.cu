@@ -385,6 +385,11 @@ k_merkle_verify_batch(const u64* __restrict__ leaves, u32 leaf_len, const u64* _
 
 enum { ST_TOP = 0, ST_BOT = 1, ST_OLD0 = 2, ST_NEW1 = 3, ST_UPD = 4, ST_NA = 5 };
 
+GL_D void load_digest_canon(const u64* src, u64 d[4]) {
+    load_digest(src, d);
+#pragma unroll
+    for (int j = 0; j < 4; j++) d[j] = gl_canon(d[j]);
+}
 GL_D bool is_zero4(const u64 h[4]) { return (h[0] | h[1] | h[2] | h[3]) == 0; }
 GL_D bool eq4(const u64 a[4], const u64 b[4]) {
     return a[0] == b[0] && a[1] == b[1] && a[2] == b[2] && a[3] == b[3];
@@ -413,12 +418,14 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
     u64 old_key[4], old_value[4], old_root[4], new_key[4], new_value[4], new_root[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        old_key[j] = flip ? pf->new_key[j] : pf->old_key[j];
-        old_value[j] = flip ? pf->new_value[j] : pf->old_value[j];
-        old_root[j] = flip ? pf->new_root[j] : pf->old_root[j];
-        new_key[j] = flip ? pf->old_key[j] : pf->new_key[j];
-        new_value[j] = flip ? pf->old_value[j] : pf->new_value[j];
-        new_root[j] = flip ? pf->old_root[j] : pf->new_root[j];
+        // every header word is a field element: the reference reads key bits through HashOut::to_bytes (canonical,
+        // src/smt/proof/process.rs:193-203) and compares roots / keys / values as field elements, so any u64 is taken mod p
+        old_key[j] = gl_canon(flip ? pf->new_key[j] : pf->old_key[j]);
+        old_value[j] = gl_canon(flip ? pf->new_value[j] : pf->old_value[j]);
+        old_root[j] = gl_canon(flip ? pf->new_root[j] : pf->old_root[j]);
+        new_key[j] = gl_canon(flip ? pf->old_key[j] : pf->new_key[j]);
+        new_value[j] = gl_canon(flip ? pf->old_value[j] : pf->new_value[j]);
+        new_root[j] = gl_canon(flip ? pf->old_root[j] : pf->new_root[j]);
     }
     u64 ns64 = sib_off[t + 1] - sib_off[t];
     if (ns64 >= (u64)LEVELS) { status[t] = 1; return; }   // assert!(siblings.len() < n2b_new.len())
@@ -429,7 +436,7 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
     int ins_level = 0;
     for (int i = (int)ns; i >= 1; i--) {
         u64 sb[4];
-        load_digest(sibs + 4 * (i - 1), sb);
+        load_digest_canon(sibs + 4 * (i - 1), sb);
         if (!is_zero4(sb)) { ins_level = i; break; }
     }
     // assert!(is_zeros.last()) cannot fire: ns < 256, so level 255 holds a padded zero
@@ -479,7 +486,7 @@ k_smt_verify_process(const gl_smt_proof_hdr* __restrict__ proofs, const u64* __r
         int st = (int)((smw[i / 10] >> (3 * (i % 10))) & 7u);
         bool pos = key_bit(new_key, i) != 0;
         u64 sb[4];
-        if ((u32)i < ns) load_digest(sibs + 4 * i, sb);
+        if ((u32)i < ns) load_digest_canon(sibs + 4 * i, sb);
         else { sb[0] = sb[1] = sb[2] = sb[3] = 0; }
         u64 l[4], r[4], old_hash[4] = {0, 0, 0, 0}, new_hash[4] = {0, 0, 0, 0};
         if (st == ST_TOP) {

@@ -18,6 +18,45 @@
 #include "gl_field.cuh"
 #include "ntt_kernels.h"
 
+// Start-up self-test of the carry-chain arithmetic (gl_add / gl_sub / gl_mul / gl_reduce128) on wrap-around operands:
+// every pair of the `count` probes, results canonical: out[(i * count + j) * 3 + {0, 1, 2}] = a+b, a-b, a*b.
+__global__ void k_field_selftest(const u64* __restrict__ probes, unsigned count, u64* __restrict__ out) {
+    unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * count) return;
+    u64 a = probes[t / count], b = probes[t % count];
+    out[3 * t] = gl_canon(gl_add(a, b));
+    out[3 * t + 1] = gl_canon(gl_sub(a, b));
+    out[3 * t + 2] = gl_canon(gl_mul(a, b));
+}
+int gl_field_selftest(cudaStream_t st) {
+    static const u64 probes[] = {0, 1, 2, GL_P - 1, GL_P, GL_P + 1, 0xFFFFFFFFULL, 0x100000000ULL, 0xFFFFFFFFFFFFFFFFULL,
+                                 0xFFFFFFFF00000000ULL, 0xFFFFFFFEFFFFFFFFULL, 0x8000000000000000ULL, 0x7FFFFFFF80000001ULL,
+                                 0x0123456789ABCDEFULL, 0xFEDCBA9876543210ULL, 0xFFFFFFFF7FFFFFFFULL};
+    const unsigned count = sizeof(probes) / sizeof(probes[0]);
+    u64 *d_in = nullptr, *d_out = nullptr;
+    static u64 got[3 * 16 * 16];
+    cudaError_t e = cudaMalloc(&d_in, sizeof(probes));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(got));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, probes, sizeof(probes), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        k_field_selftest<<<(count * count + 127) / 128, 128, 0, st>>>(d_in, count, d_out);
+        ++g_gl_launches;
+        e = cudaMemcpyAsync(got, d_out, sizeof(got), cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return -(int)e;
+    for (unsigned i = 0; i < count; i++)
+        for (unsigned j = 0; j < count; j++) {
+            const u64* g = got + 3 * (i * count + j);
+            if (g[0] != glh::add(probes[i], probes[j]) || g[1] != glh::sub(probes[i], probes[j]) ||
+                g[2] != glh::mul(probes[i], probes[j]))
+                return 1 + (int)(i * count + j);
+        }
+    return 0;
+}
+
 // base^e from a 3 x 1024 table (e < 2^30)
 GL_D u64 powtab_eval(const u64* __restrict__ tab, u64 e) {
     u64 r = __ldg(tab + (e & 1023));
@@ -222,6 +261,35 @@ __global__ void k_gather_paths(const u64* __restrict__ digests, unsigned sub_bit
 void launch_gather_paths(const u64* digests, unsigned sub_bits, const u64* idx, u32 k, u64* paths, cudaStream_t st) {
     u64 total = (u64)k * sub_bits;
     if (total) { k_gather_paths<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(digests, sub_bits, idx, k, paths); ++g_gl_launches; }
+}
+
+// gl_group_commit_open: rows and paths of the `mine` leaves this shard owns, written at their slots of the exchange
+// buffer: out[slot * per + col] = row, out[slot * per + c + 4 * layer + w] = sibling digest of `layer`.
+__global__ void k_gather_open(const u64* __restrict__ cols, u64 ld, u32 c, const u64* __restrict__ digests, unsigned sub_bits,
+                              const u64* __restrict__ loc, const u64* __restrict__ slot, u32 mine, u64* __restrict__ out,
+                              u64 per) {
+    u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (g >= (u64)mine * per) return;
+    u64 q = g / per, e = g % per;
+    u64 leaf = loc[q];
+    u64* dst = out + slot[q] * per + e;
+    if (e < c) {
+        *dst = cols[e * ld + leaf];
+        return;
+    }
+    unsigned layer = (unsigned)((e - c) >> 2), w = (unsigned)((e - c) & 3);
+    u64 subtree = leaf >> sub_bits;
+    u64 pair = (leaf & (((u64)1 << sub_bits) - 1)) >> layer;
+    u64 parity = pair & 1;
+    pair >>= 1;
+    u64 sib = 2 * ((pair << (layer + 1)) + ((u64)1 << layer) - 1) + (1 - parity);
+    u64 per_subtree = 2 * (((u64)1 << sub_bits) - 1);
+    *dst = digests[4 * (subtree * per_subtree + sib) + w];
+}
+void launch_gather_open(const u64* cols, u64 ld, u32 c, const u64* digests, unsigned sub_bits, const u64* loc, const u64* slot,
+                        u32 mine, u64* out, u64 per, cudaStream_t st) {
+    u64 total = (u64)mine * per;
+    if (total) { k_gather_open<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cols, ld, c, digests, sub_bits, loc, slot, mine, out, per); ++g_gl_launches; }
 }
 
 // FRI layer leaves, column-major: element (leaf j, column 2a+e) = values_ext[bitrev(j * arity + a)][e]

@@ -62,3 +62,8 @@ struct ntt16_args {
 void launch_fill_powers(uint64_t* out, uint64_t len, const uint64_t* powtab, cudaStream_t st);
 bool launch_ntt16(const ntt16_args& a, unsigned M, bool inverse, uint64_t n, uint32_t columns, uint32_t cosets,
                   cudaStream_t st);
+// gl_add / gl_sub / gl_mul against exact host arithmetic on wrap-around operands; 0 = ok, > 0 = first failing pair + 1,
+// < 0 = -cudaError.  Run once per context (gl_ctx_create), next to the Poseidon constants fingerprint.
+int gl_field_selftest(cudaStream_t st);
+void launch_gather_open(const uint64_t* cols, uint64_t ld, uint32_t c, const uint64_t* digests, unsigned sub_bits,
+                        const uint64_t* loc, const uint64_t* slot, uint32_t mine, uint64_t* out, uint64_t per, cudaStream_t st);

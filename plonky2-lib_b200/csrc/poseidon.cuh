@@ -73,8 +73,8 @@ GL_D u64 poseidon_fold(double al, double ah) {
     asm("{\n\t"
         ".reg .u32 m;\n\t"
         "add.cc.u32 %1, %3, %4;\n\t"
-        "subc.u32 m, 0, 0;\n\t"          // carry - 1
-        "not.b32 m, m;\n\t"              // carry * (2^32 - 1)
+        "addc.u32 m, 0, 0;\n\t"          // carry (add family only)
+        "neg.s32 m, m;\n\t"              // carry * (2^32 - 1)
         "add.cc.u32 %0, %2, m;\n\t"
         "addc.u32 %1, %1, 0;\n\t"
         "}"

@@ -45,6 +45,8 @@ k_smt_leaves(smt_build_buffers b) {
         s[4 + j] = b.values[4 * (u64)src + j];
         s[8 + j] = 0;
     }
+    // SparseMerkleTree::insert: "value must be non-zero" (a bulk build has no removals)
+    if (b.zero_values && (gl_canon(s[4]) | gl_canon(s[5]) | gl_canon(s[6]) | gl_canon(s[7])) == 0) atomicAdd(b.zero_values, 1u);
     smt_permute_call(s);
     s[0] = 1; s[1] = 1; s[2] = 0; s[3] = 1;   // hash_no_pad([k, v, 1, 1, 0, 1]): second chunk overwrites lanes 0..3
     smt_permute_call(s);

@@ -25,6 +25,7 @@ struct smt_build_buffers {
     uint16_t* form_depth;// [m]: 0xFFFF = key is not the first key of a live group
     uint8_t* last_valid; // [m]
     uint32_t* hist;      // [257] pairs per lcp value (256 = duplicate keys)
+    uint32_t* zero_values; // counter of entries whose value is all zero (mod p), or null when zero values are allowed
     void* sort_tmp;
     size_t sort_tmp_bytes;
     // outputs (device)

@@ -605,6 +605,157 @@ class PolynomialBatch:
 
 
 # ------------------------------------------------------------------------------------------------
+# gl_group: one commit sharded over several GPUs, NCCL behind the C ABI
+# ------------------------------------------------------------------------------------------------
+class Group:
+    """gl_group.  `Group.local(devices)` holds every rank in this process (what a Rust prover driving a whole box does);
+    `Group.from_token(ctx, rank, nranks, token)` holds one rank of a group that spans processes (rank 0 makes the token
+    with `Group.unique_id()` and hands the 128 bytes to the others, e.g. over torch.distributed or a file)."""
+
+    def __init__(self, ctxs: Sequence[Context], rank0: int, nranks: int, token: Optional[bytes]):
+        self._lib = N.load()
+        self.ctxs = list(ctxs)
+        self.nlocal, self.rank0, self.nranks = len(self.ctxs), rank0, nranks
+        arr = (C.c_void_p * self.nlocal)(*[c._h for c in self.ctxs])
+        tok = (C.c_uint8 * N.GL_GROUP_ID_BYTES).from_buffer_copy(token) if token is not None else None
+        h = C.c_void_p()
+        rc = self._lib.gl_group_create(arr, self.nlocal, rank0, nranks, tok, C.byref(h))
+        if rc:
+            raise GlPanic(rc, (self._lib.gl_group_last_error(None) or b"").decode())
+        self._h = h
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = N.load()
+        buf = (C.c_uint8 * N.GL_GROUP_ID_BYTES)()
+        rc = lib.gl_group_unique_id(buf)
+        if rc:
+            raise GlPanic(rc, (lib.gl_group_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    @classmethod
+    def local(cls, devices: Sequence[int]) -> "Group":
+        return cls([Context(d) for d in devices], 0, len(devices), None)
+
+    @classmethod
+    def from_token(cls, ctx: Context, rank: int, nranks: int, token: bytes) -> "Group":
+        return cls([ctx], rank, nranks, token)
+
+    def check(self, rc: int):
+        if rc:
+            raise GlPanic(rc, (self._lib.gl_group_last_error(self._h) or b"").decode())
+
+    @property
+    def nccl_version(self) -> int:
+        v = C.c_int(0)
+        self.check(self._lib.gl_group_info(self._h, None, None, None, C.byref(v)))
+        return v.value
+
+    def commit_phase_ms(self) -> dict:
+        out = (C.c_float * 6)()
+        self.check(self._lib.gl_group_commit_phase_ms(self._h, out))
+        return dict(zip(Context.PHASES, [float(x) for x in out]))
+
+    def commit(self, inputs, rate_bits: int, cap_height: int, is_values: bool = True, want_coeffs: bool = True,
+               stream_hash: bool = False) -> "ShardedPolynomialBatch":
+        """PolynomialBatch::from_values / from_coeffs over the group.  `inputs`: one host array [c][n] (shared by the local
+        ranks), or a list with one CUDA tensor per local rank (the whole batch on each GPU)."""
+        dev = isinstance(inputs, (list, tuple)) and len(inputs) == self.nlocal and all(_is_torch(x) and x.is_cuda for x in inputs)
+        if dev:
+            c, n = int(inputs[0].shape[0]), int(inputs[0].shape[1])
+            bufs = [_Buf(x) for x in inputs]
+            ptrs = (C.c_void_p * self.nlocal)(*[b.ptr for b in bufs])
+            space = N.GL_DEVICE
+        else:
+            inputs = _h(inputs)
+            if inputs.ndim != 2:
+                raise GlPanic(N.GL_E_ARG, "polynomials must be [columns][n]")
+            c, n = int(inputs.shape[0]), int(inputs.shape[1])
+            ptrs = (C.c_void_p * self.nlocal)(*[inputs.ctypes.data] * self.nlocal)
+            space = N.GL_HOST
+        if n == 0 or n & (n - 1):
+            raise GlPanic(N.GL_E_ARG, "log2_strict: polynomial length is not a power of two")
+        lg = n.bit_length() - 1
+        caps = [np.zeros((1 << cap_height, 4), dtype=np.uint64) for _ in range(self.nlocal)]
+        coeffs = None
+        hs = (C.c_void_p * self.nlocal)()
+        flags = N.GL_COMMIT_STREAM_HASH if stream_hash else 0
+        if dev:
+            import torch
+
+            cap_dev = [torch.zeros((1 << cap_height, 4), dtype=torch.int64, device=x.device) for x in inputs]
+            cap_ptrs = (C.c_void_p * self.nlocal)(*[t.data_ptr() for t in cap_dev])
+        else:
+            cap_ptrs = (C.c_void_p * self.nlocal)(*[a.ctypes.data for a in caps])
+        if is_values:
+            co_ptrs = None
+            if want_coeffs:
+                if dev:
+                    import torch
+
+                    coeffs = [torch.empty_like(x) for x in inputs]
+                    co_ptrs = (C.c_void_p * self.nlocal)(*[t.data_ptr() for t in coeffs])
+                else:
+                    coeffs = np.zeros_like(inputs)      # every local rank writes ITS polynomials into the one array
+                    co_ptrs = (C.c_void_p * self.nlocal)(*[coeffs.ctypes.data] * self.nlocal)
+            rc = self._lib.gl_group_commit_from_values(self._h, ptrs, lg, c, rate_bits, cap_height, co_ptrs, cap_ptrs, hs, space, flags)
+        else:
+            rc = self._lib.gl_group_commit_from_coeffs(self._h, ptrs, lg, c, rate_bits, cap_height, cap_ptrs, hs, space, flags)
+        self.check(rc)
+        if dev:
+            caps = [t.cpu().numpy().view(np.uint64) for t in cap_dev]
+        return ShardedPolynomialBatch(self, [C.c_void_p(h) for h in hs], caps, coeffs, lg, c, rate_bits, cap_height)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gl_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedPolynomialBatch:
+    """The local shards of one PolynomialBatch committed over a Group: the whole cap on every rank, `open` for any leaf."""
+
+    def __init__(self, group: Group, handles, caps, coeffs, degree_log, c, rate_bits, cap_height):
+        self.group, self._hs, self.caps, self.coeffs = group, handles, caps, coeffs
+        self.degree_log, self.num_columns, self.rate_bits, self.cap_height = degree_log, c, rate_bits, cap_height
+        self.cap = caps[0]
+
+    def open(self, leaf_indices: Sequence[int]):
+        """(rows [k][c], paths [k][L][4]) for GLOBAL leaf indices, whoever owns them (gl_group_commit_open); the same
+        arrays on every local rank, the first rank's are returned."""
+        g = self.group
+        idx = _h(np.asarray(leaf_indices))
+        k = idx.shape[0]
+        L = self.degree_log + self.rate_bits - self.cap_height
+        rows = [np.empty((k, self.num_columns), dtype=np.uint64) for _ in range(g.nlocal)]
+        paths = [np.empty((k, L, 4), dtype=np.uint64) for _ in range(g.nlocal)]
+        hs = (C.c_void_p * g.nlocal)(*[h.value for h in self._hs])
+        rp = (C.c_void_p * g.nlocal)(*[a.ctypes.data for a in rows])
+        pp = (C.c_void_p * g.nlocal)(*[a.ctypes.data for a in paths])
+        g.check(g._lib.gl_group_commit_open(g._h, hs, idx.ctypes.data, k, rp, pp, N.GL_HOST))
+        self.all_rows, self.all_paths = rows, paths
+        return rows[0], paths[0]
+
+    def free(self):
+        for h in self._hs:
+            if h and h.value:
+                self.group._lib.gl_commit_free(h)
+        self._hs = []
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------
 # plonky2_field::fft / polynomial
 # ------------------------------------------------------------------------------------------------
 def _fft_call(name, data, shift, ctx):
@@ -778,18 +929,41 @@ def smt_check_process_proofs(headers: np.ndarray, sib_pool: np.ndarray, sib_off:
     return status
 
 
+def _smt_final_map(k: np.ndarray, v: np.ndarray):
+    """What a sequence of `tree.set(k[t], v[t])` calls leaves: per key the LAST value, keys whose last value is zero are
+    gone (set with the default value removes, src/smt/tree.rs:143-155).  The compact tree depends only on this map."""
+    kc = np.where(k >= np.uint64(P), k - np.uint64(P), k)
+    vc = np.where(v >= np.uint64(P), v - np.uint64(P), v)
+    rows = np.ascontiguousarray(kc).view([("k", "<u8", 4)]).reshape(-1)
+    _, first_rev = np.unique(rows[::-1], return_index=True)          # first occurrence in the reversed order = last call
+    last = np.sort(kc.shape[0] - 1 - first_rev)
+    keep = last[(vc[last] != 0).any(axis=1)]
+    return np.ascontiguousarray(k[keep]), np.ascontiguousarray(v[keep])
+
+
 def smt_build_tree(keys, values, want_nodes: bool = False, ctx=None):
     """N2: the sparse Merkle tree of src/smt/tree.rs holding `keys -> values`, built in one pass on the device.
     Returns root [4] (and, with want_nodes, the internal nodes [(hash, left, right)] as an [k][12] array plus the
-    leaf hashes [m][4]): what m successive `tree.set(key, value)` calls leave in the root and node stores.
-    Entries whose value is all zero are dropped first (`set` with the default value is a removal, tree.rs:143-155)."""
+    leaf hashes [m'][4] of the entries that remain): what m successive `tree.set(key, value)` calls leave in the root
+    and node stores.  As with `set`, keys may repeat (the last value wins) and a zero value removes its key: such
+    batches are first reduced to the map they leave (the tree is history independent); gl_smt_build itself takes
+    distinct keys with non-zero values and returns GL_E_ARG otherwise, like SparseMerkleTree::insert."""
     ctx = _ctx(ctx)
     k, v = _h(keys).reshape(-1, 4), _h(values).reshape(-1, 4)
     if k.shape != v.shape:
         raise GlPanic(N.GL_E_ARG, "smt_build_tree: keys and values differ in shape")
-    keep = (v[:, 0] | v[:, 1] | v[:, 2] | v[:, 3]) != 0
-    if not keep.all():                       # the usual batch has no removals: no copies then
-        k, v = np.ascontiguousarray(k[keep]), np.ascontiguousarray(v[keep])
+    if ((v % np.uint64(P)) == 0).all(axis=1).any():     # removals in the batch: order matters, resolve it first
+        k, v = _smt_final_map(k, v)
+    try:
+        return _smt_build_distinct(ctx, k, v, want_nodes)
+    except GlPanic as e:
+        if "already exists" not in str(e):
+            raise
+    k, v = _smt_final_map(k, v)                          # repeated keys: updates, the last value wins
+    return _smt_build_distinct(ctx, k, v, want_nodes)
+
+
+def _smt_build_distinct(ctx, k, v, want_nodes: bool):
     m = k.shape[0]
     root = np.zeros(4, dtype=np.uint64)
     count = C.c_uint64(0)

@@ -1,0 +1,118 @@
+"""gl_group: one commit sharded over ranks behind the C ABI -- column-sharded IFFT, NCCL all-gather of the
+coefficients, coset-sharded LDE + subtrees, NCCL all-gather of the cap, NCCL exchange of query openings -- against the
+oracle's unsharded commit.  The 2-rank cases need two GPUs (run with `gpurun --gpus 2`); the 1-rank group runs the same
+code path without collectives on any box."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _check_against_oracle(glb, oracle, group, lg_n, c, r, h, device_inputs=False, stream_hash=False):
+    values = oracle.synthetic_values(c, 1 << lg_n)
+    want = oracle.commit_from_values(values, r, h)
+    if device_inputs:
+        import torch
+
+        inp = [torch.from_numpy(values.view(np.int64)).to(f"cuda:{cx.device}") for cx in group.ctxs]
+    else:
+        inp = values
+    b = group.commit(inp, r, h, stream_hash=stream_hash)
+    for cap in b.caps:                      # the WHOLE cap on every local rank
+        assert np.array_equal(cap, want["cap"])
+    if device_inputs:
+        for co in b.coeffs:                 # every rank holds all coefficients
+            assert np.array_equal(co.cpu().numpy().view(np.uint64), want["coeffs"])
+    elif group.nlocal == group.nranks:      # one process holds every rank: the shared host array is complete
+        assert np.array_equal(b.coeffs, want["coeffs"])
+    N = (1 << lg_n) << r
+    idx = sorted({0, 1, N // 2 - 1, N // 2, N - 1, N // 8, 3 * N // 8 + 5, (0x9E3779B97F4A7C15 % N)})
+    rows, paths = b.open(idx)               # global indices, owned by different ranks
+    assert np.array_equal(rows, want["leaves"][idx])
+    for q, i in enumerate(idx):
+        assert np.array_equal(paths[q], oracle.merkle_prove(want["digests"], N, h, i))
+        assert oracle.merkle_verify(rows[q], i, paths[q], want["cap"], h)
+    for r_, p_ in zip(b.all_rows, b.all_paths):
+        assert np.array_equal(r_, rows) and np.array_equal(p_, paths)
+    b.free()
+
+
+@pytest.mark.parametrize("lg_n,c", [(10, 135), (12, 20), (8, 3), (13, 136)])
+def test_one_rank_group_equals_oracle(glb, oracle, lg_n, c):
+    g = glb.Group.local([0])
+    _check_against_oracle(glb, oracle, g, lg_n, c, 3, 4)
+    _check_against_oracle(glb, oracle, g, lg_n, c, 3, 4, device_inputs=True)
+    g.close()
+
+
+@pytest.mark.parametrize("lg_n,c,r,h", [(10, 135, 3, 4), (12, 20, 3, 4), (9, 7, 1, 1), (14, 135, 3, 4), (16, 16, 3, 4)])
+def test_two_rank_group_in_one_process(glb, oracle, lg_n, c, r, h):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = glb.Group.local([0, 1])
+    assert g.nccl_version > 0
+    _check_against_oracle(glb, oracle, g, lg_n, c, r, h)
+    _check_against_oracle(glb, oracle, g, lg_n, c, r, h, device_inputs=True)
+    _check_against_oracle(glb, oracle, g, lg_n, c, r, h, stream_hash=True)
+    g.close()
+
+
+def test_group_rejects_bad_geometry(glb):
+    g = glb.Group.local([0])
+    with pytest.raises(glb.GlPanic):
+        g.commit(np.zeros((3, 12), dtype=np.uint64), 3, 4)          # log2_strict
+    with pytest.raises(glb.GlPanic):
+        g.commit(np.zeros((3, 16), dtype=np.uint64), 3, 9)          # cap_height > log2(leaves)
+    g.close()
+    c0 = glb.Context(0)
+    with pytest.raises(glb.GlPanic):
+        glb.Group([c0, glb.Context(0)], 0, 2, None)                 # two ranks on one GPU
+    with pytest.raises(glb.GlPanic):
+        glb.Group([c0], 0, 2, None)                                 # spans processes: needs the token
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ranks_in_separate_processes(world):
+    """One rank per process (torchrun, as bench.py --gpus N runs): token over torch.distributed, commit + openings checked
+    against the oracle inside every rank (tests/mp_group_worker.py)."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29500 + world), os.path.join(ROOT, "tests", "mp_group_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
+    assert out.stdout.count("group worker ok") == world
+
+
+def test_full_size_commit_over_two_ranks_matches_golden(glb, oracle):
+    """BASELINE config 2 (2^20 x 135) sharded over 2 GPUs: the gathered cap and sampled openings against the full-size
+    fixture the oracle produced (tests/golden/commit_fullsize.json)."""
+    import json
+
+    import torch
+
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = next(c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "commit_fullsize.json")))["cases"] if c["lg_n"] == 20)
+    hx = lambda a: [f"{int(x):016x}" for x in np.asarray(a).reshape(-1)]  # noqa: E731
+    values = oracle.synthetic_values(case["c"], 1 << 20)
+    g = glb.Group.local([0, 1])
+    inp = [torch.from_numpy(values.view(np.int64)).to(f"cuda:{d}") for d in (0, 1)]
+    b = g.commit(inp, 3, 4, want_coeffs=False)
+    assert hx(b.cap) == case["cap"]
+    rows, paths = b.open(case["leaf_indices"])
+    assert [hx(x) for x in rows] == case["leaf_rows"] and [hx(x) for x in paths] == case["leaf_paths"]
+    b.free()
+    g.close()

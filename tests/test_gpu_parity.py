@@ -307,6 +307,42 @@ def test_smt_process_proofs(glb, ctx, oracle, rng):
     assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
 
 
+def test_smt_process_proofs_take_header_words_mod_p(glb, ctx, oracle, rng):
+    """include/gl_b200.h: inputs may be any u64 (taken mod p).  The reference reads key bits through HashOut::to_bytes
+    (canonical, src/smt/proof/process.rs:193-203) and compares roots as field elements, so x and x + p are the same
+    key / root / value / sibling: every word that fits gets p added and the statuses must not change."""
+    recs = _smt_proofs(oracle, rng)
+    want = oracle.smt_verify_process_batch(recs)
+    nc = recs.copy()
+    small = np.uint64(0xFFFFFFFF)          # x + p < 2^64  <=>  x < 2^32 - 1
+    bumped = 0
+    for name in ("old_root", "old_key", "old_value", "new_root", "new_key", "new_value", "siblings"):
+        a = nc[name]
+        m = a < small
+        a[m] += np.uint64(P)
+        bumped += int(m.sum())
+    # from_u128-style keys (u32 limbs) guarantee non-canonical words even when random 64-bit words rarely qualify
+    assert np.array_equal(oracle.smt_verify_process_batch(nc), want)
+    hd, pool, off = _pack(glb, nc)
+    assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want)
+    # small keys: every limb < 2^32, so every key / value word is bumped
+    t = oracle.Smt()
+    rs = [t.set(oracle.from_u128(k), oracle.from_u128(v)) for k, v in [(1, 2), (12, 1), (5, 51), (5, 7), (12, 0), (99, 0)]]
+    recs2 = np.array(rs, dtype=oracle.SMT_PROOF_DTYPE)
+    want2 = oracle.smt_verify_process_batch(recs2)
+    assert (want2 == 0).all()
+    nc2 = recs2.copy()
+    for name in ("old_key", "old_value", "new_key", "new_value"):
+        a = nc2[name]
+        m = a < small
+        a[m] += np.uint64(P)
+        bumped += int(m.sum())
+    assert bumped > 50
+    hd, pool, off = _pack(glb, nc2)
+    assert np.array_equal(glb.smt_check_process_proofs(hd, pool, off), want2)
+    assert np.array_equal(oracle.smt_verify_process_batch(nc2), want2)
+
+
 def test_smt_process_proofs_with_long_common_prefixes(glb, ctx, oracle, rng):
     """Keys that agree on 3 .. 255 leading path bits: the inserts push the old leaf down a chain of Bottom levels
     before NewOne.  The kernel computes only the hashes the verifier reads (state Top / Bottom / NewOne levels);

@@ -66,16 +66,54 @@ def test_long_shared_prefixes_and_order_independence(glb, ctx, oracle, rng):
     assert all((not s.any()) or tuple(s.tolist()) in known for s in f["siblings"])
 
 
-def test_zero_values_are_dropped_and_duplicates_panic(glb, ctx, oracle, rng):
+def test_build_tree_is_what_the_sequence_of_sets_leaves(glb, ctx, oracle, rng):
+    """`set` semantics for batches that are not plain inserts: a zero value removes its key (also one inserted earlier in
+    the same batch), a repeated key is an update (the last value wins), a zero value for an absent key is a no-op."""
     keys, values = rand_field(rng, (20, 4)), rand_field(rng, (20, 4)) | np.uint64(1)
-    values[3] = 0
+    values[3] = 0                      # no-op: key 3 was never inserted
     values[11] = 0
-    keep = values.any(axis=1)
-    _, want = _oracle_root(oracle, keys[keep], values[keep])
+    _, want = _oracle_root(oracle, keys, values)
     assert np.array_equal(glb.host.smt_build_tree(keys, values), want)
+    # set(k, v); set(k, 0): k is gone (ADVICE r1: the (k, 0) entry used to be discarded and k stayed in the tree)
+    k2 = np.concatenate([keys, keys[[5]], keys[[6]], keys[[3]]])
+    v2 = np.concatenate([values, np.zeros((1, 4), dtype=np.uint64), rand_field(rng, (1, 4)) | np.uint64(1),
+                         rand_field(rng, (1, 4)) | np.uint64(1)])
+    _, want2 = _oracle_root(oracle, k2, v2)
+    assert not np.array_equal(want2, want)
+    assert np.array_equal(glb.host.smt_build_tree(k2, v2), want2)
+    # set(k, 0); set(k, v): k is there
+    k3 = np.stack([keys[0], keys[1], keys[0]])
+    v3 = np.stack([np.zeros(4, dtype=np.uint64), values[1], values[0]])
+    assert np.array_equal(glb.host.smt_build_tree(k3, v3), _oracle_root(oracle, k3, v3)[1])
+    # repeated keys without removals: updates
     keys[7] = keys[2]
-    with pytest.raises(glb.GlPanic):
-        glb.host.smt_build_tree(keys, values)
+    _, want4 = _oracle_root(oracle, keys, values)
+    assert np.array_equal(glb.host.smt_build_tree(keys, values), want4)
+    # the last root of the process proofs of the same sequence is the same tree
+    hdr, _, _ = glb.host.smt_set_proofs(k2, v2)
+    assert np.array_equal(hdr["new_root"][-1], want2)
+
+
+def test_c_entry_point_rejects_zero_values_and_duplicates(glb, ctx, rng):
+    """gl_smt_build is SparseMerkleTree::insert over a batch: "value must be non-zero", "given key already exists"."""
+    import ctypes as C
+
+    lib, N = ctx._lib, glb._native
+    keys, values = rand_field(rng, (9, 4)), rand_field(rng, (9, 4)) | np.uint64(1)
+    root, cnt = np.zeros(4, dtype=np.uint64), C.c_uint64(0)
+
+    def build(k, v):
+        return lib.gl_smt_build(ctx._h, k.ctypes.data, v.ctypes.data, k.shape[0], root.ctypes.data, None, 0, C.byref(cnt), None, N.GL_HOST)
+
+    assert build(keys, values) == N.GL_OK
+    v0 = values.copy()
+    v0[4] = 0
+    assert build(keys, v0) == N.GL_E_ARG and b"non-zero" in lib.gl_last_error(ctx._h)
+    v0[4] = np.uint64(P)               # p = 0 (mod p)
+    assert build(keys, v0) == N.GL_E_ARG
+    k0 = keys.copy()
+    k0[8] = k0[1]
+    assert build(k0, values) == N.GL_E_ARG and b"already exists" in lib.gl_last_error(ctx._h)
 
 
 def test_bulk_build_scale(glb, ctx, oracle, rng):
