@@ -233,8 +233,18 @@ def run_reference(args):
         o.commit_from_values(vc, RATE_BITS, CAP_HEIGHT, want_leaves=True)
         t_cal = time.perf_counter() - t
         lg = args.log_n
-        # measured here: a 2^20-row commit costs ~1.3x what 16 commits of 2^16 rows do (caches, page faults)
-        while lg > cal and args.steps * t_cal * (1 << (lg - cal)) * 1.3 > args.ref_budget_s:
+        budget = args.ref_budget_s
+        if budget <= 0:
+            # the driver gives a 1-GPU lease's reference arm 1800 s and each arm of the 8-GPU scaling sequence 870 s
+            # (BENCH_r01.json / SCALE_r01.json step limits): stay well inside whichever applies to this box
+            try:
+                ngpu = len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout.strip().splitlines())
+            except Exception:
+                ngpu = 0
+            budget = 1150 if ngpu <= 1 else 700
+        args.ref_budget_s = budget
+        # measured: a 2^20-row commit costs ~1.15x what 16 commits of 2^16 rows do (caches, page faults)
+        while lg > cal and args.steps * t_cal * (1 << (lg - cal)) * 1.15 > budget:
             lg -= 1
         del vc
     v = o.synthetic_values(args.cols, 1 << lg)
@@ -322,7 +332,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N)
     ap.add_argument("--cols", type=int, default=COLS)
     ap.add_argument("--ref-log-n", type=int, default=0, help="rows (log2) of the reference arm's per-step commit; 0 = the full workload if K steps fit --ref-budget-s")
-    ap.add_argument("--ref-budget-s", type=int, default=600, help="time budget of the reference arm's K timed steps")
+    ap.add_argument("--ref-budget-s", type=int, default=0, help="time budget of the reference arm's K timed steps; 0 = 1150 s on a 1-GPU box, 700 s on a multi-GPU box")
     ap.add_argument("--cpu-log-n", type=int, default=18, help="rows (log2) of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -497,7 +507,7 @@ def main():
         hvp, hcp, hcapp = (C.c_void_p * 1)(hv.ctypes.data), (C.c_void_p * 1)(hc.ctypes.data), (C.c_void_p * 1)(hcap.ctypes.data)
         # GL_COMMIT_STREAM_HASH: the leaves absorb each round as soon as it is extended, so hashing runs while the next
         # rounds are still on PCIe / NVLink (at 2 GPUs the step is bound by the arithmetic: plain hashing there)
-        eflags = N.GL_COMMIT_STREAM_HASH if world >= 4 else 0
+        eflags = N.GL_COMMIT_STREAM_HASH if world >= int(os.environ.get("BENCH_STREAM_HASH_MIN_WORLD", "4")) else 0
 
         def estep():
             group.check(lib.gl_group_commit_from_values(group._h, hvp, log_n, cols, RATE_BITS, CAP_HEIGHT, hcp, hcapp, hs,

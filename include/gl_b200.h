@@ -309,6 +309,42 @@ int gl_fri_final_poly(gl_ctx *ctx, gl_commit *const *oracles, uint32_t num_oracl
                       uint32_t num_batches, const gl_fri_poly *polys, const uint64_t alpha[2], uint32_t rate_bits,
                       uint64_t *lde_coeffs_out, uint64_t *lde_values_out, int space);
 
+/* ---- N3: compute_quotient_polys (plonky2::plonk::prover, vanishing_poly::eval_vanishing_poly_base_batch) ------------------
+ * The last prover stage that reads every LDE row: with it the three prove-time oracles never leave HBM.
+ * Reached from every data.prove(pw); the gate evaluators cover upstream's NoopGate / ConstantGate / PublicInputGate and
+ * the three gates whose source is in the reference: U32InterleaveGate (src/u32/gates/interleave_u32.rs:89-126),
+ * UninterleaveToU32Gate (uninterleave_to_u32.rs:98-145), UninterleaveToB32Gate (uninterleave_to_b32.rs:101-149) -- the
+ * circuits of src/hash/keccak256.rs:248 are built from them plus plonky2_u32's gates (not covered yet). */
+#define GL_GATE_NOOP 0
+#define GL_GATE_CONSTANT 1            /* ConstantGate { num_consts = num_ops } */
+#define GL_GATE_PUBLIC_INPUT 2
+#define GL_GATE_U32_INTERLEAVE 3
+#define GL_GATE_UNINTERLEAVE_TO_U32 4
+#define GL_GATE_UNINTERLEAVE_TO_B32 5
+typedef struct {
+    uint32_t kind, num_ops;
+    uint32_t selector_index;          /* selectors_info.selector_indices[gate]: its selector column among the constants */
+    uint32_t group_start, group_end;  /* selectors_info.groups[selector_index]; the gate's own index is its position in gates[] */
+    uint32_t reserved;
+} gl_gate;
+typedef struct {
+    uint32_t degree_bits, num_wires, num_routed_wires;
+    uint32_t num_constants;           /* constant columns INCLUDING the num_selectors selector columns, which come first */
+    uint32_t num_selectors, num_challenges;
+    uint32_t quotient_degree_factor;  /* a power of two <= 2^rate_bits (8 for every preset the reference uses) */
+    uint32_t num_gates;               /* <= 16 */
+} gl_circuit;
+/* constants_sigmas: commit of [num_constants constants | num_routed_wires sigmas]; wires: num_wires columns;
+ * zs_partial_products: [Z_0 .. Z_{nch-1} | partial products of challenge 0, 1, ..] (num_challenges * ceil(routed / qdf)
+ * columns).  All three resident on ctx with the same degree and rate_bits, unsharded.  k_is [num_routed_wires],
+ * public_inputs_hash [4], betas / gammas / alphas [num_challenges]: host.  chunks_out [num_challenges *
+ * quotient_degree_factor][2^degree_bits] = quotient_polys.flat_map(|p| p.chunks(degree)): the coefficient vectors the
+ * prover commits next (gl_commit_from_coeffs takes them as they are, also with space = GL_DEVICE). */
+int gl_quotient_polys(gl_ctx *ctx, const gl_circuit *circuit, const gl_gate *gates, const uint64_t *k_is,
+                      gl_commit *constants_sigmas, gl_commit *wires, gl_commit *zs_partial_products,
+                      const uint64_t *public_inputs_hash, const uint64_t *betas, const uint64_t *gammas,
+                      const uint64_t *alphas, uint64_t *chunks_out, int space);
+
 /* ---- P10: fri_proof_of_work ------------------------------------------------------------------- */
 /* Smallest w >= 0 such that permute(state with state[input_pos] = w)[7] (the last rate lane, as
  * `duplex_state.squeeze().last()`) has >= min_leading_zeros leading zero bits.  Upstream's rayon

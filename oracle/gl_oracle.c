@@ -10,9 +10,16 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+static double glo_now(void) {
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
 
 typedef unsigned __int128 u128;
 typedef uint64_t u64;
@@ -505,9 +512,13 @@ void glo_hash_no_pad_batch(const u64 *in, size_t len_each, size_t m, u64 *out) {
  *           with a table of roots; natural order in and out).
  * ---------------------------------------------------------------------------------------------- */
 size_t glo_reverse_bits(size_t x, unsigned bits) {
-    size_t r = 0;
-    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
-    return r;
+    if (bits == 0) return 0;
+    uint64_t v = (uint64_t)x;
+    v = ((v >> 1) & 0x5555555555555555ULL) | ((v & 0x5555555555555555ULL) << 1);
+    v = ((v >> 2) & 0x3333333333333333ULL) | ((v & 0x3333333333333333ULL) << 2);
+    v = ((v >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((v & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    v = __builtin_bswap64(v);
+    return (size_t)(v >> (64 - bits));
 }
 
 static void reverse_index_bits_u64(u64 *a, unsigned lg_n) {
@@ -695,6 +706,7 @@ int glo_commit_from_coeffs(const u64 *coeffs, unsigned lg_n, unsigned c, unsigne
     if (cap_height > lg_N) return 2;
     roots_for(lg_N);
     /* "FFT + blinding": lde_values[col] = coeffs[col].lde(rate_bits).coset_fft(7); blinding = false */
+    double t_0 = glo_now();
     u64 *lde = (u64 *)malloc((size_t)c * N * sizeof(u64));
     if (!lde) return 3;
 #pragma omp parallel for schedule(dynamic)
@@ -705,6 +717,7 @@ int glo_commit_from_coeffs(const u64 *coeffs, unsigned lg_n, unsigned c, unsigne
         glo_coset_fft(v, lg_N, 7, rate_bits);
     }
     /* "transpose LDEs" + reverse_index_bits_in_place(leaves) */
+    double t_1 = glo_now();
     u64 *leaves = leaves_out ? leaves_out : (u64 *)malloc((size_t)c * N * sizeof(u64));
     if (!leaves) { free(lde); return 3; }
 #pragma omp parallel for schedule(static)
@@ -713,12 +726,16 @@ int glo_commit_from_coeffs(const u64 *coeffs, unsigned lg_n, unsigned c, unsigne
         for (unsigned col = 0; col < c; col++) leaves[i * c + col] = lde[(size_t)col * N + src];
     }
     free(lde);
+    double t_2 = glo_now();
     /* "build Merkle tree" */
     size_t num_digests = 2 * (N - ((size_t)1 << cap_height));
     u64 *digests = digests_out ? digests_out : (u64 *)malloc((num_digests ? num_digests : 1) * 4 * sizeof(u64));
     u64 cap_local[4 * 64];
     u64 *cap = cap_out ? cap_out : (cap_height <= 6 ? cap_local : (u64 *)malloc(((size_t)4 << cap_height) * sizeof(u64)));
     int rc = glo_merkle_tree(leaves, N, c, cap_height, digests, cap);
+    if (getenv("GLO_TIMING"))
+        fprintf(stderr, "glo_commit_from_coeffs 2^%u x %u: FFT %.2f s, transpose %.2f s, Merkle %.2f s\n", lg_n, c, t_1 - t_0, t_2 - t_1,
+                glo_now() - t_2);
     if (!leaves_out) free(leaves);
     if (!digests_out) free(digests);
     if (!cap_out && cap_height > 6) free(cap);
@@ -1232,6 +1249,260 @@ void glo_eval_base_poly_at_ext(const u64 *coeffs, size_t n, const u64 point[2], 
     }
     out[0] = canon(acc[0]);
     out[1] = canon(acc[1]);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * N3  plonky2::plonk::prover: the permutation argument's Z / partial products (prover step 5) and
+ *     compute_quotient_polys (step 8), for circuits whose gates are NoopGate, ConstantGate,
+ *     PublicInputGate (upstream) and the reference's three custom gates:
+ *       U32InterleaveGate      /root/reference/src/u32/gates/interleave_u32.rs:89-126
+ *       UninterleaveToU32Gate  /root/reference/src/u32/gates/uninterleave_to_u32.rs:98-145
+ *       UninterleaveToB32Gate  /root/reference/src/u32/gates/uninterleave_to_b32.rs:101-149
+ *     Everything else (vanishing_poly.rs, ZeroPolyOnCoset, selectors) restates upstream v0.1.4 from
+ *     memory: "parity unpinned"; the reference-endorsed acceptance property is the low-degree test
+ *     (interleave_u32.rs:341-352): a satisfying witness gives a quotient of degree < 7n.
+ * ---------------------------------------------------------------------------------------------- */
+#define UNUSED_SELECTOR 0xFFFFFFFFULL /* u32::MAX */
+
+static unsigned gate_num_constraints(const glo_gate *g) {
+    switch (g->kind) {
+        case GLO_GATE_CONSTANT: return g->num_ops;
+        case GLO_GATE_PUBLIC_INPUT: return 4;
+        case GLO_GATE_U32_INTERLEAVE: return g->num_ops * 34;
+        case GLO_GATE_UNINTERLEAVE_TO_U32:
+        case GLO_GATE_UNINTERLEAVE_TO_B32: return g->num_ops * 67;
+        default: return 0;
+    }
+}
+unsigned glo_num_gate_constraints(const glo_gate *gates, unsigned num_gates) {
+    unsigned m = 0;
+    for (unsigned i = 0; i < num_gates; i++) {
+        unsigned k = gate_num_constraints(gates + i);
+        if (k > m) m = k;
+    }
+    return m;
+}
+
+/* plonk_common::reduce_with_powers(terms, alpha) = sum_j terms[j] alpha^j */
+static u64 reduce_with_powers(const u64 *terms, unsigned n, long stride, u64 alpha) {
+    u64 sum = 0;
+    for (unsigned j = n; j-- > 0;) sum = f_add(f_mul(sum, alpha), terms[(long)j * stride]);
+    return sum;
+}
+
+/* Gate::eval_unfiltered for one row; `consts` = local_constants after remove_prefix(num_selectors) */
+static void gate_eval_unfiltered(const glo_gate *g, const u64 *wires, const u64 *consts, const u64 pih[4], u64 *out) {
+    unsigned k = 0;
+    switch (g->kind) {
+        case GLO_GATE_CONSTANT: /* ConstantGate: local_constants[i] - local_wires[i] */
+            for (unsigned i = 0; i < g->num_ops; i++) out[k++] = f_sub(consts[i], wires[i]);
+            break;
+        case GLO_GATE_PUBLIC_INPUT: /* PublicInputGate: local_wires[i] - public_inputs_hash[i] */
+            for (unsigned i = 0; i < 4; i++) out[k++] = f_sub(wires[i], pih[i]);
+            break;
+        case GLO_GATE_U32_INTERLEAVE: { /* interleave_u32.rs:89-126 */
+            for (unsigned i = 0; i < g->num_ops; i++) {
+                u64 x = wires[2 * i], x_interleaved = wires[2 * i + 1];
+                const u64 *bits = wires + g->num_ops * 2 + 32 * i; /* wires_ith_bit_decomposition, big-endian */
+                /* reduce_with_powers(bits.iter().rev(), B): term_j = bits[31 - j] */
+                out[k++] = f_sub(reduce_with_powers(bits + 31, 32, -1, 2), x);
+                out[k++] = f_sub(reduce_with_powers(bits + 31, 32, -1, 4), x_interleaved);
+                for (unsigned b = 0; b < 32; b++) out[k++] = f_mul(bits[b], f_sub(bits[b], 1)); /* (bit - 0)(bit - 1) */
+            }
+            break;
+        }
+        case GLO_GATE_UNINTERLEAVE_TO_U32:   /* uninterleave_to_u32.rs:98-145 */
+        case GLO_GATE_UNINTERLEAVE_TO_B32: { /* uninterleave_to_b32.rs:101-149 */
+            for (unsigned i = 0; i < g->num_ops; i++) {
+                u64 x_interleaved = wires[3 * i], x_evens = wires[3 * i + 1], x_odds = wires[3 * i + 2];
+                const u64 *bits = wires + g->num_ops * 3 + 64 * i;
+                out[k++] = f_sub(reduce_with_powers(bits + 63, 64, -1, 2), x_interleaved);
+                u64 ev = 0, od = 0;
+                for (unsigned j = 0; j < 32; j++) {
+                    u64 coeff = g->kind == GLO_GATE_UNINTERLEAVE_TO_U32 ? ((u64)1 << (32 - j - 1)) : ((u64)1 << (2 * (32 - j - 1)));
+                    ev = f_add(ev, f_mul(coeff, bits[2 * j]));
+                    od = f_add(od, f_mul(coeff, bits[2 * j + 1]));
+                }
+                out[k++] = f_sub(ev, x_evens);
+                out[k++] = f_sub(od, x_odds);
+                for (unsigned b = 0; b < 64; b++) out[k++] = f_mul(bits[b], f_sub(bits[b], 1));
+            }
+            break;
+        }
+        default: break; /* NoopGate */
+    }
+}
+
+/* gate.rs compute_filter: prod_{i in group, i != row} (i - s) * (many_selectors ? (UNUSED_SELECTOR - s) : 1) */
+static u64 compute_filter(unsigned row, unsigned g0, unsigned g1, u64 s, int many) {
+    u64 f = 1;
+    for (unsigned i = g0; i < g1; i++)
+        if (i != row) f = f_mul(f, f_sub(i, s));
+    if (many) f = f_mul(f, f_sub(UNUSED_SELECTOR, s));
+    return f;
+}
+
+/* prover.rs wires_permutation_partial_products_and_zs / all_wires_permutation_partial_products:
+ * wires [num_wires][n], sigmas [num_routed][n] (values k_j' * w^i' of the permutation), out [nch * (1 + num_prods)][n]
+ * laid out as the prover commits them: Z_0 .. Z_{nch-1}, then the partial products of challenge 0, 1, ... */
+int glo_permutation_zs(const glo_circuit *cd, const u64 *k_is, const u64 *wires, const u64 *sigmas, const u64 *betas,
+                       const u64 *gammas, u64 *out) {
+    const size_t n = (size_t)1 << cd->degree_bits;
+    const unsigned R = cd->num_routed_wires, deg = cd->quotient_degree_factor;
+    const unsigned chunks = (R + deg - 1) / deg, num_prods = chunks - 1, nch = cd->num_challenges;
+    const u64 w = glo_primitive_root_of_unity(cd->degree_bits);
+    u64 *subgroup = (u64 *)malloc(n * sizeof(u64));
+    u64 cur = 1;
+    for (size_t i = 0; i < n; i++) { subgroup[i] = cur; cur = f_mul(cur, w); }
+    for (unsigned c = 0; c < nch; c++) {
+        const u64 beta = betas[c], gamma = gammas[c];
+        u64 *Z = out + (size_t)c * n;
+        u64 *PP = out + ((size_t)nch + (size_t)c * num_prods) * n;
+        /* the per-row chunk quotients are independent; the running product over rows is serial */
+        u64 *chunkq = (u64 *)malloc(n * chunks * sizeof(u64));
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < n; i++) {
+            const u64 x = subgroup[i];
+            for (unsigned q = 0; q < chunks; q++) {
+                u64 num = 1, den = 1;
+                for (unsigned j = q * deg; j < R && j < (q + 1) * deg; j++) {
+                    const u64 wv = wires[(size_t)j * n + i];
+                    u64 s_id = f_mul(k_is[j], x);
+                    num = f_mul(num, f_add(f_add(wv, f_mul(beta, s_id)), gamma));
+                    den = f_mul(den, f_add(f_add(wv, f_mul(beta, sigmas[(size_t)j * n + i])), gamma));
+                }
+                chunkq[i * chunks + q] = f_mul(num, glo_inv(den));
+            }
+        }
+        u64 z = 1;
+        for (size_t i = 0; i < n; i++) {
+            Z[i] = z; /* "the last term is Z(gx), but we replace it with Z(x)" */
+            u64 acc = z;
+            for (unsigned q = 0; q < chunks; q++) {
+                acc = f_mul(acc, chunkq[i * chunks + q]);
+                if (q < num_prods) PP[(size_t)q * n + i] = acc;
+            }
+            z = acc;
+        }
+        free(chunkq);
+        if (z != 1) { free(subgroup); return 1; } /* the grand product must close: sigma is not a permutation of equal values */
+    }
+    free(subgroup);
+    return 0;
+}
+
+/* vanishing_poly.rs eval_vanishing_poly_base_batch for ONE point x: fills terms[] = vanishing_z_1_terms ++
+ * vanishing_partial_products_terms ++ gate constraint slots (the list reduce_with_powers_multi takes).
+ * lcs / lw / lz / nz: the rows of constants_sigmas, wires, zs_partial_products at x and of zs_partial_products at g x. */
+static unsigned vanishing_terms(const glo_circuit *cd, const glo_gate *gates, const u64 *k_is, u64 x, u64 l0, const u64 *lcs,
+                                const u64 *lw, const u64 *lz, const u64 *nz, const u64 pih[4], const u64 *betas,
+                                const u64 *gammas, u64 *terms, u64 *gc) {
+    const unsigned nch = cd->num_challenges, R = cd->num_routed_wires, deg = cd->quotient_degree_factor;
+    const unsigned chunks = (R + deg - 1) / deg, num_prods = chunks - 1;
+    const unsigned ngc = glo_num_gate_constraints(gates, cd->num_gates);
+    const u64 *s_sigmas = lcs + cd->num_constants;
+    const int many = cd->num_selectors > 1;
+    unsigned t = 0;
+    for (unsigned c = 0; c < nch; c++) terms[t++] = f_mul(l0, f_sub(lz[c], 1)); /* vanishing_z_1_terms */
+    for (unsigned c = 0; c < nch; c++) { /* check_partial_products */
+        const u64 *pp = lz + nch + c * num_prods;
+        for (unsigned q = 0; q < chunks; q++) {
+            u64 num = 1, den = 1;
+            for (unsigned j = q * deg; j < R && j < (q + 1) * deg; j++) {
+                num = f_mul(num, f_add(f_add(lw[j], f_mul(betas[c], f_mul(k_is[j], x))), gammas[c]));
+                den = f_mul(den, f_add(f_add(lw[j], f_mul(betas[c], s_sigmas[j])), gammas[c]));
+            }
+            const u64 prev = q == 0 ? lz[c] : pp[q - 1], next = q == chunks - 1 ? nz[c] : pp[q];
+            terms[t++] = f_sub(f_mul(prev, num), f_mul(next, den));
+        }
+    }
+    /* evaluate_gate_constraints_base_batch: every gate, filtered, added into the shared slots */
+    u64 *slots = terms + t;
+    for (unsigned k = 0; k < ngc; k++) slots[k] = 0;
+    for (unsigned gi = 0; gi < cd->num_gates; gi++) {
+        const glo_gate *g = gates + gi;
+        const unsigned k = gate_num_constraints(g);
+        if (!k) continue;
+        const u64 filter = compute_filter(gi, g->group_start, g->group_end, lcs[g->selector_index], many);
+        gate_eval_unfiltered(g, lw, lcs + cd->num_selectors, pih, gc);
+        for (unsigned j = 0; j < k; j++) slots[j] = f_add(slots[j], f_mul(filter, gc[j]));
+    }
+    return t + ngc;
+}
+/* The verifier's side of the same identity (plonk/verifier.rs via eval_vanishing_poly): the alpha-reduced vanishing
+ * values at an arbitrary base-field point x, given the openings there.  out[nch]. */
+void glo_vanishing_at_point(const glo_circuit *cd, const glo_gate *gates, const u64 *k_is, u64 x, const u64 *lcs, const u64 *lw,
+                            const u64 *lz, const u64 *nz, const u64 pih[4], const u64 *betas, const u64 *gammas,
+                            const u64 *alphas, u64 *out) {
+    const size_t n = (size_t)1 << cd->degree_bits;
+    const unsigned chunks = (cd->num_routed_wires + cd->quotient_degree_factor - 1) / cd->quotient_degree_factor;
+    const unsigned ngc = glo_num_gate_constraints(gates, cd->num_gates);
+    const unsigned nterms = cd->num_challenges * (1 + chunks) + ngc;
+    u64 *terms = (u64 *)malloc(nterms * sizeof(u64)), *gc = (u64 *)malloc((ngc ? ngc : 1) * sizeof(u64));
+    /* eval_l_0(x) = (x^n - 1) / (n (x - 1)) */
+    const u64 l0 = f_mul(f_sub(glo_pow(x, (u64)n), 1), glo_inv(f_mul((u64)n % P, f_sub(x, 1))));
+    vanishing_terms(cd, gates, k_is, x, l0, lcs, lw, lz, nz, pih, betas, gammas, terms, gc);
+    for (unsigned c = 0; c < cd->num_challenges; c++) out[c] = reduce_with_powers(terms, nterms, 1, alphas[c]);
+    free(terms);
+    free(gc);
+}
+
+/* prover.rs compute_quotient_polys + vanishing_poly.rs eval_vanishing_poly_base_batch.
+ * *_lde: row-major leaves of the three commits as PolynomialBatch holds them after transpose + reverse_index_bits
+ * ([N][c], N = n << rate_bits); get_lde_values(i, step) = leaves[reverse_bits(i * step, lg N)].
+ * out: [nch * quotient_degree_factor][n] = quotient_polys.flat_map(|p| p.chunks(n)). */
+int glo_quotient_polys(const glo_circuit *cd, const glo_gate *gates, const u64 *k_is, const u64 *cs_lde, const u64 *wires_lde,
+                       const u64 *zs_lde, unsigned rate_bits, const u64 pih[4], const u64 *betas, const u64 *gammas,
+                       const u64 *alphas, u64 *out) {
+    const unsigned lg_n = cd->degree_bits, nch = cd->num_challenges, R = cd->num_routed_wires, deg = cd->quotient_degree_factor;
+    unsigned qdb = 0;
+    while ((1u << qdb) < deg) qdb++; /* log2_ceil(quotient_degree_factor) */
+    if (qdb > rate_bits) return 2;   /* "Having constraints of degree higher than the rate is not supported yet." */
+    const size_t n = (size_t)1 << lg_n, lde_size = n << qdb, step = (size_t)1 << (rate_bits - qdb), next_step = (size_t)1 << qdb;
+    const unsigned lg_N = lg_n + rate_bits;
+    const unsigned chunks = (R + deg - 1) / deg, num_prods = chunks - 1;
+    const unsigned c_cs = cd->num_constants + R, c_w = cd->num_wires, c_z = nch * (1 + num_prods);
+    const unsigned ngc = glo_num_gate_constraints(gates, cd->num_gates);
+    const unsigned nterms = nch + nch * chunks + ngc;
+    const u64 w_lde = glo_primitive_root_of_unity(lg_n + qdb);
+    /* ZeroPolyOnCoset::new(n_log, rate_bits = qdb): evals[i] = g^n * w_rate^i - 1, inverses */
+    u64 zh[64], zh_inv[64];
+    {
+        const u64 g_pow_n = glo_pow(7, (u64)n), w_rate = glo_primitive_root_of_unity(qdb);
+        u64 cur = 1;
+        for (size_t i = 0; i < next_step; i++) { zh[i] = f_sub(f_mul(g_pow_n, cur), 1); zh_inv[i] = glo_inv(zh[i]); cur = f_mul(cur, w_rate); }
+    }
+    u64 *qv = (u64 *)malloc((size_t)nch * lde_size * sizeof(u64)); /* quotient values, transposed: [nch][lde_size] */
+    u64 *points = (u64 *)malloc(lde_size * sizeof(u64));            /* F::two_adic_subgroup */
+    { u64 cur = 1; for (size_t i = 0; i < lde_size; i++) { points[i] = cur; cur = f_mul(cur, w_lde); } }
+#pragma omp parallel
+    {
+        u64 *terms = (u64 *)malloc(nterms * sizeof(u64));
+        u64 *gc = (u64 *)malloc((ngc ? ngc : 1) * sizeof(u64));
+#pragma omp for schedule(static)
+        for (size_t i = 0; i < lde_size; i++) {
+            const u64 x = f_mul(7, points[i]); /* shifted_x = F::coset_shift() * x */
+            const size_t i_next = (i + next_step) % lde_size;
+            const u64 *lcs = cs_lde + glo_reverse_bits(i * step, lg_N) * c_cs;
+            const u64 *lw = wires_lde + glo_reverse_bits(i * step, lg_N) * c_w;
+            const u64 *lz = zs_lde + glo_reverse_bits(i * step, lg_N) * c_z;
+            const u64 *nz = zs_lde + glo_reverse_bits(i_next * step, lg_N) * c_z;
+            /* z_h_on_coset.eval_l_0(index, x) = eval(index) * (n * (x - 1))^-1 */
+            const u64 l0 = f_mul(zh[i % next_step], glo_inv(f_mul((u64)n % P, f_sub(x, 1))));
+            vanishing_terms(cd, gates, k_is, x, l0, lcs, lw, lz, nz, pih, betas, gammas, terms, gc);
+            /* reduce_with_powers_multi(vanishing_terms, alphas), then * z_h_on_coset.eval_inverse(i) */
+            for (unsigned c = 0; c < nch; c++)
+                qv[(size_t)c * lde_size + i] = f_mul(reduce_with_powers(terms, nterms, 1, alphas[c]), zh_inv[i % next_step]);
+        }
+        free(terms);
+        free(gc);
+    }
+    free(points);
+    /* values.coset_ifft(F::coset_shift()), then chunks(degree) */
+    for (unsigned c = 0; c < nch; c++) glo_coset_ifft(qv + (size_t)c * lde_size, lg_n + qdb, 7);
+    memcpy(out, qv, (size_t)nch * lde_size * sizeof(u64)); /* deg == 2^qdb chunks of n per challenge, in order */
+    free(qv);
+    return (((size_t)deg << lg_n) == lde_size) ? 0 : 3;
 }
 
 int glo_num_threads(void) {

@@ -127,6 +127,30 @@ void glo_divide_by_linear(const uint64_t *poly_ext, size_t n, const uint64_t z[2
 void glo_ext_poly_scale_add(uint64_t *acc_ext, size_t n, const uint64_t scalar[2], const uint64_t *add_ext);
 void glo_eval_base_poly_at_ext(const uint64_t *coeffs, size_t n, const uint64_t point[2], uint64_t out[2]);
 
+/* ---- N3: permutation argument (Z, partial products) and compute_quotient_polys ---- */
+enum { GLO_GATE_NOOP = 0, GLO_GATE_CONSTANT = 1, GLO_GATE_PUBLIC_INPUT = 2, GLO_GATE_U32_INTERLEAVE = 3,
+       GLO_GATE_UNINTERLEAVE_TO_U32 = 4, GLO_GATE_UNINTERLEAVE_TO_B32 = 5 };
+typedef struct {
+    uint32_t kind, num_ops;      /* num_ops: ConstantGate's num_consts / the custom gates' num_ops */
+    uint32_t selector_index;     /* column of its selector polynomial among the constants */
+    uint32_t group_start, group_end; /* selectors_info.groups[selector_index]; the gate's own index is its position */
+    uint32_t reserved;
+} glo_gate;
+typedef struct {
+    uint32_t degree_bits, num_wires, num_routed_wires;
+    uint32_t num_constants;      /* constants columns INCLUDING the num_selectors selector columns that come first */
+    uint32_t num_selectors, num_challenges, quotient_degree_factor, num_gates;
+} glo_circuit;
+unsigned glo_num_gate_constraints(const glo_gate *gates, unsigned num_gates);
+int glo_permutation_zs(const glo_circuit *cd, const uint64_t *k_is, const uint64_t *wires, const uint64_t *sigmas,
+                       const uint64_t *betas, const uint64_t *gammas, uint64_t *out);
+int glo_quotient_polys(const glo_circuit *cd, const glo_gate *gates, const uint64_t *k_is, const uint64_t *cs_lde,
+                       const uint64_t *wires_lde, const uint64_t *zs_lde, unsigned rate_bits, const uint64_t pih[4],
+                       const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas, uint64_t *out);
+void glo_vanishing_at_point(const glo_circuit *cd, const glo_gate *gates, const uint64_t *k_is, uint64_t x, const uint64_t *lcs,
+                            const uint64_t *lw, const uint64_t *lz, const uint64_t *nz, const uint64_t pih[4],
+                            const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas, uint64_t *out);
+
 int glo_num_threads(void);
 void glo_set_num_threads(int n);
 

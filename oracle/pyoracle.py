@@ -121,6 +121,10 @@ def lib():
         "glo_divide_by_linear": (None, [u64p, sz, u64p, u64p]),
         "glo_ext_poly_scale_add": (None, [u64p, sz, u64p, u64p]),
         "glo_eval_base_poly_at_ext": (None, [u64p, sz, u64p, u64p]),
+        "glo_num_gate_constraints": (C.c_uint, [C.c_void_p, u]),
+        "glo_permutation_zs": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u64p, u64p, u64p]),
+        "glo_quotient_polys": (C.c_int, [C.c_void_p, C.c_void_p, u64p, u64p, u64p, u64p, u, u64p, u64p, u64p, u64p, u64p]),
+        "glo_vanishing_at_point": (None, [C.c_void_p, C.c_void_p, u64p, C.c_uint64, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p, u64p]),
         "glo_num_threads": (C.c_int, []),
         "glo_set_num_threads": (None, [C.c_int]),
     }
@@ -412,6 +416,52 @@ def eval_base_poly_at_ext(coeffs, point):
     out = np.zeros(2, dtype=np.uint64)
     lib().glo_eval_base_poly_at_ext(_p(c), c.shape[0], _p(pt), _p(out))
     return (int(out[0]), int(out[1]))
+
+
+# ---- N3: permutation argument + compute_quotient_polys ----------------------------------------------------------
+GATE_DTYPE = np.dtype([("kind", "<u4"), ("num_ops", "<u4"), ("selector_index", "<u4"), ("group_start", "<u4"), ("group_end", "<u4"),
+                       ("reserved", "<u4")])
+CIRCUIT_DTYPE = np.dtype([("degree_bits", "<u4"), ("num_wires", "<u4"), ("num_routed_wires", "<u4"), ("num_constants", "<u4"),
+                          ("num_selectors", "<u4"), ("num_challenges", "<u4"), ("quotient_degree_factor", "<u4"), ("num_gates", "<u4")])
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32 = range(6)
+
+
+def permutation_zs(circuit, k_is, wires, sigmas, betas, gammas) -> np.ndarray:
+    """Z and partial-product polynomials (values on the subgroup) [nch * (1 + num_prods)][n], prover column order."""
+    cd = np.asarray(circuit, dtype=CIRCUIT_DTYPE).reshape(1)
+    n = 1 << int(cd["degree_bits"][0])
+    nch, R, deg = int(cd["num_challenges"][0]), int(cd["num_routed_wires"][0]), int(cd["quotient_degree_factor"][0])
+    chunks = -(-R // deg)
+    out = np.zeros((nch * chunks, n), dtype=np.uint64)
+    w, sg, k, b, g = _a(wires), _a(sigmas), _a(k_is), _a(betas), _a(gammas)
+    rc = lib().glo_permutation_zs(cd.ctypes.data, _p(k), _p(w), _p(sg), _p(b), _p(g), _p(out))
+    if rc:
+        raise ValueError("the grand product does not close: copy constraints violated or sigma is not a permutation")
+    return out
+
+
+def quotient_polys(circuit, gates, k_is, cs_leaves, wires_leaves, zs_leaves, rate_bits, pih, betas, gammas, alphas) -> np.ndarray:
+    """compute_quotient_polys: [nch * quotient_degree_factor][n] coefficient chunks, from the row-major LDE leaves."""
+    cd = np.asarray(circuit, dtype=CIRCUIT_DTYPE).reshape(1)
+    gt = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+    n = 1 << int(cd["degree_bits"][0])
+    out = np.zeros((int(cd["num_challenges"][0]) * int(cd["quotient_degree_factor"][0]), n), dtype=np.uint64)
+    a = [_a(x) for x in (k_is, cs_leaves, wires_leaves, zs_leaves, pih, betas, gammas, alphas)]
+    rc = lib().glo_quotient_polys(cd.ctypes.data, gt.ctypes.data, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), rate_bits, _p(a[4]), _p(a[5]),
+                                  _p(a[6]), _p(a[7]), _p(out))
+    if rc:
+        raise ValueError(f"compute_quotient_polys would panic (code {rc})")
+    return out
+
+
+def vanishing_at_point(circuit, gates, k_is, x, lcs, lw, lz, nz, pih, betas, gammas, alphas) -> np.ndarray:
+    cd = np.asarray(circuit, dtype=CIRCUIT_DTYPE).reshape(1)
+    gt = np.ascontiguousarray(gates, dtype=GATE_DTYPE)
+    out = np.zeros(int(cd["num_challenges"][0]), dtype=np.uint64)
+    a = [_a(v) for v in (k_is, lcs, lw, lz, nz, pih, betas, gammas, alphas)]
+    lib().glo_vanishing_at_point(cd.ctypes.data, gt.ctypes.data, _p(a[0]), int(x), _p(a[1]), _p(a[2]), _p(a[3]), _p(a[4]), _p(a[5]),
+                                 _p(a[6]), _p(a[7]), _p(a[8]), _p(out))
+    return out
 
 
 def synthetic_values(c: int, n: int, seed: int = 0x706C6F6E6B7932, col0: int = 0) -> np.ndarray:

@@ -42,6 +42,19 @@ class SmtInclusionHdr(C.Structure):
     ]
 
 
+class Gate(C.Structure):
+    """gl_gate: one entry of CommonCircuitData.gates with its selector placement."""
+
+    _fields_ = [("kind", u32), ("num_ops", u32), ("selector_index", u32), ("group_start", u32), ("group_end", u32), ("reserved", u32)]
+
+
+class Circuit(C.Structure):
+    """gl_circuit: the part of CommonCircuitData compute_quotient_polys reads."""
+
+    _fields_ = [("degree_bits", u32), ("num_wires", u32), ("num_routed_wires", u32), ("num_constants", u32), ("num_selectors", u32),
+                ("num_challenges", u32), ("quotient_degree_factor", u32), ("num_gates", u32)]
+
+
 class FriBatch(C.Structure):
     _fields_ = [("point", u64 * 2), ("first_poly", u32), ("num_polys", u32)]
 
@@ -102,6 +115,7 @@ SIGNATURES = {
     "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
     "gl_fri_final_poly": (cint, [vp, vp, u32, vp, u32, vp, u64p, u32, vp, vp, cint]),
     "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
+    "gl_quotient_polys": (cint, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cint]),
     "gl_group_unique_id": (cint, [vp]),
     "gl_group_create": (cint, [vp, u32, u32, u32, vp, C.POINTER(vp)]),
     "gl_group_destroy": (None, [vp]),

@@ -32,6 +32,7 @@
 #include "host_staging.h"
 #include "ntt_kernels.h"
 #include "poseidon_constants.h"
+#include "quotient_kernels.h"
 #include "smt_kernels.h"
 #include "smt_proofs.h"
 
@@ -1817,6 +1818,105 @@ extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_
         launch_interleave2((const u64*)d_cols, N, N, d_ext, ctx->stream);
         TRY(copy_out(ctx, lde_values_out, d_ext, N * 16, space));
     }
+    return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// N3: compute_quotient_polys
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_quotient_polys(gl_ctx* ctx, const gl_circuit* cd, const gl_gate* gates, const uint64_t* k_is,
+                                 gl_commit* constants_sigmas, gl_commit* wires, gl_commit* zs_pp,
+                                 const uint64_t* public_inputs_hash, const uint64_t* betas, const uint64_t* gammas,
+                                 const uint64_t* alphas, uint64_t* chunks_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    if (!cd || !gates || !k_is || !constants_sigmas || !wires || !zs_pp || !public_inputs_hash || !betas || !gammas || !alphas ||
+        !chunks_out)
+        return fail(ctx, GL_E_ARG, "gl_quotient_polys: NULL argument");
+    const uint32_t nch = cd->num_challenges, R = cd->num_routed_wires, deg = cd->quotient_degree_factor;
+    if (nch == 0 || nch > QUOTIENT_MAX_CHALLENGES || cd->num_gates == 0 || cd->num_gates > QUOTIENT_MAX_GATES || R == 0 ||
+        R > cd->num_wires || !is_pow2(deg) || cd->num_selectors == 0 || cd->num_selectors > cd->num_constants)
+        return fail(ctx, GL_E_ARG, "gl_quotient_polys: unsupported circuit geometry");
+    const uint32_t qdb = ilog2(deg), lg_n = cd->degree_bits;
+    gl_commit* cm[3] = {constants_sigmas, wires, zs_pp};
+    for (auto* h : cm) {
+        if (h->ctx != ctx || !h->finished || !h->lde) return fail(ctx, GL_E_STATE, "gl_quotient_polys: oracle is not a finished commit of this ctx");
+        if (h->log_n != lg_n || h->rate_bits != wires->rate_bits) return fail(ctx, GL_E_ARG, "gl_quotient_polys: oracles of different degree or rate");
+        if (h->shard_count != 1) return fail(ctx, GL_E_ARG, "gl_quotient_polys: sharded oracles are not supported");
+    }
+    const uint32_t rate_bits = wires->rate_bits;
+    if (qdb > rate_bits || qdb > 5)
+        return fail(ctx, GL_E_ARG, "compute_quotient_polys: having constraints of degree higher than the rate is not supported");
+    const uint32_t chunks = (R + deg - 1) / deg, num_prods = chunks - 1;
+    if (constants_sigmas->c != cd->num_constants + R || wires->c != cd->num_wires || zs_pp->c != nch * chunks)
+        return fail(ctx, GL_E_ARG, "gl_quotient_polys: column counts do not match the circuit description");
+    quotient_args a;
+    memset(&a, 0, sizeof a);
+    uint32_t ngc = 0;
+    for (uint32_t i = 0; i < cd->num_gates; i++) {
+        const gl_gate& g = gates[i];
+        if (g.kind > GL_GATE_UNINTERLEAVE_TO_B32 || g.selector_index >= cd->num_selectors || g.group_start > i || g.group_end <= i ||
+            g.group_end > cd->num_gates)
+            return fail(ctx, GL_E_ARG, "gl_quotient_polys: bad gate descriptor");
+        uint32_t need = 0;
+        switch (g.kind) {
+            case GL_GATE_CONSTANT: need = g.num_ops; if (cd->num_selectors + g.num_ops > cd->num_constants) need = ~0u; break;
+            case GL_GATE_PUBLIC_INPUT: need = 4; break;
+            case GL_GATE_U32_INTERLEAVE: need = g.num_ops * 34; break;
+            case GL_GATE_UNINTERLEAVE_TO_U32:
+            case GL_GATE_UNINTERLEAVE_TO_B32: need = g.num_ops * 67; break;
+            default: break;
+        }
+        if (need > cd->num_wires) return fail(ctx, GL_E_ARG, "gl_quotient_polys: gate does not fit the wires / constants");
+        a.gates[i] = g;
+        ngc = std::max(ngc, quotient_gate_constraints(g));
+    }
+    Guard g(ctx);
+    const u64 n = (u64)1 << lg_n, lde_size = n << qdb;
+    const uint32_t nterms = nch * (1 + chunks) + ngc;
+    // tables: alpha powers [nch][nterms], k_is [R]
+    std::vector<u64> tab((size_t)nch * nterms + R);
+    for (uint32_t c = 0; c < nch; c++) {
+        u64 cur = 1;
+        const u64 al = glh::canon(alphas[c]);
+        for (uint32_t t = 0; t < nterms; t++) {
+            tab[(size_t)c * nterms + t] = cur;
+            cur = glh::mul(cur, al);
+        }
+    }
+    for (uint32_t j = 0; j < R; j++) tab[(size_t)nch * nterms + j] = glh::canon(k_is[j]);
+    void *d_tab, *d_vals;
+    TRY(scratch_get(ctx, 0, tab.size() * 8, &d_tab));
+    TRY(scratch_get(ctx, 4, (size_t)nch * lde_size * 8, &d_vals));
+    CK(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const u64* xtab;
+    TRY(pow_table(ctx, glh::root_of_unity(lg_n + qdb), &xtab));
+    a.cs = constants_sigmas->lde; a.cs_ld = constants_sigmas->n_local;
+    a.wires = wires->lde; a.w_ld = wires->n_local;
+    a.zs = zs_pp->lde; a.z_ld = zs_pp->n_local;
+    a.lg_lde = lg_n + qdb; a.qdb = qdb; a.nch = nch; a.R = R; a.deg = deg; a.chunks = chunks; a.num_prods = num_prods;
+    a.num_constants = cd->num_constants; a.num_selectors = cd->num_selectors; a.num_gates = cd->num_gates;
+    a.nterms = nterms; a.gate_term0 = nch * (1 + chunks);
+    a.apow = (const u64*)d_tab; a.k_is = (const u64*)d_tab + (size_t)nch * nterms; a.xtab = xtab;
+    for (uint32_t c = 0; c < nch; c++) { a.betas[c] = glh::canon(betas[c]); a.gammas[c] = glh::canon(gammas[c]); }
+    for (int i = 0; i < 4; i++) a.pih[i] = glh::canon(public_inputs_hash[i]);
+    {   // ZeroPolyOnCoset::new(degree_bits, quotient_degree_bits): g^n w_rate^i - 1 and inverses
+        const u64 g_pow_n = glh::pow(7, n), w_rate = glh::root_of_unity(qdb);
+        u64 cur = 1;
+        for (uint32_t i = 0; i < (1u << qdb); i++) {
+            a.zh[i] = glh::sub(glh::mul(g_pow_n, cur), 1);
+            a.zh_inv[i] = glh::inv(a.zh[i]);
+            cur = glh::mul(cur, w_rate);
+        }
+    }
+    a.n_field = glh::canon(n % GL_P);
+    a.out = (u64*)d_vals;
+    launch_quotient(a, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));   // `tab` dies with this call; errors surface here
+    // values.coset_ifft(F::coset_shift()) per challenge; the [nch][lde_size] result IS the chunk list
+    const u64* post;
+    TRY(pow_table(ctx, glh::inv(7), &post));
+    TRY(transform_natural(ctx, (u64*)d_vals, lg_n + qdb, nch, true, nullptr, post));
+    TRY(copy_out(ctx, chunks_out, d_vals, (size_t)nch * lde_size * 8, space));
     return finish(ctx);
 }
 

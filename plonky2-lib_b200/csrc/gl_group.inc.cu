@@ -36,9 +36,14 @@ static Api* api() {
     static Api a;
     static std::once_flag once;
     std::call_once(once, [] {
+        // 1. GL_B200_NCCL=<path> when set; 2. the copy this process already loaded (a host that imported torch shares
+        // torch's bundled NCCL: two NCCLs with one SONAME in a process do not mix); 3. the system library.
+        const char* forced = getenv("GL_B200_NCCL");
+        if (forced && *forced) a.so = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
+        if (!a.so) a.so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
         for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
-            a.so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
             if (a.so) break;
+            a.so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
         }
         if (!a.so) {
             a.error = std::string("NCCL is not available (dlopen libnccl.so.2): ") + (dlerror() ? dlerror() : "");

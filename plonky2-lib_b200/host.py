@@ -605,6 +605,30 @@ class PolynomialBatch:
 
 
 # ------------------------------------------------------------------------------------------------
+# N3: plonky2::plonk::prover::compute_quotient_polys on the resident oracles
+# ------------------------------------------------------------------------------------------------
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_U32_INTERLEAVE, GATE_UNINTERLEAVE_TO_U32, GATE_UNINTERLEAVE_TO_B32 = range(6)
+
+
+def compute_quotient_polys(circuit, gates, k_is, constants_sigmas: "PolynomialBatch", wires: "PolynomialBatch",
+                           zs_partial_products: "PolynomialBatch", public_inputs_hash, betas, gammas, alphas, ctx=None) -> np.ndarray:
+    """compute_quotient_polys (prover step 8): the num_challenges * quotient_degree_factor coefficient chunks of the quotient,
+    [chunks][n], from the three oracles resident on the device -- no LDE row crosses PCIe.  circuit: (degree_bits,
+    num_wires, num_routed_wires, num_constants incl. selectors, num_selectors, num_challenges, quotient_degree_factor,
+    num_gates); gates: [(kind, num_ops, selector_index, group_start, group_end)], gate i = index i.  The chunks go straight
+    into PolynomialBatch.from_coeffs."""
+    ctx = _ctx(ctx)
+    cd = N.Circuit(*[int(v) for v in circuit])
+    arr = (N.Gate * len(gates))(*[N.Gate(*[int(v) for v in tuple(g)[:5]], 0) for g in gates])
+    k, pih, b, g, a = _h(k_is), _h(public_inputs_hash), _h(betas), _h(gammas), _h(alphas)
+    n = 1 << cd.degree_bits
+    out = np.empty((cd.num_challenges * cd.quotient_degree_factor, n), dtype=np.uint64)
+    ctx.check(ctx._lib.gl_quotient_polys(ctx._h, C.byref(cd), arr, k.ctypes.data, constants_sigmas._h, wires._h, zs_partial_products._h,
+                                         pih.ctypes.data, b.ctypes.data, g.ctypes.data, a.ctypes.data, out.ctypes.data, N.GL_HOST))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # gl_group: one commit sharded over several GPUs, NCCL behind the C ABI (SURVEY 8e)
 # ------------------------------------------------------------------------------------------------
 class Group:
@@ -612,7 +636,19 @@ class Group:
     `Group.from_token(ctx, rank, nranks, token)` holds one rank of a group that spans processes (rank 0 makes the token
     with `Group.unique_id()` and hands the 128 bytes to the others, e.g. over torch.distributed or a file)."""
 
+    @staticmethod
+    def _share_torch_nccl():
+        """libgl_b200.so binds NCCL with dlopen at its first gl_group_* call and prefers a copy the process already holds.
+        A Python process that will ALSO use torch must let torch load its bundled NCCL first: loading the system
+        libnccl.so.2 before `import torch` makes the loader hand that older copy to libtorch_cuda (same SONAME) and the
+        import fails with missing symbols.  (A host without torch -- the Rust prover -- just gets the system NCCL.)"""
+        try:
+            import torch  # noqa: F401
+        except Exception:
+            pass
+
     def __init__(self, ctxs: Sequence[Context], rank0: int, nranks: int, token: Optional[bytes]):
+        self._share_torch_nccl()
         self._lib = N.load()
         self.ctxs = list(ctxs)
         self.nlocal, self.rank0, self.nranks = len(self.ctxs), rank0, nranks
@@ -626,6 +662,7 @@ class Group:
 
     @staticmethod
     def unique_id() -> bytes:
+        Group._share_torch_nccl()
         lib = N.load()
         buf = (C.c_uint8 * N.GL_GROUP_ID_BYTES)()
         rc = lib.gl_group_unique_id(buf)

@@ -256,6 +256,28 @@ for b in batches:
 ctx.trim()
 
 
+def quotient_bench(lg):
+    """gl_quotient_polys at standard_recursion_config geometry with the reference's three custom gates (+ Noop / Constant /
+    PublicInput): data independent cost, so random oracles are as good as a satisfying witness."""
+    n_ = 1 << lg
+    circuit = (lg, 135, 80, 4, 2, 2, 8, 6)
+    gates = [(0, 0, 0, 0, 3), (1, 2, 0, 0, 3), (2, 0, 0, 0, 3), (3, 3, 1, 3, 6), (4, 2, 1, 3, 6), (5, 2, 1, 3, 6)]
+    k_is = np.array([pow(7, j, P) for j in range(80)], dtype=np.uint64)
+    bs = [glb.PolynomialBatch.from_values(rand_dev((c, n_)), 3, False, 4, want_coeffs=False) for c in (84, 135, 20)]
+    ch = np.array([3, 5], dtype=np.uint64)
+    pih = np.arange(4, dtype=np.uint64)
+    t_ = timeit(lambda: glb.host.compute_quotient_polys(circuit, gates, k_is, *bs, pih, ch, ch + np.uint64(9), ch + np.uint64(77)), 3)
+    for b in bs:
+        b.free()
+    ctx.trim()
+    rows = n_ * 8
+    return {"rows": n_, "points": rows, "ms": t_ * 1e3, "lde_bytes_read": rows * (84 + 135 + 20 + 2) * 8,
+            "gate_constraints_per_point": 3 * 34 + 2 * 67 + 2 * 67 + 2 + 4, "what": "kernel + coset_ifft of 2 x 8n values + 16 n coefficients D2H"}
+
+
+out["quotient_polys"] = [quotient_bench(lg) for lg in (16, 18, 20)]
+
+
 def proof_trace(lg):
     n_ = 1 << lg
     vals_ = [rand_dev((c, n_)).cpu().numpy().view(np.uint64) % np.uint64(P) for c in (84, 135, 20, 16)]
