@@ -300,7 +300,16 @@ def opening_set(oracles, batches) -> list:
 
 
 def prove_openings(oracles, batches, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None) -> dict:
-    """plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params)."""
+    """plonky2::fri::oracle::PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params).
+
+    The oracles may be sharded over a gl_group (host.ShardedPolynomialBatch): every rank holds all coefficients, so the
+    FRI polynomial, the layer commits and the transcript run on the group's first local rank (every process of a
+    multi-process group computes the same transcript), and the 28 x (row + path) initial-tree openings of the query phase
+    are served by the ranks that own the leaves and exchanged over NCCL (gl_group_commit_open)."""
+    if ctx is None and oracles and hasattr(oracles[0], "group"):
+        ctx = oracles[0].group.ctxs[0]
+        if challenger._ctx is not ctx:
+            challenger._ctx = ctx
     ctx = _ctx(ctx)
     alpha = challenger.get_extension_challenge()
     lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx, resident=True)

@@ -760,8 +760,25 @@ class ShardedPolynomialBatch:
 
     def __init__(self, group: Group, handles, caps, coeffs, degree_log, c, rate_bits, cap_height):
         self.group, self._hs, self.caps, self.coeffs = group, handles, caps, coeffs
-        self.degree_log, self.num_columns, self.rate_bits, self.cap_height = degree_log, c, rate_bits, cap_height
+        self._degree_log, self.num_columns, self.rate_bits, self.cap_height = degree_log, c, rate_bits, cap_height
         self.cap = caps[0]
+
+    @property
+    def _h(self):
+        """The first local rank's shard: every rank holds ALL coefficients after the all-gather, so OpeningSet::new and
+        the FRI polynomial (gl_commit_eval, gl_fri_final_poly) run on any one rank; only leaves / digests are sharded."""
+        return self._hs[0]
+
+    @property
+    def degree_log(self) -> int:
+        return self._degree_log
+
+    def eval_at(self, point) -> np.ndarray:
+        ctx = self.group.ctxs[0]
+        pt = (C.c_uint64 * 2)(int(point[0]) % P, int(point[1]) % P)
+        out = np.empty((self.num_columns, 2), dtype=np.uint64)
+        ctx.check(ctx._lib.gl_commit_eval(self._h, pt, out.ctypes.data, N.GL_HOST))
+        return out
 
     def open(self, leaf_indices: Sequence[int]):
         """(rows [k][c], paths [k][L][4]) for GLOBAL leaf indices, whoever owns them (gl_group_commit_open); the same
@@ -769,7 +786,7 @@ class ShardedPolynomialBatch:
         g = self.group
         idx = _h(np.asarray(leaf_indices))
         k = idx.shape[0]
-        L = self.degree_log + self.rate_bits - self.cap_height
+        L = self._degree_log + self.rate_bits - self.cap_height
         rows = [np.empty((k, self.num_columns), dtype=np.uint64) for _ in range(g.nlocal)]
         paths = [np.empty((k, L, 4), dtype=np.uint64) for _ in range(g.nlocal)]
         hs = (C.c_void_p * g.nlocal)(*[h.value for h in self._hs])

@@ -116,3 +116,56 @@ def test_full_size_commit_over_two_ranks_matches_golden(glb, oracle):
     assert [hx(x) for x in rows] == case["leaf_rows"] and [hx(x) for x in paths] == case["leaf_paths"]
     b.free()
     g.close()
+
+
+def test_sharded_prove_openings_equals_single_gpu_and_verifies(glb, oracle, rng_seed=11):
+    """E2: prove_openings over oracles sharded on 2 GPUs -- the query openings come from the owning rank over
+    NCCL -- gives the same proof as the oracle's prover and passes the oracle's restatement of the upstream verifier."""
+    import importlib
+
+    from oracle import fri_oracle as fo
+
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    rng = np.random.default_rng(rng_seed)
+    degree_bits, cols = 12, (84, 135, 20, 16)
+    rate_bits, cap_height, pow_bits, rounds = 3, 4, 10, 28
+    n = 1 << degree_bits
+    g = glb.Group.local([0, 1])
+    sharded, polys, trees = [], [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=700 + k)
+        sharded.append(g.commit(v, rate_bits, cap_height))
+        res = oracle.commit_from_values(v, rate_bits, cap_height)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], cap_height))
+        assert np.array_equal(sharded[-1].cap, trees[-1].cap)
+    zeta = tuple(int(x) for x in rng.integers(0, 0xFFFFFFFF00000001, 2, dtype=np.uint64))
+    gen = oracle.lib().glo_primitive_root_of_unity(degree_bits)
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]), (fo.ext_scalar(zeta, gen), [(2, 0), (2, 1)])]
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+    ch, och, vch = fri.Challenger(g.ctxs[0]), fo.Challenger(), fo.Challenger()
+    for t in trees:
+        for c_ in (ch, och, vch):
+            c_.observe_cap(t.cap)
+    got = fri.prove_openings(sharded, instance, ch, params)
+    want = fo.prove_openings(polys, trees, instance, och, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    assert got["pow_witness"] == want["pow_witness"] and np.array_equal(got["final_poly"], want["final_poly"])
+    owners = set()
+    for ra, rb in zip(got["query_round_proofs"], want["query_round_proofs"]):
+        assert ra["x_index"] == rb["x_index"]
+        owners.add(ra["x_index"] >= (n << rate_bits) // 2)
+        for (rowa, patha), (rowb, pathb) in zip(ra["initial_trees_proof"], rb["initial_trees_proof"]):
+            assert np.array_equal(rowa, rowb) and np.array_equal(patha, pathb)
+        for sa, sb in zip(ra["steps"], rb["steps"]):
+            assert np.array_equal(sa["evals"], sb["evals"]) and np.array_equal(sa["merkle_proof"], sb["merkle_proof"])
+    assert owners == {False, True}            # the 28 queries hit leaves of both ranks
+    openings = fo.opening_set(polys, instance)
+    assert [[tuple(int(x) for x in v) for v in b] for b in fri.opening_set(sharded, instance)] == \
+           [[tuple(int(x) for x in v) for v in b] for b in openings]
+    assert fo.verify_openings(got, openings, [t.cap for t in trees], instance, vch, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    for b in sharded:
+        b.free()
+    g.close()
