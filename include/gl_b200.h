@@ -309,6 +309,48 @@ int gl_fri_final_poly(gl_ctx *ctx, gl_commit *const *oracles, uint32_t num_oracl
                       uint32_t num_batches, const gl_fri_poly *polys, const uint64_t alpha[2], uint32_t rate_bits,
                       uint64_t *lde_coeffs_out, uint64_t *lde_values_out, int space);
 
+/* Fork-version switches, all in one place (SURVEY 8c "residual risk": the plonky2 fork is not vendored, so every choice
+ * that differs between upstream revisions is isolated here and can be flipped when the fork's source is at hand):
+ *   GL_COMPAT_FRI_FINAL_POLY_TIMES_X  prove_openings multiplies the FRI polynomial by X (`final_poly.coeffs.insert(0, ZERO)`,
+ *       upstream PR #436) and the verifier's fri_combine_initial returns `sum * subgroup_x`.  Upstream later removed this
+ *       ("pad back to power of two" instead); the default (flag clear) is the later form.
+ * Other revision-dependent points and where they live: proof-of-work = duplex-state form, output lane 7
+ * (gl_pow_grind; csrc k_pow_grind takes the output lane as a parameter); hash_pad pads to SPONGE_WIDTH = 12 (forced by the
+ * reference itself, src/smt/gadgets/common.rs:87-101); Challenger = overwrite-mode duplex, outputs popped from the back. */
+#define GL_COMPAT_FRI_FINAL_POLY_TIMES_X 1u
+int gl_ctx_set_compat(gl_ctx *ctx, uint32_t flags);
+
+/* ---- N1 in one call: PolynomialBatch::prove_openings + fri_proof (plonky2::fri::oracle, fri::prover) ----------------------
+ * The Fiat-Shamir sponge (plonky2::iop::challenger::Challenger, overwrite-mode duplex) as plain data: */
+typedef struct {
+    uint64_t sponge_state[12];
+    uint64_t input_buffer[8];
+    uint64_t output_buffer[8];   /* popped from the back: output_buffer[output_len - 1] is the next challenge */
+    uint32_t input_len, output_len;
+} gl_challenger;
+#define GL_FRI_MAX_LAYERS 16
+typedef struct {
+    uint32_t rate_bits, cap_height, proof_of_work_bits, num_query_rounds;   /* FriConfig */
+    uint32_t num_reduction_layers;
+    uint32_t reduction_arity_bits[GL_FRI_MAX_LAYERS];                        /* FriParams.reduction_arity_bits */
+    uint32_t flags;                                                          /* GL_COMPAT_FRI_* (or'ed with the ctx's) */
+} gl_fri_params;
+/* Size of the proof in u64 words for oracles of oracle_columns[i] polynomials of degree 2^degree_bits. */
+int gl_fri_proof_words(const gl_fri_params *prm, const uint32_t *oracle_columns, uint32_t num_oracles, uint32_t degree_bits,
+                       uint64_t *words_out);
+/* `challenger`: in = the transcript state when prove_openings is entered (openings already observed), out = its state after
+ * the proof (what the caller's Challenger continues from).  The FRI polynomial, every layer tree, the sponge, the
+ * proof-of-work search (smallest witness) and the query openings stay on the device; ONE copy brings the proof back:
+ *   for each reduction layer: cap [2^cap_height][4]
+ *   final_poly [len][2]; pow_witness
+ *   for each query round: x_index; for each oracle: leaf row [c], Merkle path [lg N - cap_height][4];
+ *                         for each layer: evals [2^arity][2], Merkle path
+ * (FriProof { commit_phase_merkle_caps, final_poly, pow_witness, query_round_proofs } field by field, in declaration
+ * order of use).  proof_out: host buffer of proof_cap_words words; *proof_words_out = words needed / written. */
+int gl_fri_prove(gl_ctx *ctx, gl_commit *const *oracles, uint32_t num_oracles, const gl_fri_batch *batches, uint32_t num_batches,
+                 const gl_fri_poly *polys, const gl_fri_params *prm, gl_challenger *challenger, uint64_t *proof_out,
+                 uint64_t proof_cap_words, uint64_t *proof_words_out);
+
 /* ---- N3: compute_quotient_polys (plonky2::plonk::prover, vanishing_poly::eval_vanishing_poly_base_batch) ------------------
  * The last prover stage that reads every LDE row: with it the three prove-time oracles never leave HBM.
  * Reached from every data.prove(pw); the gate evaluators cover upstream's NoopGate / ConstantGate / PublicInputGate and

@@ -242,8 +242,10 @@ def ext_pow(a, e):
     return r
 
 
-def final_poly_of_openings(oracle_polys, batches, alpha):
-    """final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),  F_i = sum_j alpha^j f_ij."""
+def final_poly_of_openings(oracle_polys, batches, alpha, times_x=False):
+    """final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),  F_i = sum_j alpha^j f_ij.
+    times_x: the older upstream form (PR #436) multiplies the result by X (`final_poly.coeffs.insert(0, ZERO)`; the quotient
+    is then NOT padded with a zero, so the length is the same); the later form, the default, does not."""
     n = oracle_polys[0].shape[1]
     final = np.zeros((n, 2), dtype=np.uint64)
     for point, polys in batches:
@@ -251,13 +253,16 @@ def final_poly_of_openings(oracle_polys, batches, alpha):
         quot = o.divide_by_linear(comp, point)           # remainder dropped, padded back with a zero
         shift = ext_pow(tuple(int(x) for x in alpha), len(polys))   # ReducingFactor::shift_poly
         final = o.ext_poly_scale_add(final, shift, quot)
+    if times_x:
+        assert not final[-1].any()
+        final = np.concatenate([np.zeros((1, 2), dtype=np.uint64), final[:-1]])
     return final
 
 
 def prove_openings(oracle_polys, oracle_trees, batches, challenger, degree_bits, rate_bits=3, cap_height=4, pow_bits=16,
-                   num_query_rounds=28):
+                   num_query_rounds=28, times_x=False):
     alpha = challenger.get_extension_challenge()
-    final = final_poly_of_openings(oracle_polys, batches, alpha)
+    final = final_poly_of_openings(oracle_polys, batches, alpha, times_x)
     n = final.shape[0]
     lde_coeffs = np.zeros((n << rate_bits, 2), dtype=np.uint64)
     lde_coeffs[:n] = final
@@ -271,8 +276,9 @@ def opening_set(oracle_polys, batches):
     return [[o.eval_base_poly_at_ext(oracle_polys[oi][pi], point) for oi, pi in polys] for point, polys in batches]
 
 
-def fri_combine_initial(batches, openings, initial_rows, alpha, subgroup_x):
-    """fri::verifier::fri_combine_initial: sum_i alpha^(k_i) (reduce(evals_i) - reduce(openings_i)) / (x - z_i)."""
+def fri_combine_initial(batches, openings, initial_rows, alpha, subgroup_x, times_x=False):
+    """fri::verifier::fri_combine_initial: sum_i alpha^(k_i) (reduce(evals_i) - reduce(openings_i)) / (x - z_i);
+    times_x: the older upstream form returns sum * subgroup_x (the prover multiplied final_poly by X)."""
     alpha = tuple(int(x) for x in alpha)
     total = (0, 0)
     for (point, polys), opened in zip(batches, openings):
@@ -284,17 +290,17 @@ def fri_combine_initial(batches, openings, initial_rows, alpha, subgroup_x):
         den = ext_sub((subgroup_x, 0), (int(point[0]), int(point[1])))
         total = ext_mul(total, ext_pow(alpha, len(polys)))
         total = ext_add(total, ext_mul(num, ext_inv(den)))
-    return total
+    return ext_scalar(total, subgroup_x) if times_x else total
 
 
 def verify_openings(proof, openings, oracle_caps, batches, challenger, degree_bits, rate_bits=3, cap_height=4, pow_bits=16,
-                    num_query_rounds=28):
+                    num_query_rounds=28, times_x=False):
     """verify_fri_proof with the real fri_combine_initial: ties the opened rows of the initial trees and the
     claimed openings to the first FRI layer."""
     alpha = challenger.get_extension_challenge()
 
     def first_layer_eval(x_index, rows, subgroup_x):
-        return fri_combine_initial(batches, openings, rows, alpha, subgroup_x)
+        return fri_combine_initial(batches, openings, rows, alpha, subgroup_x, times_x)
 
     return verify_fri_proof(proof, oracle_caps, cap_height, challenger, degree_bits, first_layer_eval, rate_bits, cap_height,
                             pow_bits, num_query_rounds)

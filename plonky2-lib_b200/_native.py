@@ -55,6 +55,23 @@ class Circuit(C.Structure):
                 ("num_challenges", u32), ("quotient_degree_factor", u32), ("num_gates", u32)]
 
 
+class Challenger(C.Structure):
+    """gl_challenger: plonky2::iop::challenger::Challenger as plain data."""
+
+    _fields_ = [("sponge_state", u64 * 12), ("input_buffer", u64 * 8), ("output_buffer", u64 * 8), ("input_len", u32), ("output_len", u32)]
+
+
+GL_FRI_MAX_LAYERS = 16
+GL_COMPAT_FRI_FINAL_POLY_TIMES_X = 1
+
+
+class FriParams(C.Structure):
+    """gl_fri_params: FriConfig + FriParams.reduction_arity_bits + compat flags."""
+
+    _fields_ = [("rate_bits", u32), ("cap_height", u32), ("proof_of_work_bits", u32), ("num_query_rounds", u32),
+                ("num_reduction_layers", u32), ("reduction_arity_bits", u32 * GL_FRI_MAX_LAYERS), ("flags", u32)]
+
+
 class FriBatch(C.Structure):
     _fields_ = [("point", u64 * 2), ("first_poly", u32), ("num_polys", u32)]
 
@@ -115,6 +132,9 @@ SIGNATURES = {
     "gl_fri_fold": (cint, [vp, vp, u64, u32, u64p, u64, vp, vp, cint]),
     "gl_fri_final_poly": (cint, [vp, vp, u32, vp, u32, vp, u64p, u32, vp, vp, cint]),
     "gl_pow_grind": (cint, [vp, u64p, u32, u32, u64p]),
+    "gl_ctx_set_compat": (cint, [vp, u32]),
+    "gl_fri_proof_words": (cint, [vp, vp, u32, u32, C.POINTER(u64)]),
+    "gl_fri_prove": (cint, [vp, vp, u32, vp, u32, vp, vp, vp, vp, u64, C.POINTER(u64)]),
     "gl_quotient_polys": (cint, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, cint]),
     "gl_group_unique_id": (cint, [vp]),
     "gl_group_create": (cint, [vp, u32, u32, u32, vp, C.POINTER(vp)]),

@@ -102,11 +102,18 @@ __global__ void k_fri_div_small(const u64* __restrict__ comp, u64 n, u64 z0, u64
     }
 }
 
+// times_x: the polynomial is multiplied by X first (coefficients move up one place; the top one is the zero
+// prove_openings padded the quotient with) -- the form forks before upstream's "remove the multiplication by X" carry
 __global__ void __launch_bounds__(256)
-k_ext_to_padded_cols(const u64* __restrict__ ext, u64 n, u64 N, u64* __restrict__ cols, u64* __restrict__ padded) {
+k_ext_to_padded_cols(const u64* __restrict__ ext, u64 n, u64 N, u64* __restrict__ cols, u64* __restrict__ padded, int times_x) {
     u64 i = blockIdx.x * (u64)256 + threadIdx.x;
     if (i >= N) return;
-    u64 a = i < n ? ext[2 * i] : 0, b = i < n ? ext[2 * i + 1] : 0;
+    u64 a = 0, b = 0;
+    if (times_x) {
+        if (i >= 1 && i < n) { a = ext[2 * (i - 1)]; b = ext[2 * (i - 1) + 1]; }
+    } else if (i < n) {
+        a = ext[2 * i]; b = ext[2 * i + 1];
+    }
     cols[i] = a;
     cols[N + i] = b;
     padded[2 * i] = a;
@@ -204,7 +211,7 @@ void launch_fri_divide_accumulate(const u64* comp_ext, u64 n, const u64 z[2], co
     k_fri_div_final<<<blocks, 128, 0, st>>>(comp_ext, nseg, z[0], z[1], seg_b, shift[0], shift[1], final_ext);
     g_gl_launches += 3;
 }
-void launch_ext_to_padded_cols(const u64* ext, u64 n, u64 N, u64* cols, u64* padded_ext, cudaStream_t st) {
-    k_ext_to_padded_cols<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ext, n, N, cols, padded_ext);
+void launch_ext_to_padded_cols(const u64* ext, u64 n, u64 N, u64* cols, u64* padded_ext, int times_x, cudaStream_t st) {
+    k_ext_to_padded_cols<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(ext, n, N, cols, padded_ext, times_x);
     ++g_gl_launches;
 }

@@ -18,7 +18,7 @@ void launch_fri_divide_accumulate(const uint64_t* comp_ext, uint64_t n, const ui
                                   cudaStream_t st);
 // [n][2] extension coefficients -> two zero-padded base columns cols[0][0..N), cols[1][0..N)
 void launch_ext_to_padded_cols(const uint64_t* ext, uint64_t n, uint64_t N, uint64_t* cols, uint64_t* padded_ext,
-                               cudaStream_t st);
+                               int times_x, cudaStream_t st);
 // out[j] = polynomial j of coeffs [c][n] evaluated at the extension point z (OpeningSet::new); partial: scratch
 // [c][ceil(n / 4096)][2]; z256 = z^256, zc = z^4096
 #define FRI_EVAL_CHUNK 4096

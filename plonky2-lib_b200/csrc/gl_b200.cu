@@ -55,6 +55,7 @@ struct gl_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint32_t shard_index = 0, shard_count = 1;
+    uint32_t compat = 0;   // GL_COMPAT_*: fork-version switches (gl_ctx_set_compat)
     std::map<std::tuple<int, uint64_t, uint64_t, uint64_t>, u64*> tables;
     DevBuf scratch[6];
     std::mutex mu;
@@ -1747,10 +1748,11 @@ extern "C" int gl_fri_fold(gl_ctx* ctx, const uint64_t* coeffs_ext, uint64_t len
     return finish(ctx);
 }
 
-extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num_oracles, const gl_fri_batch* batches,
-                                 uint32_t num_batches, const gl_fri_poly* polys, const uint64_t alpha[2],
-                                 uint32_t rate_bits, uint64_t* lde_coeffs_out, uint64_t* lde_values_out, int space) {
-    if (!ctx) return GL_E_ARG;
+// prove_openings up to the FRI polynomial, everything left on the device: *d_coeffs / *d_values point into scratch
+// slot 5 / 4 ([N][2] interleaved, natural order) and stay valid until the next call that uses those slots.
+static int fri_final_poly_device(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num_oracles, const gl_fri_batch* batches,
+                                 uint32_t num_batches, const gl_fri_poly* polys, const uint64_t alpha[2], uint32_t rate_bits,
+                                 bool times_x, bool want_values, u64** d_coeffs, u64** d_values) {
     if (!oracles || !num_oracles || !batches || !num_batches || !polys || !alpha)
         return fail(ctx, GL_E_ARG, "gl_fri_final_poly: NULL or empty argument");
     const uint32_t log_n = oracles[0]->log_n;
@@ -1772,15 +1774,14 @@ extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_
     for (uint32_t j = 0; j < total; j++)
         if (polys[j].oracle_index >= num_oracles || polys[j].polynomial_index >= oracles[polys[j].oracle_index]->c)
             return fail(ctx, GL_E_ARG, "gl_fri_final_poly: polynomial index out of range");
-    Guard g(ctx);
     // scratch: 0 = pointer + power tables, 1 = transform scratch (transform_natural), 2 = composition poly,
-    // 3 = final poly, 4 = padded columns, 5 = segment carries + interleaved output
+    // 3 = final poly, 4 = padded columns then interleaved values, 5 = segment carries + interleaved coefficients
     void *d_tab, *d_comp, *d_final, *d_cols, *d_misc;
     const size_t tab_bytes = (size_t)kmax * (sizeof(u64*) + 16);
     TRY(scratch_get(ctx, 0, tab_bytes, &d_tab));
     TRY(scratch_get(ctx, 2, n * 16, &d_comp));
     TRY(scratch_get(ctx, 3, n * 16, &d_final));
-    TRY(scratch_get(ctx, 4, N * 16, &d_cols));
+    TRY(scratch_get(ctx, 4, N * 32, &d_cols));
     const size_t nseg = n / FRI_DIV_SEG + 1;
     TRY(scratch_get(ctx, 5, nseg * 32 + N * 16, &d_misc));
     u64* seg_h = (u64*)d_misc;
@@ -1809,16 +1810,255 @@ extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_
         launch_fri_divide_accumulate((const u64*)d_comp, n, zz, zt, shv, seg_h, seg_b, (u64*)d_final, ctx->stream);
     }
     // final_poly.lde(rate_bits), then coset_fft(7) over the extension = two base transforms
-    launch_ext_to_padded_cols((const u64*)d_final, n, N, (u64*)d_cols, d_ext, ctx->stream);
-    TRY(copy_out(ctx, lde_coeffs_out, d_ext, N * 16, space));
-    if (lde_values_out) {
+    launch_ext_to_padded_cols((const u64*)d_final, n, N, (u64*)d_cols, d_ext, times_x ? 1 : 0, ctx->stream);
+    *d_coeffs = d_ext;
+    *d_values = nullptr;
+    if (want_values) {
         const u64* pre;
         TRY(pow_table(ctx, 7, &pre));
         TRY(transform_natural(ctx, (u64*)d_cols, log_n + rate_bits, 2, false, pre, nullptr));
-        launch_interleave2((const u64*)d_cols, N, N, d_ext, ctx->stream);
-        TRY(copy_out(ctx, lde_values_out, d_ext, N * 16, space));
+        u64* d_vals = (u64*)d_cols + 2 * N;
+        launch_interleave2((const u64*)d_cols, N, N, d_vals, ctx->stream);
+        *d_values = d_vals;
     }
+    return GL_OK;
+}
+
+extern "C" int gl_fri_final_poly(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num_oracles, const gl_fri_batch* batches,
+                                 uint32_t num_batches, const gl_fri_poly* polys, const uint64_t alpha[2],
+                                 uint32_t rate_bits, uint64_t* lde_coeffs_out, uint64_t* lde_values_out, int space) {
+    if (!ctx) return GL_E_ARG;
+    Guard g(ctx);
+    u64 *dc, *dv;
+    TRY(fri_final_poly_device(ctx, oracles, num_oracles, batches, num_batches, polys, alpha, rate_bits,
+                              (ctx->compat & GL_COMPAT_FRI_FINAL_POLY_TIMES_X) != 0, lde_values_out != nullptr, &dc, &dv));
+    const u64 N = ((u64)1 << oracles[0]->log_n) << rate_bits;
+    TRY(copy_out(ctx, lde_coeffs_out, dc, N * 16, space));
+    if (lde_values_out) TRY(copy_out(ctx, lde_values_out, dv, N * 16, space));
     return finish(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PolynomialBatch::prove_openings + fri_proof in ONE call (plonky2::fri::oracle / fri::prover): the FRI polynomial, the
+// layer trees, the Fiat-Shamir sponge, the proof-of-work search and the query openings all stay on the device; the host
+// synchronises three times (alpha, the PoW witness, the finished proof) instead of ~70 dependent round trips.
+// ------------------------------------------------------------------------------------------------
+extern "C" int gl_fri_proof_words(const gl_fri_params* prm, const uint32_t* oracle_columns, uint32_t num_oracles, uint32_t degree_bits,
+                                  uint64_t* words_out) {
+    if (!prm || !oracle_columns || !words_out || prm->num_reduction_layers > GL_FRI_MAX_LAYERS) return GL_E_ARG;
+    const unsigned lgN = degree_bits + prm->rate_bits, h = prm->cap_height;
+    if (h > lgN) return GL_E_ARG;
+    uint64_t per_query = 1, words = 0;
+    for (uint32_t i = 0; i < num_oracles; i++) per_query += oracle_columns[i] + 4ull * (lgN - h);
+    unsigned lg = lgN;
+    for (uint32_t l = 0; l < prm->num_reduction_layers; l++) {
+        const unsigned ab = prm->reduction_arity_bits[l];
+        if (ab == 0 || ab > 8 || ab > lg || h > lg - ab) return GL_E_ARG;
+        words += 4ull << h;
+        per_query += (2ull << ab) + 4ull * (lg - ab - h);
+        lg -= ab;
+    }
+    if (lg < prm->rate_bits) return GL_E_ARG;
+    words += 2ull << (lg - prm->rate_bits);   // final_poly
+    words += 1;                               // pow_witness
+    words += per_query * prm->num_query_rounds;
+    *words_out = words;
+    return GL_OK;
+}
+
+extern "C" int gl_fri_prove(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num_oracles, const gl_fri_batch* batches,
+                            uint32_t num_batches, const gl_fri_poly* polys, const gl_fri_params* prm, gl_challenger* challenger,
+                            uint64_t* proof_out, uint64_t proof_cap_words, uint64_t* proof_words_out) {
+    if (!ctx) return GL_E_ARG;
+    if (!oracles || !num_oracles || !prm || !challenger || !proof_words_out)
+        return fail(ctx, GL_E_ARG, "gl_fri_prove: NULL argument");
+    if (challenger->input_len > 8 || challenger->output_len > 8) return fail(ctx, GL_E_ARG, "gl_fri_prove: bad challenger state");
+    if (prm->num_reduction_layers > GL_FRI_MAX_LAYERS || prm->num_query_rounds == 0 || prm->num_query_rounds > 1024 ||
+        prm->proof_of_work_bits > 48)
+        return fail(ctx, GL_E_ARG, "gl_fri_prove: unsupported FRI parameters");
+    for (uint32_t i = 0; i < num_oracles; i++)
+        if (!oracles[i] || oracles[i]->ctx != ctx || !oracles[i]->coeffs || !oracles[i]->finished || oracles[i]->shard_count != 1 ||
+            oracles[i]->rate_bits != prm->rate_bits || oracles[i]->cap_height != prm->cap_height || oracles[i]->log_n != oracles[0]->log_n)
+            return fail(ctx, GL_E_STATE, "gl_fri_prove: every oracle must be a finished, unsharded polynomial commit of this ctx with the FRI config's rate_bits / cap_height");
+    const uint32_t degree_bits = oracles[0]->log_n, rate_bits = prm->rate_bits, h = prm->cap_height, rounds = prm->num_query_rounds;
+    const unsigned lgN = degree_bits + rate_bits;
+    std::vector<uint32_t> ocols(num_oracles);
+    for (uint32_t i = 0; i < num_oracles; i++) ocols[i] = oracles[i]->c;
+    uint64_t words = 0;
+    if (gl_fri_proof_words(prm, ocols.data(), num_oracles, degree_bits, &words) != GL_OK)
+        return fail(ctx, GL_E_ARG, "gl_fri_prove: reduction_arity_bits do not fit the degree / cap_height");
+    *proof_words_out = words;
+    if (!proof_out || proof_cap_words < words) return fail(ctx, GL_E_ARG, "gl_fri_prove: proof buffer too small (see *proof_words_out)");
+    Guard g(ctx);
+    const u64 N = (u64)1 << lgN;
+    const uint32_t layers = prm->num_reduction_layers;
+    // device state: challenger | alpha/beta scratch [2] | query challenges [rounds] | pow state [12] | pow best | response |
+    // cumulative arity bits | query indices [(layers + 1)][rounds]
+    u64* d_state;
+    const size_t state_words = 32 + 2 + rounds + 12 + 2 + GL_FRI_MAX_LAYERS + (size_t)(layers + 1) * rounds;
+    TRY(dev_alloc(ctx, state_words * 8, &d_state));
+    u64* d_proof = nullptr;
+    std::vector<gl_commit*> trees;
+    auto cleanup = [&](int rc) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto* t : trees) commit_release(t);
+        dev_release(ctx, d_state, state_words * 8);
+        if (d_proof) dev_release(ctx, d_proof, words * 8);
+        return rc;
+    };
+#define FTRY(expr)                         \
+    do {                                   \
+        int rc__ = (expr);                 \
+        if (rc__) return cleanup(rc__);    \
+    } while (0)
+#define FCK(call)                                                            \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) return cleanup(cuda_fail(ctx, e__, #call));  \
+    } while (0)
+    FTRY(dev_alloc(ctx, words * 8, &d_proof));
+    static_assert(sizeof(gl_challenger) == 29 * 8, "gl_challenger layout");
+    gl_challenger* d_ch = (gl_challenger*)d_state;
+    u64* d_ab = d_state + 32;
+    u64* d_qch = d_ab + 2;
+    u64* d_pow_state = d_qch + rounds;
+    unsigned long long* d_best = (unsigned long long*)(d_pow_state + 12);
+    u64* d_resp = d_pow_state + 13;
+    uint32_t* d_cum = (uint32_t*)(d_pow_state + 14);
+    u64* d_idx = d_pow_state + 14 + GL_FRI_MAX_LAYERS;
+    FCK(cudaMemcpyAsync(d_ch, challenger, sizeof(gl_challenger), cudaMemcpyHostToDevice, ctx->stream));
+    // ---- alpha = challenger.get_extension_challenge(): the only challenge the host needs (power tables of the reduction)
+    u64 alpha[2];
+    launch_challenger_step(d_ch, nullptr, 0, d_ab, 2, nullptr, ctx->stream);
+    FCK(cudaMemcpyAsync(alpha, d_ab, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    FCK(cudaStreamSynchronize(ctx->stream));
+    u64 *d_coeffs, *d_values;
+    FTRY(fri_final_poly_device(ctx, oracles, num_oracles, batches, num_batches, polys, alpha, rate_bits,
+                               ((prm->flags | ctx->compat) & GL_COMPAT_FRI_FINAL_POLY_TIMES_X) != 0, true, &d_coeffs, &d_values));
+    // ---- fri_committed_trees: per layer tree -> observe cap -> beta -> fold -> coset_fft, no host involvement
+    u64 len = N;
+    unsigned lg = lgN;
+    u64 off = 0;                 // write position in the proof buffer
+    u64 shift = 7;
+    u64 *cur_coeffs = d_coeffs, *cur_values = d_values;
+    u64 *owned_a = nullptr, *owned_b = nullptr;   // folded buffers of the previous layer
+    size_t owned_bytes = 0;
+    uint32_t cum[GL_FRI_MAX_LAYERS] = {}, acc_bits = 0;
+    for (uint32_t l = 0; l < layers; l++) {
+        const unsigned ab = prm->reduction_arity_bits[l];
+        gl_commit* t = new (std::nothrow) gl_commit();
+        if (!t) return cleanup(fail(ctx, GL_E_OOM, "host allocation failed"));
+        trees.push_back(t);
+        t->ctx = ctx; t->log_n = lg - ab; t->c = 2u << ab; t->rate_bits = 0; t->cap_height = h;
+        t->n_local = len >> ab; t->cap_local_bits = h;
+        t->num_digests = 2 * (t->n_local - ((u64)1 << h));
+        t->lde_bytes = len * 16; t->digests_bytes = t->num_digests * 32; t->cap_bytes = (size_t)32 << h;
+        FTRY(dev_alloc(ctx, t->lde_bytes, &t->lde));
+        FTRY(dev_alloc(ctx, t->digests_bytes, &t->digests));
+        FTRY(dev_alloc(ctx, t->cap_bytes, &t->cap));
+        launch_fri_leaves(cur_values, lg, ab, t->lde, ctx->stream);
+        launch_merkle_cols(t->lde, t->n_local, t->c, t->log_n, h, t->digests, t->cap, ctx->stream);
+        FCK(cudaMemcpyAsync(d_proof + off, t->cap, t->cap_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        off += 4ull << h;
+        launch_challenger_step(d_ch, t->cap, 4u << h, d_ab, 2, nullptr, ctx->stream);   // observe_cap, beta
+        shift = glh::pow(shift, (u64)1 << ab);
+        const u64 out_len = len >> ab;
+        u64 *n_coeffs, *n_values;
+        FTRY(dev_alloc(ctx, out_len * 16, &n_coeffs));
+        FTRY(dev_alloc(ctx, out_len * 16, &n_values));
+        void* dcols;
+        FTRY(scratch_get(ctx, 2, out_len * 16, &dcols));
+        launch_fri_fold_dev(cur_coeffs, out_len, ab, d_ab, (u64*)dcols, out_len, ctx->stream);
+        launch_interleave2((const u64*)dcols, out_len, out_len, n_coeffs, ctx->stream);
+        const u64* pre;
+        FTRY(pow_table(ctx, shift, &pre));
+        FTRY(transform_natural(ctx, (u64*)dcols, lg - ab, 2, false, pre, nullptr));
+        launch_interleave2((const u64*)dcols, out_len, out_len, n_values, ctx->stream);
+        if (owned_a) { dev_release(ctx, owned_a, owned_bytes); dev_release(ctx, owned_b, owned_bytes); }   // stream-ordered reuse
+        owned_a = n_coeffs; owned_b = n_values; owned_bytes = out_len * 16;
+        cur_coeffs = n_coeffs; cur_values = n_values;
+        len = out_len; lg -= ab;
+        acc_bits += ab;
+        cum[l] = acc_bits;
+    }
+    // final_poly: "the coefficients being removed here are always zero"
+    const u64 final_len = len >> rate_bits;
+    FCK(cudaMemcpyAsync(d_proof + off, cur_coeffs, final_len * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+    launch_challenger_step(d_ch, d_proof + off, (uint32_t)(2 * final_len), nullptr, 0, d_pow_state, ctx->stream);
+    off += 2 * final_len;
+    if (owned_a) { dev_release(ctx, owned_a, owned_bytes); dev_release(ctx, owned_b, owned_bytes); }
+    // ---- fri_proof_of_work: smallest witness; the input position is the number of pending inputs, which the host can count
+    uint32_t pending = challenger->input_len;   // replay the buffer lengths of the transcript so far (values stay on the device)
+    {
+        auto observe = [&](uint64_t cnt) { pending = (uint32_t)((pending + cnt) % 8); };
+        auto squeeze = [&]() { pending = 0; };
+        squeeze();                                    // alpha
+        for (uint32_t l = 0; l < layers; l++) { observe(4ull << h); squeeze(); }
+        observe(2 * final_len);
+    }
+    const unsigned min_lz = prm->proof_of_work_bits;   // + (64 - F::order().bits()) = + 0
+    const unsigned long long none = ~0ULL;
+    FCK(cudaMemcpyAsync(d_best, &none, 8, cudaMemcpyHostToDevice, ctx->stream));
+    u64 witness = 0;
+    {
+        unsigned lg_chunk = min_lz + 2 < 14 ? 14 : (min_lz + 2 > 24 ? 24 : min_lz + 2);
+        u64 chunk = (u64)1 << lg_chunk;
+        bool found = false;
+        for (u64 start = 0; start < GL_P && !found; start += chunk, chunk = chunk < ((u64)1 << 26) ? chunk * 2 : chunk) {
+            u64 count = GL_P - start < chunk ? GL_P - start : chunk;
+            launch_pow_grind(d_pow_state, pending, 7, min_lz, start, count, d_best, ctx->stream);
+            unsigned long long best;
+            FCK(cudaMemcpyAsync(&best, d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FCK(cudaStreamSynchronize(ctx->stream));
+            if (best != none) { witness = best; found = true; }
+            else if (start >= ((u64)1 << 40)) break;
+        }
+        if (!found) return cleanup(fail(ctx, GL_E_STATE, "fri_proof_of_work: no witness found"));
+    }
+    // observe the witness, recompute the response with the normal Challenger code (as upstream does), then the query indices
+    launch_challenger_step(d_ch, (const u64*)d_best, 1, d_resp, 1, nullptr, ctx->stream);
+    FCK(cudaMemcpyAsync(d_proof + off, d_best, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    off += 1;
+    launch_challenger_step(d_ch, nullptr, 0, d_qch, rounds, nullptr, ctx->stream);
+    FCK(cudaMemcpyAsync(d_cum, cum, sizeof cum, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t query_stride = 1;
+    for (uint32_t i = 0; i < num_oracles; i++) query_stride += oracles[i]->c + 4ull * (lgN - h);
+    for (auto* t : trees) query_stride += t->c + 4ull * (t->log_n - h);
+    u64* d_queries = d_proof + off;
+    launch_fri_query_indices(d_qch, rounds, lgN, d_cum, layers, d_idx, d_queries, query_stride, ctx->stream);
+    u64 qoff = 1;
+    for (uint32_t i = 0; i < num_oracles; i++) {
+        const gl_commit* o = oracles[i];
+        launch_gather_proof(o->lde, o->n_local, o->c, o->digests, lgN - h, d_idx, rounds, d_queries + qoff, query_stride, ctx->stream);
+        qoff += o->c + 4ull * (lgN - h);
+    }
+    for (uint32_t l = 0; l < layers; l++) {
+        const gl_commit* t = trees[l];
+        launch_gather_proof(t->lde, t->n_local, t->c, t->digests, t->log_n - h, d_idx + (size_t)(l + 1) * rounds, rounds,
+                            d_queries + qoff, query_stride, ctx->stream);
+        qoff += t->c + 4ull * (t->log_n - h);
+    }
+    off += query_stride * rounds;
+    if (off != words) return cleanup(fail(ctx, GL_E_STATE, "gl_fri_prove: internal size mismatch"));
+    u64 response = 0;
+    FCK(cudaMemcpyAsync(proof_out, d_proof, words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FCK(cudaMemcpyAsync(challenger, d_ch, sizeof(gl_challenger), cudaMemcpyDeviceToHost, ctx->stream));
+    FCK(cudaMemcpyAsync(&response, d_resp, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FCK(cudaStreamSynchronize(ctx->stream));
+    FCK(cudaGetLastError());
+    if (min_lz && (response >> (64 - min_lz)) != 0)
+        return cleanup(fail(ctx, GL_E_STATE, "fri_proof_of_work: response does not have the required leading zeros"));
+    (void)witness;
+    return cleanup(GL_OK);
+#undef FTRY
+#undef FCK
+}
+
+extern "C" int gl_ctx_set_compat(gl_ctx* ctx, uint32_t flags) {
+    if (!ctx) return GL_E_ARG;
+    if (flags & ~(uint32_t)GL_COMPAT_FRI_FINAL_POLY_TIMES_X) return fail(ctx, GL_E_ARG, "gl_ctx_set_compat: unknown flag");
+    ctx->compat = flags;
+    return GL_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -318,6 +318,45 @@ __global__ void __launch_bounds__(32) k_duplex_chain(u64* __restrict__ state, co
     for (int k = 0; k < 12; k++) state[k] = s[k];
 }
 
+// plonky2::iop::challenger::Challenger resident on the device (gl_fri_prove: the Fiat-Shamir transcript never leaves HBM).
+// One thread: observe `n_obs` elements read from device memory (observe_element semantics: outputs invalidated, duplexing
+// when the rate is full), then pop `n_squeeze` challenges (duplexing first when inputs are pending or no output is left).
+GL_D void challenger_duplex(gl_challenger* ch) {
+    u64 s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = ch->sponge_state[k];
+    for (u32 k = 0; k < ch->input_len; k++) s[k] = ch->input_buffer[k];
+    ch->input_len = 0;
+    poseidon_permute_call(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) ch->sponge_state[k] = gl_canon(s[k]);
+#pragma unroll
+    for (int k = 0; k < 8; k++) ch->output_buffer[k] = ch->sponge_state[k];
+    ch->output_len = 8;
+}
+__global__ void __launch_bounds__(32)
+k_challenger_step(gl_challenger* __restrict__ ch, const u64* __restrict__ observe, u32 n_obs, u64* __restrict__ squeeze, u32 n_squeeze,
+                  u64* __restrict__ pow_state) {
+    if (threadIdx.x) return;
+    for (u32 i = 0; i < n_obs; i++) {
+        ch->output_len = 0;
+        ch->input_buffer[ch->input_len++] = gl_canon(observe[i]);
+        if (ch->input_len == 8) challenger_duplex(ch);
+    }
+    for (u32 i = 0; i < n_squeeze; i++) {
+        if (ch->input_len || ch->output_len == 0) challenger_duplex(ch);
+        squeeze[i] = ch->output_buffer[--ch->output_len];
+    }
+    if (pow_state) {   // fri_proof_of_work: the duplex state the witness is absorbed into (input buffer applied)
+        for (int k = 0; k < 12; k++) pow_state[k] = (u32)k < ch->input_len ? ch->input_buffer[k] : ch->sponge_state[k];
+    }
+}
+void launch_challenger_step(gl_challenger* ch, const u64* observe, u32 n_obs, u64* squeeze, u32 n_squeeze, u64* pow_state,
+                            cudaStream_t st) {
+    k_challenger_step<<<1, 32, 0, st>>>(ch, observe, n_obs, squeeze, n_squeeze, pow_state);
+    ++g_gl_launches;
+}
+
 GL_D void two_to_one_call(const u64 l[4], const u64 r[4], u64 out[4]) {
     u64 s[12];
 #pragma unroll

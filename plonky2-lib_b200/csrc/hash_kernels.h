@@ -32,3 +32,7 @@ void launch_merkle_cols(const uint64_t* lde, uint64_t ld, uint32_t c, unsigned l
                         uint64_t* digests, uint64_t* cap, cudaStream_t st);
 void launch_merkle_rows(const uint64_t* leaves, uint32_t leaf_len, unsigned lg_leaves, unsigned cap_height,
                         uint64_t* digests, uint64_t* cap, cudaStream_t st);
+// Challenger on the device (one thread): observe n_obs elements from `observe`, then pop n_squeeze challenges into
+// `squeeze`; pow_state (or null) receives the 12-lane duplex state fri_proof_of_work grinds on.
+void launch_challenger_step(gl_challenger* ch, const uint64_t* observe, uint32_t n_obs, uint64_t* squeeze, uint32_t n_squeeze,
+                            uint64_t* pow_state, cudaStream_t st);

@@ -272,7 +272,7 @@ __global__ void k_gather_open(const u64* __restrict__ cols, u64 ld, u32 c, const
     if (g >= (u64)mine * per) return;
     u64 q = g / per, e = g % per;
     u64 leaf = loc[q];
-    u64* dst = out + slot[q] * per + e;
+    u64* dst = out + (slot ? slot[q] : q) * per + e;
     if (e < c) {
         *dst = cols[e * ld + leaf];
         return;
@@ -290,6 +290,35 @@ void launch_gather_open(const u64* cols, u64 ld, u32 c, const u64* digests, unsi
                         u32 mine, u64* out, u64 per, cudaStream_t st) {
     u64 total = (u64)mine * per;
     if (total) { k_gather_open<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cols, ld, c, digests, sub_bits, loc, slot, mine, out, per); ++g_gl_launches; }
+}
+
+// gl_fri_prove: (row, path) of leaf idx[q] for every query round q, written into the proof buffer at out[q * stride + e],
+// e < c + 4 * sub_bits (row first, then the siblings from the leaf level up)
+__global__ void k_gather_proof(const u64* __restrict__ cols, u64 ld, u32 c, const u64* __restrict__ digests, unsigned sub_bits,
+                               const u64* __restrict__ idx, u32 k, u64* __restrict__ out, u64 stride) {
+    const u64 width = c + 4 * (u64)sub_bits;
+    u64 g = blockIdx.x * (u64)blockDim.x + threadIdx.x;
+    if (g >= (u64)k * width) return;
+    u64 q = g / width, e = g % width;
+    u64 leaf = idx[q];
+    u64* dst = out + q * stride + e;
+    if (e < c) {
+        *dst = cols[e * ld + leaf];
+        return;
+    }
+    unsigned layer = (unsigned)((e - c) >> 2), w = (unsigned)((e - c) & 3);
+    u64 subtree = leaf >> sub_bits;
+    u64 pair = (leaf & (((u64)1 << sub_bits) - 1)) >> layer;
+    u64 parity = pair & 1;
+    pair >>= 1;
+    u64 sib = 2 * ((pair << (layer + 1)) + ((u64)1 << layer) - 1) + (1 - parity);
+    u64 per_subtree = 2 * (((u64)1 << sub_bits) - 1);
+    *dst = digests[4 * (subtree * per_subtree + sib) + w];
+}
+void launch_gather_proof(const u64* cols, u64 ld, u32 c, const u64* digests, unsigned sub_bits, const u64* idx, u32 k, u64* out,
+                         u64 stride, cudaStream_t st) {
+    u64 total = (u64)k * (c + 4 * (u64)sub_bits);
+    if (total) { k_gather_proof<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cols, ld, c, digests, sub_bits, idx, k, out, stride); ++g_gl_launches; }
 }
 
 // FRI layer leaves, column-major: element (leaf j, column 2a+e) = values_ext[bitrev(j * arity + a)][e]
@@ -325,6 +354,43 @@ k_fri_fold(const u64* __restrict__ coeffs_ext, u64 out_len, unsigned arity_bits,
     out_cols[k] = gl_canon(acc.a);
     out_cols[out_ld + k] = gl_canon(acc.b);
 }
+// the same fold with beta read from device memory (gl_fri_prove: the challenge never visits the host)
+__global__ void __launch_bounds__(256)
+k_fri_fold_dev(const u64* __restrict__ coeffs_ext, u64 out_len, unsigned arity_bits, const u64* __restrict__ beta_dev,
+               u64* __restrict__ out_cols, u64 out_ld) {
+    u64 k = blockIdx.x * (u64)256 + threadIdx.x;
+    if (k >= out_len) return;
+    unsigned arity = 1u << arity_bits;
+    gl_ext beta = {__ldg(beta_dev), __ldg(beta_dev + 1)}, acc = {0, 0};
+    const u64* p = coeffs_ext + 2 * (k << arity_bits);
+    for (int j = (int)arity - 1; j >= 0; j--) {
+        gl_ext cj = {p[2 * j], p[2 * j + 1]};
+        acc = gl_ext_add(gl_ext_mul(acc, beta), cj);
+    }
+    out_cols[k] = gl_canon(acc.a);
+    out_cols[out_ld + k] = gl_canon(acc.b);
+}
+void launch_fri_fold_dev(const u64* coeffs_ext, u64 out_len, unsigned arity_bits, const u64* beta_dev, u64* out_cols, u64 out_ld,
+                         cudaStream_t st) {
+    { k_fri_fold_dev<<<(unsigned)((out_len + 255) / 256), 256, 0, st>>>(coeffs_ext, out_len, arity_bits, beta_dev, out_cols, out_ld); ++g_gl_launches; }
+}
+// fri_prover_query_rounds: x_index = challenge % N for every round; idx[0][q] = x_index, idx[l + 1][q] = x_index >> (arity bits
+// folded up to and including layer l); the x_index also goes to its slot of the proof buffer
+__global__ void k_fri_query_indices(const u64* __restrict__ challenges, u32 rounds, unsigned lg_N, const u32* __restrict__ cum_bits,
+                                    u32 layers, u64* __restrict__ idx, u64* __restrict__ proof_x, u64 query_stride) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= rounds) return;
+    u64 x = challenges[q] & (((u64)1 << lg_N) - 1);     // canonical challenge mod N, N a power of two
+    idx[q] = x;
+    proof_x[(u64)q * query_stride] = x;
+    for (u32 l = 0; l < layers; l++) idx[(u64)(l + 1) * rounds + q] = x >> cum_bits[l];
+}
+void launch_fri_query_indices(const u64* challenges, u32 rounds, unsigned lg_N, const u32* cum_bits, u32 layers, u64* idx,
+                              u64* proof_x, u64 query_stride, cudaStream_t st) {
+    k_fri_query_indices<<<(rounds + 63) / 64, 64, 0, st>>>(challenges, rounds, lg_N, cum_bits, layers, idx, proof_x, query_stride);
+    ++g_gl_launches;
+}
+
 void launch_fri_fold(const u64* coeffs_ext, u64 out_len, unsigned arity_bits, u64 b0, u64 b1, u64* out_cols,
                      u64 out_ld, cudaStream_t st) {
     { k_fri_fold<<<(unsigned)((out_len + 255) / 256), 256, 0, st>>>(coeffs_ext, out_len, arity_bits, b0, b1, out_cols, out_ld); ++g_gl_launches; }

@@ -67,3 +67,9 @@ bool launch_ntt16(const ntt16_args& a, unsigned M, bool inverse, uint64_t n, uin
 int gl_field_selftest(cudaStream_t st);
 void launch_gather_open(const uint64_t* cols, uint64_t ld, uint32_t c, const uint64_t* digests, unsigned sub_bits,
                         const uint64_t* loc, const uint64_t* slot, uint32_t mine, uint64_t* out, uint64_t per, cudaStream_t st);
+void launch_fri_fold_dev(const uint64_t* coeffs_ext, uint64_t out_len, unsigned arity_bits, const uint64_t* beta_dev,
+                         uint64_t* out_cols, uint64_t out_ld, cudaStream_t st);
+void launch_fri_query_indices(const uint64_t* challenges, uint32_t rounds, unsigned lg_N, const uint32_t* cum_bits, uint32_t layers,
+                              uint64_t* idx, uint64_t* proof_x, uint64_t query_stride, cudaStream_t st);
+void launch_gather_proof(const uint64_t* cols, uint64_t ld, uint32_t c, const uint64_t* digests, unsigned sub_bits, const uint64_t* idx,
+                         uint32_t k, uint64_t* out, uint64_t stride, cudaStream_t st);

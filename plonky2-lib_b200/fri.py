@@ -91,6 +91,7 @@ class FriParams:
     degree_bits: int
     hiding: bool = False
     reduction_arity_bits: Sequence[int] = ()
+    final_poly_times_x: bool = False      # GL_COMPAT_FRI_FINAL_POLY_TIMES_X: the pre-"remove multiplication by X" form
 
     @staticmethod
     def for_degree(config: FriConfig, degree_bits: int) -> "FriParams":
@@ -283,6 +284,88 @@ def fri_final_poly(oracles, batches, alpha, rate_bits: int, ctx: Optional[Contex
     return coeffs, values
 
 
+def _instance_arrays(batches):
+    nb = len(batches)
+    total = sum(len(p) for _, p in batches)
+    cb = (N.FriBatch * nb)()
+    cp = (N.FriPoly * total)()
+    at = 0
+    for i, (point, polys) in enumerate(batches):
+        cb[i].point[0], cb[i].point[1] = int(point[0]) % P, int(point[1]) % P
+        cb[i].first_poly, cb[i].num_polys = at, len(polys)
+        for oi, pi in polys:
+            cp[at].oracle_index, cp[at].polynomial_index = oi, pi
+            at += 1
+    return cb, nb, cp
+
+
+def parse_flat_proof(flat: np.ndarray, oracle_columns: Sequence[int], fri_params: FriParams) -> dict:
+    """The word stream gl_fri_prove writes (include/gl_b200.h) -> FriProof as the dict fri_proof returns."""
+    cfg = fri_params.config
+    lgN, h = fri_params.degree_bits + cfg.rate_bits, cfg.cap_height
+    at = 0
+
+    def take(k, shape=None):
+        nonlocal at
+        a = flat[at:at + k]
+        at += k
+        return a.reshape(shape) if shape else a
+
+    caps = [take(4 << h, (1 << h, 4)).copy() for _ in fri_params.reduction_arity_bits]
+    lg = lgN - sum(fri_params.reduction_arity_bits)
+    final = take(2 << (lg - cfg.rate_bits), (-1, 2)).copy()
+    pow_witness = int(take(1)[0])
+    rounds = []
+    for _ in range(cfg.num_query_rounds):
+        x = int(take(1)[0])
+        init = [(take(c).copy(), take(4 * (lgN - h), (lgN - h, 4)).copy()) for c in oracle_columns]
+        steps, cur = [], lgN
+        for ab in fri_params.reduction_arity_bits:
+            ev = take(2 << ab, (-1, 2)).copy()
+            L = cur - ab - h
+            steps.append({"evals": ev, "merkle_proof": take(4 * L, (L, 4)).copy()})
+            cur -= ab
+        rounds.append({"x_index": x, "initial_trees_proof": init, "steps": steps})
+    assert at == flat.shape[0]
+    return {"commit_phase_merkle_caps": caps, "query_round_proofs": rounds, "final_poly": final, "pow_witness": pow_witness}
+
+
+def prove_openings_device(oracles, batches, challenger: Challenger, fri_params: FriParams, ctx: Optional[Context] = None,
+                          flat: bool = False):
+    """PolynomialBatch::prove_openings through ONE C-ABI call (gl_fri_prove): the transcript runs on the device from the
+    Challenger's current state and comes back advanced past the proof; three host synchronisations in total."""
+    import ctypes as C
+
+    ctx = _ctx(ctx)
+    cfg = fri_params.config
+    prm = N.FriParams()
+    prm.rate_bits, prm.cap_height, prm.proof_of_work_bits, prm.num_query_rounds = cfg.rate_bits, cfg.cap_height, cfg.proof_of_work_bits, cfg.num_query_rounds
+    prm.num_reduction_layers = len(fri_params.reduction_arity_bits)
+    for i, ab in enumerate(fri_params.reduction_arity_bits):
+        prm.reduction_arity_bits[i] = ab
+    prm.flags = N.GL_COMPAT_FRI_FINAL_POLY_TIMES_X if fri_params.final_poly_times_x else 0
+    ch = N.Challenger()
+    for i in range(12):
+        ch.sponge_state[i] = int(challenger.sponge_state[i])
+    for i, v in enumerate(challenger.input_buffer):
+        ch.input_buffer[i] = int(v)
+    for i, v in enumerate(challenger.output_buffer):
+        ch.output_buffer[i] = int(v)
+    ch.input_len, ch.output_len = len(challenger.input_buffer), len(challenger.output_buffer)
+    cb, nb, cp = _instance_arrays(batches)
+    handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
+    cols = (C.c_uint32 * len(oracles))(*[o.num_columns for o in oracles])
+    words = C.c_uint64(0)
+    ctx.check(ctx._lib.gl_fri_proof_words(C.byref(prm), cols, len(oracles), fri_params.degree_bits, C.byref(words)))
+    out = np.empty(words.value, dtype=np.uint64)
+    ctx.check(ctx._lib.gl_fri_prove(ctx._h, handles, len(oracles), cb, nb, cp, C.byref(prm), C.byref(ch), out.ctypes.data,
+                                    out.shape[0], C.byref(words)))
+    challenger.sponge_state = np.array(list(ch.sponge_state), dtype=np.uint64)
+    challenger.input_buffer = [int(ch.input_buffer[i]) for i in range(ch.input_len)]
+    challenger.output_buffer = [int(ch.output_buffer[i]) for i in range(ch.output_len)]
+    return out if flat else parse_flat_proof(out, [o.num_columns for o in oracles], fri_params)
+
+
 def opening_set(oracles, batches) -> list:
     """OpeningSet::new / FriOpenings: for every batch (point, [(oracle_index, polynomial_index), ...]) the values of its
     polynomials at its point, evaluated on the device from the resident coefficients (gl_commit_eval: one call per oracle
@@ -312,7 +395,11 @@ def prove_openings(oracles, batches, challenger: Challenger, fri_params: FriPara
             challenger._ctx = ctx
     ctx = _ctx(ctx)
     alpha = challenger.get_extension_challenge()
-    lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx, resident=True)
+    ctx.check(ctx._lib.gl_ctx_set_compat(ctx._h, N.GL_COMPAT_FRI_FINAL_POLY_TIMES_X if fri_params.final_poly_times_x else 0))
+    try:
+        lde_coeffs, lde_values = fri_final_poly(oracles, batches, alpha, fri_params.config.rate_bits, ctx, resident=True)
+    finally:
+        ctx.check(ctx._lib.gl_ctx_set_compat(ctx._h, 0))
     try:
         return fri_proof(oracles, lde_coeffs, lde_values, challenger, fri_params, ctx)
     finally:

@@ -100,9 +100,11 @@ def precomputed_reduced_openings(openings: Sequence[Sequence[Ext]], alpha: Ext) 
     return out
 
 
-def fri_combine_initial(instance, initial_rows, alpha: Ext, subgroup_x: int, reduced_openings: Sequence[Ext]) -> Ext:
+def fri_combine_initial(instance, initial_rows, alpha: Ext, subgroup_x: int, reduced_openings: Sequence[Ext],
+                        times_x: bool = False) -> Ext:
     """sum over the batches of alpha^(polys so far) * (reduce(evals) - reduce(openings)) / (x - z), accumulated the way
-    ReducingFactor::shift does (multiply what is there by alpha^len before adding the next quotient)."""
+    ReducingFactor::shift does (multiply what is there by alpha^len before adding the next quotient).  times_x
+    (FriParams.final_poly_times_x, GL_COMPAT_FRI_FINAL_POLY_TIMES_X): the older upstream form returns sum * subgroup_x."""
     total: Ext = (0, 0)
     for (point, polys), red_open in zip(instance, reduced_openings):
         red_eval: Ext = (0, 0)
@@ -110,7 +112,7 @@ def fri_combine_initial(instance, initial_rows, alpha: Ext, subgroup_x: int, red
             red_eval = _eadd(_emul(red_eval, alpha), (int(initial_rows[oi][pi]) % P, 0))
         quotient = _emul(_esub(red_eval, red_open), _einv(_esub((subgroup_x, 0), _e(point))))
         total = _eadd(_emul(total, _epow(alpha, len(polys))), quotient)
-    return total
+    return _escale(total, subgroup_x) if times_x else total
 
 
 def compute_evaluation(x: int, x_index_within_coset: int, arity_bits: int, evals, beta: Ext) -> Ext:
@@ -142,6 +144,77 @@ def _eval_final_poly(coeffs, x: int) -> Ext:
     return acc
 
 
+# ---- validate_fri_proof_shape ------------------------------------------------------------------------------------------
+def validate_fri_proof_shape(proof: dict, instance, initial_merkle_caps, params: FriParams, oracle_columns=None) -> None:
+    """plonky2::fri::validate_shape::validate_fri_proof_shape: everything about the proof's SHAPE is fixed by the parameters,
+    never taken from the proof -- cap sizes, number of layers / rounds / steps, evals per step, Merkle path lengths
+    (lg N - cap_height, minus the arity bits folded so far for layer trees), row widths per oracle -- and every word must be
+    a canonical field element.  Raises FriVerifyError before any hashing happens."""
+    cfg = params.config
+    arities = list(params.reduction_arity_bits)
+    lg_n, h = params.degree_bits + cfg.rate_bits, cfg.cap_height
+
+    def canonical(a, what):
+        a = np.asarray(a)
+        if a.dtype.kind not in "ui" or (a.astype(np.uint64, copy=False) >= np.uint64(P)).any():
+            raise FriVerifyError(f"{what}: not a canonical field element")
+        return a
+
+    try:
+        caps = proof["commit_phase_merkle_caps"]
+        rounds = proof["query_round_proofs"]
+        final = np.asarray(proof["final_poly"])
+        pow_witness = int(proof["pow_witness"])
+    except (KeyError, TypeError, ValueError) as e:
+        raise FriVerifyError(f"malformed proof: {e!r}")
+    if not 0 <= pow_witness < P:
+        raise FriVerifyError("pow_witness: not a canonical field element")
+    if len(caps) != len(arities):
+        raise FriVerifyError("The number of committed layers does not match the reduction strategy.")
+    for cap in list(caps) + list(initial_merkle_caps):
+        if np.asarray(cap).shape != (1 << h, 4):
+            raise FriVerifyError("Merkle cap of the wrong height.")
+        canonical(cap, "cap")
+    if sum(arities) > params.degree_bits or final.shape != ((1 << params.degree_bits) >> sum(arities), 2):
+        raise FriVerifyError("Final polynomial has wrong degree.")
+    canonical(final, "final_poly")
+    if len(rounds) != cfg.num_query_rounds:
+        raise FriVerifyError("Number of query rounds does not match config.")
+    if oracle_columns is None:
+        oracle_columns = [None] * len(initial_merkle_caps)
+        for _, polys in instance:
+            for oi, pi in polys:
+                if oi >= len(oracle_columns):
+                    raise FriVerifyError("instance refers to an oracle without a cap")
+                oracle_columns[oi] = max(oracle_columns[oi] or 0, pi + 1)
+        exact = False
+    else:
+        exact = True
+    for rnd in rounds:
+        try:
+            init, steps = rnd["initial_trees_proof"], rnd["steps"]
+        except (KeyError, TypeError) as e:
+            raise FriVerifyError(f"malformed query round: {e!r}")
+        if len(init) != len(initial_merkle_caps):
+            raise FriVerifyError("Wrong number of initial trees in a query round.")
+        for (row, path), want in zip(init, oracle_columns):
+            row, path = canonical(row, "leaf"), canonical(path, "sibling")
+            if row.ndim != 1 or (want is not None and (row.shape[0] != want if exact else row.shape[0] < want)):
+                raise FriVerifyError("Initial-tree leaf of the wrong width.")
+            if path.reshape(-1, 4).shape != (lg_n - h, 4):
+                raise FriVerifyError("Initial-tree Merkle proof of the wrong length.")
+        if len(steps) != len(arities):
+            raise FriVerifyError("Wrong number of reduction steps in a query round.")
+        cur = lg_n
+        for st, ab in zip(steps, arities):
+            ev, path = canonical(st["evals"], "evals"), canonical(st["merkle_proof"], "sibling")
+            if ev.reshape(-1, 2).shape != (1 << ab, 2) or ev.size != 2 << ab:
+                raise FriVerifyError("Wrong number of evaluations in a reduction step.")
+            cur -= ab
+            if cur < h or path.reshape(-1, 4).shape != (cur - h, 4):
+                raise FriVerifyError("Reduction-layer Merkle proof of the wrong length.")
+
+
 # ---- verify_fri_proof --------------------------------------------------------------------------------------------------
 def verify_fri_proof(instance, openings, challenges: dict, initial_merkle_caps, proof: dict, params: FriParams,
                      ctx: Context = None) -> bool:
@@ -152,6 +225,8 @@ def verify_fri_proof(instance, openings, challenges: dict, initial_merkle_caps, 
     cfg = params.config
     arities = list(params.reduction_arity_bits)
     lg_n = params.degree_bits + cfg.rate_bits
+    validate_fri_proof_shape(proof, instance, initial_merkle_caps, params)
+    times_x = bool(getattr(params, "final_poly_times_x", False))
     if len(proof["final_poly"]) != (1 << params.degree_bits) >> sum(arities):
         raise FriVerifyError("Final polynomial has wrong degree.")
     # fri_verify_proof_of_work
@@ -188,7 +263,7 @@ def verify_fri_proof(instance, openings, challenges: dict, initial_merkle_caps, 
         if "x_index" in rnd and int(rnd["x_index"]) != x_index:
             raise FriVerifyError("query index does not come from the transcript")
         subgroup_x = 7 * pow(w_n, _bitrev(x_index, lg_n), P) % P
-        old_eval = fri_combine_initial(instance, [row for row, _ in rnd["initial_trees_proof"]], alpha, subgroup_x, reduced)
+        old_eval = fri_combine_initial(instance, [row for row, _ in rnd["initial_trees_proof"]], alpha, subgroup_x, reduced, times_x)
         for li, ab in enumerate(arities):
             evals = np.asarray(rnd["steps"][li]["evals"], dtype=np.uint64).reshape(-1, 2)
             within = x_index & ((1 << ab) - 1)

@@ -146,7 +146,14 @@ def test_every_entry_point_has_its_reference_side_binding_documented():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     header = open(os.path.join(root, "include", "gl_b200.h")).read()
     integ = open(os.path.join(root, "INTEGRATION.md")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(gl_[a-z0-9_]+)\s*\(", header))
     bound = set(re.findall(r"pub fn (gl_[a-z0-9_]+)", integ))
     missing = {n for n in declared - bound if n not in integ}
     assert not missing, sorted(missing)
+    # the crate a machine with cargo compiles unchanged: rust/plonky2_gl_b200_sys declares every entry point, and nothing else
+    crate = open(os.path.join(root, "rust", "plonky2_gl_b200_sys", "src", "lib.rs")).read()
+    in_crate = set(re.findall(r"pub fn (gl_[a-z0-9_]+)", crate))
+    assert in_crate == declared, sorted(in_crate ^ declared)
+    for f in ("Cargo.toml", "build.rs"):
+        assert os.path.exists(os.path.join(root, "rust", "plonky2_gl_b200_sys", f))

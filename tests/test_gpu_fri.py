@@ -314,3 +314,121 @@ def test_golden_fri_proof(glb, ctx):
     assert fv.verify_openings(instance, openings, caps, proof, transcript(), params) is True
     for b in batches:
         b.free()
+
+
+@pytest.mark.parametrize("degree_bits,cols,pow_bits,times_x", [(5, (3, 2), 6, False), (8, (4, 9, 3), 10, False), (8, (4, 9, 3), 10, True),
+                                                                (12, (84, 135, 20, 16), 16, False), (13, (84, 135, 20, 16), 16, False)])
+def test_one_call_prover_matches_oracle(glb, ctx, oracle, rng, degree_bits, cols, pow_bits, times_x):
+    """gl_fri_prove: prove_openings + fri_proof in ONE C-ABI call with the transcript on the device, against the oracle's
+    prover field by field (both fork forms), through the oracle's verifier and the product's, and with the Challenger
+    coming back in the state the oracle's ends in."""
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    fv = importlib.import_module("plonky2-lib_b200.fri_verifier")
+    rate_bits, cap_height, rounds = 3, 4, 28
+    n = 1 << degree_bits
+    batches_dev, polys, trees = [], [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=300 + k)
+        batches_dev.append(glb.PolynomialBatch.from_values(v, rate_bits, False, cap_height))
+        res = oracle.commit_from_values(v, rate_bits, cap_height)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], cap_height))
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    g = oracle.lib().glo_primitive_root_of_unity(degree_bits)
+    zs = min(len(cols) - 1, 2)
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)]),
+                (fo.ext_scalar(zeta, g), [(zs, pi) for pi in range(min(2, cols[zs]))])]
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+    params.final_poly_times_x = times_x
+    ch, och, vch, pch = fri.Challenger(), fo.Challenger(), fo.Challenger(), fri.Challenger()
+    for t in trees:
+        for c in (ch, och, vch, pch):
+            c.observe_cap(t.cap)
+    ch.observe_elements([1, 2, 3])             # a ragged input buffer when the call starts
+    och.observe_elements([1, 2, 3])
+    vch.observe_elements([1, 2, 3])
+    pch.observe_elements([1, 2, 3])
+    got = fri.prove_openings_device(batches_dev, instance, ch, params)
+    want = fo.prove_openings(polys, trees, instance, och, degree_bits, rate_bits, cap_height, pow_bits, rounds, times_x=times_x)
+    _same_proof(got, want)
+    assert ch.get_challenge() == och.get_challenge()                  # the transcript continues from the same state
+    openings = fo.opening_set(polys, instance)
+    assert fo.verify_openings(got, openings, [t.cap for t in trees], instance, vch, degree_bits, rate_bits, cap_height, pow_bits,
+                              rounds, times_x=times_x)
+    assert fv.verify_openings(instance, openings, [t.cap for t in trees], got, pch, params)
+    # the Python-driven multi-call prover gives the same proof
+    ch2 = fri.Challenger()
+    for t in trees:
+        ch2.observe_cap(t.cap)
+    ch2.observe_elements([1, 2, 3])
+    _same_proof(fri.prove_openings(batches_dev, instance, ch2, params), want)
+    for b in batches_dev:
+        b.free()
+
+
+def test_one_call_prover_matches_golden(glb, ctx):
+    """tests/golden/fri_proof.json replayed through gl_fri_prove: the flat word stream IS the fixture's proof_flat."""
+    import json
+    import os
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fri_proof.json")))
+    vals = [np.array([[int(x, 16) for x in col] for col in v], dtype=np.uint64) for v in g["values"]]
+    bs = [glb.PolynomialBatch.from_values(v, g["rate_bits"], False, g["cap_height"]) for v in vals]
+    cfg = glb.FriConfig(rate_bits=g["rate_bits"], cap_height=g["cap_height"], proof_of_work_bits=g["proof_of_work_bits"],
+                        num_query_rounds=g["num_query_rounds"])
+    params = fri.FriParams.for_degree(cfg, g["degree_bits"])
+    ch = fri.Challenger()
+    for b in bs:
+        ch.observe_cap(b.merkle_tree.cap)
+    inst = [(tuple(pt), [tuple(p_) for p_ in ps]) for pt, ps in g["instance"]]
+    flat = fri.prove_openings_device(bs, inst, ch, params, flat=True)
+    assert [f"{int(x):x}" for x in flat] == g["proof_flat"]
+    for b in bs:
+        b.free()
+
+
+def test_verifier_validates_the_proof_shape_first(glb, ctx, oracle, rng):
+    """validate_fri_proof_shape: path lengths, step counts, evals per step, row widths and canonical words are
+    fixed by the parameters; a malformed proof is a FriVerifyError, not an IndexError, and never reaches the hashing."""
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    fv = importlib.import_module("plonky2-lib_b200.fri_verifier")
+    degree_bits, cols = 8, (4, 3)
+    n = 1 << degree_bits
+    bs = [glb.PolynomialBatch.from_values(oracle.synthetic_values(c, n, seed=60 + k), 3, False, 4) for k, c in enumerate(cols)]
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    inst = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)])]
+    cfg = glb.FriConfig(rate_bits=3, cap_height=4, proof_of_work_bits=6, num_query_rounds=8)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+
+    def fresh():
+        c_ = fri.Challenger()
+        for b in bs:
+            c_.observe_cap(b.merkle_tree.cap)
+        return c_
+
+    proof = fri.prove_openings_device(bs, inst, fresh(), params)
+    openings = fri.opening_set(bs, inst)
+    caps = [b.merkle_tree.cap for b in bs]
+    assert fv.verify_openings(inst, openings, caps, proof, fresh(), params)
+    import copy
+
+    def broken(edit):
+        p_ = copy.deepcopy(proof)
+        edit(p_)
+        with pytest.raises(fv.FriVerifyError):
+            fv.verify_openings(inst, openings, caps, p_, fresh(), params)
+
+    broken(lambda p_: p_["query_round_proofs"][0]["steps"].pop())                                        # a step missing
+    broken(lambda p_: p_["query_round_proofs"][1]["steps"][0].__setitem__("merkle_proof", p_["query_round_proofs"][1]["steps"][0]["merkle_proof"][:-1]))   # shorter path
+    broken(lambda p_: p_["query_round_proofs"][2]["steps"][0].__setitem__("evals", p_["query_round_proofs"][2]["steps"][0]["evals"][:-1]))
+    broken(lambda p_: p_["query_round_proofs"][3].__setitem__("initial_trees_proof", p_["query_round_proofs"][3]["initial_trees_proof"][:1]))
+    broken(lambda p_: p_.__setitem__("pow_witness", p_["pow_witness"] + P))                              # non-canonical witness
+    broken(lambda p_: p_["final_poly"].__setitem__((0, 0), np.uint64(P)))                               # non-canonical coefficient
+    broken(lambda p_: p_.__setitem__("commit_phase_merkle_caps", p_["commit_phase_merkle_caps"][:-1]))
+    broken(lambda p_: p_["query_round_proofs"].pop())
+    for b in bs:
+        b.free()

@@ -107,3 +107,30 @@ def test_prove_openings_then_verify(oracle, rng):
         vch.observe_cap(t.cap)
     with pytest.raises(AssertionError):
         fo.verify_openings(proof, openings, [t.cap for t in trees], batches, vch, degree_bits, rate_bits, cap_height, 6, 5)
+
+
+@pytest.mark.parametrize("times_x", [False, True])
+def test_prove_openings_then_verify_in_both_fork_forms(oracle, rng, times_x):
+    """The one fork-version switch of the FRI layer (GL_COMPAT_FRI_FINAL_POLY_TIMES_X): prover and verifier agree in either
+    form, and a proof of one form is rejected by a verifier of the other."""
+    from oracle import fri_oracle as fo
+
+    degree_bits, cols = 6, (4, 3)
+    n = 1 << degree_bits
+    polys, trees = [], []
+    for k, c in enumerate(cols):
+        res = oracle.commit_from_values(oracle.synthetic_values(c, n, seed=50 + k), 3, 4)
+        polys.append(res["coeffs"])
+        trees.append(fo.MerkleTree(res["leaves"], 4))
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)])]
+    ch, vch, xch = fo.Challenger(), fo.Challenger(), fo.Challenger()
+    for t in trees:
+        for c in (ch, vch, xch):
+            c.observe_cap(t.cap)
+    proof = fo.prove_openings(polys, trees, instance, ch, degree_bits, pow_bits=6, num_query_rounds=10, times_x=times_x)
+    openings = fo.opening_set(polys, instance)
+    caps = [t.cap for t in trees]
+    assert fo.verify_openings(proof, openings, caps, instance, vch, degree_bits, pow_bits=6, num_query_rounds=10, times_x=times_x)
+    with pytest.raises(AssertionError):
+        fo.verify_openings(proof, openings, caps, instance, xch, degree_bits, pow_bits=6, num_query_rounds=10, times_x=not times_x)
