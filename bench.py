@@ -143,7 +143,7 @@ def proof_trace(glb, ctx, torch, lg=16):
             ch = fri.Challenger(ctx)
             for b in bs:
                 ch.observe_cap(b.merkle_tree.cap)
-            proof = fri.prove_openings(bs, inst, ch, prm, ctx)
+            proof = fri.prove_openings_device(bs, inst, ch, prm, ctx)      # gl_fri_prove: one C-ABI call, transcript on the device
             for b in bs[1:]:
                 b.free()
             return proof
@@ -155,12 +155,36 @@ def proof_trace(glb, ctx, torch, lg=16):
             proof = once()
             dt = time.perf_counter() - t
             best = dt if best is None else min(best, dt)
+        # the same trace with the witness already in HBM (what a device-side witness generator / N3 pipeline hands over)
+        dvals = [torch.from_numpy(v.view(np.int64)).to(ctx_device(ctx)) for v in vals[1:]]
+
+        def once_resident():
+            bs = [const_sigmas] + [glb.PolynomialBatch.from_values(v, RATE_BITS, False, CAP_HEIGHT, want_coeffs=False, ctx=ctx) for v in dvals]
+            ch = fri.Challenger(ctx)
+            for b in bs:
+                ch.observe_cap(b.merkle_tree.cap)
+            fri.prove_openings_device(bs, inst, ch, prm, ctx, flat=True)
+            for b in bs[1:]:
+                b.free()
+
+        once_resident()
+        best_res = None
+        for _ in range(3):
+            t = time.perf_counter()
+            once_resident()
+            dt = time.perf_counter() - t
+            best_res = dt if best_res is None else min(best_res, dt)
         const_sigmas.free()
-        return {"config1_ecdsa_2^%d_rows_ms" % lg: best * 1e3, "fri_layers": len(proof["commit_phase_merkle_caps"]),
+        return {"config1_ecdsa_2^%d_rows_ms" % lg: best * 1e3, "config1_ecdsa_2^%d_rows_resident_inputs_ms" % lg: best_res * 1e3,
+                "fri_layers": len(proof["commit_phase_merkle_caps"]),
                 "query_rounds": len(proof["query_round_proofs"]),
-                "what": "3 commits (135 + 20 + 16 polynomials, page-able host arrays, coefficients out) + prove_openings over 4 oracles; wall clock"}
+                "what": "3 commits (135 + 20 + 16 polynomials, page-able host arrays, coefficients out) + prove_openings over 4 oracles (gl_fri_prove, one call); wall clock"}
     except Exception as e:  # noqa: BLE001
         return {"error": repr(e)}
+
+
+def ctx_device(ctx):
+    return "cuda:%d" % ctx.device
 
 
 def use_all_host_threads(o):

@@ -239,6 +239,15 @@ def run_open():
     return fri.prove_openings(batches, instance, ch, params)
 
 
+def run_open_one_call():
+    ch = fri.Challenger()
+    for b in batches:
+        ch.observe_cap(b.merkle_tree.cap)
+    return fri.prove_openings_device(batches, instance, ch, params)
+
+
+t = timeit(run_open_one_call, 3)
+out["prove_openings_2^20_one_call"] = {"oracles": list(cols), "ms": t * 1e3, "note": "gl_fri_prove: the same proof through one C-ABI call, transcript on the device"}
 t0 = time.perf_counter()
 alpha = (111, 222)
 fc, fv = fri.fri_final_poly(batches, instance, alpha, 3)
@@ -278,7 +287,7 @@ def quotient_bench(lg):
 out["quotient_polys"] = [quotient_bench(lg) for lg in (16, 18, 20)]
 
 
-def proof_trace(lg):
+def proof_trace(lg, one_call=True):
     n_ = 1 << lg
     vals_ = [rand_dev((c, n_)).cpu().numpy().view(np.uint64) % np.uint64(P) for c in (84, 135, 20, 16)]
     const_sigmas = glb.PolynomialBatch.from_values(vals_[0], 3, False, 4, want_coeffs=False)   # CircuitBuilder::build
@@ -292,7 +301,7 @@ def proof_trace(lg):
         ch = fri.Challenger()
         for b in bs:
             ch.observe_cap(b.merkle_tree.cap)
-        fri.prove_openings(bs, inst, ch, prm)
+        (fri.prove_openings_device if one_call else fri.prove_openings)(bs, inst, ch, prm)
         for b in bs[1:]:
             b.free()
 
@@ -301,8 +310,10 @@ def proof_trace(lg):
     return t_ * 1e3
 
 
+out["proof_trace_multi_call_ms"] = {"what": "the same trace with the Python-driven prover (host Challenger, ~70 dependent round trips)",
+                                    "config1_ecdsa_2^16_rows": proof_trace(16, False), "config5_outer_recursion_2^13_rows": proof_trace(13, False)}
 out["proof_trace_ms"] = {
-    "what": "3 commits (135 + 20 + 16 columns, pageable host buffers in and coefficients out) + prove_openings over 4 oracles",
+    "what": "3 commits (135 + 20 + 16 columns, pageable host buffers in and coefficients out) + prove_openings over 4 oracles (gl_fri_prove: one call, transcript on the device)",
     "config1_ecdsa_2^16_rows": proof_trace(16),
     "config4_smt_256_inclusions_2^15_rows": proof_trace(15),
     "config3_keccak_64_blocks_2^18_rows": proof_trace(18),
