@@ -185,7 +185,12 @@ extern "C" int gl_group_create(gl_ctx* const* ctxs, uint32_t nlocal, uint32_t ra
     }
     for (uint32_t i = 0; i < nlocal && rc == GL_OK; i++) {
         cudaSetDevice(ctxs[i]->device);
-        cudaError_t e = cudaStreamCreateWithFlags(&g->r[i].comm_stream, cudaStreamNonBlocking);
+        // highest priority: the block scheduler places the collective's few CTAs ahead of the thousands of queued LDE /
+        // hashing CTAs of the compute stream, so a gather is on the wire as soon as its data exists instead of when the
+        // running compute kernel drains (measured at 8 GPUs: gather 0 finished at 3.0 ms instead of 0.8 ms without this)
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        cudaError_t e = cudaStreamCreateWithPriority(&g->r[i].comm_stream, cudaStreamNonBlocking, hi);
         if (e != cudaSuccess) { rc = GL_E_CUDA; msg = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); }
     }
     if (prev >= 0) cudaSetDevice(prev);
@@ -288,6 +293,33 @@ static GroupPlan group_plan(uint32_t c, uint32_t nranks) {
 }
 static inline uint32_t clampc(uint32_t x, uint32_t c) { return x < c ? x : c; }
 
+// GL_B200_TRACE=1: device-side timeline of one collective commit (ms after its first event), rank by rank, on stderr
+struct GroupTrace {
+    bool on = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    void mark(const std::string& name, cudaStream_t st) {
+        if (!on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        marks.emplace_back(name, e);
+    }
+    void dump(uint32_t rank, cudaEvent_t origin) {
+        if (!on) return;
+        std::string line = "[gl_group trace] rank " + std::to_string(rank) + ":";
+        for (auto& m : marks) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, origin, m.second);
+            char buf[64];
+            snprintf(buf, sizeof buf, " %s=%.2f", m.first.c_str(), ms);
+            line += buf;
+            cudaEventDestroy(m.second);
+        }
+        fprintf(stderr, "%s\n", line.c_str());
+        marks.clear();
+    }
+};
+
 static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_values, uint32_t log_n, uint32_t c,
                         uint32_t rate_bits, uint32_t cap_height, uint64_t* const* coeffs_out, uint64_t* const* cap_out,
                         gl_commit** handles, int space, uint32_t flags, const char* name) {
@@ -307,6 +339,11 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
     const u64 n = (u64)1 << log_n;
     const GroupPlan plan = group_plan(c, G);
     const size_t cap_bytes = (size_t)32 << cap_height;
+    std::vector<GroupTrace> trace(nl);
+    {
+        const char* t = getenv("GL_B200_TRACE");
+        for (auto& tr : trace) tr.on = t && t[0] == '1';
+    }
     int prev = -1;
     cudaGetDevice(&prev);
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
@@ -373,7 +410,9 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
         const uint32_t c0 = plan.base[j], c1 = clampc(c0 + plan.w[j] * G, c);
         if (c1 > c0) {
             int rc = commit_lde_columns(ctx, h, c0, c1 - c0);
+            trace[i].mark("lde" + std::to_string(j), ctx->stream);
             if (rc == GL_OK) rc = commit_absorb_block(ctx, h, c0, c1 - c0);
+            if (h->stream_hash) trace[i].mark("abs" + std::to_string(j), ctx->stream);
             if (rc != GL_OK) return gfail(g, rc, ctx->err);
         }
         return GL_OK;
@@ -399,6 +438,7 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
                     if (rc != GL_OK) return bail(gfail(g, rc, ctx->err));
                     cudaEventRecord(rk.ev[2 * j], ctx->h2d_stream);
                     cudaStreamWaitEvent(ctx->stream, rk.ev[2 * j], 0);
+                    trace[i].mark("up" + std::to_string(j), ctx->h2d_stream);
                 }
                 if (is_values) {
                     int rc = transform_natural(ctx, dcol, log_n, o1 - o0, true, nullptr, nullptr);   // "IFFT" of this rank's columns
@@ -406,6 +446,7 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
                 }
             }
             cudaEventRecord(rk.ev[2 * j], ctx->stream);
+            trace[i].mark("ifft" + std::to_string(j), ctx->stream);
             if (o1 > o0 && is_values && coeffs_out && coeffs_out[i] && space == GL_HOST) {
                 int rc = d2h_copy(ctx, {staging::HostSeg{coeffs_out[i] + (size_t)o0 * n, (size_t)(o1 - o0) * n * 8}},
                                   h->coeffs + (size_t)o0 * n, rk.ev[2 * j]);
@@ -431,6 +472,7 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
         for (uint32_t i = 0; i < nl; i++) {
             cudaSetDevice(g->r[i].ctx->device);
             cudaEventRecord(g->r[i].ev[2 * j + 1], g->r[i].comm_stream);
+            trace[i].mark("gath" + std::to_string(j), g->r[i].comm_stream);
         }
         if (j > 0)
             for (uint32_t i = 0; i < nl; i++) {
@@ -453,6 +495,7 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
         int rc = commit_tree(ctx, h, nullptr, GL_DEVICE, h->stream_hash && h->hashed_cols == h->c);
         if (rc != GL_OK) return bail(gfail(g, rc, ctx->err));
         cudaEventRecord(rk.ev[tail], ctx->stream);
+        trace[i].mark("tree", ctx->stream);
         cudaStreamWaitEvent(rk.comm_stream, rk.ev[tail], 0);
     }
     if (G > 1) {
@@ -493,6 +536,8 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
             int rc2 = downloads_wait(ctx);
             if (rc == GL_OK && rc2 != GL_OK) rc = gfail(g, rc2, ctx->err);
         }
+        trace[i].mark("cap+d2h", rk.comm_stream);
+        if (trace[i].on) { cudaStreamSynchronize(rk.comm_stream); trace[i].dump(g->rank0 + i, ctx->ev[0]); }
         if (h->hstate) {
             dev_release(ctx, h->hstate, h->hstate_bytes);
             h->hstate = nullptr;
