@@ -303,7 +303,7 @@ static int finish(gl_ctx* ctx) {
 // ------------------------------------------------------------------------------------------------
 // tables (built on the host with exact 128-bit arithmetic, cached on the device)
 // ------------------------------------------------------------------------------------------------
-enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3, TAB_FULL = 4, TAB_DIRECT = 5, TAB_COSETS_DIRECT = 6 };
+enum { TAB_SMALL = 1, TAB_POW = 2, TAB_COSETS = 3, TAB_FULL = 4, TAB_DIRECT = 5, TAB_COSETS_DIRECT = 6, TAB_TMA_POST = 7 };
 
 static void fill_pow_table(u64* t, u64 base) {  // [3][1024]: base^e, base^(1024 e), base^(2^20 e)
     u64 b = glh::canon(base);
@@ -461,9 +461,48 @@ static unsigned plan_passes(unsigned L, unsigned ms[4], bool fast[4]) {
     return 3;
 }
 
+// tables of the TMA path: post3 [cosets][256][2^s] followed by rowfac [cosets][256] (see ntt_kernels.h)
+static int tma_tables(gl_ctx* ctx, const NttJob& j, const u64* post_tab, const u64** post3, const u64** rowfac) {
+    const unsigned s = j.L - 8;
+    auto key = std::make_tuple((int)TAB_TMA_POST, (uint64_t)(uintptr_t)j.pre_tab, ((uint64_t)j.L << 1) | (uint64_t)j.inverse,
+                               (uint64_t)j.cosets);
+    const size_t t_elems = ((size_t)j.cosets << 8) << s;
+    auto it = ctx->tables.find(key);
+    u64* d;
+    if (it != ctx->tables.end()) {
+        d = const_cast<u64*>(it->second);
+    } else {
+        TRY(dev_alloc(ctx, (t_elems + (size_t)j.cosets * 256) * sizeof(u64), &d));
+        launch_ntt_tma_tables(d, d + t_elems, post_tab, j.pre_tab, s, j.cosets, ctx->stream);
+        ctx->tables[key] = d;
+    }
+    *post3 = d;
+    *rowfac = j.pre_tab ? d + t_elems : nullptr;
+    return GL_OK;
+}
+
 static int run_dif(gl_ctx* ctx, const NttJob& j) {
     if (j.columns == 0) return GL_OK;
     const u64 n = (u64)1 << j.L;
+    static const bool tma_off = getenv("GL_B200_NTT_TMA") && atoi(getenv("GL_B200_NTT_TMA")) == 0;
+    if (!tma_off && ntt_tma_supported(j.L) && j.final_scale == 1 && (!j.pre_tab || j.pre_direct_ok) &&
+        (j.in_coset_stride == 0 || j.in_coset_stride == n) && (j.cosets == 1 || j.out_coset_stride == n)) {
+        u64 w = glh::root_of_unity(j.L);
+        if (j.inverse) w = glh::inv(w);
+        const u64* post;
+        TRY(pow_table(ctx, w, &post));
+        ntt_tma_job t;
+        memset(&t, 0, sizeof t);
+        t.in = j.in; t.in_ld = j.in_ld; t.in_coset_stride = j.in_coset_stride;
+        t.out = j.out; t.out_ld = j.out_ld; t.out_coset_stride = j.out_coset_stride;
+        t.L = j.L; t.columns = j.columns; t.cosets = j.cosets; t.inverse = j.inverse;
+        t.canonical_out = j.canonical_out;
+        TRY(full_table(ctx, 8, j.inverse, &t.wt1));
+        TRY(full_table(ctx, j.L - 8, j.inverse, &t.wt2));
+        TRY(tma_tables(ctx, j, post, &t.post3, &t.rowfac));
+        if (launch_ntt_tma(t, ctx->stream)) return GL_OK;
+        return fail(ctx, GL_E_CUDA, "ntt: TMA pass launch failed");
+    }
     unsigned ms[4];
     bool fast[4];
     const unsigned np = plan_passes(j.L, ms, fast);

@@ -73,3 +73,33 @@ void launch_fri_query_indices(const uint64_t* challenges, uint32_t rounds, unsig
                               uint64_t* idx, uint64_t* proof_x, uint64_t query_stride, cudaStream_t st);
 void launch_gather_proof(const uint64_t* cols, uint64_t ld, uint32_t c, const uint64_t* digests, unsigned sub_bits, const uint64_t* idx,
                          uint32_t k, uint64_t* out, uint64_t stride, cudaStream_t st);
+
+// ---- TMA path (ntt_tma.cu): 2^16 .. 2^20 points as a strided 256-point pass + a contiguous 2^(L-8)-point pass ----
+struct ntt_tma_args {
+    const uint64_t* wt1;      // w_256^e (direction applied), e < 256
+    const uint64_t* rowfac;   // [cosets][256]: shift_coset^(row << s), or null (no coset shift)
+    const uint64_t* post3;    // [cosets][256][2^s]: (shift_coset * w_{2^L}^brev8(row))^j
+    uint64_t* out;            // pass 2 works in place on the output
+    uint64_t out_ld, out_coset_stride;
+    const uint64_t* wt2;      // w_{2^s}^e (direction applied), e < 2^s
+    uint32_t s;               // L - 8
+    uint32_t columns, cosets;
+    uint32_t in_coset_rows;   // 256 when the input has one block per coset, else 0
+    int canonical_out;
+};
+struct ntt_tma_job {
+    const uint64_t* in;
+    uint64_t in_ld, in_coset_stride;
+    uint64_t* out;
+    uint64_t out_ld, out_coset_stride;
+    unsigned L;
+    uint32_t columns, cosets;
+    bool inverse;
+    const uint64_t *wt1, *wt2, *rowfac, *post3;
+    int canonical_out;
+};
+bool ntt_tma_supported(unsigned L);
+// T = post3, rowfac as above, from the 3 x 1024 power tables of w_{2^L} (post_tab) and of the coset shifts (pre_tabs, may be null)
+void launch_ntt_tma_tables(uint64_t* T, uint64_t* rowfac, const uint64_t* post_tab, const uint64_t* pre_tabs, unsigned s,
+                           uint32_t cosets, cudaStream_t st);
+bool launch_ntt_tma(const ntt_tma_job& j, cudaStream_t st);

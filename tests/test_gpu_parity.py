@@ -118,6 +118,40 @@ def test_fft_fast_pass_sizes(glb, ctx, oracle, rng, lg):
     assert np.array_equal(glb.coset_fft(a, 7)[1], oracle.coset_fft(a[1], 7))
 
 
+@pytest.mark.parametrize("lg", [16, 17, 18, 19, 20])
+def test_fft_tma_path_extreme_inputs(glb, ctx, oracle, rng, lg):
+    """The TMA two-pass kernels (csrc/ntt_tma.cu: carry-save butterflies, 2^16 .. 2^20 points): forward and inverse
+    transforms of the adversarial columns (all p - 1, p - 1 - i, 32-bit limbs, bits) and of non-canonical inputs
+    (2^64 - 1, p, p + i: taken mod p like every u64 the ABI accepts) against the oracle."""
+    n = 1 << lg
+    adv = adversarial_columns(n)
+    r = np.arange(n, dtype=np.uint64)
+    noncanon = np.stack([np.full(n, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64), np.uint64(P) + (r & np.uint64(0xFFFFFFFE)),
+                         np.where(r % np.uint64(3) == 0, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(P - 1))])
+    a = np.concatenate([adv[1:], noncanon, rand_field(rng, (1, n))])
+    red = (a.astype(object) % P).astype(np.uint64)
+    assert np.array_equal(glb.fft(a), np.stack([oracle.fft(r) for r in red]))
+    assert np.array_equal(glb.ifft(a), np.stack([oracle.ifft(r) for r in red]))
+
+
+@pytest.mark.parametrize("lg_n,c,rate_bits,cap_height", [(16, 5, 3, 4), (17, 3, 2, 4), (18, 2, 1, 3), (16, 9, 0, 0)])
+def test_commit_tma_path_matches_oracle(glb, ctx, oracle, lg_n, c, rate_bits, cap_height):
+    """from_values at sizes that take the TMA LDE (several cosets per launch): coefficients, every leaf, every digest
+    and the cap equal the oracle's."""
+    n = 1 << lg_n
+    values = oracle.synthetic_values(c, n, seed=lg_n)
+    values[0] = adversarial_columns(n)[1]
+    if c > 1:
+        values[1] = adversarial_columns(n)[4]
+    want = oracle.commit_from_values(values, rate_bits, cap_height)
+    b = glb.PolynomialBatch.from_values(values, rate_bits, False, cap_height)
+    assert np.array_equal(b.polynomials, want["coeffs"])
+    assert np.array_equal(b.merkle_tree.cap, want["cap"])
+    assert np.array_equal(b.merkle_tree.leaves, want["leaves"])
+    assert np.array_equal(b.merkle_tree.digests, want["digests"])
+    b.free()
+
+
 @pytest.mark.parametrize("lg", [21, 22, 24])
 def test_fft_three_pass_sizes(glb, ctx, oracle, rng, lg):
     a = rand_field(rng, (1, 1 << lg))
