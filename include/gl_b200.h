@@ -172,7 +172,8 @@ int gl_coset_ifft_batch(gl_ctx *ctx, uint64_t *data, uint32_t log_n, uint32_t c,
  * src/hash/keccak256.rs:248, src/smt/gadgets/process/mod.rs:82, src/zkdsa/circuits/mod.rs:326) and
  * builder.build::<C>() (41 sites, e.g. src/ecdsa/gadgets/ecdsa.rs:298).
  * values / coeffs: [c][2^log_n], one contiguous column after another (Vec<PolynomialValues<F>>).
- * blinding is always false for the reference's configs (zero_knowledge: false) and is not taken.
+ * These two entry points are the blinding = false form (every config of the reference: zero_knowledge: false); the _ex
+ * forms below take upstream's `blinding` argument.
  * coeffs_out [c][2^log_n] (PolynomialBatch.polynomials; may be NULL), cap_out [2^cap_height][4]
  * (with a shard set: only this shard's 2^cap_height/count entries, written at their global index).
  * The LDE leaves and the digests stay on the device behind *handle ("resident mode"). */
@@ -194,6 +195,23 @@ int gl_commit_from_values_cols(gl_ctx *ctx, const uint64_t *const *values, uint3
 int gl_commit_from_coeffs_cols(gl_ctx *ctx, const uint64_t *const *coeffs, uint32_t log_n, uint32_t c,
                                uint32_t rate_bits, uint32_t cap_height, uint64_t *cap_out,
                                gl_commit **handle);
+/* Upstream's full signatures, `blinding` included (plonky2::fri::oracle::PolynomialBatch::from_values(values, rate_bits,
+ * blinding, cap_height, ..) / from_coeffs): with blinding != 0 every leaf carries SALT_SIZE = 4 uniform random field
+ * elements after its c polynomial values (lde_values(): `.chain((0..salt_size).map(|_| F::rand_vec(n << rate_bits)))`), so
+ * MerkleTree.leaves[i].len() = c + 4 -- gl_commit_open, gl_commit_download, gl_group_commit_open and the rows of
+ * gl_fri_prove have that width (gl_commit_leaf_len) -- while gl_commit_get_lde_values strips the salt as upstream does
+ * and the polynomials stay c.  Pass the polynomials either as one array (values / coeffs, `space` memory) or as one host
+ * array each (values_cols / coeffs_cols; the other pointer NULL).  The salt comes from a counter-mode generator on the
+ * device seeded from the OS entropy source at gl_ctx_create; gl_ctx_set_salt_seed makes it reproducible (tests). */
+#define GL_SALT_SIZE 4u
+int gl_commit_from_values_ex(gl_ctx *ctx, const uint64_t *values, const uint64_t *const *values_cols, uint32_t log_n,
+                             uint32_t c, uint32_t rate_bits, uint32_t blinding, uint32_t cap_height, uint64_t *coeffs_out,
+                             uint64_t *const *coeffs_out_cols, uint64_t *cap_out, gl_commit **handle, int space);
+int gl_commit_from_coeffs_ex(gl_ctx *ctx, const uint64_t *coeffs, const uint64_t *const *coeffs_cols, uint32_t log_n,
+                             uint32_t c, uint32_t rate_bits, uint32_t blinding, uint32_t cap_height, uint64_t *cap_out,
+                             gl_commit **handle, int space);
+int gl_ctx_set_salt_seed(gl_ctx *ctx, uint64_t seed);
+int gl_commit_leaf_len(const gl_commit *h, uint32_t *len);   /* c, or c + GL_SALT_SIZE for a blinded commit */
 /* The same commit fed column block by column block (from_coeffs as a stream): begin allocates the resident buffers,
  * add_coeffs copies the coefficients of polynomials [col0, col0 + ncols) ([ncols][2^log_n]) behind the handle and runs
  * their LDE, finish hashes the leaves and builds the tree once every column has arrived.  Lets a caller overlap the
@@ -204,6 +222,7 @@ int gl_commit_begin(gl_ctx *ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits,
  * blocks that have arrived overlaps the arrival (PCIe, NCCL) of the next ones instead of starting after the last;
  * costs 96 B of state per leaf until finish.  Same digests either way. */
 #define GL_COMMIT_STREAM_HASH 1u
+#define GL_COMMIT_BLINDING 2u   /* salted leaves, as gl_commit_from_coeffs_ex(blinding = 1); also taken by gl_group_commit_* */
 int gl_commit_begin_ex(gl_ctx *ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height, uint32_t flags,
                        gl_commit **handle);
 int gl_commit_add_coeffs(gl_commit *h, uint32_t col0, uint32_t ncols, const uint64_t *coeffs, int space);

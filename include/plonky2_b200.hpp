@@ -304,6 +304,7 @@ class PolynomialBatch {
     MerkleCap cap;                            // merkle_tree.cap
     uint32_t degree_log = 0, rate_bits = 0, cap_height = 0;
     bool blinding = false;
+    uint32_t leaf_len = 0;   // merkle_tree.leaves[i].len(): polynomials.size() + SALT_SIZE when blinding
 
     // values: one Vec per polynomial (Vec<PolynomialValues<F>>); `timing` / `fft_root_table` of the upstream
     // signature have no meaning on the device and are not taken.
@@ -317,7 +318,7 @@ class PolynomialBatch {
     }
     // (tree.get(i), tree.prove(i)) for every i
     std::pair<std::vector<std::vector<F>>, std::vector<MerkleProof>> open(const std::vector<uint64_t>& idx) const {
-        const uint32_t k = (uint32_t)idx.size(), cols = (uint32_t)polynomials.size();
+        const uint32_t k = (uint32_t)idx.size(), cols = leaf_len;
         const uint32_t L = degree_log + rate_bits - cap_height;
         std::vector<F> rows((size_t)k * cols), paths((size_t)k * L * 4);
         ctx_->check(gl_commit_open(h_, idx.data(), k, rows.data(), paths.data(), GL_HOST));
@@ -349,7 +350,7 @@ class PolynomialBatch {
     void download(std::vector<F>* leaves_row_major, std::vector<HashOut>* digests) const {
         uint64_t lo, hi;
         gl_commit_info(h_, nullptr, nullptr, nullptr, nullptr, &lo, &hi);
-        if (leaves_row_major) leaves_row_major->resize((hi - lo) * polynomials.size());
+        if (leaves_row_major) leaves_row_major->resize((hi - lo) * leaf_len);
         uint64_t caps_local = (uint64_t)cap.size() * (hi - lo) >> (degree_log + rate_bits);
         if (digests) digests->resize(2 * ((hi - lo) - caps_local));
         ctx_->check(gl_commit_download(h_, leaves_row_major ? leaves_row_major->data() : nullptr,
@@ -363,6 +364,8 @@ class PolynomialBatch {
         std::swap(degree_log, o.degree_log);
         std::swap(rate_bits, o.rate_bits);
         std::swap(cap_height, o.cap_height);
+        std::swap(blinding, o.blinding);
+        std::swap(leaf_len, o.leaf_len);
         std::swap(h_, o.h_);
         std::swap(ctx_, o.ctx_);
         return *this;
@@ -375,7 +378,6 @@ class PolynomialBatch {
     PolynomialBatch() = default;
     static PolynomialBatch make(const Context& c, const std::vector<std::vector<F>>& polys, bool is_values,
                                 uint32_t rate_bits, bool blinding, uint32_t cap_height) {
-        if (blinding) throw Panic(GL_E_ARG, "blinding (zero_knowledge) is not supported: every reference config uses false");
         if (polys.empty()) throw Panic(GL_E_ARG, "PolynomialBatch: empty batch");
         const size_t n = polys[0].size();
         if (n == 0 || (n & (n - 1))) throw Panic(GL_E_ARG, "log2_strict: polynomial length is not a power of two");
@@ -398,14 +400,16 @@ class PolynomialBatch {
             b.polynomials.assign(polys.size(), std::vector<F>(n));
             std::vector<uint64_t*> outs;
             for (auto& p : b.polynomials) outs.push_back(p.data());
-            rc = gl_commit_from_values_cols(c.raw(), cols.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height, outs.data(),
-                                            &b.cap[0].elements[0], &b.h_);
+            rc = gl_commit_from_values_ex(c.raw(), nullptr, cols.data(), lg, (uint32_t)polys.size(), rate_bits, blinding ? 1 : 0,
+                                          cap_height, nullptr, outs.data(), &b.cap[0].elements[0], &b.h_, GL_HOST);
         } else {
-            rc = gl_commit_from_coeffs_cols(c.raw(), cols.data(), lg, (uint32_t)polys.size(), rate_bits, cap_height,
-                                            &b.cap[0].elements[0], &b.h_);
+            rc = gl_commit_from_coeffs_ex(c.raw(), nullptr, cols.data(), lg, (uint32_t)polys.size(), rate_bits, blinding ? 1 : 0,
+                                          cap_height, &b.cap[0].elements[0], &b.h_, GL_HOST);
             if (rc == GL_OK) b.polynomials = polys;
         }
         c.check(rc);
+        b.blinding = blinding;
+        c.check(gl_commit_leaf_len(b.h_, &b.leaf_len));
         return b;
     }
     gl_commit* h_ = nullptr;

@@ -115,6 +115,10 @@ SIGNATURES = {
     "gl_commit_from_coeffs": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp), cint]),
     "gl_commit_from_values_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, vp, C.POINTER(vp)]),
     "gl_commit_from_coeffs_cols": (cint, [vp, vp, u32, u32, u32, u32, vp, C.POINTER(vp)]),
+    "gl_commit_from_values_ex": (cint, [vp, vp, vp, u32, u32, u32, u32, u32, vp, vp, vp, C.POINTER(vp), cint]),
+    "gl_commit_from_coeffs_ex": (cint, [vp, vp, vp, u32, u32, u32, u32, u32, vp, C.POINTER(vp), cint]),
+    "gl_ctx_set_salt_seed": (cint, [vp, u64]),
+    "gl_commit_leaf_len": (cint, [vp, C.POINTER(u32)]),
     "gl_commit_begin": (cint, [vp, u32, u32, u32, u32, C.POINTER(vp)]),
     "gl_commit_begin_ex": (cint, [vp, u32, u32, u32, u32, u32, C.POINTER(vp)]),
     "gl_commit_add_coeffs": (cint, [vp, u32, u32, vp, cint]),

@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <random>
 #include <mutex>
 #include <new>
 #include <string>
@@ -56,6 +57,7 @@ struct gl_ctx {
     std::string err;
     uint32_t shard_index = 0, shard_count = 1;
     uint32_t compat = 0;   // GL_COMPAT_*: fork-version switches (gl_ctx_set_compat)
+    uint64_t salt_seed = 0, salt_counter = 0;   // blinding salt: seed from the OS at creation (gl_ctx_set_salt_seed overrides)
     std::map<std::tuple<int, uint64_t, uint64_t, uint64_t>, u64*> tables;
     DevBuf scratch[6];
     std::mutex mu;
@@ -79,12 +81,13 @@ struct gl_ctx {
 struct gl_commit {
     gl_ctx* ctx = nullptr;
     uint32_t log_n = 0, c = 0, rate_bits = 0, cap_height = 0;
+    uint32_t salt = 0;         // blinding: SALT_SIZE = 4 random columns after the c polynomial columns of every leaf
     uint32_t shard_index = 0, shard_count = 1;
     uint64_t n_local = 0;      // leaves held here
     uint64_t leaf_begin = 0;   // global index of the first local leaf
     uint32_t cap_local_bits = 0;
     u64* coeffs = nullptr;     // [c][n]
-    u64* lde = nullptr;        // [c][n_local]
+    u64* lde = nullptr;        // [c + salt][n_local]
     u64* digests = nullptr;    // [2*(n_local - 2^cap_local_bits)][4]
     u64* cap = nullptr;        // [2^cap_local_bits][4]
     uint64_t num_digests = 0;
@@ -97,6 +100,8 @@ struct gl_commit {
     u64* hstate = nullptr;     // [12][n_local] sponge states between blocks
     size_t hstate_bytes = 0;
 };
+
+static inline uint32_t leaf_len(const gl_commit* h) { return h->c + h->salt; }   // MerkleTree.leaves[i].len()
 
 static int fail(gl_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -632,6 +637,10 @@ extern "C" int gl_ctx_create(int device, gl_ctx** out) {
                                                         std::to_string(st - 1) + ")");
         gl_ctx_destroy(ctx);
         return rc;
+    }
+    {   // salt seed for blinded commits: the OS entropy source (upstream: F::rand_vec on the thread RNG)
+        std::random_device rd;
+        ctx->salt_seed = ((uint64_t)rd() << 32) ^ (uint64_t)rd() ^ ((uint64_t)(uintptr_t)ctx << 7);
     }
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
     *out = ctx;
@@ -1191,7 +1200,7 @@ static int commit_prepare(gl_ctx* ctx, gl_commit* h) {
     h->leaf_begin = (u64)h->shard_index * h->n_local;
     h->cap_local_bits = h->cap_height - lc;
     h->num_digests = 2 * (h->n_local - ((u64)1 << h->cap_local_bits));
-    h->lde_bytes = (size_t)h->c * h->n_local * 8;
+    h->lde_bytes = (size_t)leaf_len(h) * h->n_local * 8;
     h->digests_bytes = h->num_digests * 32;
     h->cap_bytes = (size_t)32 << h->cap_local_bits;
     TRY(dev_alloc(ctx, h->lde_bytes, &h->lde));
@@ -1218,9 +1227,14 @@ static int commit_lde_columns(gl_ctx* ctx, gl_commit* h, uint32_t col0, uint32_t
 // "build Merkle tree"
 static int commit_tree(gl_ctx* ctx, gl_commit* h, uint64_t* cap_out, int space, bool leaves_hashed = false) {
     const unsigned lg_local = h->log_n + h->rate_bits - ilog2(h->shard_count);
+    if (h->salt) {
+        // lde_values(): `.chain((0..salt_size).map(|_| F::rand_vec(degree << rate_bits)))` -- uniform field elements
+        launch_salt_fill(h->lde + (size_t)h->c * h->n_local, (u64)h->salt * h->n_local, ctx->salt_seed,
+                         (ctx->salt_counter++ << 8) | h->shard_index, ctx->stream);
+    }
     mark(ctx, 4);
     if (!leaves_hashed)
-        launch_leaf_hash_cols(h->lde, h->n_local, h->c, lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
+        launch_leaf_hash_cols(h->lde, h->n_local, leaf_len(h), lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 5);
     launch_merkle_levels(lg_local, h->cap_local_bits, h->digests, h->cap, ctx->stream);
     mark(ctx, 6);
@@ -1332,7 +1346,7 @@ static int commit_pipeline_host(gl_ctx* ctx, gl_commit* h, const HostCols& input
 
 static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uint32_t log_n, uint32_t c,
                          uint32_t rate_bits, uint32_t cap_height, const HostCols& coeffs_out, uint64_t* cap_out,
-                         gl_commit** handle, int space, const char* name) {
+                         gl_commit** handle, int space, const char* name, bool blinding = false) {
     if (!ctx) return GL_E_ARG;
     if (!handle || !input) return fail(ctx, GL_E_ARG, std::string(name) + ": NULL argument");
     *handle = nullptr;
@@ -1346,6 +1360,7 @@ static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uin
     gl_commit* h = new (std::nothrow) gl_commit();
     if (!h) return fail(ctx, GL_E_OOM, "host allocation failed");
     h->ctx = ctx; h->log_n = log_n; h->c = c; h->rate_bits = rate_bits; h->cap_height = cap_height;
+    h->salt = blinding ? GL_SALT_SIZE : 0;
     h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
     const u64 n = (u64)1 << log_n;
     const size_t poly_bytes = (size_t)c * n * 8;
@@ -1358,7 +1373,7 @@ static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uin
         mark(ctx, 1);
         mark(ctx, 2);
         mark(ctx, 3);
-        h->stream_hash = c > 4 && nblocks_host(h) > 1;
+        h->stream_hash = c > 4 && nblocks_host(h) > 1 && !h->salt;   // the salt columns only exist at the end
         rc = commit_pipeline_host(ctx, h, input, is_values, coeffs_out);
     } else if (rc == GL_OK) {
         cudaError_t e = cudaMemcpyAsync(h->coeffs, input.flat, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
@@ -1437,6 +1452,49 @@ extern "C" int gl_commit_from_coeffs_cols(gl_ctx* ctx, const uint64_t* const* co
                          "PolynomialBatch::from_coeffs");
 }
 
+// upstream's full signatures: from_values(values, rate_bits, blinding, cap_height, ..) / from_coeffs(..)
+extern "C" int gl_commit_from_values_ex(gl_ctx* ctx, const uint64_t* values, const uint64_t* const* values_cols, uint32_t log_n,
+                                        uint32_t c, uint32_t rate_bits, uint32_t blinding, uint32_t cap_height,
+                                        uint64_t* coeffs_out, uint64_t* const* coeffs_out_cols, uint64_t* cap_out,
+                                        gl_commit** handle, int space) {
+    if (!ctx) return GL_E_ARG;
+    if ((values != nullptr) == (values_cols != nullptr))
+        return fail(ctx, GL_E_ARG, "PolynomialBatch::from_values: pass the polynomials either as one array or as one array each");
+    if (values_cols && space != GL_HOST) return fail(ctx, GL_E_ARG, "PolynomialBatch::from_values: per-polynomial arrays are host memory");
+    HostCols in, out;
+    in.flat = const_cast<uint64_t*>(values);
+    in.cols = const_cast<uint64_t* const*>(values_cols);
+    if (values_cols) out.cols = coeffs_out_cols;
+    else out.flat = coeffs_out;
+    return commit_common(ctx, in, true, log_n, c, rate_bits, cap_height, out, cap_out, handle, space,
+                         "PolynomialBatch::from_values", blinding != 0);
+}
+extern "C" int gl_commit_from_coeffs_ex(gl_ctx* ctx, const uint64_t* coeffs, const uint64_t* const* coeffs_cols, uint32_t log_n,
+                                        uint32_t c, uint32_t rate_bits, uint32_t blinding, uint32_t cap_height, uint64_t* cap_out,
+                                        gl_commit** handle, int space) {
+    if (!ctx) return GL_E_ARG;
+    if ((coeffs != nullptr) == (coeffs_cols != nullptr))
+        return fail(ctx, GL_E_ARG, "PolynomialBatch::from_coeffs: pass the polynomials either as one array or as one array each");
+    if (coeffs_cols && space != GL_HOST) return fail(ctx, GL_E_ARG, "PolynomialBatch::from_coeffs: per-polynomial arrays are host memory");
+    HostCols in;
+    in.flat = const_cast<uint64_t*>(coeffs);
+    in.cols = const_cast<uint64_t* const*>(coeffs_cols);
+    return commit_common(ctx, in, false, log_n, c, rate_bits, cap_height, HostCols(), cap_out, handle, space,
+                         "PolynomialBatch::from_coeffs", blinding != 0);
+}
+extern "C" int gl_ctx_set_salt_seed(gl_ctx* ctx, uint64_t seed) {
+    if (!ctx) return GL_E_ARG;
+    Guard g(ctx);
+    ctx->salt_seed = seed;
+    ctx->salt_counter = 0;
+    return GL_OK;
+}
+extern "C" int gl_commit_leaf_len(const gl_commit* h, uint32_t* len) {
+    if (!h || !len) return GL_E_ARG;
+    *len = leaf_len(h);
+    return GL_OK;
+}
+
 extern "C" int gl_commit_begin(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint32_t rate_bits, uint32_t cap_height,
                                gl_commit** handle) {
     return gl_commit_begin_ex(ctx, log_n, c, rate_bits, cap_height, 0, handle);
@@ -1445,7 +1503,7 @@ extern "C" int gl_commit_begin_ex(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint3
                                   uint32_t flags, gl_commit** handle) {
     if (!ctx) return GL_E_ARG;
     if (!handle) return fail(ctx, GL_E_ARG, "gl_commit_begin: NULL handle");
-    if (flags & ~(uint32_t)GL_COMMIT_STREAM_HASH) return fail(ctx, GL_E_ARG, "gl_commit_begin_ex: unknown flag");
+    if (flags & ~(uint32_t)(GL_COMMIT_STREAM_HASH | GL_COMMIT_BLINDING)) return fail(ctx, GL_E_ARG, "gl_commit_begin_ex: unknown flag");
     *handle = nullptr;
     TRY(commit_check(ctx, log_n, c, rate_bits, cap_height, "PolynomialBatch::from_coeffs"));
     Guard g(ctx);
@@ -1455,7 +1513,9 @@ extern "C" int gl_commit_begin_ex(gl_ctx* ctx, uint32_t log_n, uint32_t c, uint3
     h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
     h->coeffs_bytes = ((size_t)c << log_n) * 8;
     h->finished = false;
-    h->stream_hash = (flags & GL_COMMIT_STREAM_HASH) && c > 4;   // <= 4 polynomials: hash_or_noop copies, nothing to absorb
+    h->salt = (flags & GL_COMMIT_BLINDING) ? GL_SALT_SIZE : 0;
+    // <= 4 polynomials: hash_or_noop copies, nothing to absorb; salted leaves: the salt columns only exist at the end
+    h->stream_hash = (flags & GL_COMMIT_STREAM_HASH) && c > 4 && !h->salt;
     int rc = dev_alloc(ctx, h->coeffs_bytes, &h->coeffs);
     if (rc == GL_OK) rc = commit_prepare(ctx, h);
     if (rc != GL_OK) {
@@ -1567,14 +1627,14 @@ extern "C" int gl_commit_download(gl_commit* h, uint64_t* leaves_out, uint64_t* 
     if (digests_out) TRY(copy_out(ctx, digests_out, h->digests, h->num_digests * 32, space));
     if (leaves_out) {
         if (space == GL_DEVICE) {
-            launch_transpose_to_rows(h->lde, h->n_local, h->c, 0, h->n_local, leaves_out, ctx->stream);
+            launch_transpose_to_rows(h->lde, h->n_local, leaf_len(h), 0, h->n_local, leaves_out, ctx->stream);
         } else {
             const u64 chunk = h->n_local < ((u64)1 << 16) ? h->n_local : ((u64)1 << 16);
             void* stage;
-            TRY(scratch_get(ctx, 0, (size_t)chunk * h->c * 8, &stage));
+            TRY(scratch_get(ctx, 0, (size_t)chunk * leaf_len(h) * 8, &stage));
             for (u64 r0 = 0; r0 < h->n_local; r0 += chunk) {
-                launch_transpose_to_rows(h->lde, h->n_local, h->c, r0, chunk, (u64*)stage, ctx->stream);
-                TRY(copy_out(ctx, leaves_out + (size_t)r0 * h->c, stage, (size_t)chunk * h->c * 8, GL_HOST));
+                launch_transpose_to_rows(h->lde, h->n_local, leaf_len(h), r0, chunk, (u64*)stage, ctx->stream);
+                TRY(copy_out(ctx, leaves_out + (size_t)r0 * leaf_len(h), stage, (size_t)chunk * leaf_len(h) * 8, GL_HOST));
                 CK(cudaStreamSynchronize(ctx->stream));   // `stage` is reused by the next chunk
             }
         }
@@ -1626,11 +1686,11 @@ extern "C" int gl_commit_open(gl_commit* h, const uint64_t* leaf_indices, uint32
         u64* d_rows = rows_out;
         if (space == GL_HOST) {
             void* t;
-            TRY(scratch_get(ctx, 0, (size_t)k * h->c * 8, &t));
+            TRY(scratch_get(ctx, 0, (size_t)k * leaf_len(h) * 8, &t));
             d_rows = (u64*)t;
         }
-        launch_gather_rows(h->lde, h->n_local, h->c, d_idx, k, d_rows, ctx->stream);
-        TRY(copy_out(ctx, rows_out, d_rows, (size_t)k * h->c * 8, space));
+        launch_gather_rows(h->lde, h->n_local, leaf_len(h), d_idx, k, d_rows, ctx->stream);
+        TRY(copy_out(ctx, rows_out, d_rows, (size_t)k * leaf_len(h) * 8, space));
     }
     if (paths_out && sub_bits) {
         u64* d_paths = paths_out;
@@ -1922,7 +1982,7 @@ extern "C" int gl_fri_prove(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num
     const uint32_t degree_bits = oracles[0]->log_n, rate_bits = prm->rate_bits, h = prm->cap_height, rounds = prm->num_query_rounds;
     const unsigned lgN = degree_bits + rate_bits;
     std::vector<uint32_t> ocols(num_oracles);
-    for (uint32_t i = 0; i < num_oracles; i++) ocols[i] = oracles[i]->c;
+    for (uint32_t i = 0; i < num_oracles; i++) ocols[i] = leaf_len(oracles[i]);
     uint64_t words = 0;
     if (gl_fri_proof_words(prm, ocols.data(), num_oracles, degree_bits, &words) != GL_OK)
         return fail(ctx, GL_E_ARG, "gl_fri_prove: reduction_arity_bits do not fit the degree / cap_height");
@@ -2061,15 +2121,15 @@ extern "C" int gl_fri_prove(gl_ctx* ctx, gl_commit* const* oracles, uint32_t num
     launch_challenger_step(d_ch, nullptr, 0, d_qch, rounds, nullptr, ctx->stream);
     FCK(cudaMemcpyAsync(d_cum, cum, sizeof cum, cudaMemcpyHostToDevice, ctx->stream));
     uint64_t query_stride = 1;
-    for (uint32_t i = 0; i < num_oracles; i++) query_stride += oracles[i]->c + 4ull * (lgN - h);
+    for (uint32_t i = 0; i < num_oracles; i++) query_stride += leaf_len(oracles[i]) + 4ull * (lgN - h);
     for (auto* t : trees) query_stride += t->c + 4ull * (t->log_n - h);
     u64* d_queries = d_proof + off;
     launch_fri_query_indices(d_qch, rounds, lgN, d_cum, layers, d_idx, d_queries, query_stride, ctx->stream);
     u64 qoff = 1;
     for (uint32_t i = 0; i < num_oracles; i++) {
         const gl_commit* o = oracles[i];
-        launch_gather_proof(o->lde, o->n_local, o->c, o->digests, lgN - h, d_idx, rounds, d_queries + qoff, query_stride, ctx->stream);
-        qoff += o->c + 4ull * (lgN - h);
+        launch_gather_proof(o->lde, o->n_local, leaf_len(o), o->digests, lgN - h, d_idx, rounds, d_queries + qoff, query_stride, ctx->stream);
+        qoff += leaf_len(o) + 4ull * (lgN - h);
     }
     for (uint32_t l = 0; l < layers; l++) {
         const gl_commit* t = trees[l];

@@ -370,12 +370,13 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
         if (!h) return bail(gfail(g, GL_E_OOM, "host allocation failed"));
         hs[i] = h;
         h->ctx = ctx; h->log_n = log_n; h->c = c; h->rate_bits = rate_bits; h->cap_height = cap_height;
+        h->salt = (flags & GL_COMMIT_BLINDING) ? GL_SALT_SIZE : 0;   // every rank salts its own leaves
         h->shard_index = ctx->shard_index; h->shard_count = ctx->shard_count;
         h->coeffs_bytes = (size_t)plan.cpad * n * 8;
         int rc = dev_alloc(ctx, h->coeffs_bytes, &h->coeffs);
         if (rc == GL_OK) rc = commit_prepare(ctx, h);
         if (rc != GL_OK) return bail(gfail(g, rc, ctx->err));
-        h->stream_hash = (flags & GL_COMMIT_STREAM_HASH) && c > 4;
+        h->stream_hash = (flags & GL_COMMIT_STREAM_HASH) && c > 4 && !h->salt;
         while (rk.ev.size() < 2 * (size_t)plan.rounds + 2) {
             cudaEvent_t e;
             cudaError_t ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -591,13 +592,13 @@ extern "C" int gl_group_commit_open(gl_group* g, gl_commit* const* handles, cons
     if (!h0) return gfail(g, GL_E_ARG, "gl_group_commit_open: NULL handle");
     const unsigned L = h0->log_n + h0->rate_bits - h0->cap_height;
     const u64 N = (u64)1 << (h0->log_n + h0->rate_bits);
-    const size_t row_words = h0->c, per = row_words + 4 * (size_t)L, words = per * k;
+    const size_t row_words = leaf_len(h0), per = row_words + 4 * (size_t)L, words = per * k;
     for (uint32_t q = 0; q < k; q++)
         if (leaf_indices[q] >= N) return gfail(g, GL_E_ARG, "MerkleTree::get / prove: leaf index out of range");
     for (uint32_t i = 0; i < nl; i++) {
         gl_group_rank& rk = g->r[i];
         const gl_commit* h = handles[i];
-        if (!h || h->ctx != rk.ctx || !h->finished || h->c != h0->c || h->log_n != h0->log_n || h->rate_bits != h0->rate_bits ||
+        if (!h || h->ctx != rk.ctx || !h->finished || h->c != h0->c || h->salt != h0->salt || h->log_n != h0->log_n || h->rate_bits != h0->rate_bits ||
             h->cap_height != h0->cap_height || h->shard_count != g->nranks)
             return gfail(g, GL_E_STATE, "gl_group_commit_open: handles[i] is not this group's shard of one commit");
         gl_ctx* ctx = rk.ctx;
@@ -630,7 +631,7 @@ extern "C" int gl_group_commit_open(gl_group* g, gl_commit* const* handles, cons
             GCK(g, cudaStreamSynchronize(ctx->stream));   // `meta` dies with this iteration
             const u64* d_loc = (const u64*)d;
             const u64* d_slot = d_loc + mine;
-            launch_gather_open(h->lde, h->n_local, h->c, h->digests, L, d_loc, d_slot, mine, rk.open_buf, per, ctx->stream);
+            launch_gather_open(h->lde, h->n_local, leaf_len(h), h->digests, L, d_loc, d_slot, mine, rk.open_buf, per, ctx->stream);
         }
         GCK(g, cudaEventRecord(ctx->dl_ev, ctx->stream));
         GCK(g, cudaStreamWaitEvent(rk.comm_stream, ctx->dl_ev, 0));

@@ -637,6 +637,33 @@ void launch_merkle_rows(const u64* leaves, u32 leaf_len, unsigned lg_leaves, uns
     }
 }
 
+// Blinding salt: `count` uniform field elements (plonky2's F::rand_vec = rng.gen_range(0..ORDER) per element).  Counter
+// mode: element i = mix(seed, stream, i) through two rounds of splitmix64, redrawn with a bumped counter while it falls
+// in [p, 2^64) (probability 2^-32 per draw).
+__device__ __forceinline__ u64 salt_mix(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(256) k_salt_fill(u64* __restrict__ out, u64 count, u64 seed, u64 stream) {
+    const u64 key = salt_mix(seed ^ salt_mix(stream));
+    for (u64 i = blockIdx.x * (u64)256 + threadIdx.x; i < count; i += (u64)gridDim.x * 256) {
+        u64 v, redraw = 0;
+        do {
+            v = salt_mix(salt_mix(key + i) ^ (redraw++ << 56) ^ key);
+        } while (v >= GL_P);
+        out[i] = v;
+    }
+}
+void launch_salt_fill(u64* out, u64 count, u64 seed, u64 stream, cudaStream_t st) {
+    if (!count) return;
+    u64 blocks = (count + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    k_salt_fill<<<(unsigned)blocks, 256, 0, st>>>(out, count, seed, stream);
+    ++g_gl_launches;
+}
+
 // N2: SMT bulk build (shares this translation unit's Poseidon constants)
 #include "smt_kernels.cu"
 #include "smt_proofs.cu"

@@ -36,3 +36,6 @@ void launch_merkle_rows(const uint64_t* leaves, uint32_t leaf_len, unsigned lg_l
 // `squeeze`; pow_state (or null) receives the 12-lane duplex state fri_proof_of_work grinds on.
 void launch_challenger_step(gl_challenger* ch, const uint64_t* observe, uint32_t n_obs, uint64_t* squeeze, uint32_t n_squeeze,
                             uint64_t* pow_state, cudaStream_t st);
+
+// blinding: `count` uniform field elements from (seed, stream) in counter mode
+void launch_salt_fill(uint64_t* out, uint64_t count, uint64_t seed, uint64_t stream, cudaStream_t st);

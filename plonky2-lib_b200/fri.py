@@ -354,7 +354,7 @@ def prove_openings_device(oracles, batches, challenger: Challenger, fri_params: 
     ch.input_len, ch.output_len = len(challenger.input_buffer), len(challenger.output_buffer)
     cb, nb, cp = _instance_arrays(batches)
     handles = (C.c_void_p * len(oracles))(*[o._h for o in oracles])
-    cols = (C.c_uint32 * len(oracles))(*[o.num_columns for o in oracles])
+    cols = (C.c_uint32 * len(oracles))(*[getattr(o, 'leaf_len', o.num_columns) for o in oracles])
     words = C.c_uint64(0)
     ctx.check(ctx._lib.gl_fri_proof_words(C.byref(prm), cols, len(oracles), fri_params.degree_bits, C.byref(words)))
     out = np.empty(words.value, dtype=np.uint64)
@@ -363,7 +363,7 @@ def prove_openings_device(oracles, batches, challenger: Challenger, fri_params: 
     challenger.sponge_state = np.array(list(ch.sponge_state), dtype=np.uint64)
     challenger.input_buffer = [int(ch.input_buffer[i]) for i in range(ch.input_len)]
     challenger.output_buffer = [int(ch.output_buffer[i]) for i in range(ch.output_len)]
-    return out if flat else parse_flat_proof(out, [o.num_columns for o in oracles], fri_params)
+    return out if flat else parse_flat_proof(out, [getattr(o, 'leaf_len', o.num_columns) for o in oracles], fri_params)
 
 
 def opening_set(oracles, batches) -> list:

@@ -138,6 +138,10 @@ class Context:
     def set_shard(self, index: int, count: int):
         self.check(self._lib.gl_ctx_set_shard(self._h, index, count))
 
+    def set_salt_seed(self, seed: int):
+        """Reproducible blinding salt (tests); by default the seed comes from the OS entropy source."""
+        self.check(self._lib.gl_ctx_set_salt_seed(self._h, seed & 0xFFFFFFFFFFFFFFFF))
+
     def sync(self):
         self.check(self._lib.gl_ctx_sync(self._h))
 
@@ -394,7 +398,7 @@ class ResidentMerkleTree:
         b = self._b
         lib, ctx = b._ctx._lib, b._ctx
         if want_leaves and self._leaves is None:
-            self._leaves = np.empty((b.num_local_leaves, b.num_columns), dtype=np.uint64)
+            self._leaves = np.empty((b.num_local_leaves, b.leaf_len), dtype=np.uint64)
             ctx.check(lib.gl_commit_download(b._h, self._leaves.ctypes.data, None, N.GL_HOST))
         if want_digests and self._digests is None:
             nd = 2 * (b.num_local_leaves - (1 << b.cap_local_bits))
@@ -447,11 +451,10 @@ class PolynomialBatch:
 
     @classmethod
     def _make(cls, inputs, is_values: bool, rate_bits: int, blinding: bool, cap_height: int, ctx, want_coeffs):
-        if blinding:
-            raise GlPanic(N.GL_E_ARG, "blinding (zero_knowledge) is not supported: every reference config uses zero_knowledge = false")
+        blinding = bool(blinding)
         ctx = _ctx(ctx)
         if isinstance(inputs, (list, tuple)) and inputs and all(isinstance(a, np.ndarray) and a.ndim == 1 for a in inputs):
-            return cls._make_cols(list(inputs), is_values, rate_bits, cap_height, ctx, want_coeffs)
+            return cls._make_cols(list(inputs), is_values, rate_bits, blinding, cap_height, ctx, want_coeffs)
         dev = _is_torch(inputs) and inputs.is_cuda
         if not dev:
             inputs = _h(inputs)
@@ -463,7 +466,7 @@ class PolynomialBatch:
         lg = n.bit_length() - 1
         self = object.__new__(cls)
         self._ctx = ctx
-        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, False, cap_height
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, blinding, cap_height
         self.num_columns = c
         cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
         h = C.c_void_p()
@@ -486,10 +489,17 @@ class PolynomialBatch:
                 else:
                     co = np.empty_like(inputs)
             bo = _Buf(co, True)
-            rc = ctx._lib.gl_commit_from_values(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bo.ptr, bc.ptr, C.byref(h), bi.space)
+            if blinding:
+                rc = ctx._lib.gl_commit_from_values_ex(ctx._h, bi.ptr, None, lg, c, rate_bits, 1, cap_height, bo.ptr, None, bc.ptr,
+                                                       C.byref(h), bi.space)
+            else:
+                rc = ctx._lib.gl_commit_from_values(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bo.ptr, bc.ptr, C.byref(h), bi.space)
             self._polys = co
         else:
-            rc = ctx._lib.gl_commit_from_coeffs(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bc.ptr, C.byref(h), bi.space)
+            if blinding:
+                rc = ctx._lib.gl_commit_from_coeffs_ex(ctx._h, bi.ptr, None, lg, c, rate_bits, 1, cap_height, bc.ptr, C.byref(h), bi.space)
+            else:
+                rc = ctx._lib.gl_commit_from_coeffs(ctx._h, bi.ptr, lg, c, rate_bits, cap_height, bc.ptr, C.byref(h), bi.space)
             self._polys = inputs
         ctx.check(rc)
         if dev:
@@ -498,7 +508,7 @@ class PolynomialBatch:
         return self
 
     @classmethod
-    def _make_cols(cls, cols, is_values: bool, rate_bits: int, cap_height: int, ctx, want_coeffs):
+    def _make_cols(cls, cols, is_values: bool, rate_bits: int, blinding: bool, cap_height: int, ctx, want_coeffs):
         """One host array per polynomial, as the reference holds them (Vec<PolynomialValues<F>>): no flattening,
         gl_commit_from_values_cols / gl_commit_from_coeffs_cols."""
         cols = [_h(a) for a in cols]
@@ -510,7 +520,7 @@ class PolynomialBatch:
         lg = n.bit_length() - 1
         self = object.__new__(cls)
         self._ctx = ctx
-        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, False, cap_height
+        self.degree_log, self.rate_bits, self.blinding, self.cap_height = lg, rate_bits, blinding, cap_height
         self.num_columns = c
         cap = np.zeros((1 << cap_height, 4), dtype=np.uint64)
         h = C.c_void_p()
@@ -520,10 +530,18 @@ class PolynomialBatch:
             if want_coeffs:
                 co = [np.empty(n, dtype=np.uint64) for _ in range(c)]
                 optrs = (C.c_void_p * c)(*[a.ctypes.data for a in co])
-            rc = ctx._lib.gl_commit_from_values_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, optrs, cap.ctypes.data, C.byref(h))
+            if blinding:
+                rc = ctx._lib.gl_commit_from_values_ex(ctx._h, None, ptrs, lg, c, rate_bits, 1, cap_height, None, optrs, cap.ctypes.data,
+                                                       C.byref(h), N.GL_HOST)
+            else:
+                rc = ctx._lib.gl_commit_from_values_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, optrs, cap.ctypes.data, C.byref(h))
             self._polys = co
         else:
-            rc = ctx._lib.gl_commit_from_coeffs_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, cap.ctypes.data, C.byref(h))
+            if blinding:
+                rc = ctx._lib.gl_commit_from_coeffs_ex(ctx._h, None, ptrs, lg, c, rate_bits, 1, cap_height, cap.ctypes.data, C.byref(h),
+                                                       N.GL_HOST)
+            else:
+                rc = ctx._lib.gl_commit_from_coeffs_cols(ctx._h, ptrs, lg, c, rate_bits, cap_height, cap.ctypes.data, C.byref(h))
             self._polys = cols
         ctx.check(rc)
         self._finish_make(h, cap, n)
@@ -536,6 +554,9 @@ class PolynomialBatch:
         ctx.check(ctx._lib.gl_commit_info(h, None, None, None, None, C.byref(lb), C.byref(le)))
         self.leaf_begin, self.leaf_end = lb.value, le.value
         self.num_local_leaves = le.value - lb.value
+        ll = C.c_uint32()
+        ctx.check(ctx._lib.gl_commit_leaf_len(h, C.byref(ll)))
+        self.leaf_len = ll.value   # MerkleTree.leaves[i].len(): num_columns, + SALT_SIZE when blinding
         total = n << self.rate_bits
         self.cap_local_bits = self.cap_height - ((total // self.num_local_leaves).bit_length() - 1)
         self.merkle_tree = ResidentMerkleTree(self, cap)
@@ -577,11 +598,12 @@ class PolynomialBatch:
         return out[0] if np.ndim(index) == 0 else out
 
     def open(self, leaf_indices: Sequence[int]):
-        """(rows [k][columns], paths [k][L][4]) = (tree.get(i), tree.prove(i).siblings) for every i."""
+        """(rows [k][leaf_len], paths [k][L][4]) = (tree.get(i), tree.prove(i).siblings) for every i; a blinded batch's rows
+        carry their SALT_SIZE salt elements after the polynomial values."""
         idx = _h(np.asarray(leaf_indices))
         k = idx.shape[0]
         L = self.degree_log + self.rate_bits - self.cap_height
-        rows = np.empty((k, self.num_columns), dtype=np.uint64)
+        rows = np.empty((k, self.leaf_len), dtype=np.uint64)
         paths = np.empty((k, L, 4), dtype=np.uint64)
         self._ctx.check(self._ctx._lib.gl_commit_open(self._h, idx.ctypes.data, k, rows.ctypes.data, paths.ctypes.data, N.GL_HOST))
         return rows, paths

@@ -46,6 +46,16 @@ extern "C" {
                                       coeffs_out: *const *mut u64, cap_out: *mut u64, handle: *mut *mut gl_commit) -> c_int;
     pub fn gl_commit_from_coeffs_cols(ctx: *mut gl_ctx, coeffs: *const *const u64, log_n: u32, c: u32, rate_bits: u32, cap_height: u32,
                                       cap_out: *mut u64, handle: *mut *mut gl_commit) -> c_int;
+    // upstream's full signatures (`blinding` taken): SALT_SIZE = 4 random elements appended to every leaf when blinding != 0
+    pub fn gl_commit_from_values_ex(ctx: *mut gl_ctx, values: *const u64, values_cols: *const *const u64, log_n: u32, c: u32,
+                                    rate_bits: u32, blinding: u32, cap_height: u32, coeffs_out: *mut u64,
+                                    coeffs_out_cols: *const *mut u64, cap_out: *mut u64, handle: *mut *mut gl_commit,
+                                    space: c_int) -> c_int;
+    pub fn gl_commit_from_coeffs_ex(ctx: *mut gl_ctx, coeffs: *const u64, coeffs_cols: *const *const u64, log_n: u32, c: u32,
+                                    rate_bits: u32, blinding: u32, cap_height: u32, cap_out: *mut u64,
+                                    handle: *mut *mut gl_commit, space: c_int) -> c_int;
+    pub fn gl_ctx_set_salt_seed(ctx: *mut gl_ctx, seed: u64) -> c_int;
+    pub fn gl_commit_leaf_len(h: *const gl_commit, len: *mut u32) -> c_int;
     // plonky2_field::fft on batches of columns, in place on [c][2^log_n] (PolynomialCoeffs::fft, PolynomialValues::ifft, coset_*)
     pub fn gl_fft_batch(ctx: *mut gl_ctx, data: *mut u64, log_n: u32, c: u32, space: c_int) -> c_int;
     pub fn gl_ifft_batch(ctx: *mut gl_ctx, data: *mut u64, log_n: u32, c: u32, space: c_int) -> c_int;

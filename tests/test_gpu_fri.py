@@ -369,6 +369,47 @@ def test_one_call_prover_matches_oracle(glb, ctx, oracle, rng, degree_bits, cols
         b.free()
 
 
+def test_one_call_prover_with_blinded_oracles(glb, ctx, oracle, rng):
+    """Salted (blinding = true) oracles through gl_fri_prove and the multi-call prover: the opened rows carry the SALT_SIZE
+    salt elements after the polynomial values, the proof equals the oracle prover's over the same salted trees, and both
+    verifiers (which index the evaluations by polynomial, i.e. ignore the salt as upstream's unsalted_evals does) accept."""
+    from oracle import fri_oracle as fo
+
+    fri = importlib.import_module("plonky2-lib_b200.fri")
+    fv = importlib.import_module("plonky2-lib_b200.fri_verifier")
+    degree_bits, cols, pow_bits, rate_bits, cap_height, rounds = 8, (6, 9, 3), 8, 3, 4, 28
+    n = 1 << degree_bits
+    ctx.set_salt_seed(99)
+    batches_dev, polys, trees = [], [], []
+    for k, c in enumerate(cols):
+        v = oracle.synthetic_values(c, n, seed=500 + k)
+        b = glb.PolynomialBatch.from_values(v, rate_bits, k != 1, cap_height)      # oracles 0 and 2 salted, 1 plain
+        batches_dev.append(b)
+        polys.append(oracle.commit_from_values(v, rate_bits, cap_height)["coeffs"])
+        trees.append(fo.MerkleTree(b.merkle_tree.leaves, cap_height))
+        assert np.array_equal(trees[-1].cap, b.merkle_tree.cap)
+        assert b.leaf_len == c + (4 if k != 1 else 0)
+    zeta = tuple(int(x) for x in rand_field(rng, (2,)))
+    instance = [(zeta, [(oi, pi) for oi, c in enumerate(cols) for pi in range(c)])]
+    cfg = glb.FriConfig(rate_bits=rate_bits, cap_height=cap_height, proof_of_work_bits=pow_bits, num_query_rounds=rounds)
+    params = fri.FriParams.for_degree(cfg, degree_bits)
+    ch, och, vch, pch, ch2 = fri.Challenger(), fo.Challenger(), fo.Challenger(), fri.Challenger(), fri.Challenger()
+    for t in trees:
+        for c in (ch, och, vch, pch, ch2):
+            c.observe_cap(t.cap)
+    got = fri.prove_openings_device(batches_dev, instance, ch, params)
+    want = fo.prove_openings(polys, trees, instance, och, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    _same_proof(got, want)
+    for rnd in got["query_round_proofs"]:
+        assert [len(row) for row, _ in rnd["initial_trees_proof"]] == [10, 9, 7]
+    openings = fo.opening_set(polys, instance)
+    assert fo.verify_openings(got, openings, [t.cap for t in trees], instance, vch, degree_bits, rate_bits, cap_height, pow_bits, rounds)
+    assert fv.verify_openings(instance, openings, [t.cap for t in trees], got, pch, params)
+    _same_proof(fri.prove_openings(batches_dev, instance, ch2, params), want)
+    for b in batches_dev:
+        b.free()
+
+
 def test_one_call_prover_matches_golden(glb, ctx):
     """tests/golden/fri_proof.json replayed through gl_fri_prove: the flat word stream IS the fixture's proof_flat."""
     import json

@@ -208,8 +208,6 @@ def test_commit_panics_like_upstream(glb, ctx, rng):
         glb.PolynomialBatch.from_values(rand_field(rng, (3, 12)), 3, False, 4)  # log2_strict
     with pytest.raises(glb.GlPanic):
         glb.PolynomialBatch.from_values(rand_field(rng, (3, 2)), 1, False, 4)  # cap_height > log2(N)
-    with pytest.raises(glb.GlPanic):
-        glb.PolynomialBatch.from_values(rand_field(rng, (3, 8)), 3, True, 4)  # blinding unsupported
 
 
 @pytest.mark.parametrize("count", [2, 4, 8])
@@ -568,7 +566,7 @@ def test_streamed_leaf_hashing_gives_the_same_commit(glb, ctx, oracle, rng, c, l
     ctx.check(lib.gl_commit_download(h, None, digests.ctypes.data, N.GL_HOST))
     assert np.array_equal(digests, want["digests"])
     lib.gl_commit_free(h)
-    assert lib.gl_commit_begin_ex(ctx._h, lg, c, 3, 4, 2, C.byref(h)) == N.GL_E_ARG      # unknown flag
+    assert lib.gl_commit_begin_ex(ctx._h, lg, c, 3, 4, 0x80, C.byref(h)) == N.GL_E_ARG   # unknown flag
 
 
 def test_streamed_leaf_hashing_sharded(glb, oracle, rng):
@@ -640,3 +638,45 @@ def test_merkle_verify_batch_accepts_openings_and_rejects_tampering(glb, ctx, or
     cap2[int(idx[5]) >> paths.shape[1], 3] ^= np.uint64(1)
     got = glb.host.merkle_verify_batch(rows, idx, paths, cap2)
     assert not got[5] and np.array_equal(got, np.array([oracle.merkle_verify(rows[i], int(idx[i]), paths[i], cap2, cap_height) for i in range(k)]))
+
+
+# ---- blinding = true (upstream signature; never set by the reference's configs) -------------------
+@pytest.mark.parametrize("lg_n,c,rate_bits,cap_height", [(6, 5, 3, 4), (10, 20, 3, 4), (3, 2, 1, 0), (16, 9, 3, 4)])
+def test_commit_with_blinding(glb, ctx, oracle, lg_n, c, rate_bits, cap_height):
+    """PolynomialBatch::from_values(.., blinding = true, ..): every leaf = the c LDE values + SALT_SIZE = 4 uniform field
+    elements (lde_values' `.chain(F::rand_vec)`); the tree is the oracle's MerkleTree::new over those leaves; openings carry
+    the salt and verify; get_lde_values strips it; the salt is reproducible under a seed and fresh otherwise."""
+    n, N = 1 << lg_n, (1 << lg_n) << rate_bits
+    values = oracle.synthetic_values(c, n, seed=7)
+    plain = glb.PolynomialBatch.from_values(values, rate_bits, False, cap_height)
+    ctx.set_salt_seed(1234)
+    b = glb.PolynomialBatch.from_values(values, rate_bits, True, cap_height)
+    assert b.blinding and b.leaf_len == c + 4 and b.num_columns == c
+    assert np.array_equal(b.polynomials, plain.polynomials)
+    leaves = b.merkle_tree.leaves
+    assert leaves.shape == (N, c + 4)
+    assert np.array_equal(leaves[:, :c], plain.merkle_tree.leaves)
+    salt = leaves[:, c:]
+    assert (salt < np.uint64(P)).all()
+    assert len(np.unique(salt)) > 0.99 * salt.size or salt.size < 64          # uniform 64-bit draws do not repeat
+    assert 0.3 < (salt >> np.uint64(63)).mean() < 0.7
+    want_digests, want_cap = oracle.merkle_tree(leaves, cap_height)
+    assert np.array_equal(b.merkle_tree.digests, want_digests)
+    assert np.array_equal(b.merkle_tree.cap, want_cap)
+    assert not np.array_equal(b.merkle_tree.cap, plain.merkle_tree.cap)
+    idx = sorted({0, N - 1, N // 3})
+    rows, paths = b.open(idx)
+    for q, i in enumerate(idx):
+        assert np.array_equal(rows[q], leaves[i])
+        assert oracle.merkle_verify(rows[q], i, paths[q], b.merkle_tree.cap, cap_height)
+    step = 1 << rate_bits
+    got = b.get_lde_values(n // 2, step)
+    assert got.shape == (c,) and np.array_equal(got, plain.get_lde_values(n // 2, step))
+    # same seed -> same salt; the default seed (OS entropy, then a counter) -> different salt on every commit
+    ctx.set_salt_seed(1234)
+    b2 = glb.PolynomialBatch.from_coeffs(np.ascontiguousarray(b.polynomials), rate_bits, True, cap_height)
+    assert np.array_equal(b2.merkle_tree.cap, b.merkle_tree.cap)
+    b3 = glb.PolynomialBatch.from_values([v.copy() for v in values], rate_bits, True, cap_height)   # one array per polynomial
+    assert not np.array_equal(b3.merkle_tree.cap, b.merkle_tree.cap) and b3.leaf_len == c + 4
+    for x in (plain, b, b2, b3):
+        x.free()
