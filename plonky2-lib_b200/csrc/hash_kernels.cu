@@ -10,36 +10,25 @@
 
 #include "hash_kernels.h"
 #include "poseidon.cuh"
+#include "poseidon_constants.h"
 
 #define HASH_BLOCK 128
 
 int gl_poseidon_upload_constants(const u64* rc360) {
     cudaError_t e = cudaMemcpyToSymbol(c_poseidon_rc, rc360, sizeof(u64) * POSEIDON_ROUNDS * POSEIDON_WIDTH);
     if (e != cudaSuccess) return (int)e;
-    // bit patterns of the two 32-bit halves, read by the FP64 MDS as denormal doubles
+    // bit patterns of the constants the FP64 linear layers add (poseidon_constants.h: linear_layer_tables)
     static u64 split[(POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH * 2];
-    for (int i = 0; i < POSEIDON_ROUNDS * POSEIDON_WIDTH; i++) {
-        split[2 * i] = rc360[i] & 0xFFFFFFFFULL;
-        split[2 * i + 1] = rc360[i] >> 32;
-    }
-    for (int i = POSEIDON_ROUNDS * POSEIDON_WIDTH * 2; i < (POSEIDON_ROUNDS + 1) * POSEIDON_WIDTH * 2; i++) split[i] = 0;
+    static u64 pk[(POSEIDON_PARTIAL / 2) * POSEIDON_WIDTH * 2];
+    static const int circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#ifdef POSEIDON_SPLIT_SBOX
+    const bool signed_sbox = true;
+#else
+    const bool signed_sbox = false;
+#endif
+    poseidon_constants::linear_layer_tables(rc360, circ, 8, signed_sbox, split, pk);
     e = cudaMemcpyToSymbol(c_poseidon_rc_split, split, sizeof(split));
     if (e != cudaSuccess) return (int)e;
-    // fused partial pairs: K[pair][lane] half sums (exact integers < 2^41)
-    static u64 pk[(POSEIDON_PARTIAL / 2) * POSEIDON_WIDTH * 2];
-    for (int pair = 0; pair < POSEIDON_PARTIAL / 2; pair++) {
-        const u64* r1 = rc360 + (POSEIDON_FULL_HALF + 2 * pair + 1) * 12;
-        const u64* r2 = rc360 + (POSEIDON_FULL_HALF + 2 * pair + 2) * 12;
-        for (int lane = 0; lane < 12; lane++) {
-            u64 lo = r2[lane] & 0xFFFFFFFFULL, hi = r2[lane] >> 32;
-            for (int i = 1; i < 12; i++) {
-                lo += (u64)poseidon_mds_entry(lane, i) * (r1[i] & 0xFFFFFFFFULL);
-                hi += (u64)poseidon_mds_entry(lane, i) * (r1[i] >> 32);
-            }
-            pk[(pair * 12 + lane) * 2] = lo;
-            pk[(pair * 12 + lane) * 2 + 1] = hi;
-        }
-    }
     return (int)cudaMemcpyToSymbol(c_poseidon_pair_k, pk, sizeof(pk));
 }
 

@@ -46,6 +46,30 @@ GL_D u64 poseidon_sbox(u64 x) {
 GL_D double u32_as_denormal(u32 x) { return __hiloint2double(0, (int)x); }
 GL_D u64 double_bits(double d) { return (u64)__double_as_longlong(d); }
 
+#ifndef POSEIDON_NO_SPLIT_SBOX
+#define POSEIDON_SPLIT_SBOX 1
+#endif
+#ifdef POSEIDON_SPLIT_SBOX
+// x^7 handed to the FP64 linear layer without the last modular reduction: the 128-bit product x^3 * x^4 =
+// r0 + r1 phi + r2 phi^2 + r3 phi^3 (phi = 2^32, phi^2 = phi - 1, phi^3 = -1) is (r0 - r2 - r3) + (r1 + r2) phi, and
+// the two coefficients are formed by three exact FP64 additions on the limbs' denormal images: dl in (-2^33, 2^32),
+// dh in [0, 2^33).  The linear layers are exact on signed integers below 2^52; the constants they add carry an offset
+// that is a multiple of p and makes every sum positive again (POSEIDON_OFF_*), so the fold is unchanged.
+GL_D void poseidon_sbox_split(u64 x, double& dl, double& dh) {
+    const u64 x2 = gl_sqr(x), x4 = gl_sqr(x2), x3 = gl_mul(x2, x);
+    const unsigned __int128 p = (unsigned __int128)x3 * x4;
+    const u64 lo = (u64)p, hi = (u64)(p >> 64);
+    const double r0 = u32_as_denormal((u32)lo), r1 = u32_as_denormal((u32)(lo >> 32));
+    const double r2 = u32_as_denormal((u32)hi), r3 = u32_as_denormal((u32)(hi >> 32));
+    dl = (r0 - r2) - r3;
+    dh = r1 + r2;
+}
+#endif
+// (the offsets live in the constant tables: poseidon_constants.h, linear_layer_tables(signed_sbox = true).  Exactness: every
+// operand is an integer multiple of 2^-1074, so FP64 sums and products are exact while they stay below 2^53: a full
+// round's layer sees |inputs| < 2^33 and peaks below 2^44; the fused pair's CIRC^2 form sees lane 0 in (-2^33, 2^32) and the
+// other lanes in [0, 2^32) and peaks below 2^49, its outputs landing in [0, 2^50) after the 2^48 offset.)
+
 // MDS entries: M[r][j] = CIRC[(j - r) mod 12] + (r == j ? DIAG[r] : 0)
 __host__ __device__ constexpr int poseidon_mds_entry(int r, int j) {
     constexpr int C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
@@ -146,9 +170,13 @@ GL_D void poseidon_full_round(u64 s[12], const double2* __restrict__ rc) {
     double dl[12], dh[12], yl[12], yh[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) {
+#ifdef POSEIDON_SPLIT_SBOX
+        poseidon_sbox_split(s[j], dl[j], dh[j]);
+#else
         const u64 x = poseidon_sbox(s[j]);
         dl[j] = u32_as_denormal((u32)x);
         dh[j] = u32_as_denormal((u32)(x >> 32));
+#endif
     }
     poseidon_circ12<0>(dl, yl);
     poseidon_circ12<0>(dh, yh);
@@ -182,14 +210,23 @@ GL_D void poseidon_partial_pair(u64 s[12], int pair) {
         yl = __fma_rn((double)poseidon_mds_entry(0, j), dl[j], yl);
         yh = __fma_rn((double)poseidon_mds_entry(0, j), dh[j], yh);
     }
+#ifdef POSEIDON_SPLIT_SBOX
+    poseidon_sbox_split(s[0], dl[0], dh[0]);
+#else
     const u64 x0 = poseidon_sbox(s[0]);
     dl[0] = u32_as_denormal((u32)x0);
     dh[0] = u32_as_denormal((u32)(x0 >> 32));
+#endif
     yl = __fma_rn((double)poseidon_mds_entry(0, 0), dl[0], yl);      // Yraw
     yh = __fma_rn((double)poseidon_mds_entry(0, 0), dh[0], yh);
     const double2 ky = c_poseidon_rc_split[(POSEIDON_FULL_HALF + 2 * pair + 1) * 12];
+#ifdef POSEIDON_SPLIT_SBOX
+    double gl, gh;
+    poseidon_sbox_split(poseidon_fold(yl + ky.x, yh + ky.y), gl, gh);
+#else
     const u64 sigma = poseidon_sbox(poseidon_fold(yl + ky.x, yh + ky.y));
     const double gl = u32_as_denormal((u32)sigma), gh = u32_as_denormal((u32)(sigma >> 32));
+#endif
     double zl[12], zh[12];
     poseidon_circ12<1>(dl, zl);
     poseidon_circ12<1>(dh, zh);

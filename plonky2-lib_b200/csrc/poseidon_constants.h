@@ -78,4 +78,50 @@ inline bool generate(uint64_t* rc) {
     return x == 0xd95d3c3bb2fe42e3ULL && rc[0] == 0xb585f766f2144405ULL && rc[359] == 0xbc8dfb627fe558fcULL;
 }
 
+// The constant tables of the FP64 linear layers (poseidon.cuh), as integer bit patterns of denormal doubles:
+//   split[(round) * 12 + lane] = (rc & 0xffffffff, rc >> 32), one extra all-zero round 30;
+//   pair_k[pair * 12 + lane]   = sum_{i>=1} M[lane][i] * rc[a+1][i] + rc[a+2][lane], a = 4 + 2 pair, by 32-bit halves.
+// signed_sbox: the S-box hands the linear layer (r0 - r2 - r3, r1 + r2) of its last 128-bit product, the first of which
+// can be as low as -2^33; every constant a sum with such a term meets then carries an offset that is 0 mod p and makes
+// the low accumulator positive: value = A + 2^32 B, p = 1 + 2^32 (2^32 - 1), so (A, B) += (2^e + k, k (2^32 - 1) - 2^(e-32))
+// with k = 1 (e = 42: one linear layer, gain <= 280) or k = 2^16 (e = 48: the fused pair, gain < 2^14.1 on lane 0).
+inline void linear_layer_tables(const uint64_t* rc, const int mds_circ[12], int mds_diag0, bool signed_sbox,
+                                uint64_t* split /* [31 * 12 * 2] */, uint64_t* pair_k /* [11 * 12 * 2] */) {
+    auto entry = [&](int r, int j) { return mds_circ[(j - r + 12) % 12] + ((r == 0 && j == 0) ? mds_diag0 : 0); };
+    for (int i = 0; i < 31 * 12; i++) {
+        const uint64_t v = i < 360 ? rc[i] : 0;
+        split[2 * i] = v & 0xFFFFFFFFULL;
+        split[2 * i + 1] = v >> 32;
+    }
+    if (signed_sbox) {
+        const uint64_t offA = (1ULL << 42) + 1, offB = 0xFFFFFFFFULL - (1ULL << 10);
+        for (int round = 0; round < 31; round++) {
+            const bool full_layer = (round >= 1 && round <= 4) || (round >= 27 && round <= 30);   // added by a full round's layer
+            const bool lane0_only = round >= 5 && round <= 25 && (round & 1);                   // y0 of a fused pair
+            for (int lane = 0; lane < 12; lane++)
+                if (full_layer || (lane0_only && lane == 0)) {
+                    split[2 * (round * 12 + lane)] += offA;
+                    split[2 * (round * 12 + lane) + 1] += offB;
+                }
+        }
+    }
+    for (int pair = 0; pair < 11; pair++) {
+        const uint64_t* r1 = rc + (4 + 2 * pair + 1) * 12;
+        const uint64_t* r2 = rc + (4 + 2 * pair + 2) * 12;
+        for (int lane = 0; lane < 12; lane++) {
+            uint64_t lo = r2[lane] & 0xFFFFFFFFULL, hi = r2[lane] >> 32;
+            for (int i = 1; i < 12; i++) {
+                lo += (uint64_t)entry(lane, i) * (r1[i] & 0xFFFFFFFFULL);
+                hi += (uint64_t)entry(lane, i) * (r1[i] >> 32);
+            }
+            if (signed_sbox) {
+                lo += (1ULL << 48) + (1ULL << 16);
+                hi += (1ULL << 16) * 0xFFFFFFFFULL - (1ULL << 16);
+            }
+            pair_k[(pair * 12 + lane) * 2] = lo;
+            pair_k[(pair * 12 + lane) * 2 + 1] = hi;
+        }
+    }
+}
+
 }  // namespace poseidon_constants

@@ -62,27 +62,55 @@ __global__ void k_circ_extremes(const u64* halves, int cases, int* bad) {
         if (double_bits(y1[r]) != c1[r] || double_bits(y2[r]) != c2[r]) atomicAdd(bad, 1);
 }
 
+// The same check for the SIGNED inputs of the split S-box: lanes in (-2^33, 2^32) for one layer (SQ = 0); lane 0 in that
+// range and lanes 1..11 in [0, 2^32) for the fused pair (SQ = 1).  v[t][i] = (a, b): the lane is denormal(a) - 2 denormal(b).
+__global__ void k_circ_signed(const u32* ab, int cases, int* bad) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cases) return;
+    const u32* h = ab + 24 * t;
+    const int C[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+    for (int sq = 0; sq < 2; sq++) {
+        double x[12], y[12];
+        long long xi[12], c1[12], c2[12];
+        for (int i = 0; i < 12; i++) {
+            const bool sgn = sq == 0 || i == 0;
+            const double a = u32_as_denormal(h[2 * i]), b = u32_as_denormal(h[2 * i + 1]);
+            x[i] = sgn ? (a - b) - b : a;
+            xi[i] = sgn ? (long long)h[2 * i] - 2 * (long long)h[2 * i + 1] : (long long)h[2 * i];
+        }
+        if (sq == 0) poseidon_circ12<0>(x, y);
+        else poseidon_circ12<1>(x, y);
+        for (int r = 0; r < 12; r++) {
+            long long acc = 0;
+            for (int i = 0; i < 12; i++) acc += (long long)C[i] * xi[(i + r) % 12];
+            c1[r] = acc;
+        }
+        for (int r = 0; r < 12; r++) {
+            long long acc = 0;
+            for (int i = 0; i < 12; i++) acc += (long long)C[i] * c1[(i + r) % 12];
+            c2[r] = acc;
+        }
+        for (int r = 0; r < 12; r++) {
+            // y is an integer multiple of 2^-1074 below 2^53 in magnitude: scale it up exactly and compare as an integer
+            const long long got = (long long)((y[r] * 0x1p537) * 0x1p537);
+            if (got != (sq ? c2[r] : c1[r])) atomicAdd(bad, 1);
+        }
+    }
+}
+
 int main() {
     u64 rc[360];
     if (!poseidon_constants::generate(rc)) { printf("constants fingerprint mismatch\n"); return 1; }
     cudaMemcpyToSymbol(c_poseidon_rc, rc, sizeof rc);
-    static u64 split[31 * 12 * 2];
-    for (int i = 0; i < 360; i++) { split[2 * i] = rc[i] & 0xFFFFFFFFULL; split[2 * i + 1] = rc[i] >> 32; }
+    static u64 split[31 * 12 * 2], pk[11 * 12 * 2];
+    static const int circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#ifdef POSEIDON_SPLIT_SBOX
+    const bool signed_sbox = true;
+#else
+    const bool signed_sbox = false;
+#endif
+    poseidon_constants::linear_layer_tables(rc, circ, 8, signed_sbox, split, pk);
     cudaMemcpyToSymbol(c_poseidon_rc_split, split, sizeof split);
-    static u64 pk[11 * 12 * 2];
-    for (int pair = 0; pair < 11; pair++) {
-        const u64* r1 = rc + (4 + 2 * pair + 1) * 12;
-        const u64* r2 = rc + (4 + 2 * pair + 2) * 12;
-        for (int lane = 0; lane < 12; lane++) {
-            u64 lo = r2[lane] & 0xFFFFFFFFULL, hi = r2[lane] >> 32;
-            for (int i = 1; i < 12; i++) {
-                lo += (u64)poseidon_mds_entry(lane, i) * (r1[i] & 0xFFFFFFFFULL);
-                hi += (u64)poseidon_mds_entry(lane, i) * (r1[i] >> 32);
-            }
-            pk[(pair * 12 + lane) * 2] = lo;
-            pk[(pair * 12 + lane) * 2 + 1] = hi;
-        }
-    }
     cudaMemcpyToSymbol(c_poseidon_pair_k, pk, sizeof pk);
     u64 h[12], *d;
     cudaMalloc(&d, 96);
@@ -124,6 +152,33 @@ int main() {
         k_circ_extremes<<<cases / 128, 128>>>(dh, cases, dbad);
         cudaMemcpy(&hbad, dbad, 4, cudaMemcpyDeviceToHost);
         printf("{\"circ12_extreme_cases\": %d, \"mismatches\": %d}\n", cases, hbad);
+        ok &= hbad == 0;
+        free(hh);
+    }
+    {
+        const int cases = 1 << 16;
+        u32* hh = (u32*)malloc((size_t)cases * 24 * 4);
+        u64 st = 0x9E3779B97F4A7C15ULL;
+        for (int t = 0; t < cases; t++)
+            for (int i = 0; i < 24; i++) {
+                st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+                u32 v = (u32)st;
+                const int mode = t & 7;   // extremes of a - 2b: all most negative, all most positive, alternating, random
+                if (mode == 0) v = (i & 1) ? 0xFFFFFFFFu : 0u;
+                else if (mode == 1) v = (i & 1) ? 0u : 0xFFFFFFFFu;
+                else if (mode == 2) v = (((i >> 1) + (t >> 3)) & 1) ? ((i & 1) ? 0xFFFFFFFFu : 0u) : ((i & 1) ? 0u : 0xFFFFFFFFu);
+                else if (mode == 3 && (st >> 40) % 3 == 0) v = 0xFFFFFFFFu;
+                hh[(size_t)t * 24 + i] = v;
+            }
+        u32* dh;
+        int *dbad, hbad = 0;
+        cudaMalloc(&dh, (size_t)cases * 96);
+        cudaMalloc(&dbad, 4);
+        cudaMemcpy(dh, hh, (size_t)cases * 96, cudaMemcpyHostToDevice);
+        cudaMemset(dbad, 0, 4);
+        k_circ_signed<<<cases / 128, 128>>>(dh, cases, dbad);
+        cudaMemcpy(&hbad, dbad, 4, cudaMemcpyDeviceToHost);
+        printf("{\"circ12_signed_cases\": %d, \"mismatches\": %d}\n", cases, hbad);
         ok &= hbad == 0;
         free(hh);
     }
