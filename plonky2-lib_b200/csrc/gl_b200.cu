@@ -57,6 +57,7 @@ struct gl_ctx {
     std::string err;
     uint32_t shard_index = 0, shard_count = 1;
     uint32_t compat = 0;   // GL_COMPAT_*: fork-version switches (gl_ctx_set_compat)
+    int tma_shift_tables = 0;   // cached TMA twiddle tables that belong to caller-chosen coset shifts (bounded)
     uint64_t salt_seed = 0, salt_counter = 0;   // blinding salt: seed from the OS at creation (gl_ctx_set_salt_seed overrides)
     std::map<std::tuple<int, uint64_t, uint64_t, uint64_t>, u64*> tables;
     DevBuf scratch[6];
@@ -466,6 +467,11 @@ static unsigned plan_passes(unsigned L, unsigned ms[4], bool fast[4]) {
     return 3;
 }
 
+static bool tma_table_cached(gl_ctx* ctx, const NttJob& j) {
+    auto key = std::make_tuple((int)TAB_TMA_POST, (uint64_t)(uintptr_t)j.pre_tab, ((uint64_t)j.L << 1) | (uint64_t)j.inverse,
+                               (uint64_t)j.cosets);
+    return ctx->tables.find(key) != ctx->tables.end();
+}
 // tables of the TMA path: post3 [cosets][256][2^s] followed by rowfac [cosets][256] (see ntt_kernels.h)
 static int tma_tables(gl_ctx* ctx, const NttJob& j, const u64* post_tab, const u64** post3, const u64** rowfac) {
     const unsigned s = j.L - 8;
@@ -480,6 +486,7 @@ static int tma_tables(gl_ctx* ctx, const NttJob& j, const u64* post_tab, const u
         TRY(dev_alloc(ctx, (t_elems + (size_t)j.cosets * 256) * sizeof(u64), &d));
         launch_ntt_tma_tables(d, d + t_elems, post_tab, j.pre_tab, s, j.cosets, ctx->stream);
         ctx->tables[key] = d;
+        if (j.pre_tab && !j.pre_direct_ok) ctx->tma_shift_tables++;
     }
     *post3 = d;
     *rowfac = j.pre_tab ? d + t_elems : nullptr;
@@ -490,7 +497,10 @@ static int run_dif(gl_ctx* ctx, const NttJob& j) {
     if (j.columns == 0) return GL_OK;
     const u64 n = (u64)1 << j.L;
     static const bool tma_off = getenv("GL_B200_NTT_TMA") && atoi(getenv("GL_B200_NTT_TMA")) == 0;
-    if (!tma_off && ntt_tma_supported(j.L) && j.final_scale == 1 && (!j.pre_tab || j.pre_direct_ok) &&
+    // a caller-chosen coset shift gets its own 2^L-entry table: fine for the handful a prover uses (7, 7^-1, FRI shifts), so
+    // the cache takes at most 24 of them and later shifts run on the radix-16 kernels below
+    const bool tma_tables_ok = !j.pre_tab || j.pre_direct_ok || tma_table_cached(ctx, j) || ctx->tma_shift_tables < 24;
+    if (!tma_off && ntt_tma_supported(j.L) && j.final_scale == 1 && tma_tables_ok &&
         (j.in_coset_stride == 0 || j.in_coset_stride == n) && (j.cosets == 1 || j.out_coset_stride == n)) {
         u64 w = glh::root_of_unity(j.L);
         if (j.inverse) w = glh::inv(w);
