@@ -607,12 +607,12 @@ def main():
         "note": "integer-pipe bound kernel (17 Poseidon permutations per 1080-byte leaf): see roofline_int",
     }
     # integer roofline: algorithmic work in 32x32->64 multiply-add equivalents against the MEASURED
-    # mad.wide.u32 issue rate of this GPU (tools/pipe_peaks.cu -> profiles/r1_pipe_peaks.json)
+    # mad.wide.u32 issue rate of this GPU (tools/pipe_peaks.cu -> profiles/r2_pipe_peaks.json)
     imad_peak, imad_src = 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1965 MHz"
     try:
         pk = json.load(open(os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")))
         imad_peak = float(pk["imad_wide"]["ops_per_s"])
-        imad_src = "measured mad.wide.u32 rate, profiles/r1_pipe_peaks.json (tools/pipe_peaks.cu)"
+        imad_src = "measured mad.wide.u32 rate, profiles/r2_pipe_peaks.json (tools/pipe_peaks.cu)"
     except Exception:
         pass
     perms_commit = N_local * ((cols + 7) // 8) + (N_local - (1 << CAP_HEIGHT) // world)
@@ -629,7 +629,7 @@ def main():
     roofline_int["frac"] = roofline_int["achieved"] / roofline_int["peak"]
     roofline_int["whole_commit_frac"] = roofline_int["whole_commit_achieved"] / roofline_int["peak"]
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_leaf_hash_traffic.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_leaf_hash_traffic.json")))
         if tr.get("cols") == cols:
             roofline["traffic"] = tr["dram_bytes_per_leaf"] * N_local
             roofline["traffic_source"] = tr.get("source")
