@@ -610,7 +610,7 @@ def main():
     # mad.wide.u32 issue rate of this GPU (tools/pipe_peaks.cu -> profiles/r2_pipe_peaks.json)
     imad_peak, imad_src = 148 * 64 * 1.965e9, "nominal 148 SM x 64 lanes x 1965 MHz"
     try:
-        pk = json.load(open(os.path.join(ROOT, "profiles", "r1_pipe_peaks.json")))
+        pk = json.load(open(os.path.join(ROOT, "profiles", "r2_pipe_peaks.json")))
         imad_peak = float(pk["imad_wide"]["ops_per_s"])
         imad_src = "measured mad.wide.u32 rate, profiles/r2_pipe_peaks.json (tools/pipe_peaks.cu)"
     except Exception:
