@@ -15,6 +15,8 @@ GL_OK, GL_E_ARG, GL_E_CUDA, GL_E_OOM, GL_E_STATE, GL_E_NCCL = 0, 1, 2, 3, 4, 5
 GL_GROUP_ID_BYTES = 128
 GL_HOST, GL_DEVICE = 0, 1
 GL_COMMIT_STREAM_HASH = 1
+GL_COMMIT_BLINDING = 2
+GL_SALT_SIZE = 4
 
 u64p = C.POINTER(C.c_uint64)
 vp = C.c_void_p

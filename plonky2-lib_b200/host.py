@@ -716,7 +716,7 @@ class Group:
         return dict(zip(Context.PHASES, [float(x) for x in out]))
 
     def commit(self, inputs, rate_bits: int, cap_height: int, is_values: bool = True, want_coeffs: bool = True,
-               stream_hash: bool = False) -> "ShardedPolynomialBatch":
+               stream_hash: bool = False, blinding: bool = False) -> "ShardedPolynomialBatch":
         """PolynomialBatch::from_values / from_coeffs over the group.  `inputs`: one host array [c][n] (shared by the local
         ranks), or a list with one CUDA tensor per local rank (the whole batch on each GPU)."""
         dev = isinstance(inputs, (list, tuple)) and len(inputs) == self.nlocal and all(_is_torch(x) and x.is_cuda for x in inputs)
@@ -738,7 +738,7 @@ class Group:
         caps = [np.zeros((1 << cap_height, 4), dtype=np.uint64) for _ in range(self.nlocal)]
         coeffs = None
         hs = (C.c_void_p * self.nlocal)()
-        flags = N.GL_COMMIT_STREAM_HASH if stream_hash else 0
+        flags = (N.GL_COMMIT_STREAM_HASH if stream_hash else 0) | (N.GL_COMMIT_BLINDING if blinding else 0)
         if dev:
             import torch
 
@@ -763,7 +763,8 @@ class Group:
         self.check(rc)
         if dev:
             caps = [t.cpu().numpy().view(np.uint64) for t in cap_dev]
-        return ShardedPolynomialBatch(self, [C.c_void_p(h) for h in hs], caps, coeffs, lg, c, rate_bits, cap_height)
+        return ShardedPolynomialBatch(self, [C.c_void_p(h) for h in hs], caps, coeffs, lg, c, rate_bits, cap_height,
+                                      c + (N.GL_SALT_SIZE if blinding else 0))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -780,9 +781,10 @@ class Group:
 class ShardedPolynomialBatch:
     """The local shards of one PolynomialBatch committed over a Group: the whole cap on every rank, `open` for any leaf."""
 
-    def __init__(self, group: Group, handles, caps, coeffs, degree_log, c, rate_bits, cap_height):
+    def __init__(self, group: Group, handles, caps, coeffs, degree_log, c, rate_bits, cap_height, leaf_len=None):
         self.group, self._hs, self.caps, self.coeffs = group, handles, caps, coeffs
         self._degree_log, self.num_columns, self.rate_bits, self.cap_height = degree_log, c, rate_bits, cap_height
+        self.leaf_len = leaf_len or c          # c + SALT_SIZE for a blinded commit
         self.cap = caps[0]
 
     @property
@@ -809,7 +811,7 @@ class ShardedPolynomialBatch:
         idx = _h(np.asarray(leaf_indices))
         k = idx.shape[0]
         L = self._degree_log + self.rate_bits - self.cap_height
-        rows = [np.empty((k, self.num_columns), dtype=np.uint64) for _ in range(g.nlocal)]
+        rows = [np.empty((k, self.leaf_len), dtype=np.uint64) for _ in range(g.nlocal)]
         paths = [np.empty((k, L, 4), dtype=np.uint64) for _ in range(g.nlocal)]
         hs = (C.c_void_p * g.nlocal)(*[h.value for h in self._hs])
         rp = (C.c_void_p * g.nlocal)(*[a.ctypes.data for a in rows])

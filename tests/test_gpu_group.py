@@ -69,6 +69,31 @@ def test_two_rank_group_in_one_process(glb, oracle, lg_n, c, r, h):
     g.close()
 
 
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_group_commit_with_blinding(glb, oracle, nranks):
+    """GL_COMMIT_BLINDING over a group: every rank salts its own leaves; the gathered cap is the oracle's MerkleTree::new over
+    the salted leaves as opened through gl_group_commit_open (every leaf, so the exchange is exercised for every owner)."""
+    if _ngpu() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    lg_n, c, r, h = 8, 11, 2, 3
+    g = glb.Group.local(list(range(nranks)))
+    values = oracle.synthetic_values(c, 1 << lg_n, seed=5)
+    plain = oracle.commit_from_values(values, r, h)
+    b = g.commit(values, r, h, blinding=True)
+    N = (1 << lg_n) << r
+    rows, paths = b.open(list(range(N)))
+    assert rows.shape == (N, c + 4) and b.leaf_len == c + 4
+    assert np.array_equal(rows[:, :c], plain["leaves"])
+    assert (rows[:, c:] < np.uint64(0xFFFFFFFF00000001)).all() and len(np.unique(rows[:, c:])) > 0.99 * 4 * N
+    digests, cap = oracle.merkle_tree(rows, h)
+    for cp in b.caps:
+        assert np.array_equal(cp, cap)
+    for i in (0, N // 2 - 1, N // 2, N - 1):
+        assert np.array_equal(paths[i], oracle.merkle_prove(digests, N, h, i))
+    b.free()
+    g.close()
+
+
 def test_group_rejects_bad_geometry(glb):
     g = glb.Group.local([0])
     with pytest.raises(glb.GlPanic):
