@@ -18,6 +18,7 @@
 #include <array>
 #include <string>
 #include <utility>
+#include <cstring>
 #include <vector>
 
 #include "gl_b200.h"
@@ -654,5 +655,186 @@ inline FriProof prove_openings(const Context& c, const std::vector<FriBatchInfo>
                               polys.data(), alpha, fp.config.rate_bits, coeffs.u64(), values.u64(), GL_DEVICE));
     return fri_proof_resident(c, oracles, coeffs.u64(), values.u64(), n, challenger, fp);
 }
+
+// PolynomialBatch::prove_openings + fri_proof through ONE C-ABI call (gl_fri_prove): the Fiat-Shamir transcript runs on the
+// device from `challenger`'s current state and comes back advanced past the proof; one copy brings the proof back.
+// final_poly_times_x selects the fork form of upstream PR #436 (GL_COMPAT_FRI_FINAL_POLY_TIMES_X).
+inline FriProof prove_openings_device(const Context& c, const std::vector<FriBatchInfo>& instance,
+                                      const std::vector<const PolynomialBatch*>& oracles, Challenger& challenger,
+                                      const FriParams& fp, bool final_poly_times_x = false) {
+    if (fp.reduction_arity_bits.size() > GL_FRI_MAX_LAYERS) throw Panic(GL_E_ARG, "too many FRI reduction layers");
+    std::vector<gl_fri_batch> batches;
+    std::vector<gl_fri_poly> polys;
+    for (auto& b : instance) {
+        gl_fri_batch gb;
+        gb.point[0] = b.point[0];
+        gb.point[1] = b.point[1];
+        gb.first_poly = (uint32_t)polys.size();
+        gb.num_polys = (uint32_t)b.polynomials.size();
+        for (auto& pr : b.polynomials) polys.push_back({pr.first, pr.second});
+        batches.push_back(gb);
+    }
+    gl_fri_params prm;
+    std::memset(&prm, 0, sizeof prm);
+    prm.rate_bits = fp.config.rate_bits;
+    prm.cap_height = fp.config.cap_height;
+    prm.proof_of_work_bits = fp.config.proof_of_work_bits;
+    prm.num_query_rounds = fp.config.num_query_rounds;
+    prm.num_reduction_layers = (uint32_t)fp.reduction_arity_bits.size();
+    for (size_t i = 0; i < fp.reduction_arity_bits.size(); i++) prm.reduction_arity_bits[i] = fp.reduction_arity_bits[i];
+    prm.flags = final_poly_times_x ? GL_COMPAT_FRI_FINAL_POLY_TIMES_X : 0;
+    gl_challenger ch;
+    std::memset(&ch, 0, sizeof ch);
+    for (int i = 0; i < 12; i++) ch.sponge_state[i] = challenger.sponge_state[i];
+    ch.input_len = (uint32_t)challenger.input_buffer.size();
+    ch.output_len = (uint32_t)challenger.output_buffer.size();
+    for (uint32_t i = 0; i < ch.input_len; i++) ch.input_buffer[i] = challenger.input_buffer[i];
+    for (uint32_t i = 0; i < ch.output_len; i++) ch.output_buffer[i] = challenger.output_buffer[i];
+    std::vector<gl_commit*> handles;
+    std::vector<uint32_t> widths;
+    for (auto* o : oracles) {
+        handles.push_back(o->raw_handle());
+        widths.push_back(o->leaf_len);
+    }
+    uint64_t words = 0;
+    c.check(gl_fri_proof_words(&prm, widths.data(), (uint32_t)widths.size(), fp.degree_bits, &words));
+    std::vector<uint64_t> flat(words);
+    c.check(gl_fri_prove(c.raw(), handles.data(), (uint32_t)handles.size(), batches.data(), (uint32_t)batches.size(), polys.data(),
+                         &prm, &ch, flat.data(), words, &words));
+    for (int i = 0; i < 12; i++) challenger.sponge_state[i] = ch.sponge_state[i];
+    challenger.input_buffer.assign(ch.input_buffer, ch.input_buffer + ch.input_len);
+    challenger.output_buffer.assign(ch.output_buffer, ch.output_buffer + ch.output_len);
+    // the word stream -> FriProof (field order of include/gl_b200.h)
+    FriProof proof;
+    size_t at = 0;
+    const uint32_t h = fp.config.cap_height, lgN = fp.degree_bits + fp.config.rate_bits;
+    auto take_path = [&](uint32_t len) {
+        MerkleProof mp;
+        for (uint32_t l = 0; l < len; l++) {
+            HashOut d;
+            for (int e = 0; e < 4; e++) d.elements[e] = flat[at++];
+            mp.siblings.push_back(d);
+        }
+        return mp;
+    };
+    uint32_t lg = lgN;
+    for (uint32_t ab : fp.reduction_arity_bits) {
+        MerkleCap cap(1ull << h);
+        for (auto& d : cap)
+            for (int e = 0; e < 4; e++) d.elements[e] = flat[at++];
+        proof.commit_phase_merkle_caps.push_back(std::move(cap));
+        lg -= ab;
+    }
+    const size_t final_words = (size_t)2 << (lg - fp.config.rate_bits);
+    proof.final_poly.assign(flat.begin() + at, flat.begin() + at + final_words);
+    at += final_words;
+    proof.pow_witness = flat[at++];
+    proof.query_round_proofs.resize(fp.config.num_query_rounds);
+    for (auto& rnd : proof.query_round_proofs) {
+        rnd.x_index = flat[at++];
+        for (uint32_t w : widths) {
+            std::vector<F> row(flat.begin() + at, flat.begin() + at + w);
+            at += w;
+            MerkleProof mp = take_path(lgN - h);
+            rnd.initial_trees_proof.emplace_back(std::move(row), std::move(mp));
+        }
+        uint32_t cur = lgN;
+        for (uint32_t ab : fp.reduction_arity_bits) {
+            FriQueryStep st;
+            st.evals.assign(flat.begin() + at, flat.begin() + at + ((size_t)2 << ab));
+            at += (size_t)2 << ab;
+            cur -= ab;
+            st.merkle_proof = take_path(cur - h);
+            rnd.steps.push_back(std::move(st));
+        }
+    }
+    if (at != flat.size()) throw Panic(GL_E_STATE, "gl_fri_prove: proof stream of unexpected length");
+    return proof;
+}
+
+// plonky2::plonk::prover compute_quotient_polys on the three resident prove-time oracles (gl_quotient_polys): returns
+// quotient_polys.flat_map(|p| p.chunks(degree)), num_challenges * quotient_degree_factor coefficient vectors of 2^degree_bits.
+inline std::vector<std::vector<F>> compute_quotient_polys(const Context& c, const gl_circuit& circuit, const std::vector<gl_gate>& gates,
+                                                          const std::vector<F>& k_is, const PolynomialBatch& constants_sigmas,
+                                                          const PolynomialBatch& wires, const PolynomialBatch& zs_partial_products,
+                                                          const HashOut& public_inputs_hash, const std::vector<F>& betas,
+                                                          const std::vector<F>& gammas, const std::vector<F>& alphas) {
+    const size_t n = (size_t)1 << circuit.degree_bits, chunks = (size_t)circuit.num_challenges * circuit.quotient_degree_factor;
+    std::vector<F> flat(chunks * n);
+    c.check(gl_quotient_polys(c.raw(), &circuit, gates.data(), k_is.data(), constants_sigmas.raw_handle(), wires.raw_handle(),
+                              zs_partial_products.raw_handle(), public_inputs_hash.elements, betas.data(), gammas.data(),
+                              alphas.data(), flat.data(), GL_HOST));
+    std::vector<std::vector<F>> out;
+    for (size_t i = 0; i < chunks; i++) out.emplace_back(flat.begin() + i * n, flat.begin() + (i + 1) * n);
+    return out;
+}
+
+// One commit sharded over the GPUs of a box (gl_group_*: NCCL behind the C ABI); this process holds every rank.
+class Group {
+   public:
+    explicit Group(const std::vector<const Context*>& ctxs) : ctxs_(ctxs) {
+        std::vector<gl_ctx*> raw;
+        for (auto* c : ctxs) raw.push_back(c->raw());
+        int rc = gl_group_create(raw.data(), (uint32_t)raw.size(), 0, (uint32_t)raw.size(), nullptr, &g_);
+        if (rc) throw Panic(rc, gl_last_error(nullptr));
+    }
+    ~Group() { gl_group_destroy(g_); }
+    Group(const Group&) = delete;
+    Group& operator=(const Group&) = delete;
+    void check(int rc) const {
+        if (rc) throw Panic(rc, gl_group_last_error(g_));
+    }
+    struct Sharded {   // the local shards of one PolynomialBatch + the whole cap
+        std::vector<gl_commit*> handles;
+        MerkleCap cap;
+        std::vector<F> coefficients;   // [c][n]: every rank writes its polynomials into the one array
+        uint32_t c = 0, degree_log = 0, rate_bits = 0, cap_height = 0, leaf_len = 0;
+    };
+    // values: [c][n] contiguous host array shared by the ranks
+    Sharded commit_from_values(const std::vector<F>& values, uint32_t c, uint32_t log_n, uint32_t rate_bits, uint32_t cap_height,
+                               uint32_t flags = 0) {
+        const size_t nl = ctxs_.size();
+        Sharded s;
+        s.c = c; s.degree_log = log_n; s.rate_bits = rate_bits; s.cap_height = cap_height;
+        s.leaf_len = c + ((flags & GL_COMMIT_BLINDING) ? GL_SALT_SIZE : 0);
+        s.coefficients.resize(values.size());
+        s.handles.assign(nl, nullptr);
+        std::vector<std::vector<F>> caps(nl, std::vector<F>((size_t)4 << cap_height));
+        std::vector<const uint64_t*> in(nl, values.data());
+        std::vector<uint64_t*> co(nl, s.coefficients.data()), cp;
+        for (auto& v : caps) cp.push_back(v.data());
+        check(gl_group_commit_from_values(g_, in.data(), log_n, c, rate_bits, cap_height, co.data(), cp.data(), s.handles.data(),
+                                          GL_HOST, flags));
+        s.cap.resize(1ull << cap_height);
+        for (size_t i = 0; i < s.cap.size(); i++)
+            for (int e = 0; e < 4; e++) s.cap[i].elements[e] = caps[0][4 * i + e];
+        return s;
+    }
+    // rows [k][leaf_len] and paths [k][L][4] for GLOBAL leaf indices, whoever owns them
+    void open(const Sharded& s, const std::vector<uint64_t>& idx, std::vector<F>* rows, std::vector<F>* paths) {
+        const size_t nl = ctxs_.size(), k = idx.size(), L = s.degree_log + s.rate_bits - s.cap_height;
+        std::vector<std::vector<F>> r(nl, std::vector<F>(k * s.leaf_len)), p(nl, std::vector<F>(k * L * 4 + 4));
+        std::vector<uint64_t*> rp, pp;
+        for (size_t i = 0; i < nl; i++) {
+            rp.push_back(r[i].data());
+            pp.push_back(p[i].data());
+        }
+        check(gl_group_commit_open(g_, s.handles.data(), idx.data(), (uint32_t)k, rp.data(), pp.data(), GL_HOST));
+        if (rows) *rows = r[0];
+        if (paths) {
+            p[0].resize(k * L * 4);
+            *paths = p[0];
+        }
+    }
+    static void free(Sharded& s) {
+        for (auto* h : s.handles)
+            if (h) gl_commit_free(h);
+        s.handles.clear();
+    }
+
+   private:
+    std::vector<const Context*> ctxs_;
+    gl_group* g_ = nullptr;
+};
 
 }  // namespace plonky2_b200

@@ -583,13 +583,14 @@ static int run_dif(gl_ctx* ctx, const NttJob& j) {
 }
 
 // natural -> natural transform of [c][n] columns at `data` (device), through scratch slot 1
+// `src` (default: data itself) holds the input columns; the result always lands in `data`
 static int transform_natural(gl_ctx* ctx, u64* data, unsigned L, uint32_t c, bool inverse, const u64* pre_tab,
-                             const u64* post_scale_tab) {
+                             const u64* post_scale_tab, const u64* src = nullptr) {
     const u64 n = (u64)1 << L;
     void* tmp;
     TRY(scratch_get(ctx, 1, (size_t)c * n * sizeof(u64), &tmp));
     NttJob j;
-    j.in = data; j.in_ld = n; j.out = (u64*)tmp; j.out_ld = n;
+    j.in = src ? src : data; j.in_ld = n; j.out = (u64*)tmp; j.out_ld = n;
     j.L = L; j.columns = c; j.cosets = 1; j.inverse = inverse; j.pre_tab = pre_tab;
     TRY(run_dif(ctx, j));
     u64 scale = inverse ? glh::inv(glh::canon(n % GL_P)) : 1;
@@ -1386,11 +1387,14 @@ static int commit_common(gl_ctx* ctx, const HostCols& input, bool is_values, uin
         h->stream_hash = c > 4 && nblocks_host(h) > 1 && !h->salt;   // the salt columns only exist at the end
         rc = commit_pipeline_host(ctx, h, input, is_values, coeffs_out);
     } else if (rc == GL_OK) {
-        cudaError_t e = cudaMemcpyAsync(h->coeffs, input.flat, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
-        if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials");
+        if (!is_values) {
+            cudaError_t e = cudaMemcpyAsync(h->coeffs, input.flat, poly_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = cuda_fail(ctx, e, "copy polynomials");
+        }
         mark(ctx, 1);
         if (rc == GL_OK && is_values) {
-            rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr);  // "IFFT"
+            // "IFFT": reads the caller's values where they lie, the coefficients land behind the handle
+            rc = transform_natural(ctx, h->coeffs, log_n, c, true, nullptr, nullptr, input.flat);
             mark(ctx, 2);
             if (rc == GL_OK) rc = copy_out(ctx, coeffs_out.flat, h->coeffs, poly_bytes, space);
         } else {

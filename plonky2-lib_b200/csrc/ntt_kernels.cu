@@ -424,7 +424,8 @@ void launch_deinterleave2(const u64* ext, u64 n, u64* cols, u64 ld, cudaStream_t
 //            twiddle w_{2^M}^(k1 * low) from a shared-memory table;
 //   round 2: after one exchange through shared memory, radix-16 over the next 4 bits, twiddle
 //            w_{2^(M-4)}^(k2 * low);
-//   round 3: the last M-8 <= 2 bits are warp-shuffle butterflies; results go straight to HBM with
+//   round 3: the last M-8 <= 2 bits after a second exchange through shared memory (its own swizzle), as 2^(4-LB)
+//            independent radix-2^LB blocks per thread; results go straight to HBM with
 //            the four-step twiddle w_{2^(s+M)}^(k * j_lo).
 // 2^192 = 1 (mod p): every root of unity of order <= 64 is a power of two (plonky2's w_16 is 2^156),
 // so the 17 twiddles inside a radix-16 block are compile-time constants with one or two set bits per

@@ -42,7 +42,8 @@ void launch_fri_fold(const uint64_t* coeffs_ext, uint64_t out_len, unsigned arit
 void launch_interleave2(const uint64_t* cols, uint64_t ld, uint64_t n, uint64_t* ext, cudaStream_t st);
 void launch_deinterleave2(const uint64_t* ext, uint64_t n, uint64_t* cols, uint64_t ld, cudaStream_t st);
 
-// ---- fast pass: 2^M-point DFTs (M = 8, 9, 10) as two radix-16 register rounds + warp-shuffle stages ----
+// ---- fast pass: 2^M-point DFTs (M = 8, 9, 10) as two radix-16 register rounds + a radix-2^(M-8) round, one exchange
+// through shared memory between rounds (sizes and shifts the TMA path below does not take) ----
 struct ntt16_args {
     const uint64_t* in;
     uint64_t in_ld, in_coset_stride;

@@ -9,7 +9,8 @@
 //       load into shared memory and written back by one TMA box store, so HBM sees whole 128-byte lines both ways.
 //       Coset shift and four-step twiddle are one coalesced table read: T[coset][row][j] = (shift * w^brev(row))^j.
 //   pass 2 (k_ntt_tma_contig): 2^s-point DFTs (s = 8..12) over contiguous 4096-element (32 KB) blocks, fetched by
-//       one cp.async.bulk each; results leave the registers as 16-byte stores that complete whole lines.
+//       one cp.async.bulk each; the finished tile is laid out in the TMA engine's 128-byte swizzle (every thread owns
+//       whole 16-byte chunks of 128-byte rows, conflict-free) and leaves through one swizzled box store.
 //
 // Both kernels are persistent (two CTAs of 256 threads per SM), double-buffered: while a CTA works on tile t the TMA
 // engine fills the other buffer with tile t + 1, so no warp ever waits on a strided global load.

@@ -65,8 +65,72 @@ int main(int argc, char** argv) {
                 for (int e = 0; e < 4; e++) put(h.elements[e]);
         }
     }
-    put(ch.get_challenge());  // the transcript ends in the same state
+    const F last = ch.get_challenge();
+    put(last);  // the transcript ends in the same state
     std::fclose(f);
+
+    // the one-call prover (gl_fri_prove, transcript on the device) returns the same FriProof and the same transcript
+    {
+        Challenger ch1(ctx);
+        for (auto* o : oracles) ch1.observe_cap(o->cap);
+        FriProof one = prove_openings_device(ctx, {b0, b1}, oracles, ch1, fp);
+        bool same = one.pow_witness == proof.pow_witness && one.final_poly == proof.final_poly &&
+                    one.commit_phase_merkle_caps.size() == proof.commit_phase_merkle_caps.size() &&
+                    one.query_round_proofs.size() == proof.query_round_proofs.size() && ch1.get_challenge() == last;
+        for (size_t i = 0; same && i < one.commit_phase_merkle_caps.size(); i++)
+            for (size_t j = 0; j < one.commit_phase_merkle_caps[i].size(); j++)
+                for (int e = 0; e < 4; e++)
+                    same = same && one.commit_phase_merkle_caps[i][j].elements[e] == proof.commit_phase_merkle_caps[i][j].elements[e];
+        auto same_path = [](const MerkleProof& a, const MerkleProof& b) {
+            if (a.siblings.size() != b.siblings.size()) return false;
+            for (size_t i = 0; i < a.siblings.size(); i++)
+                for (int e = 0; e < 4; e++)
+                    if (a.siblings[i].elements[e] != b.siblings[i].elements[e]) return false;
+            return true;
+        };
+        for (size_t q = 0; same && q < one.query_round_proofs.size(); q++) {
+            auto &x = one.query_round_proofs[q], &y = proof.query_round_proofs[q];
+            same = x.x_index == y.x_index && x.initial_trees_proof.size() == y.initial_trees_proof.size() && x.steps.size() == y.steps.size();
+            for (size_t i = 0; same && i < x.initial_trees_proof.size(); i++)
+                same = x.initial_trees_proof[i].first == y.initial_trees_proof[i].first &&
+                       same_path(x.initial_trees_proof[i].second, y.initial_trees_proof[i].second);
+            for (size_t i = 0; same && i < x.steps.size(); i++)
+                same = x.steps[i].evals == y.steps[i].evals && same_path(x.steps[i].merkle_proof, y.steps[i].merkle_proof);
+        }
+        if (!same) {
+            std::puts("prove_openings_device differs from prove_openings");
+            return 3;
+        }
+    }
+    // a one-rank Group runs the sharded commit path (no collective needed) and must reproduce oracle 1's cap and rows
+    try {
+        Group grp({&ctx});
+        const uint32_t c1 = cols[1], n1 = 1u << degree_bits;
+        std::vector<F> flat((size_t)c1 * n1);
+        for (uint32_t j = 0; j < c1; j++)
+            for (uint32_t i = 0; i < n1; i++) flat[(size_t)j * n1 + i] = splitmix((700 + 1) ^ (((uint64_t)j << 32) + i));
+        Group::Sharded sh = grp.commit_from_values(flat, c1, degree_bits, cfg.rate_bits, cfg.cap_height);
+        bool ok = sh.cap.size() == batches[1].cap.size();
+        for (size_t i = 0; ok && i < sh.cap.size(); i++)
+            for (int e = 0; e < 4; e++) ok = ok && sh.cap[i].elements[e] == batches[1].cap[i].elements[e];
+        std::vector<uint64_t> idx = {0, 5, (uint64_t)(n1 << cfg.rate_bits) - 1};
+        std::vector<F> rows, paths;
+        grp.open(sh, idx, &rows, &paths);
+        auto ref = batches[1].open(idx);
+        for (size_t q = 0; ok && q < idx.size(); q++)
+            for (uint32_t j = 0; j < c1; j++) ok = ok && rows[q * c1 + j] == ref.first[q][j];
+        for (uint32_t j = 0; ok && j < c1; j++)
+            for (uint32_t i = 0; i < n1; i++) ok = ok && sh.coefficients[(size_t)j * n1 + i] == batches[1].polynomials[j][i];
+        Group::free(sh);
+        if (!ok) {
+            std::puts("Group commit differs from PolynomialBatch::from_values");
+            return 4;
+        }
+        std::puts("group ok");
+    } catch (const Panic& e) {
+        if (e.code != GL_E_NCCL) throw;
+        std::printf("group skipped: %s\n", e.what());   // no libnccl.so.2 for a stand-alone binary on this machine
+    }
     std::puts("fri_mirror_test ok");
     return 0;
 }
