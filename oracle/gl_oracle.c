@@ -383,22 +383,39 @@ static inline u64 add_nc(u64 a, u64 b_canonical) { /* a any u64, b < p: at most 
     u64 t = a + b_canonical;
     return t + (EPS & (0 - (u64)(t < b_canonical)));
 }
+/* One full round.  The S-box runs stage by stage over the twelve lanes (twelve independent multiply chains in flight) and the
+ * MDS layer works on 32-bit halves with the shift as the outer loop, which is how upstream's mds_row_shf schedule reads
+ * and what lets the compiler keep twelve accumulators in vector registers (32x32->64 products). */
+static const u32 MDS_CIRC32[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 static inline void full_round_nc(u64 s[12], const u64 *rc) {
-    for (int i = 0; i < 12; i++) s[i] = sbox7_nc(add_nc(s[i], rc[i]));
-    u64 lo[24], hi[24];
+    u64 x[12], x2[12], x3[12], x4[12];
+    for (int i = 0; i < 12; i++) x[i] = add_nc(s[i], rc[i]);
+    for (int i = 0; i < 12; i++) x2[i] = mul_nc(x[i], x[i]);
+    for (int i = 0; i < 12; i++) x4[i] = mul_nc(x2[i], x2[i]);
+    for (int i = 0; i < 12; i++) x3[i] = mul_nc(x2[i], x[i]);
+    for (int i = 0; i < 12; i++) s[i] = mul_nc(x3[i], x4[i]);
+    u32 lo[24] __attribute__((aligned(32))), hi[24] __attribute__((aligned(32)));
     for (int i = 0; i < 12; i++) {
-        lo[i] = lo[i + 12] = s[i] & EPS;
-        hi[i] = hi[i + 12] = s[i] >> 32;
+        lo[i] = lo[i + 12] = (u32)s[i];
+        hi[i] = hi[i + 12] = (u32)(s[i] >> 32);
     }
-    for (int r = 0; r < 12; r++) {
-        u64 al = 0, ah = 0;
-        for (int i = 0; i < 12; i++) {
-            al += lo[r + i] * MDS_CIRC[i];
-            ah += hi[r + i] * MDS_CIRC[i];
+    u64 al[12] __attribute__((aligned(32))) = {0}, ah[12] __attribute__((aligned(32))) = {0};
+    for (int i = 0; i < 12; i++) {
+        const u64 c = MDS_CIRC32[i];
+        for (int r = 0; r < 12; r++) {
+            al[r] += (u64)lo[r + i] * c;
+            ah[r] += (u64)hi[r + i] * c;
         }
-        if (r == 0) { al += lo[0] * MDS_DIAG0; ah += hi[0] * MDS_DIAG0; }
-        s[r] = red128_nc((u128)al + ((u128)ah << 32));
     }
+    al[0] += (u64)lo[0] * MDS_DIAG0;
+    ah[0] += (u64)hi[0] * MDS_DIAG0;
+    for (int r = 0; r < 12; r++) s[r] = red128_nc((u128)al[r] + ((u128)ah[r] << 32));
+}
+/* sum of up to 2^4 128-bit products kept as two running sums of their 64-bit halves (no overflow tests): lo + 2^64 hi with
+ * both below 2^68; 2^64 = 2^32 - 1 (mod p) */
+static inline u64 red_split(u128 lo_sum, u128 hi_sum) {
+    const u64 rh = red128_nc(hi_sum);
+    return red128_nc((u128)rh * EPS + lo_sum); /* < 2^96 + 2^68 */
 }
 
 /* The permutation every other oracle routine uses: upstream's schedule, canonical output. */
@@ -411,33 +428,27 @@ void glo_poseidon_permute(u64 s[12]) {
     for (int i = 0; i < 12; i++) t[i] = add_nc(s[i], FP_FIRST[i]);
     s[0] = t[0];
     for (int i = 0; i < 11; i++) {
-        u128 acc = 0;
-        u32 top = 0;
+        u128 lo_sum = 0, hi_sum = 0;
         for (int k = 0; k < 11; k++) {
-            u128 pr = (u128)t[1 + k] * FP_INIT[i][k];
-            acc += pr;
-            top += acc < pr;
+            const u128 pr = (u128)t[1 + k] * FP_INIT[i][k];
+            lo_sum += (u64)pr;
+            hi_sum += (u64)(pr >> 64);
         }
-        /* acc + top * 2^128, 2^128 = -2^32 (mod p) */
-        u64 r0 = red128_nc(acc);
-        u64 corr = (u64)top << 32; /* < 2^36 */
-        u64 d = r0 - corr;
-        d -= EPS & (0 - (u64)(r0 < corr));
-        s[1 + i] = add_nc(d, FP_POST[i]);
+        s[1 + i] = add_nc(red_split(lo_sum, hi_sum), FP_POST[i]);
     }
     for (int r = 0; r < NP; r++) {
-        const u64 s0 = sbox7_nc(s[0]);
-        u128 acc = (u128)s0 * (MDS_CIRC[0] + MDS_DIAG0);
-        u32 top = 0;
+        /* mds_partial_layer_fast: the part of the first row that does not wait for the S-box goes first */
+        u128 lo_sum = 0, hi_sum = 0;
         for (int k = 0; k < 11; k++) {
-            u128 pr = (u128)s[1 + k] * FP_V[r][k];
-            acc += pr;
-            top += acc < pr;
+            const u128 pr = (u128)s[1 + k] * FP_V[r][k];
+            lo_sum += (u64)pr;
+            hi_sum += (u64)(pr >> 64);
         }
-        u64 r0 = red128_nc(acc);
-        u64 corr = (u64)top << 32;
-        u64 d = r0 - corr;
-        d -= EPS & (0 - (u64)(r0 < corr));
+        const u64 s0 = sbox7_nc(s[0]);
+        const u128 p0 = (u128)s0 * (MDS_CIRC[0] + MDS_DIAG0);
+        lo_sum += (u64)p0;
+        hi_sum += (u64)(p0 >> 64);
+        const u64 d = red_split(lo_sum, hi_sum);
         for (int k = 0; k < 11; k++) {
             /* multiply_accumulate: s[k] + s0 * w, one 128-bit sum (s0 * w <= (2^64-1)^2, + s[k] cannot overflow) */
             s[1 + k] = red128_nc((u128)s0 * FP_W[r][k] + s[1 + k]);
