@@ -13,6 +13,9 @@
 #include "poseidon_constants.h"
 
 #define HASH_BLOCK 128
+#ifndef HASH_MIN_CTAS
+#define HASH_MIN_CTAS 5   // 94 registers, no spills: 1.549 G permutations/s against 1.530 at 4 (tools/poseidon_bench, profiles/README.md)
+#endif
 
 int gl_poseidon_upload_constants(const u64* rc360) {
     cudaError_t e = cudaMemcpyToSymbol(c_poseidon_rc, rc360, sizeof(u64) * POSEIDON_ROUNDS * POSEIDON_WIDTH);
@@ -53,7 +56,7 @@ GL_D void load_digest(const u64* src, u64 d[4]) {
 // ------------------------------------------------------------------------------------------------
 // Poseidon batch entry points (P5, P6)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HASH_BLOCK, 4) k_permute_batch(u64* states, u64 m) {
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS) k_permute_batch(u64* states, u64 m) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
     if (i >= m) return;
     ulonglong2* p = reinterpret_cast<ulonglong2*>(states + 12 * i);
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(HASH_BLOCK, 4) k_permute_batch(u64* states, u6
     for (int k = 0; k < 6; k++) p[k] = make_ulonglong2(gl_canon(s[2 * k]), gl_canon(s[2 * k + 1]));
 }
 
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_two_to_one_batch(const u64* __restrict__ l, const u64* __restrict__ r, u64* __restrict__ out, u64 m) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
     if (i >= m) return;
@@ -81,7 +84,7 @@ k_two_to_one_batch(const u64* __restrict__ l, const u64* __restrict__ r, u64* __
 }
 
 // hash_no_pad over m rows of `len` elements each, row-major input ([m][len]).
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_hash_no_pad_rows(const u64* __restrict__ in, u32 len, u64 m, u64* __restrict__ out) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
     if (i >= m) return;
@@ -121,7 +124,7 @@ GL_D void smt_leaf_hash(const u64 k[4], const u64 v[4], u64 out[4]) {
     for (int i = 0; i < 4; i++) out[i] = gl_canon(s[i]);
 }
 
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_smt_leaf_hash_batch(const u64* __restrict__ keys, const u64* __restrict__ values, u64* __restrict__ out, u64 m) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
     if (i >= m) return;
@@ -147,7 +150,7 @@ GL_D u64* node_slot(u64* digests, u64* cap, unsigned sub_bits, unsigned layer, u
 }
 
 // leaves column-major: element (leaf i, column j) at lde[j * ld + i]
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_leaf_hash_cols(const u64* __restrict__ lde, u64 ld, u32 c, u64 num_leaves, unsigned sub_bits,
                  u64* __restrict__ digests, u64* __restrict__ cap) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
@@ -182,7 +185,7 @@ k_leaf_hash_cols(const u64* __restrict__ lde, u64 ld, u32 c, u64 num_leaves, uns
 // 8-column groups of [col_begin, col_end) into the per-leaf sponge state (state[k * num_leaves + i], k < 12), so the
 // hashing of the polynomials that are already extended overlaps the arrival of the next ones.  col_begin is a multiple
 // of 8; col_end is a multiple of 8 or c; `first` starts from the zero state, `last` (col_end == c) writes the digests.
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_leaf_absorb_cols(const u64* __restrict__ lde, u64 ld, u32 col_begin, u32 col_end, u64 num_leaves, unsigned sub_bits,
                    u64* __restrict__ state, int first, int last, u64* __restrict__ digests, u64* __restrict__ cap) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
@@ -211,7 +214,7 @@ k_leaf_absorb_cols(const u64* __restrict__ lde, u64 ld, u32 col_begin, u32 col_e
 }
 
 // leaves row-major ([num_leaves][leaf_len]) -- MerkleTree::new(leaves: Vec<Vec<F>>, cap_height)
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_leaf_hash_rows(const u64* __restrict__ leaves, u32 leaf_len, u64 num_leaves, unsigned sub_bits,
                  u64* __restrict__ digests, u64* __restrict__ cap) {
     u64 i = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
@@ -239,7 +242,7 @@ k_leaf_hash_rows(const u64* __restrict__ leaves, u32 leaf_len, u64 num_leaves, u
 }
 
 // layer >= 1: node q = two_to_one(children 2q, 2q+1 of layer-1); children are adjacent in the layout
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_merkle_level(u64* __restrict__ digests, u64* __restrict__ cap, unsigned sub_bits, unsigned layer, u64 num_nodes) {
     u64 g = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
     if (g >= num_nodes) return;
@@ -254,7 +257,7 @@ k_merkle_level(u64* __restrict__ digests, u64* __restrict__ cap, unsigned sub_bi
 // ------------------------------------------------------------------------------------------------
 // P10 fri_proof_of_work: candidates start .. start+count; atomicMin keeps the smallest hit
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(HASH_BLOCK, 4)
+__global__ void __launch_bounds__(HASH_BLOCK, HASH_MIN_CTAS)
 k_pow_grind(const u64* __restrict__ state12, unsigned pos, unsigned out_pos, unsigned min_lz, u64 start,
             u64 count, unsigned long long* __restrict__ best) {
     u64 k = blockIdx.x * (u64)HASH_BLOCK + threadIdx.x;
