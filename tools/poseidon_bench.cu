@@ -17,6 +17,35 @@
 #define MINB 1
 #endif
 
+#ifdef TWO_STATES
+// experiment: two independent states per thread, their rounds in the same basic block (does ptxas overlap the FP64 layers
+// of one with the integer S-boxes of the other?)
+__device__ __forceinline__ void poseidon_permute2(u64 s[12], u64 t[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) { s[i] = gl_add_c(s[i], c_poseidon_rc[i]); t[i] = gl_add_c(t[i], c_poseidon_rc[i]); }
+#pragma unroll 1
+    for (int phase = 0; phase < 2; phase++) {
+        const double2* rc = c_poseidon_rc_split + 12 * (phase ? POSEIDON_FULL_HALF + POSEIDON_PARTIAL + 1 : 1);
+#pragma unroll 1
+        for (int r = 0; r < POSEIDON_FULL_HALF; r++, rc += 12) { poseidon_full_round(s, rc); poseidon_full_round(t, rc); }
+        if (phase == 0) {
+#pragma unroll 1
+            for (int pair = 0; pair < POSEIDON_PARTIAL / 2; pair++) { poseidon_partial_pair(s, pair); poseidon_partial_pair(t, pair); }
+        }
+    }
+}
+__global__ void __launch_bounds__(BLOCK, MINB) k_bench(u64* out, u64 seed) {
+    u64 s[12], t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { s[i] = seed * (threadIdx.x + 1 + blockIdx.x * (u64)blockDim.x) + i; t[i] = s[i] ^ 0x5555; }
+#pragma unroll 1
+    for (int r = 0; r < REPS / 2; r++) poseidon_permute2(s, t);
+    u64 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc ^= s[i] ^ t[i];
+    out[blockIdx.x * (u64)blockDim.x + threadIdx.x] = acc;
+}
+#else
 __global__ void __launch_bounds__(BLOCK, MINB) k_bench(u64* out, u64 seed) {
     u64 s[12];
 #pragma unroll
@@ -28,6 +57,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_bench(u64* out, u64 seed) {
     for (int i = 0; i < 12; i++) acc ^= s[i];
     out[blockIdx.x * (u64)blockDim.x + threadIdx.x] = acc;
 }
+
+#endif
 
 __global__ void k_kat(u64* io) {
     u64 s[12];
