@@ -218,10 +218,19 @@ k_ntt_tma_strided(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     u64* wt = buf + 2 * TILE;                      // w_256^e
     u64* bars = wt + 256;
     const unsigned tid = threadIdx.x, d = tid & 15, q = tid >> 4;
-    const u64 tiles = ((u64)1 << a.s) >> 4;
+    const u32 tiles = (1u << a.s) >> 4;
     const u64 total = (u64)a.cosets * a.columns * tiles;
     const u64 first = blockIdx.x, step = gridDim.x;
     const u64 count = first < total ? (total - first + step - 1) / step : 0;
+    // item = (coset * columns + col) * tiles + jt, advanced by `step` per iteration without dividing again
+    const u32 step_jt = (u32)(step % tiles), step_col = (u32)((step / tiles) % a.columns), step_coset = (u32)(step / tiles / a.columns);
+    auto advance = [&](u32& jt, u32& col, u32& coset) {
+        jt += step_jt;
+        col += step_col;
+        coset += step_coset;
+        if (jt >= tiles) { jt -= tiles; col++; }
+        if (col >= a.columns) { col -= a.columns; coset++; }
+    };
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -231,25 +240,23 @@ k_ntt_tma_strided(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     wt[tid] = __ldg(a.wt1 + brev4(tid >> 4) * (tid & 15));   // wt[i * 16 + q] = w_256^(brev4(i) * q)
     __syncthreads();
 
-    auto issue_load = [&](u64 k) {
-        const u64 item = first + k * step;
-        const u64 jt = item % tiles, rest = item / tiles;
-        const u32 col = (u32)(rest % a.columns), coset = (u32)(rest / a.columns);
+    // (jt, col, coset) of the tile being computed, and (thread 0 only) of the next tile to fetch
+    u32 jt = (u32)(first % tiles), col = (u32)((first / tiles) % a.columns), coset = (u32)(first / tiles / a.columns);
+    u32 ljt = jt, lcol = col, lcoset = coset;
+    auto issue_load = [&](u64 k) {   // loads are issued in order k = 0, 1, 2, ...
         u64* bar = &bars[k & 1];
         mbar_expect_tx(bar, TILE_BYTES);
-        tma_load_3d(buf + (k & 1) * TILE, &tm_in, bar, (int)(jt << 4), (int)(a.in_coset_rows * coset), (int)col);
+        tma_load_3d(buf + (k & 1) * TILE, &tm_in, bar, (int)(ljt << 4), (int)(a.in_coset_rows * lcoset), (int)lcol);
+        advance(ljt, lcol, lcoset);
     };
     if (tid == 0) {
         if (count > 0) issue_load(0);
         if (count > 1) issue_load(1);
     }
 
-    for (u64 k = 0; k < count; k++) {
-        const u64 item = first + k * step;
-        const u64 jt = item % tiles, rest = item / tiles;
-        const u32 col = (u32)(rest % a.columns), coset = (u32)(rest / a.columns);
+    for (u64 k = 0; k < count; k++, advance(jt, col, coset)) {
         u64* b = buf + (k & 1) * TILE;
-        const u64 jlo = (jt << 4) + d;
+        const u64 jlo = ((u64)jt << 4) + d;
         u64 x[16];
         // ---- round 1: rows i * 16 + q --------------------------------------------------------------------------
         u64 rf[16];
