@@ -501,7 +501,7 @@ static int run_dif(gl_ctx* ctx, const NttJob& j) {
     // the cache takes at most 24 of them and later shifts run on the radix-16 kernels below
     const bool tma_tables_ok = !j.pre_tab || j.pre_direct_ok || tma_table_cached(ctx, j) || ctx->tma_shift_tables < 24;
     if (!tma_off && ntt_tma_supported(j.L) && j.final_scale == 1 && tma_tables_ok &&
-        (j.in_coset_stride == 0 || j.in_coset_stride == n) && (j.cosets == 1 || j.out_coset_stride == n)) {
+        (j.cosets == 1 || (j.in_coset_stride == 0 && j.out_coset_stride == n))) {   // the LDE's geometry: one input, blocks of n out
         u64 w = glh::root_of_unity(j.L);
         if (j.inverse) w = glh::inv(w);
         const u64* post;

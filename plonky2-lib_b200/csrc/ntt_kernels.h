@@ -85,7 +85,6 @@ struct ntt_tma_args {
     const uint64_t* wt2;      // w_{2^s}^e (direction applied), e < 2^s
     uint32_t s;               // L - 8
     uint32_t columns, cosets;
-    uint32_t in_coset_rows;   // 256 when the input has one block per coset, else 0
     int canonical_out;
 };
 struct ntt_tma_job {

@@ -246,7 +246,7 @@ k_ntt_tma_strided(const __grid_constant__ CUtensorMap tm_in, const __grid_consta
     auto issue_load = [&](u64 k) {   // loads are issued in order k = 0, 1, 2, ...
         u64* bar = &bars[k & 1];
         mbar_expect_tx(bar, TILE_BYTES);
-        tma_load_3d(buf + (k & 1) * TILE, &tm_in, bar, (int)(ljt << 4), (int)(a.in_coset_rows * lcoset), (int)lcol);
+        tma_load_3d(buf + (k & 1) * TILE, &tm_in, bar, (int)(ljt << 4), 0, (int)lcol);   // every coset reads the same input tile
         advance(ljt, lcol, lcoset);
     };
     if (tid == 0) {
@@ -529,7 +529,7 @@ bool launch_ntt_tma(const ntt_tma_job& j, cudaStream_t st) {
     if (!ntt_tma_supported(j.L)) return false;
     const unsigned s = j.L - 8;
     const u64 n = (u64)1 << j.L;
-    if (j.in_coset_stride != 0 && j.in_coset_stride != n) return false;
+    if (j.cosets > 1 && j.in_coset_stride != 0) return false;   // every coset reads the same coefficients (the LDE)
     if (j.cosets > 1 && j.out_coset_stride != n) return false;
     if (g_sms == 0) {
         int dev = 0;
@@ -537,8 +537,7 @@ bool launch_ntt_tma(const ntt_tma_job& j, cudaStream_t st) {
         cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     CUtensorMap tm_in, tm_out;
-    const bool in_cosets = j.in_coset_stride != 0 && j.cosets > 1;
-    if (!make_map(&tm_in, j.in, (u64)1 << s, in_cosets ? 256ull * j.cosets : 256ull, j.in_ld, j.columns, false)) return false;
+    if (!make_map(&tm_in, j.in, (u64)1 << s, 256ull, j.in_ld, j.columns, false)) return false;
     if (!make_map(&tm_out, j.out, (u64)1 << s, 256ull * j.cosets, j.out_ld, j.columns, false)) return false;
     CUtensorMap tm_rows;   // the output as 128-byte rows, for the swizzled store of pass 2
     if (!make_map(&tm_rows, j.out, 16, (n * j.cosets) >> 4, j.out_ld, j.columns, true)) return false;
@@ -546,7 +545,6 @@ bool launch_ntt_tma(const ntt_tma_job& j, cudaStream_t st) {
     a.wt1 = j.wt1; a.rowfac = j.rowfac; a.post3 = j.post3;
     a.out = j.out; a.out_ld = j.out_ld; a.out_coset_stride = j.cosets > 1 ? j.out_coset_stride : 0;
     a.wt2 = j.wt2; a.s = s; a.columns = j.columns; a.cosets = j.cosets;
-    a.in_coset_rows = in_cosets ? 256 : 0;
     a.canonical_out = 0;
     const u64 items1 = (u64)j.cosets * j.columns * (((u64)1 << s) >> 4);
     const u64 items2 = (u64)j.cosets * j.columns * (n / TILE);
