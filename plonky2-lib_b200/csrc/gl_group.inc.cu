@@ -15,6 +15,7 @@
 #include <nccl.h>
 #include <sched.h>
 
+#include <chrono>
 #include <fstream>
 #include <sstream>
 
@@ -72,11 +73,17 @@ struct gl_group_rank {
     gl_ctx* ctx = nullptr;
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t prep_stream = nullptr;   // uploads' consumers: the rank's own copy-in + IFFT of every round, ahead of the LDE queue
     std::vector<cudaEvent_t> ev;   // per round: [2j] own coefficients ready, [2j+1] round gathered; + tail events
     u64* cap_all = nullptr;        // [2^cap_height][4] gathered cap (device)
     size_t cap_all_bytes = 0;
     u64* open_buf = nullptr;       // [k][c + 4 L] rows + paths exchanged by gl_group_commit_open
     size_t open_bytes = 0;
+    // peer-memory plane (see "coefficient exchange over peer memory" below)
+    u64* xbuf = nullptr;           // this rank's exchange buffer: [XB_FLAGS] ready flags, then its published coefficient slices
+    std::vector<u64*> peer_x;      // [nranks]: every rank's xbuf as this device addresses it (own rank: xbuf)
+    std::vector<char> peer_ipc;    // 1 = opened with cudaIpcOpenMemHandle
+    u64** d_peer_x = nullptr;      // the same table on the device
 };
 struct gl_group {
     uint32_t nlocal = 0, rank0 = 0, nranks = 1;
@@ -84,7 +91,13 @@ struct gl_group {
     std::string err;
     std::mutex mu;
     float phase_ms[GL_PHASES] = {};
+    // coefficient exchange over peer memory: -1 = not tried yet, 0 = NCCL all-gather, 1 = pull kernels over NVLink
+    int p2p = -1;
+    size_t xbuf_words = 0;         // capacity of every rank's exchange buffer (the same everywhere)
+    uint64_t epoch = 0;            // commits made with the peer-memory exchange; the value the ready flags carry
 };
+
+static void group_unmap_peers(gl_group* g);
 
 static int gfail(gl_group* g, int code, const std::string& msg) {
     if (g) g->err = msg;
@@ -129,7 +142,17 @@ extern "C" void gl_group_destroy(gl_group* g) {
     auto* a = glnccl::api();
     for (auto& rk : g->r) {
         if (!rk.ctx) continue;
+        cudaSetDevice(rk.ctx->device);
+        cudaStreamSynchronize(rk.ctx->stream);
+        if (rk.comm_stream) cudaStreamSynchronize(rk.comm_stream);
+    }
+    group_unmap_peers(g);
+    for (auto& rk : g->r) {
+        if (!rk.ctx) continue;
         Guard gd(rk.ctx);
+        cudaSetDevice(rk.ctx->device);
+        if (rk.xbuf) cudaFree(rk.xbuf);
+        if (rk.d_peer_x) cudaFree(rk.d_peer_x);
         cudaStreamSynchronize(rk.ctx->stream);
         if (rk.comm_stream) cudaStreamSynchronize(rk.comm_stream);
         if (rk.comm && a->CommDestroy) a->CommDestroy(rk.comm);
@@ -137,6 +160,7 @@ extern "C" void gl_group_destroy(gl_group* g) {
         if (rk.cap_all) cudaFree(rk.cap_all);
         if (rk.open_buf) cudaFree(rk.open_buf);
         if (rk.comm_stream) cudaStreamDestroy(rk.comm_stream);
+        if (rk.prep_stream) cudaStreamDestroy(rk.prep_stream);
         rk.ctx->shard_index = 0;
         rk.ctx->shard_count = 1;
     }
@@ -191,6 +215,7 @@ extern "C" int gl_group_create(gl_ctx* const* ctxs, uint32_t nlocal, uint32_t ra
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         cudaError_t e = cudaStreamCreateWithPriority(&g->r[i].comm_stream, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g->r[i].prep_stream, cudaStreamNonBlocking, hi);
         if (e != cudaSuccess) { rc = GL_E_CUDA; msg = std::string("cudaStreamCreate: ") + cudaGetErrorString(e); }
     }
     if (prev >= 0) cudaSetDevice(prev);
@@ -198,6 +223,7 @@ extern "C" int gl_group_create(gl_ctx* const* ctxs, uint32_t nlocal, uint32_t ra
         for (auto& rk : g->r) {
             if (rk.comm) a->CommDestroy(rk.comm);
             if (rk.comm_stream) cudaStreamDestroy(rk.comm_stream);
+            if (rk.prep_stream) cudaStreamDestroy(rk.prep_stream);
         }
         delete g;
         return gfail(nullptr, rc, msg);
@@ -266,6 +292,184 @@ extern "C" int gl_ctx_bind_host_numa(gl_ctx* ctx) {
     return GL_OK;
 }
 
+// ---- coefficient exchange over peer memory -------------------------------------------------------------------------------
+// The all-gather of the inverse-transformed polynomials as the ranks' OWN kernels over NVLink / NVSwitch peer memory
+// instead of ncclAllGather.  Every rank owns an exchange buffer that every other rank maps (cudaIpcOpenMemHandle across
+// processes, cudaDeviceEnablePeerAccess inside one).  Round j: the owner copies its slice into the buffer and raises
+// ready flag j to the commit's epoch (k_group_signal: system-scope fence, then the store); its peers' pull kernels wait on
+// that flag THROUGH the mapping and then stream the slice into their own coefficient array with 16-byte loads that bypass
+// L1 (the line's home is the owner's L2).  No host thread and no copy engine takes part, so the exchange neither waits
+// for nor slows the host<->device DMA of the end-to-end path, and a rank starts pulling from each peer the moment that
+// peer has published, not when the slowest one has.  Reuse of the buffer across commits is safe because every commit ends
+// with the cap all-gather: a rank passes it only after every rank has built its tree, i.e. finished all its pulls.
+#define XB_FLAGS 64u   // u64 words reserved for ready flags (rounds per commit <= 64)
+
+__global__ void k_group_signal(u64* flag, u64 value) {
+    __threadfence_system();
+    *reinterpret_cast<volatile u64*>(flag) = value;
+}
+// grid (CTAs per peer, nranks): blockIdx.y = the rank pulled from.  src_words: offset of the round's slice in a peer's
+// exchange buffer; dst: this rank's [nranks][count] block of the round (slot p receives rank p's slice).
+__global__ void __launch_bounds__(256)
+k_group_pull(u64* const* __restrict__ peer_x, u32 me, u32 flag_index, u64 epoch, u64 src_words, u64* __restrict__ dst, u64 count) {
+    const u32 p = blockIdx.y;
+    if (p == me) return;
+    const u64* px = peer_x[p];
+    if (threadIdx.x == 0) {
+        const volatile u64* f = px + flag_index;
+        while (*f < epoch) __nanosleep(100);
+        __threadfence_system();
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(px + src_words);
+    uint4* out = reinterpret_cast<uint4*>(dst + (u64)p * count);
+    const u64 vecs = count >> 1, stride = (u64)gridDim.x * 256;
+    u64 i = blockIdx.x * (u64)256 + threadIdx.x;
+    for (; i + 3 * stride < vecs; i += 4 * stride) {
+        const uint4 a = __ldcg(src + i), b = __ldcg(src + i + stride), c = __ldcg(src + i + 2 * stride), d = __ldcg(src + i + 3 * stride);
+        out[i] = a; out[i + stride] = b; out[i + 2 * stride] = c; out[i + 3 * stride] = d;
+    }
+    for (; i < vecs; i += stride) out[i] = __ldcg(src + i);
+}
+
+static void group_unmap_peers(gl_group* g) {
+    for (auto& rk : g->r) {
+        if (!rk.ctx) continue;
+        cudaSetDevice(rk.ctx->device);
+        for (size_t r = 0; r < rk.peer_x.size(); r++)
+            if (rk.peer_ipc[r] && rk.peer_x[r]) cudaIpcCloseMemHandle(rk.peer_x[r]);
+        rk.peer_x.clear();
+        rk.peer_ipc.clear();
+    }
+}
+// Collective.  Makes sure every rank has an exchange buffer of at least `words` and a mapping of everybody else's; decides
+// ONCE, for the whole group, whether the peer-memory exchange is used (g->p2p).
+static int group_ensure_exchange(gl_group* g, size_t words) {
+    auto* a = glnccl::api();
+    const uint32_t G = g->nranks, nl = g->nlocal;
+    if (g->p2p == 0) return GL_OK;
+    if (g->p2p == 1 && g->xbuf_words >= words) return GL_OK;
+    // every rank reaches this point for the same commit (same geometry => same `words`): (re)build the plane together
+    for (auto& rk : g->r) {
+        cudaSetDevice(rk.ctx->device);
+        cudaStreamSynchronize(rk.ctx->stream);
+        cudaStreamSynchronize(rk.comm_stream);
+    }
+    group_unmap_peers(g);
+    const size_t cap = words + words / 4;
+    int ok = 1;
+    std::vector<cudaIpcMemHandle_t> mine(nl);
+    for (uint32_t i = 0; i < nl; i++) {
+        gl_group_rank& rk = g->r[i];
+        cudaSetDevice(rk.ctx->device);
+        if (rk.xbuf) cudaFree(rk.xbuf);
+        rk.xbuf = nullptr;
+        if (cudaMalloc(&rk.xbuf, cap * 8) != cudaSuccess || cudaMemset(rk.xbuf, 0, XB_FLAGS * 8) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine[i], rk.xbuf) != cudaSuccess) {
+            cudaGetLastError();
+            ok = 0;
+        }
+        if (!rk.d_peer_x && cudaMalloc(&rk.d_peer_x, G * sizeof(u64*)) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // handles of all ranks (NCCL as the bootstrap: one small all-gather per local rank)
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    std::vector<unsigned char*> d_h(nl, nullptr);
+    std::vector<std::vector<unsigned char>> all(nl, std::vector<unsigned char>(G * hb));
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        if (cudaMalloc(&d_h[i], G * hb) != cudaSuccess) { cudaGetLastError(); return gfail(g, GL_E_OOM, "gl_group: exchange set-up allocation failed"); }
+        cudaMemcpy(d_h[i] + (size_t)(g->rank0 + i) * hb, &mine[i], hb, cudaMemcpyHostToDevice);
+    }
+    if (nl > 1) NCK(g, a->GroupStart());
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        ncclResult_t r = a->AllGather(d_h[i] + (size_t)(g->rank0 + i) * hb, d_h[i], hb, ncclUint8, g->r[i].comm, g->r[i].comm_stream);
+        if (r != ncclSuccess) {
+            if (nl > 1) a->GroupEnd();
+            return gfail(g, GL_E_NCCL, std::string("ncclAllGather (exchange handles): ") + a->GetErrorString(r));
+        }
+    }
+    if (nl > 1) NCK(g, a->GroupEnd());
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        cudaStreamSynchronize(g->r[i].comm_stream);
+        cudaMemcpy(all[i].data(), d_h[i], G * hb, cudaMemcpyDeviceToHost);
+        cudaFree(d_h[i]);
+    }
+    for (uint32_t i = 0; i < nl && ok; i++) {
+        gl_group_rank& rk = g->r[i];
+        cudaSetDevice(rk.ctx->device);
+        rk.peer_x.assign(G, nullptr);
+        rk.peer_ipc.assign(G, 0);
+        for (uint32_t r = 0; r < G && ok; r++) {
+            if (r >= g->rank0 && r < g->rank0 + nl) {           // a rank of this process: its pointer, with peer access
+                gl_group_rank& other = g->r[r - g->rank0];
+                if (r != g->rank0 + i) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, rk.ctx->device, other.ctx->device);
+                    cudaError_t pe = can ? cudaDeviceEnablePeerAccess(other.ctx->device, 0) : cudaErrorInvalidDevice;
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                    cudaGetLastError();
+                }
+                rk.peer_x[r] = other.xbuf;
+            } else {
+                cudaIpcMemHandle_t h;
+                memcpy(&h, all[i].data() + (size_t)r * hb, hb);
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                } else {
+                    rk.peer_x[r] = (u64*)ptr;
+                    rk.peer_ipc[r] = 1;
+                }
+            }
+        }
+        if (ok && cudaMemcpy(rk.d_peer_x, rk.peer_x.data(), G * sizeof(u64*), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    }
+    // one decision for the whole group: the minimum of the ranks' outcomes
+    std::vector<u64*> d_ok(nl, nullptr);
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        const u64 v = (u64)ok;
+        if (cudaMalloc(&d_ok[i], 8) != cudaSuccess) { cudaGetLastError(); return gfail(g, GL_E_OOM, "gl_group: exchange set-up allocation failed"); }
+        cudaMemcpy(d_ok[i], &v, 8, cudaMemcpyHostToDevice);
+    }
+    if (nl > 1) NCK(g, a->GroupStart());
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        ncclResult_t r = a->AllReduce(d_ok[i], d_ok[i], 1, ncclUint64, ncclMin, g->r[i].comm, g->r[i].comm_stream);
+        if (r != ncclSuccess) {
+            if (nl > 1) a->GroupEnd();
+            return gfail(g, GL_E_NCCL, std::string("ncclAllReduce (exchange set-up): ") + a->GetErrorString(r));
+        }
+    }
+    if (nl > 1) NCK(g, a->GroupEnd());
+    u64 all_ok = 1;
+    for (uint32_t i = 0; i < nl; i++) {
+        cudaSetDevice(g->r[i].ctx->device);
+        cudaStreamSynchronize(g->r[i].comm_stream);
+        u64 v = 0;
+        cudaMemcpy(&v, d_ok[i], 8, cudaMemcpyDeviceToHost);
+        cudaFree(d_ok[i]);
+        if (!v) all_ok = 0;
+    }
+    if (!all_ok) {   // no peer access somewhere: everybody stays on ncclAllGather
+        group_unmap_peers(g);
+        for (auto& rk : g->r) {
+            cudaSetDevice(rk.ctx->device);
+            if (rk.xbuf) cudaFree(rk.xbuf);
+            rk.xbuf = nullptr;
+        }
+        g->p2p = 0;
+        g->xbuf_words = 0;
+        return GL_OK;
+    }
+    g->p2p = 1;
+    g->xbuf_words = cap;
+    return GL_OK;
+}
+
 // ---- the collective commit ---------------------------------------------------------------------------------------
 // Column plan: round 0 holds ONE polynomial per rank (nothing can run under its IFFT + gather, so it is short), the
 // others W each; round j occupies the padded columns [base_j, base_j + nranks * w_j) and rank r inverse-transforms the
@@ -297,11 +501,15 @@ static inline uint32_t clampc(uint32_t x, uint32_t c) { return x < c ? x : c; }
 struct GroupTrace {
     bool on = false;
     std::vector<std::pair<std::string, cudaEvent_t>> marks;
+    std::vector<std::pair<std::string, double>> host;   // when the host thread ENQUEUED the step (ms after the first mark)
+    std::chrono::steady_clock::time_point t0;
     void mark(const std::string& name, cudaStream_t st) {
         if (!on) return;
         cudaEvent_t e;
         if (cudaEventCreate(&e) != cudaSuccess) return;
         cudaEventRecord(e, st);
+        if (marks.empty() && host.empty()) t0 = std::chrono::steady_clock::now();
+        host.emplace_back(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         marks.emplace_back(name, e);
     }
     void dump(uint32_t rank, cudaEvent_t origin) {
@@ -315,8 +523,15 @@ struct GroupTrace {
             line += buf;
             cudaEventDestroy(m.second);
         }
+        line += " | enqueued:";
+        for (auto& h : host) {
+            char buf[64];
+            snprintf(buf, sizeof buf, " %s=%.2f", h.first.c_str(), h.second);
+            line += buf;
+        }
         fprintf(stderr, "%s\n", line.c_str());
         marks.clear();
+        host.clear();
     }
 };
 
@@ -339,6 +554,22 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
     const u64 n = (u64)1 << log_n;
     const GroupPlan plan = group_plan(c, G);
     const size_t cap_bytes = (size_t)32 << cap_height;
+    // this rank's slices of all rounds, published one after the other behind the flags of its exchange buffer
+    std::vector<u64> xoff(plan.rounds + 1, XB_FLAGS);
+    for (uint32_t j = 0; j < plan.rounds; j++) xoff[j + 1] = xoff[j] + (u64)plan.w[j] * n;
+    // Which exchange: with host buffers the rounds arrive at the pace of PCIe and the pull kernels, which take each peer's
+    // slice the moment it is published and share nothing with the DMA engines, win (8 GPUs: 22.4 against 24.1 ms end to
+    // end); with everything resident ncclAllGather's few CTAs disturb the hashing slightly less (15.7 against 15.9 ms).
+    // GL_B200_GROUP_P2P = 0: NCCL always, 2: pull kernels always.
+    static const int p2p_mode = getenv("GL_B200_GROUP_P2P") ? atoi(getenv("GL_B200_GROUP_P2P")) : 1;
+    const bool want_p2p = G > 1 && plan.rounds <= XB_FLAGS && log_n >= 1 &&   // 16-byte copies: two coefficients at least
+                          (p2p_mode == 2 || (p2p_mode == 1 && space == GL_HOST));
+    if (want_p2p) {
+        int rc = group_ensure_exchange(g, (size_t)xoff[plan.rounds]);
+        if (rc != GL_OK) return rc;
+    }
+    const bool p2p = want_p2p && g->p2p == 1;
+    if (p2p) g->epoch++;
     std::vector<GroupTrace> trace(nl);
     {
         const char* t = getenv("GL_B200_TRACE");
@@ -354,6 +585,7 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
             cudaSetDevice(ctx->device);
             cudaStreamSynchronize(ctx->stream);
             cudaStreamSynchronize(g->r[i].comm_stream);
+            cudaStreamSynchronize(g->r[i].prep_stream);
             cudaStreamSynchronize(ctx->h2d_stream);
             cudaStreamSynchronize(ctx->d2h_stream);
             cudaGetLastError();
@@ -427,6 +659,15 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
             GCK(g, cudaSetDevice(ctx->device));
             const uint32_t own0 = plan.base[j] + (g->rank0 + i) * plan.w[j];
             const uint32_t o0 = clampc(own0, c), o1 = clampc(own0 + plan.w[j], c);
+            // This rank's copy-in + IFFT of round j run on the prep stream: they start when the upload lands, not when
+            // the LDE / hashing of earlier rounds queued on the main stream has drained, so the exchange of round j is
+            // never held up by the compute backlog (and the main stream never waits for an upload it does not need yet).
+            struct StreamSwap {
+                gl_ctx* c; cudaStream_t saved;
+                StreamSwap(gl_ctx* c_, cudaStream_t s) : c(c_), saved(c_->stream) { c->stream = s; }
+                ~StreamSwap() { c->stream = saved; }
+            } on_prep(ctx, rk.prep_stream);
+            if (j == 0) cudaStreamWaitEvent(rk.prep_stream, ctx->ev[3], 0);   // buffers allocated / padded on the main stream
             if (o1 > o0) {
                 u64* dcol = h->coeffs + (size_t)o0 * n;
                 const size_t bytes = (size_t)(o1 - o0) * n * 8;
@@ -455,7 +696,31 @@ static int group_commit(gl_group* g, const uint64_t* const* inputs, bool is_valu
             }
             cudaStreamWaitEvent(rk.comm_stream, rk.ev[2 * j], 0);
         }
-        if (G > 1) {
+        if (p2p) {
+            // publish: own slice into the exchange buffer, then the flag; pull: everybody else's slice as soon as its flag is up
+            const size_t count = (size_t)plan.w[j] * n;
+            for (uint32_t i = 0; i < nl; i++) {
+                gl_group_rank& rk = g->r[i];
+                cudaSetDevice(rk.ctx->device);
+                u64* base = hs[i]->coeffs + (size_t)plan.base[j] * n;
+                cudaError_t ce = cudaMemcpyAsync(rk.xbuf + xoff[j], base + (size_t)(g->rank0 + i) * count, count * 8,
+                                                 cudaMemcpyDeviceToDevice, rk.comm_stream);
+                if (ce != cudaSuccess) return bail(gfail(g, GL_E_CUDA, cudaGetErrorString(ce)));
+                k_group_signal<<<1, 1, 0, rk.comm_stream>>>(rk.xbuf + j, g->epoch);
+                ++g_gl_launches;
+            }
+            for (uint32_t i = 0; i < nl; i++) {
+                gl_group_rank& rk = g->r[i];
+                cudaSetDevice(rk.ctx->device);
+                u64* base = hs[i]->coeffs + (size_t)plan.base[j] * n;
+                // 56 CTAs x 256 threads x 4 x 16 B = 0.9 MB of loads in flight per GPU: at 8 GPUs 28 CTAs cost 1.2 ms of a
+                // commit, 126 cost 0.3 ms (they crowd the hashing), 56 are the best of the three
+                static const unsigned pull_ctas = getenv("GL_B200_GROUP_PULL_CTAS") ? (unsigned)atoi(getenv("GL_B200_GROUP_PULL_CTAS")) : 56u;
+                const unsigned per_peer = count >= ((size_t)1 << 18) ? (pull_ctas + G - 2) / (G - 1) : 2u;
+                k_group_pull<<<dim3(per_peer, G), 256, 0, rk.comm_stream>>>(rk.d_peer_x, g->rank0 + i, j, g->epoch, xoff[j], base, count);
+                ++g_gl_launches;
+            }
+        } else if (G > 1) {
             if (nl > 1) NCK(g, a->GroupStart());
             for (uint32_t i = 0; i < nl; i++) {
                 gl_group_rank& rk = g->r[i];
