@@ -254,8 +254,10 @@ void gl_commit_free(gl_commit *h);
 
 /* ---- (e) multi-GPU: one commit sharded over the GPUs of a box, NCCL behind this ABI -----------------------
  * One rank = one gl_ctx = one GPU.  Rank r owns leaf block r of nranks (LDE cosets = whole top-level Merkle subtrees and
- * their cap entries); the IFFT is sharded by polynomial and the coefficients are all-gathered round by round while the
- * previous round is extended; the cap is all-gathered; query openings are exchanged by gl_group_commit_open.  A process
+ * their cap entries); the IFFT is sharded by polynomial and the coefficients are exchanged round by round while the
+ * previous round is extended -- by ncclAllGather when the inputs are resident, by the ranks' own pull kernels over peer
+ * memory (NVLink; exchange buffers mapped with CUDA IPC across processes) when they are host buffers; the cap is
+ * all-gathered; query openings are exchanged by gl_group_commit_open.  A process
  * may hold all ranks (the Rust prover: one process, 8 GPUs, id = NULL) or some of them (one rank per process under a
  * torchrun-style launcher: rank 0 calls gl_group_unique_id and hands the 128 bytes to the others out of band).
  * NCCL is bound at run time (dlopen): nothing else in this header needs it.  Replaces the rayon data parallelism of
