@@ -576,8 +576,8 @@ def main():
         if rank == 0:
             e2e = {"value": cells / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(cells * 8),
                    "d2h_bytes_per_step": int(cells * 8 + world * cap_host.nbytes), "ms_per_step": ems,
-                   "api": "gl_group_commit_from_values(space=GL_HOST%s): per rank its polynomials H2D from pinned memory, its "
-                          "coefficient vectors D2H, the whole cap D2H" % (", GL_COMMIT_STREAM_HASH" if eflags else "")}
+                   "api": "gl_group_commit_from_values(space=GL_HOST%s): per rank its polynomials H2D from pinned memory, the coefficient "
+                          "exchange by the ranks' own pull kernels over peer memory (NVLink), its coefficient vectors D2H, the whole cap D2H" % (", GL_COMMIT_STREAM_HASH" if eflags else "")}
         del hv, hc
 
     if rank != 0:

@@ -8,9 +8,10 @@
 // point other than gl_group_* works on a machine without NCCL.
 //
 // Sharding: rank r owns leaf block r of nranks = LDE cosets k with bitrev_r(k) in that block = whole
-// top-level Merkle subtrees + their cap entries (gl_ctx_set_shard).  Two collectives carry data: the all-gather of
-// coefficients (the IFFT is sharded by column: 1.13 GB in total at config 2, pipelined with the LDE) and the all-gather
-// of the cap (512 B); the query openings of a proof are exchanged by gl_group_commit_open.
+// top-level Merkle subtrees + their cap entries (gl_ctx_set_shard).  Two exchanges carry data: the all-gather of
+// coefficients (the IFFT is sharded by column: 1.13 GB in total at config 2, pipelined with the LDE; ncclAllGather for
+// resident inputs, the ranks' own pull kernels over peer memory for host buffers: "coefficient exchange over peer memory"
+// below) and the all-gather of the cap (512 B); the query openings of a proof are exchanged by gl_group_commit_open.
 #include <dlfcn.h>
 #include <nccl.h>
 #include <sched.h>
