@@ -157,3 +157,26 @@ def test_every_entry_point_has_its_reference_side_binding_documented():
     assert in_crate == declared, sorted(in_crate ^ declared)
     for f in ("Cargo.toml", "build.rs"):
         assert os.path.exists(os.path.join(root, "rust", "plonky2_gl_b200_sys", f))
+
+
+def test_cpp_mirror_compiles_and_links_without_a_gpu(tmp_path):
+    """include/plonky2_b200.hpp (the host side above the C ABI where the reference is compiled code) and the two C++ test
+    programs build against the in-tree library with plain g++: every entry point the mirror uses exists with the signature
+    it expects.  Nothing is run here (no device)."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "plonky2-lib_b200")
+    if not os.path.exists(os.path.join(libdir, "libgl_b200.so")):
+        pytest.skip("library not built")
+    for name in ("host_mirror_test", "fri_mirror_test"):
+        out = subprocess.run(["g++", "-std=c++17", "-O0", "-Wall", "-I", os.path.join(root, "include"),
+                              os.path.join(root, "tests", "cpp", name + ".cpp"), "-L", libdir, "-lgl_b200", f"-Wl,-rpath,{libdir}",
+                              "-o", str(tmp_path / name)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
