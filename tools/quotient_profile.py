@@ -1,5 +1,10 @@
-import importlib, sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+"""gl_quotient_polys at standard_recursion_config geometry (2^lg rows, default 18): wall clock of three calls; run it
+under `ncu --metrics gpu__time_duration.sum -k regex:k_quotient` for the kernel's share."""
+import importlib, os, sys, time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 glb = importlib.import_module("plonky2-lib_b200")
 ctx = glb.Context.default()
