@@ -180,3 +180,22 @@ def test_cpp_mirror_compiles_and_links_without_a_gpu(tmp_path):
                               os.path.join(root, "tests", "cpp", name + ".cpp"), "-L", libdir, "-lgl_b200", f"-Wl,-rpath,{libdir}",
                               "-o", str(tmp_path / name)], capture_output=True, text=True)
         assert out.returncode == 0, out.stderr
+
+
+def test_poseidon_linear_layer_tables_on_the_cpu(tmp_path):
+    """tests/cpp/poseidon_tables_test.cpp: the constant tables the FP64 linear layers add (signed S-box offsets included)
+    replayed with exact integers in the device's own schedule: every accumulator the fold sees stays in [0, 2^50) and the
+    permutation equals its definition."""
+    import os
+    import shutil
+    import subprocess
+
+    import pytest
+
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "poseidon_tables_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", os.path.join(root, "tests", "cpp", "poseidon_tables_test.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "poseidon_tables_test ok" in out.stdout, out.stdout + out.stderr
