@@ -279,7 +279,8 @@ int gl_group_commit_phase_ms(const gl_group *g, float *out6); /* first local ran
  * coeffs_out [nlocal] or NULL: GL_DEVICE: every rank receives all c coefficient vectors; GL_HOST: a rank writes only ITS
  * polynomials into coeffs_out[i] (one shared array is complete when the process holds every rank).
  * cap_out [nlocal] or NULL: the WHOLE cap [2^cap_height][4] on every rank.  handles [nlocal]: this rank's shard
- * (gl_commit_open serves its own leaves, gl_group_commit_open any leaf).  flags: GL_COMMIT_STREAM_HASH. */
+ * (gl_commit_open serves its own leaves, gl_group_commit_open any leaf).  flags: GL_COMMIT_STREAM_HASH, GL_COMMIT_BLINDING
+ * (every rank salts its own leaves). */
 int gl_group_commit_from_values(gl_group *g, const uint64_t *const *values, uint32_t log_n, uint32_t c, uint32_t rate_bits,
                                 uint32_t cap_height, uint64_t *const *coeffs_out, uint64_t *const *cap_out,
                                 gl_commit **handles, int space, uint32_t flags);
